@@ -1,0 +1,221 @@
+"""Generate golden vectors by running the UNMODIFIED reference
+(/root/reference/pyroved) on CPU under oracle/pyro_min, with epsilon injected.
+
+Run in the authoring container only (the reference does not travel):
+    python oracle/make_golden.py
+Writes tests/golden/<case>.npz (inputs, weights with the reference's
+state_dict keys, and outputs: loss, per-parameter gradients, reconstruction
+`loc`, encoder mu/sigma and the weights after one SVI step with Adam).
+TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "pyro_min"))
+sys.path.insert(0, "/root/reference")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import pyro  # noqa: E402
+import pyro.poutine as poutine  # noqa: E402
+from pyro.poutine import runtime  # noqa: E402
+import pyroved as pv  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(4)
+
+
+def blobs(n, h, w, seed=0, binary=True):
+    """SURVEY 8(d) cfg2 synthetic data: rotated/shifted anisotropic blobs."""
+    g = torch.Generator().manual_seed(seed)
+    th = (torch.rand(n, generator=g) * 2 - 1) * np.pi / 3
+    t = (torch.rand(n, 2, generator=g) * 2 - 1) * 0.1
+    xx = torch.linspace(-1, 1, h)
+    yy = torch.linspace(1, -1, w)
+    gx, gy = torch.meshgrid(xx, yy, indexing="ij")
+    gx = gx[None] - t[:, 0, None, None]
+    gy = gy[None] - t[:, 1, None, None]
+    c, s = torch.cos(th)[:, None, None], torch.sin(th)[:, None, None]
+    u = c * gx + s * gy
+    v = -s * gx + c * gy
+    p = torch.exp(-(u ** 2 / (2 * 0.15 ** 2) + v ** 2 / (2 * 0.45 ** 2)))
+    if binary:
+        return (torch.rand(n, h, w, generator=g) < p).float()
+    return p.float()
+
+
+def spectra(n, length, seed=1):
+    """examples/shiftVAE.ipynb cell 7 style: noisy shifted Gaussian peaks."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.linspace(-12, 12, length)
+    mu = (torch.rand(n, generator=g) - 0.5) * 14
+    sig = 1.0 + torch.rand(n, generator=g)
+    y = torch.exp(-0.5 * ((x[None] - mu[:, None]) / sig[:, None]) ** 2)
+    y = y + 0.05 * torch.randn(n, length, generator=g)
+    y = (y - y.min()) / (y.max() - y.min())
+    return y.float()
+
+
+def run_case(name, model, trainer_kw, args, eps_by_site, step_kw, aux=False,
+             model_fns=None):
+    """One SVI step of the reference with injected eps; saves everything."""
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    enum = trainer_kw.get("enumerate_parallel", False)
+
+    def hook(site, fn):
+        e = eps_by_site.get(site)
+        return e
+
+    runtime.EPS_HOOK[0] = hook
+    try:
+        # 1. loss + grads without optimizer (fresh autograd)
+        if aux:
+            tr = pv.trainers.auxSVItrainer(model, **trainer_kw)
+            svi = tr.loss_basic
+        else:
+            tr = pv.trainers.SVItrainer(model, **trainer_kw)
+            svi = tr.svi
+        model.load_state_dict(sd0)
+        for p in model.parameters():
+            p.grad = None
+        loss = svi.loss.loss_and_grads(svi.model, svi.guide, *args, **step_kw)
+        grads = {k: (p.grad.detach().clone() if p.grad is not None else None)
+                 for k, p in model.named_parameters()}
+        # reconstruction / encoder outputs from the traces
+        with torch.no_grad():
+            mt, gt = svi.loss._traces(svi.model, svi.guide, args, step_kw)
+        extra = {}
+        for n, site in mt.nodes.items():
+            if site["type"] == "sample" and site["is_observed"] and n in ("obs", "x"):
+                base = getattr(site["fn"], "base_dist", site["fn"])
+                extra["loc"] = (base.probs if hasattr(base, "probs") and not hasattr(base, "loc")
+                                else base.loc).detach().clone()
+        for n, site in gt.nodes.items():
+            if site["type"] == "sample":
+                base = getattr(site["fn"], "base_dist", site["fn"])
+                if hasattr(base, "loc") and hasattr(base, "scale"):
+                    extra["mu"] = base.loc.detach().clone()
+                    extra["sigma"] = base.scale.detach().clone()
+                    extra["z"] = site["value"].detach().clone()
+                elif hasattr(base, "probs"):
+                    extra["alpha"] = base.probs.detach().clone()
+        # 2. a real SVI step (loss_and_grads + Adam) from the same weights
+        model.load_state_dict(sd0)
+        for p in model.parameters():
+            p.grad = None
+        if aux:
+            tr = pv.trainers.auxSVItrainer(model, **trainer_kw)
+            model.load_state_dict(sd0)
+            loss_step = tr.compute_loss(*args, **step_kw)
+        else:
+            tr = pv.trainers.SVItrainer(model, **trainer_kw)
+            model.load_state_dict(sd0)
+            loss_step = tr.svi.step(*args, **step_kw)
+        sd1 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    finally:
+        runtime.EPS_HOOK[0] = None
+    out = {"loss": np.float64(loss), "loss_step": np.float64(loss_step)}
+    for i, a in enumerate(args):
+        if a is not None:
+            out["arg{}".format(i)] = a.numpy()
+    for k, v in eps_by_site.items():
+        out["eps." + k] = v.numpy()
+    for k, v in sd0.items():
+        out["w0." + k] = v.numpy()
+    # weights after one SVI step: small tensors whole, large ones as a fixed
+    # random subsample (keeps the fixtures small)
+    for k, v in sd1.items():
+        flat = v.reshape(-1)
+        if flat.numel() <= 4096:
+            out["w1." + k] = v.numpy()
+        else:
+            idx = torch.randperm(flat.numel(), generator=torch.Generator().manual_seed(99))[:512]
+            out["w1idx." + k] = idx.numpy()
+            out["w1sub." + k] = flat[idx].numpy()
+    for k, v in grads.items():
+        if v is not None:
+            out["grad." + k] = v.numpy()
+    for k, v in extra.items():
+        out[k] = v.numpy()
+    for k, v in step_kw.items():
+        out["kw." + k] = np.asarray(v, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("{:28s} loss {:.6f}  loss_step {:.6f}  ({} arrays)".format(
+        name, loss, loss_step, len(out)))
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def main():
+    dev = dict(device="cpu")
+    # cfg1: 1-D shift-invariant iVAE (BASELINE configs[0], reduced batch)
+    x = spectra(16, 64)[:, None, :]  # [B,1,64] as in the notebook
+    m = pv.models.iVAE((64,), latent_dim=2, invariances=["t"], seed=1, **dev)
+    run_case("ivae_1d_t", m, dev, (x,), {"latent": torch.randn(16, 3, generator=gen(1234))}, {})
+
+    # cfg2 (reduced batch): 28x28 rot+trans Bernoulli
+    x = blobs(16, 28, 28, seed=0)
+    m = pv.models.iVAE((28, 28), latent_dim=2, invariances=["r", "t"], seed=1, **dev)
+    eps = torch.randn(16, 5, generator=gen(1234))
+    run_case("ivae_28_rt", m, dev, (x,), {"latent": eps}, {})
+    m = pv.models.iVAE((28, 28), latent_dim=2, invariances=["r", "t"], seed=1, **dev)
+    run_case("ivae_28_rt_beta3", m, dev, (x,), {"latent": eps}, {"scale_factor": 3.0})
+
+    # r+t+s, class-conditional, gaussian sampler, relu (option coverage)
+    x = blobs(8, 12, 12, seed=3, binary=False)[:, None]  # [B,1,12,12] (Concat quirk)
+    y = pv.utils.to_onehot(torch.randint(0, 3, (8,), generator=gen(5)), 3)
+    m = pv.models.iVAE((12, 12), latent_dim=3, invariances=["r", "t", "s"], c_dim=3,
+                       activation="relu", sampler_d="gaussian", sigmoid_d=False,
+                       seed=2, sc_prior=0.2, dx_prior=0.15, dy_prior=0.05, **dev)
+    run_case("ivae_12_rts_cond_gauss", m, dev, (x, y),
+             {"latent": torch.randn(8, 7, generator=gen(7))}, {"scale_factor": 2.0})
+
+    # vanilla VAE (no invariances -> fcDecoderNet)
+    x = blobs(8, 12, 12, seed=4)
+    m = pv.models.iVAE((12, 12), latent_dim=2, invariances=None, seed=3, **dev)
+    run_case("ivae_12_vanilla", m, dev, (x,),
+             {"latent": torch.randn(8, 2, generator=gen(8))}, {})
+
+    # scale only, softplus activation, non-default hidden dims
+    x = blobs(8, 16, 16, seed=6)
+    m = pv.models.iVAE((16, 16), latent_dim=2, invariances=["s"], seed=4,
+                       hidden_dim_e=[64, 32], hidden_dim_d=[64, 64, 64],
+                       activation="softplus", **dev)
+    run_case("ivae_16_s_softplus", m, dev, (x,),
+             {"latent": torch.randn(8, 3, generator=gen(9))}, {})
+
+    # cfg3 (reduced): jiVAE rot-invariant, enumerated discrete latent
+    x = blobs(8, 28, 28, seed=10)
+    m = pv.models.jiVAE((28, 28), latent_dim=2, discrete_dim=3, invariances=["r"], seed=1, **dev)
+    run_case("jivae_28_r", m, dict(enumerate_parallel=True, **dev), (x,),
+             {"latent_cont": torch.randn(8, 3, generator=gen(11))},
+             {"scale_factor": [3.0, 2.0]})
+
+    # cfg4 (reduced): ssiVAE, unsupervised (enumerated y) and supervised
+    x = blobs(8, 16, 16, seed=12).flatten(1)  # [B,N]: Concat only flattens >=4-D (utils/nn.py:69)
+    m = pv.models.ssiVAE((16, 16), latent_dim=2, num_classes=4, invariances=["r"], seed=1, **dev)
+    run_case("ssivae_16_r_unsup", m, dev, (x, None),
+             {"z": torch.randn(4, 8, 3, generator=gen(13))},
+             {"aux_loss_multiplier": 50.0}, aux=True)
+    ys = pv.utils.to_onehot(torch.randint(0, 4, (8,), generator=gen(14)), 4)
+    m = pv.models.ssiVAE((16, 16), latent_dim=2, num_classes=4, invariances=["r"], seed=1, **dev)
+    run_case("ssivae_16_r_sup", m, dev, (x, ys),
+             {"z": torch.randn(8, 3, generator=gen(15))},
+             {"aux_loss_multiplier": 50.0}, aux=True)
+
+    if "--ved" not in sys.argv:
+        return
+    # cfg5 (reduced): VED image -> spectrum (large fixture: generated on demand)
+    x = blobs(4, 32, 32, seed=16, binary=False)[:, None]
+    ysp = spectra(4, 64, seed=17)[:, None]
+    m = pv.models.VED((32, 32), (64,), latent_dim=2, seed=1)
+    run_case("ved_32_64", m, dev, (x, ysp),
+             {"z": torch.randn(4, 2, generator=gen(18))}, {"scale_factor": 4.0})
+
+
+if __name__ == "__main__":
+    main()

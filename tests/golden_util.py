@@ -1,0 +1,66 @@
+"""Load golden fixtures written by oracle/make_golden.py (outputs of the
+unmodified reference run under oracle/pyro_min)."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CASES = {
+    # name: (model kind, constructor kwargs)
+    "ivae_1d_t": ("ivae", dict(data_dim=(64,), latent_dim=2, invariances=["t"])),
+    "ivae_28_rt": ("ivae", dict(data_dim=(28, 28), latent_dim=2, invariances=["r", "t"])),
+    "ivae_28_rt_beta3": ("ivae", dict(data_dim=(28, 28), latent_dim=2, invariances=["r", "t"])),
+    "ivae_12_rts_cond_gauss": ("ivae", dict(
+        data_dim=(12, 12), latent_dim=3, invariances=["r", "t", "s"], c_dim=3,
+        activation="relu", sampler_d="gaussian", sigmoid_d=False,
+        sc_prior=0.2, dx_prior=0.15, dy_prior=0.05)),
+    "ivae_12_vanilla": ("ivae", dict(data_dim=(12, 12), latent_dim=2, invariances=None)),
+    "ivae_16_s_softplus": ("ivae", dict(
+        data_dim=(16, 16), latent_dim=2, invariances=["s"], activation="softplus",
+        hidden_dim_e=[64, 32], hidden_dim_d=[64, 64, 64])),
+    "jivae_28_r": ("jivae", dict(data_dim=(28, 28), latent_dim=2, discrete_dim=3,
+                                 invariances=["r"])),
+    "ssivae_16_r_unsup": ("ssivae", dict(data_dim=(16, 16), latent_dim=2, num_classes=4,
+                                         invariances=["r"])),
+    "ssivae_16_r_sup": ("ssivae", dict(data_dim=(16, 16), latent_dim=2, num_classes=4,
+                                       invariances=["r"])),
+}
+
+
+class Golden:
+    def __init__(self, name):
+        self.name = name
+        self.kind, self.kwargs = CASES[name]
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.raw = {k: z[k] for k in z.files}
+        self.loss = float(self.raw["loss"])
+        self.loss_step = float(self.raw["loss_step"])
+
+    def t(self, key, dtype=torch.float32):
+        return torch.from_numpy(self.raw[key]).to(dtype)
+
+    def has(self, key):
+        return key in self.raw
+
+    def group(self, prefix, dtype=torch.float32):
+        out = OrderedDict()
+        for k, v in self.raw.items():
+            if k.startswith(prefix + "."):
+                out[k[len(prefix) + 1:]] = torch.from_numpy(v).to(dtype)
+        return out
+
+    def args(self, dtype=torch.float32):
+        x = self.t("arg0", dtype)
+        y = self.t("arg1", dtype) if self.has("arg1") else None
+        return x, y
+
+    def eps(self, dtype=torch.float32):
+        e = self.group("eps", dtype)
+        assert len(e) == 1
+        return next(iter(e.values()))
+
+    def kw(self):
+        return {k[3:]: v for k, v in self.raw.items() if k.startswith("kw.")}
