@@ -1,0 +1,207 @@
+/*
+ * pvb.h -- C ABI of libpvb.so: the hand-written sm_100a kernels behind
+ * pyroved_b200 (B200-native SVI hot path of pyroVED).
+ *
+ * The reference (pure Python, /root/reference/pyroved) has NO FFI/operator
+ * interface for this path: its boundary is the Python class
+ * API.  The entry points below are therefore the operators a maintainer
+ * would bind from the reference's Python via ctypes (INTEGRATION.md shows the
+ * stubs); each cites the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer to contiguous fp32 (unless noted)
+ *   - weights use torch's nn.Linear layout  W[out][in]  row-major
+ *   - `stream` is a cudaStream_t passed as void*; kernels are launched on it
+ *     and the call never synchronises, allocates or keeps state (re-entrant)
+ *   - return value: 0 ok, <0 bad argument (see pvb_last_error_string),
+ *     >0 a cudaError_t
+ *   - "instance" i in [0, I): one (enumeration index k, sample b) pair,
+ *     i = k*B + b ; I = B for iVAE, I = K*B for enumerated jiVAE / ssiVAE
+ *     (reference models/jivae.py:182-194, models/ssivae.py:217-227)
+ *   - "row" r = i*N + p : pixel p of instance i through the spatial decoder
+ */
+#ifndef PVB_H_
+#define PVB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation codes (reference utils/nn.py:118-124, torch module defaults) */
+enum {
+  PVB_ACT_NONE = 0,
+  PVB_ACT_TANH = 1,
+  PVB_ACT_RELU = 2,
+  PVB_ACT_LRELU = 3,    /* slope 0.01 */
+  PVB_ACT_SOFTPLUS = 4, /* beta 1, threshold 20 */
+  PVB_ACT_GELU = 5,     /* erf form */
+  PVB_ACT_SIGMOID = 6
+};
+
+/* decoder samplers (reference utils/prob.py:25-29) */
+enum {
+  PVB_SAMPLER_BERNOULLI = 0,
+  PVB_SAMPLER_GAUSSIAN = 1,
+  PVB_SAMPLER_CONT_BERNOULLI = 2
+};
+
+/* invariance flags (reference models/base.py:54-67, 107-118) */
+enum { PVB_INV_R = 1, PVB_INV_T = 2, PVB_INV_S = 4 };
+
+int pvb_version(void);
+const char* pvb_last_error_string(void);
+/* number of kernels this library has launched in this process (statistics) */
+long long pvb_launch_count(void);
+/* 1 if the library was built with the tcgen05 spatial-decoder kernel */
+int pvb_has_tcgen05(void);
+
+/* ---- dense layers: nn.Linear + activation (nets/fc.py:55-61,307-324) ---- */
+/* y[M,N] = act(x[M,K] W[N,K]^T + b[N]);  pre (optional, may be NULL) receives
+ * the pre-activation (only needed for PVB_ACT_GELU backward). */
+int pvb_linear_fwd(const float* x, const float* W, const float* b, float* y,
+                   float* pre, int64_t M, int N, int K, int act, void* stream);
+/* Given dy (gradient wrt y), the saved output y (and pre for gelu):
+ *   dpre = dy * act'(.)            (written to dpre_ws [M,N], may alias dy)
+ *   dx[M,K]  = dpre W              (skipped if dx == NULL; dx_accumulate adds)
+ *   dW[N,K] += dpre^T x ; db[N] += colsum(dpre)   (always accumulate) */
+int pvb_linear_bwd(const float* x, const float* W, const float* y,
+                   const float* pre, const float* dy, float* dpre_ws,
+                   float* dx, int dx_accumulate, float* dW, float* db,
+                   int64_t M, int N, int K, int act, void* stream);
+
+/* ---- latent sample + sampled KL (models/ivae.py:182-183,217-221) ---- */
+/* eps[n] ~ N(0,1): Philox4x32-10 + Box-Muller, element e gets counter
+ * (first_index + e, *step_counter), key = seed: identical for any sharding. */
+int pvb_randn(float* eps, int64_t n, uint64_t seed, const int32_t* step_counter,
+              int64_t first_index, void* stream);
+/* sigma = softplus(s_pre); z = mu + sigma*eps;
+ * kl[i] = sum_d(-z^2/2 + eps^2/2 + log sigma) = log p(z_i) - log q(z_i). */
+int pvb_latent_fwd(const float* mu, const float* s_pre, const float* eps,
+                   float* sigma, float* z, float* kl, int64_t I, int Z,
+                   void* stream);
+/* loss = -sum_i w_i (ll_i + beta kl_i) [+ ...]; gz = dloss/dz through the
+ * decoder.  Writes dloss/dmu and dloss/ds_pre.  w may be NULL (all ones). */
+int pvb_latent_bwd(const float* gz, const float* eps, const float* sigma,
+                   const float* s_pre, const float* z, const float* w,
+                   float beta, float* gmu, float* gs_pre, int64_t I, int Z,
+                   void* stream);
+
+/* ---- coordinate transform folded into the first decoder layer ----------
+ * Replaces split_latent + transform_coordinates + coord_latent pre-activation
+ * (models/base.py:97-119, models/ivae.py:187-192, utils/coord.py:47-88,
+ * nets/fc.py:226-235; algebra: SURVEY.md Appendix C):
+ *   pre0[i,p,:] = Uv[i,0,:]*gx_p + Uv[i,1,:]*gy_p + Uv[i,2,:]
+ * z [I,Z] holds (phi | dx dy | s | content[L]) in that fixed order;
+ * cond [I,C] (one-hot / class vector concatenated to the content code, may be
+ * NULL when C == 0).  Wc [Hd, ndim], bc [Hd], Wz [Hd, L+C] (no bias). */
+typedef struct {
+  int32_t ndim;        /* 1 or 2 */
+  int32_t inv;         /* PVB_INV_* flags (1-D: PVB_INV_T only) */
+  int32_t latent_dim;  /* L */
+  int32_t cond_dim;    /* C */
+  int32_t hidden;      /* Hd */
+  float dx_prior, dy_prior, sc_prior;
+} pvb_fold_cfg;
+int pvb_fold_fwd(const pvb_fold_cfg* cfg, const float* z, const float* cond,
+                 const float* Wc, const float* bc, const float* Wz, float* Uv,
+                 int64_t I, void* stream);
+/* gUv [I,3,Hd] -> gz [I,Z] (overwritten), gcond [I,C] (optional, overwritten),
+ * and weight-gradient partials: part[G][Hd*(ndim+1+L+C)] laid out as
+ * (gWc[Hd][ndim] | gbc[Hd] | gWz[Hd][L+C]); reduce with pvb_reduce_partials.
+ * G = pvb_fold_bwd_num_partials(). */
+int pvb_fold_bwd_num_partials(void);
+int pvb_fold_bwd(const pvb_fold_cfg* cfg, const float* z, const float* cond,
+                 const float* Wc, const float* Wz, const float* gUv, float* gz,
+                 float* gcond, float* part, int64_t I, void* stream);
+
+/* ---- spatial decoder, generic fp32 path (any hidden sizes / activation) --
+ * h0[r,:] = tanh(pre0) with the grid regenerated from the pixel index
+ * (utils/coord.py:14-18,43; nets/fc.py:216-218,236-237 -- always tanh). */
+int pvb_sdec_h0_fwd(const float* Uv, float* h0, int64_t I, int H, int W,
+                    int ndim, int Hd, void* stream);
+/* dh0 [R,Hd] (gradient wrt h0) + saved h0 -> gUv [I,3,Hd] */
+int pvb_sdec_h0_bwd(const float* dh0, const float* h0, float* gUv, int64_t I,
+                    int H, int W, int ndim, int Hd, void* stream);
+
+/* ---- observation log-likelihood + ELBO reduction -----------------------
+ * logit[R] = decoder `out` layer pre-activation, x [B,N] targets, row r of
+ * instance i scores against x[i % B] (utils/prob.py:25-29; torch Bernoulli /
+ * Normal log_prob; models/ivae.py:200-202).
+ *   rowll[r]  = log p(x | loc)              (per pixel)
+ *   dlogit[r] = w_i * d(-rowll)/dlogit      (seed of the backward pass)
+ *   loc[r]    = reconstruction (sigmoid(logit) if sigmoid_d else logit); may be NULL
+ * w may be NULL (all ones). */
+int pvb_obs_loglik(const float* logit, const float* x, const float* w,
+                   float* rowll, float* dlogit, float* loc, int64_t I,
+                   int64_t B, int N, int sampler, int sigmoid_d,
+                   float decoder_sig, void* stream);
+/* ll[i] = sum_p rowll[i,p] (deterministic warp-shuffle tree);
+ * loss_out[0] (+)= -sum_i w_i (ll_i + beta kl_i);  kl, w may be NULL. */
+int pvb_elbo_reduce(const float* rowll, const float* kl, const float* w,
+                    float beta, float* ll, float* loss_out, int accumulate,
+                    int64_t I, int N, void* stream);
+
+/* ---- enumerated discrete latent (TraceEnum_ELBO expectation) -----------
+ * alpha = softmax(logits [B,K]); w[k*B+b] = alpha[b,k]
+ * (nets/fc.py:101-108,264-271; models/jivae.py:199-220; ssivae.py:198-215) */
+int pvb_enum_head_fwd(const float* logits, float* alpha, float* w, int64_t B,
+                      int K, void* stream);
+/* cost[k*B+b] = ll + beta_z*kl (ssiVAE) or ll (jiVAE);
+ * elbo_b = sum_k alpha_bk (cost_kb + beta_d (log(1/K) - log alpha_bk));
+ * loss_out[0] -= sum_b elbo_b ; glogits = dloss/dlogits through the softmax.
+ * glogits must have room for B*K + B floats (the tail is per-sample scratch). */
+int pvb_enum_head_bwd(const float* alpha, const float* cost, float beta_d,
+                      float* glogits, float* loss_out, int64_t B, int K,
+                      void* stream);
+/* supervised classification term (ssivae.py:229-242):
+ * loss_out[0] -= mult * sum_b log alpha[b, y_b]; glogits written
+ * (room for B*K + B floats, as above). */
+int pvb_class_nll(const float* logits, const float* y_onehot, float mult,
+                  float* glogits, float* loss_out, int64_t B, int K,
+                  void* stream);
+
+/* ---- optimizer / reductions -------------------------------------------- */
+/* out[j] (+)= sum_g part[g*part_stride + j], j < n, fixed order (deterministic) */
+int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,
+                        int64_t part_stride, int accumulate, void* stream);
+int pvb_counter_add(int32_t* counter, int32_t v, void* stream);
+/* torch.optim.Adam defaults (Pyro optim.Adam, trainers/svi.py:79-81):
+ * t = *step_counter (already incremented for this step). */
+int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
+                  float lr, float beta1, float beta2, float eps,
+                  const int32_t* step_counter, void* stream);
+
+/* ---- spatial decoder, fused tcgen05 path (Hd = 128, two tanh layers) ----
+ * One persistent kernel per step: grid -> h0 -> (128x128 tcgen05 GEMM + tanh)
+ * x2 -> out layer -> log-lik -> full backward, activations never leave the
+ * SM (nets/fc.py:189-237 forward; autograd backward of the same).
+ * Outputs: rowll[R], loc[R] (optional), and when `backward` != 0:
+ *   gUv_part [T][slots=5][3][128]  per-tile partial sums (T = #tiles of 128 rows)
+ *   wgrad_part [G][PVB_TC_WGRAD_FLOATS]  per-CTA weight-gradient partials
+ * Workspace sizes via pvb_sdec_tc_sizes. */
+typedef struct {
+  int64_t tiles;         /* T */
+  int32_t ctas;          /* G */
+  int64_t gUv_part_floats;
+  int64_t wgrad_part_floats; /* G * PVB_TC_WGRAD_FLOATS */
+} pvb_tc_sizes;
+#define PVB_TC_WGRAD_FLOATS (2 * 128 * 128 + 2 * 128 + 128 + 1)
+int pvb_sdec_tc_sizes(int64_t I, int N, pvb_tc_sizes* out);
+int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
+                     const float* W1, const float* b1, const float* W2,
+                     const float* b2, const float* wo, const float* bo,
+                     float* rowll, float* loc, float* gUv_part,
+                     float* wgrad_part, int64_t I, int64_t B, int H, int W,
+                     int ndim, int sampler, int sigmoid_d, float decoder_sig,
+                     int backward, void* stream);
+/* gUv_part -> gUv [I,3,128] (deterministic) */
+int pvb_sdec_tc_gather_gUv(const float* gUv_part, float* gUv, int64_t I, int N,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVB_H_ */

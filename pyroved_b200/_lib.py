@@ -1,0 +1,97 @@
+"""ctypes binding of libpvb.so (the C ABI declared in include/pvb.h).
+
+The CUDA library is the ONLY compute path of this package: if it is missing
+the import of any compute entry point fails loudly (no CPU / eager fallback).
+Build it with `python -c "import __graft_entry__ as g; g.build()"` or
+`pyroved_b200/csrc/build.sh`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpvb.so")
+
+_f = C.c_void_p      # device pointer (float*)
+_i64 = C.c_int64
+_i32 = C.c_int
+_fl = C.c_float
+_st = C.c_void_p     # cudaStream_t
+
+
+class FoldCfg(C.Structure):
+    """pvb_fold_cfg"""
+    _fields_ = [("ndim", C.c_int32), ("inv", C.c_int32), ("latent_dim", C.c_int32),
+                ("cond_dim", C.c_int32), ("hidden", C.c_int32),
+                ("dx_prior", C.c_float), ("dy_prior", C.c_float), ("sc_prior", C.c_float)]
+
+
+class TcSizes(C.Structure):
+    """pvb_tc_sizes"""
+    _fields_ = [("tiles", C.c_int64), ("ctas", C.c_int32),
+                ("gUv_part_floats", C.c_int64), ("wgrad_part_floats", C.c_int64)]
+
+
+# name -> argtypes ; every entry returns int except where noted.  This table
+# must list every symbol of include/pvb.h (tests/test_abi.py checks it).
+SIGNATURES = {
+    "pvb_version": [],
+    "pvb_last_error_string": [],
+    "pvb_launch_count": [],
+    "pvb_has_tcgen05": [],
+    "pvb_linear_fwd": [_f, _f, _f, _f, _f, _i64, _i32, _i32, _i32, _st],
+    "pvb_linear_bwd": [_f, _f, _f, _f, _f, _f, _f, _i32, _f, _f, _i64, _i32, _i32, _i32, _st],
+    "pvb_randn": [_f, _i64, C.c_uint64, _f, _i64, _st],
+    "pvb_latent_fwd": [_f, _f, _f, _f, _f, _f, _i64, _i32, _st],
+    "pvb_latent_bwd": [_f, _f, _f, _f, _f, _f, _fl, _f, _f, _i64, _i32, _st],
+    "pvb_fold_fwd": [C.POINTER(FoldCfg), _f, _f, _f, _f, _f, _f, _i64, _st],
+    "pvb_fold_bwd_num_partials": [],
+    "pvb_fold_bwd": [C.POINTER(FoldCfg), _f, _f, _f, _f, _f, _f, _f, _f, _i64, _st],
+    "pvb_sdec_h0_fwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
+    "pvb_sdec_h0_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _st],
+    "pvb_obs_loglik": [_f, _f, _f, _f, _f, _f, _i64, _i64, _i32, _i32, _i32, _fl, _st],
+    "pvb_elbo_reduce": [_f, _f, _f, _fl, _f, _f, _i32, _i64, _i32, _st],
+    "pvb_enum_head_fwd": [_f, _f, _f, _i64, _i32, _st],
+    "pvb_enum_head_bwd": [_f, _f, _fl, _f, _f, _i64, _i32, _st],
+    "pvb_class_nll": [_f, _f, _fl, _f, _f, _i64, _i32, _st],
+    "pvb_reduce_partials": [_f, _f, _i32, _i64, _i64, _i32, _st],
+    "pvb_counter_add": [_f, _i32, _st],
+    "pvb_adam_flat": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _st],
+    "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
+    "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
+                         _i32, _i32, _i32, _i32, _i32, _fl, _i32, _st],
+    "pvb_sdec_tc_gather_gUv": [_f, _f, _i64, _i32, _st],
+}
+
+# floats per CTA in pvb_sdec_tc_step's weight-gradient partials (PVB_TC_WGRAD_FLOATS)
+TC_WGRAD_FLOATS = 2 * 128 * 128 + 2 * 128 + 128 + 1
+
+_LIB = None
+
+
+class PvbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libpvb.so once; raise loudly if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise PvbError(
+                "pyroved_b200: CUDA extension {} is missing. There is no CPU fallback; "
+                "build it with pyroved_b200/csrc/build.sh (needs nvcc, sm_100a).".format(LIB_PATH))
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = (C.c_char_p if name == "pvb_last_error_string" else
+                          C.c_longlong if name == "pvb_launch_count" else C.c_int)
+        _LIB = handle
+    return _LIB
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().pvb_last_error_string()
+        raise PvbError("{} failed (code {}): {}".format(
+            what or "libpvb call", rc, msg.decode() if msg else ""))

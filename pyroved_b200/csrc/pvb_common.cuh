@@ -1,0 +1,104 @@
+// Shared device/host helpers for libpvb (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "../../include/pvb.h"
+
+namespace pvb {
+
+void set_error(const char* fmt, ...);
+void count_launch();  // statistics only: kernels launched by this library
+
+#define PVB_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      pvb::set_error(__VA_ARGS__);          \
+      return -1;                            \
+    }                                       \
+  } while (0)
+
+static inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("CUDA launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- activations (torch module defaults) ---------------------------------
+__device__ __forceinline__ float softplus_f(float x) {
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case PVB_ACT_TANH: return tanhf(x);
+    case PVB_ACT_RELU: return x > 0.f ? x : 0.f;
+    case PVB_ACT_LRELU: return x > 0.f ? x : 0.01f * x;
+    case PVB_ACT_SOFTPLUS: return softplus_f(x);
+    case PVB_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case PVB_ACT_SIGMOID: return sigmoid_f(x);
+    default: return x;
+  }
+}
+// derivative expressed from the saved OUTPUT y (pre only needed for gelu)
+__device__ __forceinline__ float act_grad(float y, float pre, int act) {
+  switch (act) {
+    case PVB_ACT_TANH: return 1.f - y * y;
+    case PVB_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case PVB_ACT_LRELU: return y > 0.f ? 1.f : 0.01f;
+    case PVB_ACT_SOFTPLUS: return 1.f - expf(-y);  // sigmoid(pre), y = log(1+e^pre)
+    case PVB_ACT_GELU: {
+      float c = 0.5f * (1.f + erff(pre * 0.70710678118654752f));
+      return c + pre * 0.3989422804014327f * expf(-0.5f * pre * pre);
+    }
+    case PVB_ACT_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (result valid in every thread)
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem32[wid] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  float r = (lane < nw) ? smem32[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// pixel p -> grid coordinates, utils/coord.py:14-18 (2-D) and :43 (1-D).
+// torch.linspace(a, b, n)[i] = a + i*(b-a)/(n-1) for the first half and
+// b - (n-1-i)*step for the second half (symmetric evaluation).
+__device__ __forceinline__ float linspace_at(float a, float b, int n, int i) {
+  if (n == 1) return a;
+  float step = (b - a) / (float)(n - 1);
+  return (i < n / 2) ? a + step * (float)i : b - step * (float)(n - 1 - i);
+}
+__device__ __forceinline__ void grid_xy(int p, int H, int W, int ndim, float& gx, float& gy) {
+  if (ndim == 1) {
+    gx = linspace_at(1.f, -1.f, H, p);
+    gy = 0.f;
+  } else {
+    int i = p / W, j = p - i * W;
+    gx = linspace_at(-1.f, 1.f, H, i);
+    gy = linspace_at(1.f, -1.f, W, j);
+  }
+}
+
+}  // namespace pvb

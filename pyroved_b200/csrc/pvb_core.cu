@@ -1,0 +1,100 @@
+// libpvb: error state, version, small utility kernels (reduce, counter, Adam).
+#include <atomic>
+#include <cstdarg>
+#include "pvb_common.cuh"
+
+namespace pvb {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace pvb
+
+extern "C" long long pvb_launch_count(void) { return pvb::g_launches.load(); }
+extern "C" int pvb_version(void) { return 100; }
+extern "C" const char* pvb_last_error_string(void) { return pvb::g_err; }
+
+// ---------------------------------------------------------------------------
+__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                       int G, int64_t n, int64_t stride, int accumulate) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int g = 0; g < G; ++g) s += part[(int64_t)g * stride + i];
+  out[i] = accumulate ? out[i] + s : s;
+}
+extern "C" int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,
+                                   int64_t part_stride, int accumulate, void* stream) {
+  PVB_CHECK_ARG(part && out && G > 0 && n >= 0 && part_stride >= n, "pvb_reduce_partials: bad argument");
+  if (n == 0) return 0;
+  reduce_partials_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(part, out, G, n,
+                                                                              part_stride, accumulate); pvb::count_launch();
+  return pvb::launch_status();
+}
+
+__global__ void counter_add_kernel(int32_t* c, int32_t v) { *c += v; }
+extern "C" int pvb_counter_add(int32_t* counter, int32_t v, void* stream) {
+  PVB_CHECK_ARG(counter, "pvb_counter_add: null counter");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, v); pvb::count_launch();
+  return pvb::launch_status();
+}
+
+// torch.optim.Adam (defaults; no amsgrad / weight decay):
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2
+//   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                 float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                 float b1, float b2, float eps,
+                                 const int32_t* __restrict__ step_counter) {
+  const float t = (float)(*step_counter);
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2s = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 P = *reinterpret_cast<float4*>(p + i);
+    const float4 Gv = *reinterpret_cast<const float4*>(g + i);
+    float4 Mv = *reinterpret_cast<float4*>(m + i);
+    float4 Vv = *reinterpret_cast<float4*>(v + i);
+    float* pp = reinterpret_cast<float*>(&P);
+    const float* gg = reinterpret_cast<const float*>(&Gv);
+    float* mm = reinterpret_cast<float*>(&Mv);
+    float* vv = reinterpret_cast<float*>(&Vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] = b1 * mm[k] + (1.f - b1) * gg[k];
+      vv[k] = b2 * vv[k] + (1.f - b2) * gg[k] * gg[k];
+      pp[k] -= step_size * mm[k] / (sqrtf(vv[k]) / bc2s + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = P;
+    *reinterpret_cast<float4*>(m + i) = Mv;
+    *reinterpret_cast<float4*>(v + i) = Vv;
+  } else {
+    for (int64_t j = i; j < n; ++j) {
+      float gj = g[j];
+      float mj = b1 * m[j] + (1.f - b1) * gj;
+      float vj = b2 * v[j] + (1.f - b2) * gj * gj;
+      m[j] = mj;
+      v[j] = vj;
+      p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
+    }
+  }
+}
+extern "C" int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                             float beta1, float beta2, float eps, const int32_t* step_counter,
+                             void* stream) {
+  PVB_CHECK_ARG(p && g && m && v && step_counter && n >= 0, "pvb_adam_flat: bad argument");
+  PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                    ((uintptr_t)v % 16 == 0),
+                "pvb_adam_flat: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  int64_t n4 = (n + 3) / 4;
+  adam_flat_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1,
+                                                                         beta2, eps, step_counter); pvb::count_launch();
+  return pvb::launch_status();
+}

@@ -1,0 +1,215 @@
+// Generic fp32 SIMT GEMM + nn.Linear forward/backward built on it.
+// Used for the (small) encoder / classifier layers and by the generic
+// spatial-decoder path; the hot 128x128 decoder layers run on tcgen05
+// (pvb_sdec_tc.cu).
+#include "pvb_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+// C[M,N] = epi( sum_k opA(A)[m,k] * opB(B)[k,n] )   row-major everywhere
+//   TA == 0: A is [M,K] (lda)   TA == 1: A is [K,M] (lda)   (op = transpose)
+//   TB == 0: B is [K,N] (ldb)   TB == 1: B is [N,K] (ldb)
+// epilogue: + bias[n], activation, optional pre-activation store, accumulate.
+// gridDim.z > 1: split-K, partial sums atomically added into C (C must be
+// pre-initialised; bias/act must be off).
+template <int TA, int TB>
+__global__ void __launch_bounds__(NT)
+sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+             float* __restrict__ Cpre, const float* __restrict__ bias, int64_t M, int N, int64_t K,
+             int64_t lda, int64_t ldb, int64_t ldc, int act, int accumulate, int64_t k_chunk) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  const int64_t ke = (kb + k_chunk < K) ? kb + k_chunk : K;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    // ---- stage A tile (BM x BK) ----
+#pragma unroll
+    for (int it = 0; it < (BM * BK) / NT; ++it) {
+      int idx = tid + it * NT;
+      int m, k;
+      if (TA == 0) { k = idx % BK; m = idx / BK; }   // k fastest (contiguous in memory)
+      else         { m = idx % BM; k = idx / BM; }   // m fastest
+      int64_t gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < ke) v = (TA == 0) ? A[gm * lda + gk] : A[gk * lda + gm];
+      As[k][m] = v;
+    }
+    // ---- stage B tile (BK x BN) ----
+#pragma unroll
+    for (int it = 0; it < (BN * BK) / NT; ++it) {
+      int idx = tid + it * NT;
+      int n, k;
+      if (TB == 0) { n = idx % BN; k = idx / BN; }
+      else         { k = idx % BK; n = idx / BK; }
+      int gn = n0 + n;
+      int64_t gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < ke) v = (TB == 0) ? B[gk * ldb + gn] : B[(int64_t)gn * ldb + gk];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      float* c = C + gm * ldc + gn;
+      if (gridDim.z > 1) {
+        atomicAdd(c, v);
+      } else {
+        if (bias) v += bias[gn];
+        if (Cpre) Cpre[gm * ldc + gn] = v;
+        v = pvb::act_fwd(v, act);
+        *c = accumulate ? *c + v : v;
+      }
+    }
+  }
+}
+
+template <int TA, int TB>
+int launch_sgemm(const float* A, const float* B, float* C, float* Cpre, const float* bias,
+                 int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int act,
+                 int accumulate, int splits, cudaStream_t st) {
+  if (M == 0 || N == 0) return 0;
+  int64_t gy = (M + BM - 1) / BM;
+  PVB_CHECK_ARG(gy <= 65535 * 16, "sgemm: M too large");
+  int64_t k_chunk = K;
+  if (splits > 1) {
+    k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+    splits = (int)((K + k_chunk - 1) / k_chunk);
+  }
+  // gridDim.y limit is 65535: fold extra row-blocks by looping on the host
+  for (int64_t y0 = 0; y0 < gy; y0 += 65535) {
+    int64_t ny = (gy - y0 < 65535) ? gy - y0 : 65535;
+    dim3 grid((N + BN - 1) / BN, (unsigned)ny, splits > 1 ? splits : 1);
+    int64_t moff = y0 * BM;
+    const float* Ao = (TA == 0) ? A + moff * lda : A + moff;
+    sgemm_kernel<TA, TB><<<grid, NT, 0, st>>>(Ao, B, C + moff * ldc, Cpre ? Cpre + moff * ldc : nullptr,
+                                              bias, M - moff, N, K, lda, ldb, ldc, act, accumulate,
+                                              k_chunk); pvb::count_launch();
+  }
+  return pvb::launch_status();
+}
+
+// dpre = dy * act'(y)   (elementwise; may run in place)
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                               const float* __restrict__ pre, float* __restrict__ dpre, int64_t n,
+                               int act) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float p = pre ? pre[i] : 0.f;
+    dpre[i] = dy[i] * pvb::act_grad(y[i], p, act);
+  }
+}
+
+// db[n] += sum_m dpre[m,n]: each block sums a chunk of rows for 32 columns and
+// adds its partial atomically.
+constexpr int CS_ROWS = 2048;
+__global__ void colsum_kernel(const float* __restrict__ a, float* __restrict__ out, int64_t M,
+                              int N) {
+  __shared__ float sm[32][33];
+  int n = blockIdx.x * 32 + threadIdx.x;
+  int64_t m_begin = (int64_t)blockIdx.y * CS_ROWS;
+  int64_t m_end = m_begin + CS_ROWS < M ? m_begin + CS_ROWS : M;
+  float s = 0.f;
+  if (n < N)
+    for (int64_t m = m_begin + threadIdx.y; m < m_end; m += 32) s += a[m * N + n];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
+    atomicAdd(out + n, t);
+  }
+}
+
+}  // namespace
+
+extern "C" int pvb_linear_fwd(const float* x, const float* W, const float* b, float* y, float* pre,
+                              int64_t M, int N, int K, int act, void* stream) {
+  PVB_CHECK_ARG(x && W && y && M >= 0 && N > 0 && K > 0, "pvb_linear_fwd: bad argument");
+  PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID, "pvb_linear_fwd: unknown activation %d", act);
+  return launch_sgemm<0, 1>(x, W, y, pre, b, M, N, K, K, K, N, act, 0, 1, (cudaStream_t)stream);
+}
+
+extern "C" int pvb_linear_bwd(const float* x, const float* W, const float* y, const float* pre,
+                              const float* dy, float* dpre_ws, float* dx, int dx_accumulate,
+                              float* dW, float* db, int64_t M, int N, int K, int act,
+                              void* stream) {
+  PVB_CHECK_ARG(x && W && dy && dpre_ws && M >= 0 && N > 0 && K > 0, "pvb_linear_bwd: bad argument");
+  PVB_CHECK_ARG(act == PVB_ACT_NONE || y, "pvb_linear_bwd: saved output required");
+  PVB_CHECK_ARG(act != PVB_ACT_GELU || pre, "pvb_linear_bwd: gelu needs the pre-activation");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) return 0;
+  const float* dpre = dy;
+  if (act != PVB_ACT_NONE) {
+    int64_t n = M * N;
+    int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    act_bwd_kernel<<<blocks, 256, 0, st>>>(dy, y, pre, dpre_ws, n, act); pvb::count_launch();
+    dpre = dpre_ws;
+  }
+  int rc;
+  if (dx) {
+    // dx[M,K] = dpre[M,N] W[N,K]
+    rc = launch_sgemm<0, 0>(dpre, W, dx, nullptr, nullptr, M, K, N, N, K, K, PVB_ACT_NONE,
+                            dx_accumulate, 1, st);
+    if (rc) return rc;
+  }
+  if (dW) {
+    // dW[N,K] += dpre^T[N,M] x[M,K]   (reduction over M: split-K when long)
+    int splits = 1;
+    int64_t tiles = (int64_t)((N + BN - 1) / BN) * ((K + BM - 1) / BM);
+    if (M >= 4096) {
+      int64_t want = (148 * 4 + tiles - 1) / tiles;
+      int64_t maxs = M / 512;
+      splits = (int)(want < maxs ? want : maxs);
+      if (splits < 1) splits = 1;
+    }
+    if (splits > 1) {
+      rc = launch_sgemm<1, 0>(dpre, x, dW, nullptr, nullptr, N, K, M, N, K, K, PVB_ACT_NONE, 1,
+                              splits, st);
+    } else {
+      rc = launch_sgemm<1, 0>(dpre, x, dW, nullptr, nullptr, N, K, M, N, K, K, PVB_ACT_NONE, 1, 1,
+                              st);
+    }
+    if (rc) return rc;
+  }
+  if (db) {
+    dim3 blk(32, 32);
+    dim3 grid((N + 31) / 32, (unsigned)((M + CS_ROWS - 1) / CS_ROWS));
+    colsum_kernel<<<grid, blk, 0, st>>>(dpre, db, M, N); pvb::count_launch();
+  }
+  return pvb::launch_status();
+}

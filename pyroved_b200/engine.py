@@ -1,0 +1,496 @@
+"""SVI step engine: the B200-native replacement for what the reference gets
+from `pyro.infer.SVI(model, guide, Adam, Trace_ELBO/TraceEnum_ELBO).step`
+(reference trainers/svi.py:81-91,107; trainers/auxsvi.py:67-81,88-100).
+
+One `step` = encoder forward -> reparameterised latent sample -> affine fold
+-> spatial decoder forward+backward -> latent/encoder backward -> (NCCL
+all-reduce of the flat gradient) -> fused Adam, all as hand-written CUDA
+kernels launched through the C ABI on torch's current stream and replayed as
+CUDA graphs.  PyTorch supplies device memory, streams and torch.distributed.
+
+Layout in HBM
+  * all parameters live in ONE flat fp32 buffer (`FlatParams.p`); each
+    nn.Parameter is a view into it, so state_dict()/load_state_dict() keep the
+    reference's keys; gradients, Adam m and v are flat buffers of the same
+    layout; the last slot of the gradient buffer holds the loss so that one
+    all-reduce(SUM) moves both.
+  * activations/workspaces are allocated once per (batch shape) and reused.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import TC_WGRAD_FLOATS
+from .nets.fc import linear_layers
+
+
+def _align4(n):
+    return (n + 3) // 4 * 4
+
+
+class FlatParams:
+    """Flat parameter / gradient / Adam-state buffers with per-parameter views."""
+
+    def __init__(self, module: nn.Module, device):
+        self.module = module
+        self.device = torch.device(device)
+        self._build()
+
+    def _build(self):
+        named = [(n, p) for n, p in self.module.named_parameters()]
+        self.names = [n for n, _ in named]
+        self.offsets = {}
+        off = 0
+        for n, p in named:
+            self.offsets[n] = (off, p.numel(), tuple(p.shape))
+            off += _align4(p.numel())
+        self.total = off
+        dev = self.device
+        new_p = torch.zeros(self.total, device=dev, dtype=torch.float32)
+        for n, p in named:
+            o, k, shp = self.offsets[n]
+            new_p[o:o + k].copy_(p.data.reshape(-1).to(dev, torch.float32))
+        self.p = new_p
+        # gradient buffer: [grads | loss, pad3]
+        self.g = torch.zeros(self.total + 4, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(self.total, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(self.total, device=dev, dtype=torch.float32)
+        self._views = {}
+        for n, p in named:
+            o, k, shp = self.offsets[n]
+            p.data = self.p[o:o + k].view(shp)
+            p.grad = self.g[o:o + k].view(shp)
+            self._views[id(p)] = n
+        self.loss = self.g[self.total:self.total + 1]
+        self._ptrs = [(p, p.data_ptr()) for _, p in named]
+
+    def intact(self):
+        """False if the module's parameters were re-allocated (e.g. .to())."""
+        named = list(self.module.named_parameters())
+        if len(named) != len(self._ptrs):
+            return False
+        return all(p is q and p.data_ptr() == ptr for (_, p), (q, ptr) in zip(named, self._ptrs))
+
+    def ensure(self):
+        if not self.intact():
+            m, v = self.m, self.v
+            old_total = self.total
+            self._build()
+            if self.total == old_total:   # keep optimizer state across a rebuild
+                self.m.copy_(m)
+                self.v.copy_(v)
+            return True
+        return False
+
+    def pv(self, param):
+        return param.data
+
+    def gv(self, param):
+        n = self._views[id(param)]
+        o, k, shp = self.offsets[n]
+        return self.g[o:o + k].view(shp)
+
+    def offset(self, param):
+        return self.offsets[self._views[id(param)]][0]
+
+
+class MLP:
+    """A stack of Linear+activation layers with preallocated activations."""
+
+    def __init__(self, layers, act, M, device, flat: FlatParams):
+        self.layers = layers
+        self.act = act
+        self.M = M
+        self.flat = flat
+        self.h = [torch.empty(M, l.out_features, device=device) for l in layers]
+        self.pre = ([torch.empty(M, l.out_features, device=device) for l in layers]
+                    if act == "gelu" else [None] * len(layers))
+        self.x = None
+
+    def forward(self, x):
+        self.x = x
+        cur = x
+        for l, h, pre in zip(self.layers, self.h, self.pre):
+            ops.linear_fwd(cur, l.weight.data, l.bias.data if l.bias is not None else None,
+                           self.act, out=h, pre=pre)
+            cur = h
+        return cur
+
+    def backward(self, d_last, scratch, need_dx):
+        """d_last: gradient wrt the last activation (overwritten). `scratch`:
+        two flat buffers of >= M*max_width floats used ping-pong for dx.
+        Returns gradient wrt the stack input (or None)."""
+        d = d_last
+        n = len(self.layers)
+        for k in range(n - 1, -1, -1):
+            l = self.layers[k]
+            xin = self.h[k - 1] if k > 0 else self.x
+            want_dx = (k > 0) or need_dx
+            dx = None
+            if want_dx:
+                dx = scratch[k % 2][:self.M * l.in_features].view(self.M, l.in_features)
+            ops.linear_bwd(xin, l.weight.data, self.h[k], self.pre[k], d, d, dx, False,
+                           self.flat.gv(l.weight),
+                           self.flat.gv(l.bias) if l.bias is not None else None, self.act)
+            d = dx
+        return d
+
+
+class StepProgram:
+    """Static buffers + kernel sequence for one (model, batch shape)."""
+
+    def __init__(self, engine, B, has_y):
+        self.engine = engine
+        self.B = B
+        self.has_y = has_y
+
+
+class SpatialVAEProgram(StepProgram):
+    """iVAE (Trace_ELBO) step: reference models/ivae.py:165-221."""
+
+    def __init__(self, engine, B, has_y):
+        super().__init__(engine, B, has_y)
+        m = engine.model
+        dev = engine.device
+        flat = engine.flat
+        self.N = m._n_pix
+        self.Z = m.z_dim
+        self.C = m.c_dim if has_y else 0
+        if m.c_dim > 0 and not has_y:
+            raise ValueError("model was built with c_dim={} but no y was passed".format(m.c_dim))
+        N, Z, C = self.N, self.Z, self.C
+        f32 = dict(device=dev, dtype=torch.float32)
+        # inputs
+        self.enc_in = torch.zeros(B, N + C, **f32)
+        self.x = torch.zeros(B, N, **f32) if C > 0 else self.enc_in
+        self.y = torch.zeros(B, C, **f32) if C > 0 else None
+        self.eps = torch.zeros(B, Z, **f32)
+        # encoder
+        enc = m.encoder_z
+        self.enc = MLP(linear_layers(enc.fc_layers), enc.activation, B, dev, flat)
+        He = enc.fc11.in_features
+        self.mu = torch.empty(B, Z, **f32)
+        self.s_pre = torch.empty(B, Z, **f32)
+        self.sigma = torch.empty(B, Z, **f32)
+        self.z = torch.empty(B, Z, **f32)
+        self.kl = torch.empty(B, **f32)
+        self.gz = torch.zeros(B, Z, **f32)
+        self.gmu = torch.empty(B, Z, **f32)
+        self.gs_pre = torch.empty(B, Z, **f32)
+        self.dh_e = torch.empty(B, He, **f32)
+        wmax = max([He] + [l.in_features for l in self.enc.layers[1:]] + [1])
+        self.enc_scratch = [torch.empty(B * wmax, **f32) for _ in range(2)]
+        self.ll = torch.empty(B, **f32)
+        dec = m.decoder
+        self.spatial = m.coord > 0
+        if self.spatial:
+            self._init_spatial(dec, B, dev, flat, f32)
+        else:
+            self._init_fc(dec, B, dev, flat, f32)
+
+    # ---- decoder buffers -------------------------------------------------
+    def _init_spatial(self, dec, I, dev, flat, f32):
+        m = self.engine.model
+        self.I = I
+        N = self.N
+        R = I * N
+        cl = dec.coord_latent
+        Hd0 = cl.fc_coord.out_features
+        self.fold_cfg = ops.make_fold_cfg(m.ndim, m.invariances, m._latent_dim, self.C, Hd0,
+                                          m._dx_prior, m._dy_prior, m._sc_prior)
+        self.Uv = torch.empty(I, 3, Hd0, **f32)
+        self.gUv = torch.empty(I, 3, Hd0, **f32)
+        self.G_fold = ops.fold_bwd_num_partials()
+        self.fold_per = Hd0 * (m.ndim + 1 + m._latent_dim + self.C)
+        self.fold_part = torch.empty(self.G_fold, self.fold_per, **f32)
+        self.gcond = torch.empty(I, max(self.C, 1), **f32) if self.C > 0 else None
+        self.rowll = torch.empty(R, **f32)
+        self.loc = torch.empty(R, **f32)
+        layers = linear_layers(dec.fc_layers)
+        self.use_tc = self.engine.tc_eligible(dec, N)
+        if self.use_tc:
+            s = ops.sdec_tc_sizes(I, N)
+            self.tc_sizes = s
+            self.gUv_part = torch.empty(max(s.gUv_part_floats, 1), **f32)
+            self.wgrad_part = torch.empty(max(s.wgrad_part_floats, 1), **f32)
+        else:
+            self.h0 = torch.empty(R, Hd0, **f32)
+            self.dmlp = MLP(layers, dec.activation, R, dev, flat)
+            Hl = layers[-1].out_features if layers else Hd0
+            self.logit = torch.empty(R, 1, **f32)
+            self.dlogit = torch.empty(R, 1, **f32)
+            wmax = max([Hd0, Hl] + [l.in_features for l in layers])
+            self.dec_scratch = [torch.empty(R * wmax, **f32) for _ in range(3)]
+
+    def _init_fc(self, dec, I, dev, flat, f32):
+        self.I = I
+        layers = linear_layers(dec.fc_layers)
+        self.dec_in = torch.zeros(I, self.Z + self.C, **f32)
+        self.dmlp = MLP(layers, dec.activation, I, dev, flat)
+        Hl = layers[-1].out_features
+        self.logit = torch.empty(I, self.N, **f32)
+        self.dlogit = torch.empty(I, self.N, **f32)
+        self.rowll = torch.empty(I * self.N, **f32)
+        self.loc = torch.empty(I * self.N, **f32)
+        wmax = max([Hl, self.Z + self.C] + [l.in_features for l in layers])
+        self.dec_scratch = [torch.empty(I * wmax, **f32) for _ in range(3)]
+
+    # ---- inputs ------------------------------------------------------------
+    def load(self, x, y):
+        B, N = self.B, self.N
+        x = x.reshape(B, -1)
+        if x.shape[1] != N:
+            raise ValueError("expected {} features per sample, got {}".format(N, x.shape[1]))
+        if self.C > 0:
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y.reshape(B, -1), non_blocking=True)
+            self.enc_in[:, :N].copy_(self.x)
+            self.enc_in[:, N:].copy_(self.y)
+        else:
+            self.enc_in.copy_(x, non_blocking=True)
+
+    # ---- kernel sequences ----------------------------------------------------
+    def forward(self, beta, want_grad, gen_eps):
+        eng = self.engine
+        m = eng.model
+        flat = eng.flat
+        enc = m.encoder_z
+        if gen_eps:
+            ops.randn(self.eps, eng.seed, eng.step_counter, eng.eps_first_index(self.B * self.Z))
+        h = self.enc.forward(self.enc_in)
+        ops.linear_fwd(h, enc.fc11.weight.data, enc.fc11.bias.data, None, out=self.mu)
+        ops.linear_fwd(h, enc.fc12.weight.data, enc.fc12.bias.data, None, out=self.s_pre)
+        ops.latent_fwd(self.mu, self.s_pre, self.eps, self.sigma, self.z, self.kl)
+        samp = m.sampler_d
+        dec = m.decoder
+        if self.spatial:
+            cl = dec.coord_latent
+            ops.fold_fwd(self.fold_cfg, self.z, self.y, cl.fc_coord.weight.data,
+                         cl.fc_coord.bias.data, cl.fc_latent.weight.data, self.Uv)
+            if self.use_tc:
+                L = linear_layers(dec.fc_layers)
+                ops.sdec_tc_step(self.Uv, self.x, None, L[0].weight.data, L[0].bias.data,
+                                 L[1].weight.data, L[1].bias.data, dec.out.weight.data,
+                                 dec.out.bias.data, self.rowll, self.loc, self.gUv_part,
+                                 self.wgrad_part, self.I, self.B, m._H, m._W, m.ndim, samp.name,
+                                 dec.sigmoid_out, samp.decoder_sig, want_grad)
+            else:
+                ops.sdec_h0_fwd(self.Uv, self.h0, m._H, m._W, m.ndim)
+                hl = self.dmlp.forward(self.h0)
+                ops.linear_fwd(hl, dec.out.weight.data, dec.out.bias.data, None, out=self.logit)
+                ops.obs_loglik(self.logit, self.x, None, self.rowll,
+                               self.dlogit if want_grad else None, self.loc, self.I, self.B,
+                               self.N, samp.name, dec.sigmoid_out, samp.decoder_sig)
+        else:
+            self.dec_in[:, :self.Z].copy_(self.z)
+            if self.C > 0:
+                self.dec_in[:, self.Z:].copy_(self.y)
+            hl = self.dmlp.forward(self.dec_in)
+            ops.linear_fwd(hl, dec.out.weight.data, dec.out.bias.data, None, out=self.logit)
+            ops.obs_loglik(self.logit, self.x, None, self.rowll,
+                           self.dlogit if want_grad else None, self.loc, self.I, self.B, self.N,
+                           samp.name, dec.sigmoid_out, samp.decoder_sig)
+        ops.elbo_reduce(self.rowll, self.kl, None, beta, self.ll, flat.loss, False, self.I, self.N)
+
+    def backward(self, beta):
+        eng = self.engine
+        m = eng.model
+        flat = eng.flat
+        dec = m.decoder
+        enc = m.encoder_z
+        if self.spatial:
+            cl = dec.coord_latent
+            if self.use_tc:
+                L = linear_layers(dec.fc_layers)
+                s = self.tc_sizes
+                n_w = TC_WGRAD_FLOATS
+                # partial layout == flat layout of (fc0.w, fc0.b, fc2.w, fc2.b, out.w, out.b)
+                base = flat.offset(L[0].weight)
+                ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], s.ctas, n_w, n_w, True)
+                ops.sdec_tc_gather_gUv(self.gUv_part, self.gUv, self.I, self.N)
+            else:
+                hl = self.dmlp.h[-1] if self.dmlp.layers else self.h0
+                d_hl = self.dec_scratch[2][:hl.numel()].view_as(hl)
+                ops.linear_bwd(hl, dec.out.weight.data, None, None, self.dlogit, self.dlogit, d_hl,
+                               False, flat.gv(dec.out.weight), flat.gv(dec.out.bias), None)
+                dh0 = self.dmlp.backward(d_hl, self.dec_scratch, True)
+                ops.sdec_h0_bwd(dh0, self.h0, self.gUv, m._H, m._W, m.ndim)
+            ops.fold_bwd(self.fold_cfg, self.z, self.y, cl.fc_coord.weight.data,
+                         cl.fc_latent.weight.data, self.gUv, self.gz, self.gcond, self.fold_part)
+            Hd0 = cl.fc_coord.out_features
+            nd = m.ndim
+            LC = m._latent_dim + self.C
+            G, per = self.G_fold, self.fold_per
+            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.weight), G, Hd0 * nd, per, True, 0)
+            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.bias), G, Hd0, per, True, Hd0 * nd)
+            if LC > 0:
+                ops.reduce_partials(self.fold_part, flat.gv(cl.fc_latent.weight), G, Hd0 * LC, per,
+                                    True, Hd0 * (nd + 1))
+            gz = self.gz
+        else:
+            hl = self.dmlp.h[-1]
+            d_hl = self.dec_scratch[2][:hl.numel()].view_as(hl)
+            ops.linear_bwd(hl, dec.out.weight.data, None, None, self.dlogit, self.dlogit, d_hl,
+                           False, flat.gv(dec.out.weight), flat.gv(dec.out.bias), None)
+            d_in = self.dmlp.backward(d_hl, self.dec_scratch, True)
+            self.gz.copy_(d_in[:, :self.Z])
+            gz = self.gz
+        ops.latent_bwd(gz, self.eps, self.sigma, self.s_pre, self.z, None, beta, self.gmu,
+                       self.gs_pre)
+        h = self.enc.h[-1]
+        ops.linear_bwd(h, enc.fc11.weight.data, None, None, self.gmu, self.gmu, self.dh_e, False,
+                       flat.gv(enc.fc11.weight), flat.gv(enc.fc11.bias), None)
+        ops.linear_bwd(h, enc.fc12.weight.data, None, None, self.gs_pre, self.gs_pre, self.dh_e,
+                       True, flat.gv(enc.fc12.weight), flat.gv(enc.fc12.bias), None)
+        self.enc.backward(self.dh_e, self.enc_scratch, False)
+
+
+class SVIEngine:
+    """Drop-in for the object the reference keeps in `SVItrainer.svi`
+    (`pyro.infer.SVI`): `.step(x[, y], **kwargs) -> float` runs one optimisation
+    step on a mini-batch and returns the (batch-sum) loss."""
+
+    def __init__(self, model, lr=1e-3, enumerate_parallel=False, seed=1, device=None,
+                 use_graphs=None):
+        if device is None:
+            device = getattr(model, "device", "cuda")
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:{}".format(
+            torch.cuda.current_device() if torch.cuda.is_available() else 0))
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                "pyroved_b200 runs on CUDA devices only (no CPU fallback); got device={!r}".format(
+                    str(device)))
+        self.model = model
+        self.lr = float(lr)
+        self.enumerate_parallel = enumerate_parallel
+        self.seed = int(seed)
+        self.flat = FlatParams(model, self.device)
+        self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.programs = {}
+        self.graphs = {}
+        if use_graphs is None:
+            use_graphs = os.environ.get("PVB_CUDA_GRAPHS", "1") != "0"
+        self.use_graphs = use_graphs
+        self.force_generic = os.environ.get("PVB_FORCE_GENERIC", "0") == "1"
+        self.launches_per_step = 0
+        # data-parallel state (pyroved_b200.parallel)
+        self.world_size = 1
+        self.rank = 0
+        self.process_group = None
+        self._attach_distributed()
+
+    # ---- distributed -----------------------------------------------------
+    def _attach_distributed(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            self.world_size = dist.get_world_size()
+            self.rank = dist.get_rank()
+
+    def eps_first_index(self, n_local):
+        """Global index of this rank's first noise element: the noise of a
+        sample depends on its GLOBAL position, so the ELBO does not depend on
+        the number of GPUs."""
+        return self.rank * n_local
+
+    # ---- program selection -------------------------------------------------
+    def tc_eligible(self, dec, N):
+        if self.force_generic or not ops.has_tcgen05():
+            return False
+        layers = linear_layers(dec.fc_layers)
+        return (len(layers) == 2 and all(l.in_features == 128 and l.out_features == 128
+                                         for l in layers)
+                and dec.coord_latent.fc_coord.out_features == 128
+                and dec.activation == "tanh" and N >= 32
+                and self.model.sampler_d.name in ("bernoulli", "gaussian"))
+
+    def _program(self, B, has_y):
+        key = (B, has_y)
+        prog = self.programs.get(key)
+        if prog is None:
+            prog = self.model._make_program(self, B, has_y)
+            self.programs[key] = prog
+        return prog
+
+    # ---- one step -------------------------------------------------------------
+    def _run(self, prog, beta, train, gen_eps, update):
+        flat = self.flat
+        if train or update:
+            flat.g.zero_()
+        prog.forward(beta, train, gen_eps)
+        if train:
+            prog.backward(beta)
+        if update:
+            self._update()
+
+    def _update(self):
+        flat = self.flat
+        ops.counter_add(self.step_counter, 1)
+        ops.adam_flat(flat.p, flat.g, flat.m, flat.v, flat.total, self.lr, self.step_counter)
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.flat.g, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def _execute(self, key, fn):
+        """Eager on first sight of `key`, captured on the second, replayed after."""
+        if not self.use_graphs:
+            fn()
+            return
+        entry = self.graphs.get(key)
+        if entry is None:
+            fn()
+            self.graphs[key] = "warm"
+            return
+        if entry == "warm":
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                fn()
+            self.graphs[key] = g
+            entry = g
+        entry.replay()
+
+    def step(self, *args, **kwargs):
+        return self._step(args, kwargs, train=True)
+
+    def evaluate_loss(self, *args, **kwargs):
+        return self._step(args, kwargs, train=False, update=False)
+
+    def loss_and_grads(self, *args, **kwargs):
+        """Loss + gradients (left in every parameter's .grad) without an
+        optimizer update -- used by the parity tests."""
+        return self._step(args, kwargs, train=True, update=False)
+
+    def _step(self, args, kwargs, train=True, update=True):
+        self.flat.ensure() and self._invalidate()
+        x = args[0]
+        y = args[1] if len(args) > 1 else None
+        eps = kwargs.pop("_eps", None)
+        sync = kwargs.pop("_sync", True)
+        beta = self.model._beta(kwargs)
+        B = x.shape[0]
+        prog = self._program(B, y is not None)
+        prog.load(x, y)
+        if eps is not None:
+            prog.eps.copy_(eps.reshape(prog.eps.shape), non_blocking=True)
+        gen_eps = eps is None
+        bkey = tuple(beta) if isinstance(beta, (list, tuple)) else float(beta)
+        key = (B, y is not None, bkey, train, gen_eps, update)
+        if self.world_size > 1 and train:
+            self._execute(key + ("grads",), lambda: self._run(prog, beta, True, gen_eps, False))
+            self._allreduce()
+            if update:
+                self._execute(("update",), self._update)
+        else:
+            self._execute(key, lambda: self._run(prog, beta, train, gen_eps, update))
+        if not sync:
+            return self.flat.loss     # device scalar, no host synchronisation
+        return float(self.flat.loss.item())
+
+    def _invalidate(self):
+        self.programs.clear()
+        self.graphs.clear()
+        return True

@@ -1,0 +1,177 @@
+"""Tensor-level wrappers over the C ABI (raw device pointers + current stream).
+
+PyTorch is used for device memory and streams only; every arithmetic op on the
+hot path is one of the hand-written kernels in csrc/.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import FoldCfg, TcSizes, check
+
+ACT = {None: 0, "none": 0, "tanh": 1, "relu": 2, "lrelu": 3, "softplus": 4, "gelu": 5,
+       "sigmoid": 6}
+SAMPLER = {"bernoulli": 0, "gaussian": 1, "continuous_bernoulli": 2}
+INV = {"r": 1, "t": 2, "s": 4}
+
+
+def _p(t):
+    """device pointer of a contiguous fp32 CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.PvbError("pyroved_b200 kernels need CUDA tensors (no CPU fallback); got a "
+                            "{} tensor".format(t.device))
+    if t.dtype not in (torch.float32, torch.int32) or not t.is_contiguous():
+        raise _lib.PvbError("expected a contiguous float32 tensor, got {} {}".format(
+            t.dtype, "non-contiguous" if not t.is_contiguous() else ""))
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def linear_fwd(x, W, b, act, out=None, pre=None):
+    M = x.numel() // x.shape[-1]
+    N, K = W.shape
+    assert x.shape[-1] == K, (x.shape, W.shape)
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=torch.float32)
+    check(_lib.lib().pvb_linear_fwd(_p(x), _p(W), _p(b), _p(out), _p(pre), M, N, K, ACT[act],
+                                    _stream()), "pvb_linear_fwd")
+    return out
+
+
+def linear_bwd(x, W, y, pre, dy, dpre_ws, dx, dx_accumulate, dW, db, act):
+    M = x.numel() // x.shape[-1]
+    N, K = W.shape
+    check(_lib.lib().pvb_linear_bwd(_p(x), _p(W), _p(y), _p(pre), _p(dy), _p(dpre_ws), _p(dx),
+                                    int(dx_accumulate), _p(dW), _p(db), M, N, K, ACT[act],
+                                    _stream()), "pvb_linear_bwd")
+
+
+def randn(out, seed, step_counter, first_index=0):
+    check(_lib.lib().pvb_randn(_p(out), out.numel(), seed & 0xFFFFFFFFFFFFFFFF,
+                               _p(step_counter), first_index, _stream()), "pvb_randn")
+    return out
+
+
+def latent_fwd(mu, s_pre, eps, sigma, z, kl):
+    Z = mu.shape[-1]
+    check(_lib.lib().pvb_latent_fwd(_p(mu), _p(s_pre), _p(eps), _p(sigma), _p(z), _p(kl),
+                                    mu.numel() // Z, Z, _stream()), "pvb_latent_fwd")
+
+
+def latent_bwd(gz, eps, sigma, s_pre, z, w, beta, gmu, gs_pre):
+    Z = z.shape[-1]
+    check(_lib.lib().pvb_latent_bwd(_p(gz), _p(eps), _p(sigma), _p(s_pre), _p(z), _p(w),
+                                    float(beta), _p(gmu), _p(gs_pre), z.numel() // Z, Z,
+                                    _stream()), "pvb_latent_bwd")
+
+
+def make_fold_cfg(ndim, invariances, latent_dim, cond_dim, hidden, dx_prior, dy_prior, sc_prior):
+    inv = 0
+    for k in (invariances or []):
+        inv |= INV.get(k, 0)
+    return FoldCfg(ndim, inv, latent_dim, cond_dim, hidden, float(dx_prior), float(dy_prior),
+                   float(sc_prior))
+
+
+def fold_fwd(cfg, z, cond, Wc, bc, Wz, Uv):
+    I = Uv.shape[0]
+    check(_lib.lib().pvb_fold_fwd(C.byref(cfg), _p(z), _p(cond), _p(Wc), _p(bc), _p(Wz), _p(Uv), I,
+                                  _stream()), "pvb_fold_fwd")
+
+
+def fold_bwd_num_partials():
+    return _lib.lib().pvb_fold_bwd_num_partials()
+
+
+def fold_bwd(cfg, z, cond, Wc, Wz, gUv, gz, gcond, part):
+    I = gUv.shape[0]
+    check(_lib.lib().pvb_fold_bwd(C.byref(cfg), _p(z), _p(cond), _p(Wc), _p(Wz), _p(gUv), _p(gz),
+                                  _p(gcond), _p(part), I, _stream()), "pvb_fold_bwd")
+
+
+def sdec_h0_fwd(Uv, h0, H, W, ndim):
+    I, _, Hd = Uv.shape
+    check(_lib.lib().pvb_sdec_h0_fwd(_p(Uv), _p(h0), I, H, W, ndim, Hd, _stream()),
+          "pvb_sdec_h0_fwd")
+
+
+def sdec_h0_bwd(dh0, h0, gUv, H, W, ndim):
+    I, _, Hd = gUv.shape
+    check(_lib.lib().pvb_sdec_h0_bwd(_p(dh0), _p(h0), _p(gUv), I, H, W, ndim, Hd, _stream()),
+          "pvb_sdec_h0_bwd")
+
+
+def obs_loglik(logit, x, w, rowll, dlogit, loc, I, B, N, sampler, sigmoid_d, decoder_sig):
+    check(_lib.lib().pvb_obs_loglik(_p(logit), _p(x), _p(w), _p(rowll), _p(dlogit), _p(loc), I, B,
+                                    N, SAMPLER[sampler], int(bool(sigmoid_d)), float(decoder_sig),
+                                    _stream()), "pvb_obs_loglik")
+
+
+def elbo_reduce(rowll, kl, w, beta, ll, loss_out, accumulate, I, N):
+    check(_lib.lib().pvb_elbo_reduce(_p(rowll), _p(kl), _p(w), float(beta), _p(ll), _p(loss_out),
+                                     int(accumulate), I, N, _stream()), "pvb_elbo_reduce")
+
+
+def enum_head_fwd(logits, alpha, w):
+    B, K = logits.shape
+    check(_lib.lib().pvb_enum_head_fwd(_p(logits), _p(alpha), _p(w), B, K, _stream()),
+          "pvb_enum_head_fwd")
+
+
+def enum_head_bwd(alpha, cost, beta_d, glogits, loss_out):
+    B, K = alpha.shape
+    assert glogits.numel() >= B * K + B
+    check(_lib.lib().pvb_enum_head_bwd(_p(alpha), _p(cost), float(beta_d), _p(glogits),
+                                       _p(loss_out), B, K, _stream()), "pvb_enum_head_bwd")
+
+
+def class_nll(logits, y_onehot, mult, glogits, loss_out):
+    B, K = logits.shape
+    assert glogits.numel() >= B * K + B
+    check(_lib.lib().pvb_class_nll(_p(logits), _p(y_onehot), float(mult), _p(glogits),
+                                   _p(loss_out), B, K, _stream()), "pvb_class_nll")
+
+
+def reduce_partials(part, out, G, n, stride, accumulate, part_offset=0):
+    pp = part.data_ptr() + 4 * part_offset
+    check(_lib.lib().pvb_reduce_partials(pp, _p(out), G, n, stride, int(accumulate), _stream()),
+          "pvb_reduce_partials")
+
+
+def counter_add(counter, v):
+    check(_lib.lib().pvb_counter_add(_p(counter), v, _stream()), "pvb_counter_add")
+
+
+def adam_flat(p, g, m, v, n, lr, step_counter, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.lib().pvb_adam_flat(_p(p), _p(g), _p(m), _p(v), n, float(lr), beta1, beta2, eps,
+                                   _p(step_counter), _stream()), "pvb_adam_flat")
+
+
+def has_tcgen05():
+    return bool(_lib.lib().pvb_has_tcgen05())
+
+
+def sdec_tc_sizes(I, N):
+    s = TcSizes()
+    check(_lib.lib().pvb_sdec_tc_sizes(I, N, C.byref(s)), "pvb_sdec_tc_sizes")
+    return s
+
+
+def sdec_tc_step(Uv, x, w, W1, b1, W2, b2, wo, bo, rowll, loc, gUv_part, wgrad_part, I, B, H, W,
+                 ndim, sampler, sigmoid_d, decoder_sig, backward):
+    check(_lib.lib().pvb_sdec_tc_step(_p(Uv), _p(x), _p(w), _p(W1), _p(b1), _p(W2), _p(b2), _p(wo),
+                                      _p(bo), _p(rowll), _p(loc), _p(gUv_part), _p(wgrad_part),
+                                      I, B, H, W, ndim, SAMPLER[sampler], int(bool(sigmoid_d)),
+                                      float(decoder_sig), int(backward), _stream()),
+          "pvb_sdec_tc_step")
+
+
+def sdec_tc_gather_gUv(gUv_part, gUv, I, N):
+    check(_lib.lib().pvb_sdec_tc_gather_gUv(_p(gUv_part), _p(gUv), I, N, _stream()),
+          "pvb_sdec_tc_gather_gUv")

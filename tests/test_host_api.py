@@ -1,0 +1,112 @@
+"""CPU tests of the host-side mirror of the reference interface: constructor
+bookkeeping, state_dict layout, error conventions, helpers.  No compute calls
+(those need the GPU and fail loudly without one)."""
+import pytest
+import torch
+
+import pyroved_b200 as pv
+from pyroved_b200 import _lib
+from golden_util import Golden
+
+
+@pytest.mark.parametrize("inv, coord", [(None, 0), (['r'], 1), (['t'], 2), (['s'], 1),
+                                        (['r', 's', 't'], 4)])
+def test_coord_bookkeeping_2d(inv, coord):
+    m = pv.models.iVAE((8, 8), 2, inv, device="cpu")
+    assert m.coord == coord and m.z_dim == 2 + coord
+
+
+@pytest.mark.parametrize("inv, coord", [(None, 0), (['t'], 1)])
+def test_coord_bookkeeping_1d(inv, coord):
+    m = pv.models.iVAE((8,), 2, inv, device="cpu")
+    assert m.coord == coord
+
+
+@pytest.mark.parametrize("inv", [['r'], ['s'], ['r', 't'], ['t', 'r']])
+def test_1d_rejects_non_translation(inv):
+    with pytest.raises(ValueError):
+        pv.models.iVAE((8,), 2, inv, device="cpu")
+
+
+def test_unknown_sampler_keyerror():
+    with pytest.raises(KeyError):
+        pv.models.iVAE((8, 8), 2, ['r'], sampler_d="poisson", device="cpu")
+
+
+def test_bad_in_dim_valueerror():
+    with pytest.raises(ValueError):
+        pv.nets.fcEncoderNet((1, 2, 3, 4))
+
+
+def test_grid_not_implemented_for_3d():
+    with pytest.raises(NotImplementedError):
+        pv.utils.generate_grid((2, 2, 2))
+
+
+def test_to_onehot_assertion():
+    with pytest.raises(AssertionError):
+        pv.utils.to_onehot(torch.tensor([3]), 3)
+
+
+@pytest.mark.parametrize("name", ["ivae_1d_t", "ivae_28_rt", "ivae_12_rts_cond_gauss",
+                                  "ivae_12_vanilla", "ivae_16_s_softplus"])
+def test_state_dict_matches_reference_layout_and_init(name):
+    """Same keys, shapes AND initial values as the reference constructor
+    (same seed, same nn.Linear construction order)."""
+    g = Golden(name)
+    kw = dict(g.kwargs)
+    seeds = {"ivae_12_rts_cond_gauss": 2, "ivae_12_vanilla": 3, "ivae_16_s_softplus": 4}
+    m = pv.models.iVAE(seed=seeds.get(name, 1), device="cpu", **kw)
+    ref = g.group("w0")
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape, k
+        assert torch.equal(sd[k], ref[k]), k
+
+
+def test_grid_matches_reference_formula():
+    g = pv.utils.generate_grid((3, 4))
+    assert g.shape == (12, 2)
+    assert torch.allclose(g[0], torch.tensor([-1., 1.]))
+    assert torch.allclose(g[-1], torch.tensor([1., -1.]))
+    assert torch.allclose(g[5], torch.tensor([0., 1. - 2. / 3.]))
+    g1 = pv.utils.generate_grid((5,))
+    assert g1.shape == (5, 1) and g1[0, 0] == 1 and g1[-1, 0] == -1
+
+
+def test_split_latent_shapes():
+    m = pv.models.iVAE((8, 8), 2, ['r', 't', 's'], device="cpu")
+    phi, dx, sc, z = m.split_latent(torch.randn(5, 6))
+    assert phi.shape == (5,) and dx.shape == (5, 2) and sc.shape == (5,) and z.shape == (5, 2)
+    m1 = pv.models.iVAE((8,), 2, ['t'], device="cpu")
+    phi, dx, sc, z = m1.split_latent(torch.randn(5, 3))
+    assert phi is None and sc is None and dx.shape == (5, 1) and z.shape == (5, 2)
+
+
+def test_latent_grid_helpers():
+    z, (gx, gy) = pv.utils.generate_latent_grid(4)
+    assert z.shape == (16, 2)
+    assert torch.allclose(z[0], torch.stack([gx[0], gy[0]]))
+    assert torch.allclose(z[5], torch.stack([gx[1], gy[1]]))
+    c, d = pv.utils.generate_latent_grid_traversal(4, 2, 3, 0, 0, 16)
+    assert c.shape == (16, 2) and d.shape == (16, 3)
+    assert torch.all(d.sum(1) == 1)
+
+
+def test_no_cpu_fallback():
+    """Compute entry points refuse CPU tensors / CPU devices loudly."""
+    m = pv.models.iVAE((8, 8), 2, ['r'], device="cpu")
+    with pytest.raises(RuntimeError):
+        pv.trainers.SVItrainer(m, device="cpu")
+    with pytest.raises(_lib.PvbError):
+        m.encoder_z(torch.zeros(2, 64))
+
+
+def test_dataloader_protocol():
+    x = torch.randn(10, 4)
+    y = torch.randn(10, 2)
+    l1 = pv.utils.init_dataloader(x, batch_size=4, shuffle=False)
+    assert [len(b) for b in l1] == [1, 1, 1] and len(l1.dataset) == 10
+    l2 = pv.utils.init_dataloader(x, y, batch_size=5)
+    assert all(len(b) == 2 for b in l2)
