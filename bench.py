@@ -293,7 +293,10 @@ def run_ours(args):
                     "us": t_tc * 1e6}
             kernels[roof["kernel"]] = roof
         roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json burst: kernel timed alone)"
-        cpu = cpu_port_throughput(BATCH, 12.0)
+        if os.environ.get("PVB_BENCH_SKIP_CPU") == "1":   # profiling runs only
+            cpu = {"value": None, "cores": 0, "steps": 0, "seconds": 0.0}
+        else:
+            cpu = cpu_port_throughput(BATCH, 12.0)
         total = BATCH * world * args.steps
         line = {
             "metric": "SVI samples/sec (28x28 iVAE rot+trans)",

@@ -101,4 +101,43 @@ __device__ __forceinline__ void grid_xy(int p, int H, int W, int ndim, float& gx
   }
 }
 
+// ---- per-pixel observation terms (utils/prob.py:25-29 + torch log_prob) -------
+// torch clamp_probs eps for fp32 and the matching logit bound log((1-eps)/eps)
+#define PVB_PROB_EPS 1.1920928955078125e-07f
+
+__device__ __forceinline__ void obs_terms(float l, float x, int sampler, int sigmoid_d, float sig,
+                                          float& ll, float& dnll_dl, float& loc) {
+  if (sampler == PVB_SAMPLER_BERNOULLI) {
+    if (sigmoid_d) {
+      // probs = sigmoid(l) -> clamp(eps, 1-eps) -> logits; log_prob = x*lg - softplus(lg)
+      float p = pvb::sigmoid_f(l);
+      loc = p;
+      bool in = (p >= PVB_PROB_EPS) && (p <= 1.f - PVB_PROB_EPS);
+      float pc = fminf(fmaxf(p, PVB_PROB_EPS), 1.f - PVB_PROB_EPS);
+      float lg = in ? l : logf(pc) - log1pf(-pc);
+      float sp = lg > 0.f ? lg + log1pf(expf(-lg)) : log1pf(expf(lg));
+      ll = x * lg - sp;
+      dnll_dl = in ? (p - x) : 0.f;
+    } else {
+      float p = l;
+      loc = p;
+      bool in = (p >= PVB_PROB_EPS) && (p <= 1.f - PVB_PROB_EPS);
+      float pc = fminf(fmaxf(p, PVB_PROB_EPS), 1.f - PVB_PROB_EPS);
+      float lg = logf(pc) - log1pf(-pc);
+      float sp = lg > 0.f ? lg + log1pf(expf(-lg)) : log1pf(expf(lg));
+      ll = x * lg - sp;
+      dnll_dl = in ? (pc - x) / (pc * (1.f - pc)) : 0.f;
+    }
+  } else {  // gaussian, Normal(loc, sig).log_prob(x)
+    float m = sigmoid_d ? pvb::sigmoid_f(l) : l;
+    loc = m;
+    float d = x - m;
+    float inv_var = 1.f / (sig * sig);
+    ll = -0.5f * d * d * inv_var - logf(sig) - 0.91893853320467274f;
+    float dm = -d * inv_var;  // d(-ll)/dm
+    dnll_dl = sigmoid_d ? dm * m * (1.f - m) : dm;
+  }
+}
+
+
 }  // namespace pvb

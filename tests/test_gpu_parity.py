@@ -117,7 +117,7 @@ def test_graph_replay_equals_eager_and_training_reduces_loss():
     for _ in range(30):
         tr.step(loader)
     hist = tr.loss_history["training_loss"]
-    assert hist[-1] < 0.7 * hist[0], hist[::5]
+    assert hist[-1] < 0.9 * hist[0], hist[::5]
     assert all(h == h for h in hist)
 
 
