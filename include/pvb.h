@@ -180,15 +180,18 @@ int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
  * SM (nets/fc.py:189-237 forward; autograd backward of the same).
  * Outputs: rowll[R], loc[R] (optional), and when `backward` != 0:
  *   gUv_part [T][slots=5][3][128]  per-tile partial sums (T = #tiles of 128 rows)
- *   wgrad_part [G][PVB_TC_WGRAD_FLOATS]  per-CTA weight-gradient partials
+ *   wgrad_part [G][PVB_TC_WGRAD_STRIDE]  per-CTA weight-gradient partials, laid out
+ *              (dW1[128][128] | db1 | dW2[128][128] | db2 | dwo[128] | dbo | pad)
  * Workspace sizes via pvb_sdec_tc_sizes. */
 typedef struct {
   int64_t tiles;         /* T */
   int32_t ctas;          /* G */
   int64_t gUv_part_floats;
-  int64_t wgrad_part_floats; /* G * PVB_TC_WGRAD_FLOATS */
+  int64_t wgrad_part_floats; /* G * PVB_TC_WGRAD_STRIDE */
 } pvb_tc_sizes;
 #define PVB_TC_WGRAD_FLOATS (2 * 128 * 128 + 2 * 128 + 128 + 1)
+/* per-CTA stride of wgrad_part (16-byte aligned rows) */
+#define PVB_TC_WGRAD_STRIDE ((PVB_TC_WGRAD_FLOATS + 3) / 4 * 4)
 int pvb_sdec_tc_sizes(int64_t I, int N, pvb_tc_sizes* out);
 int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
                      const float* W1, const float* b1, const float* W2,

@@ -64,6 +64,7 @@ SIGNATURES = {
 
 # floats per CTA in pvb_sdec_tc_step's weight-gradient partials (PVB_TC_WGRAD_FLOATS)
 TC_WGRAD_FLOATS = 2 * 128 * 128 + 2 * 128 + 128 + 1
+TC_WGRAD_STRIDE = (TC_WGRAD_FLOATS + 3) // 4 * 4
 
 _LIB = None
 

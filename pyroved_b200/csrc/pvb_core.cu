@@ -24,8 +24,18 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __
                                        int G, int64_t n, int64_t stride, int accumulate) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float s = 0.f;
-  for (int g = 0; g < G; ++g) s += part[(int64_t)g * stride + i];
+  // four independent partial sums keep several loads in flight; the
+  // summation order is fixed, so the result is bitwise reproducible
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int g = 0;
+  for (; g + 3 < G; g += 4) {
+    s0 += part[(int64_t)g * stride + i];
+    s1 += part[(int64_t)(g + 1) * stride + i];
+    s2 += part[(int64_t)(g + 2) * stride + i];
+    s3 += part[(int64_t)(g + 3) * stride + i];
+  }
+  for (; g < G; ++g) s0 += part[(int64_t)g * stride + i];
+  float s = (s0 + s1) + (s2 + s3);
   out[i] = accumulate ? out[i] + s : s;
 }
 extern "C" int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,

@@ -97,10 +97,18 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
 }
 
 template <int TA, int TB>
+int launch_sgemm_small(const float* A, const float* B, float* C, float* Cpre, const float* bias,
+                       int M, int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int act,
+                       int accumulate, cudaStream_t st);
+
+template <int TA, int TB>
 int launch_sgemm(const float* A, const float* B, float* C, float* Cpre, const float* bias,
                  int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int act,
                  int accumulate, int splits, cudaStream_t st) {
   if (M == 0 || N == 0) return 0;
+  if (((M + BM - 1) / BM) * ((N + BN - 1) / BN) < 148 && M < (1 << 30) && ldc == N)
+    return launch_sgemm_small<TA, TB>(A, B, C, Cpre, bias, (int)M, N, K, lda, ldb, ldc, act,
+                                      accumulate, st);
   int64_t gy = (M + BM - 1) / BM;
   PVB_CHECK_ARG(gy <= 65535 * 16, "sgemm: M too large");
   int64_t k_chunk = K;
@@ -117,6 +125,132 @@ int launch_sgemm(const float* A, const float* B, float* C, float* Cpre, const fl
     sgemm_kernel<TA, TB><<<grid, NT, 0, st>>>(Ao, B, C + moff * ldc, Cpre ? Cpre + moff * ldc : nullptr,
                                               bias, M - moff, N, K, lda, ldb, ldc, act, accumulate,
                                               k_chunk); pvb::count_launch();
+  }
+  return pvb::launch_status();
+}
+
+// ---- small-problem variant ------------------------------------------------------
+// 32x32 output tiles, 128 threads (2x4 outputs each) and split-K over
+// gridDim.z so that the encoder-sized GEMMs (M = batch = 512, N = 128,
+// K = 784 ...) still fill the 148 SMs.  With splits > 1 partial sums are
+// atomically added into C (pre-zeroed unless accumulating) and bias +
+// activation run in a second, elementwise pass.
+constexpr int SBM = 32, SBN = 32, SBK = 32, SNT = 128;
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(SNT)
+sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                   float* __restrict__ Cpre, const float* __restrict__ bias, int M, int N,
+                   int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int act, int accumulate,
+                   int64_t k_chunk) {
+  __shared__ float As[SBK][SBM + 4];
+  __shared__ float Bs[SBK][SBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;   // 8 column quads x 16 row pairs
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  const int64_t ke = (kb + k_chunk < K) ? kb + k_chunk : K;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int64_t k0 = kb; k0 < ke; k0 += SBK) {
+#pragma unroll
+    for (int it = 0; it < (SBM * SBK) / SNT; ++it) {
+      int idx = tid + it * SNT;
+      int m, k;
+      if (TA == 0) { k = idx % SBK; m = idx / SBK; }
+      else         { m = idx % SBM; k = idx / SBM; }
+      int gm = m0 + m;
+      int64_t gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < ke) v = (TA == 0) ? A[(int64_t)gm * lda + gk] : A[gk * lda + gm];
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < (SBN * SBK) / SNT; ++it) {
+      int idx = tid + it * SNT;
+      int n, k;
+      if (TB == 0) { n = idx % SBN; k = idx / SBN; }
+      else         { k = idx % SBK; n = idx / SBK; }
+      int gn = n0 + n;
+      int64_t gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < ke) v = (TB == 0) ? B[gk * ldb + gn] : B[(int64_t)gn * ldb + gk];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SBK; ++k) {
+      float2 a2 = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      acc[0][0] = fmaf(a2.x, b4.x, acc[0][0]); acc[0][1] = fmaf(a2.x, b4.y, acc[0][1]);
+      acc[0][2] = fmaf(a2.x, b4.z, acc[0][2]); acc[0][3] = fmaf(a2.x, b4.w, acc[0][3]);
+      acc[1][0] = fmaf(a2.y, b4.x, acc[1][0]); acc[1][1] = fmaf(a2.y, b4.y, acc[1][1]);
+      acc[1][2] = fmaf(a2.y, b4.z, acc[1][2]); acc[1][3] = fmaf(a2.y, b4.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int gm = m0 + ty * 2 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      float* c = C + (int64_t)gm * ldc + gn;
+      if (gridDim.z > 1) {
+        atomicAdd(c, v);
+      } else {
+        if (bias) v += bias[gn];
+        if (Cpre) Cpre[(int64_t)gm * ldc + gn] = v;
+        v = pvb::act_fwd(v, act);
+        *c = accumulate ? *c + v : v;
+      }
+    }
+  }
+}
+
+// second pass of a split-K forward: C = act(C + bias), optional pre-activation copy
+__global__ void bias_act_kernel(float* __restrict__ C, float* __restrict__ Cpre,
+                                const float* __restrict__ bias, int64_t M, int N, int act) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float v = C[i];
+  if (bias) v += bias[i % N];
+  if (Cpre) Cpre[i] = v;
+  C[i] = pvb::act_fwd(v, act);
+}
+
+template <int TA, int TB>
+int launch_sgemm_small(const float* A, const float* B, float* C, float* Cpre, const float* bias,
+                       int M, int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int act,
+                       int accumulate, cudaStream_t st) {
+  const int tiles = ((M + SBM - 1) / SBM) * ((N + SBN - 1) / SBN);
+  int64_t splits = (2 * 148 + tiles - 1) / tiles;
+  int64_t max_splits = K / 64;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int64_t k_chunk = K;
+  if (splits > 1) {
+    k_chunk = ((K + splits - 1) / splits + SBK - 1) / SBK * SBK;
+    splits = (K + k_chunk - 1) / k_chunk;
+  }
+  dim3 grid((N + SBN - 1) / SBN, (M + SBM - 1) / SBM, (unsigned)splits);
+  if (splits > 1) {
+    PVB_CHECK_ARG(ldc == N, "sgemm: split-K needs a dense output");
+    if (!accumulate) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
+    sgemm_small_kernel<TA, TB><<<grid, SNT, 0, st>>>(A, B, C, nullptr, nullptr, M, N, K, lda, ldb,
+                                                     ldc, PVB_ACT_NONE, 1, k_chunk);
+    pvb::count_launch();
+    if (bias || Cpre || act != PVB_ACT_NONE) {
+      PVB_CHECK_ARG(!accumulate, "sgemm: split-K epilogue cannot accumulate");
+      bias_act_kernel<<<pvb::cdiv((int64_t)M * N, 256), 256, 0, st>>>(C, Cpre, bias, M, N, act);
+      pvb::count_launch();
+    }
+  } else {
+    sgemm_small_kernel<TA, TB><<<grid, SNT, 0, st>>>(A, B, C, Cpre, bias, M, N, K, lda, ldb, ldc,
+                                                     act, accumulate, k_chunk);
+    pvb::count_launch();
   }
   return pvb::launch_status();
 }

@@ -128,7 +128,7 @@ __global__ void fold_fwd_kernel(pvb_fold_cfg cfg, const float* __restrict__ z,
   }
 }
 
-constexpr int FOLD_G = 64;     // CTAs (= number of weight-gradient partials)
+constexpr int FOLD_G = 256;    // CTAs (= number of weight-gradient partials)
 constexpr int FOLD_T = 128;    // threads
 constexpr int FOLD_MAXR = 40;  // 4 transform grads + (L + C) <= 36
 

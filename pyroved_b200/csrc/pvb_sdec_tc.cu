@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
   // ---- weight-gradient partials of this CTA ---------------------------------------------------------------
   if (P.backward) {
     umma::fence_after_sync();
-    float* out = P.wgrad_part + (size_t)blockIdx.x * PVB_TC_WGRAD_FLOATS;
+    float* out = P.wgrad_part + (size_t)blockIdx.x * PVB_TC_WGRAD_STRIDE;
     // layout: dW1[128][128] | db1[128] | dW2[128][128] | db2[128] | dwo[128] | dbo
     float* o_dW1 = out;
     float* o_db1 = out + HD * HD;
@@ -531,7 +531,7 @@ extern "C" int pvb_sdec_tc_sizes(int64_t I, int N, pvb_tc_sizes* out) {
   int sms = sm_count();
   out->ctas = (int)(out->tiles < sms ? (out->tiles > 0 ? out->tiles : 1) : sms);
   out->gUv_part_floats = out->tiles * MAX_SLOTS * 3 * HD;
-  out->wgrad_part_floats = (int64_t)out->ctas * PVB_TC_WGRAD_FLOATS;
+  out->wgrad_part_floats = (int64_t)out->ctas * PVB_TC_WGRAD_STRIDE;
   return 0;
 }
 
@@ -548,6 +548,7 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
                 "pvb_sdec_tc_step: sampler %d not supported", sampler);
   PVB_CHECK_ARG(!backward || (x && gUv_part && wgrad_part), "pvb_sdec_tc_step: backward needs x and workspaces");
   PVB_CHECK_ARG(((uintptr_t)W1 % 16 == 0) && ((uintptr_t)W2 % 16 == 0), "pvb_sdec_tc_step: weights must be 16-byte aligned");
+  PVB_CHECK_ARG(!backward || ((uintptr_t)wgrad_part % 16 == 0), "pvb_sdec_tc_step: wgrad_part must be 16-byte aligned");
   const int N = (ndim == 1) ? H : H * W;
   PVB_CHECK_ARG(N >= 32, "pvb_sdec_tc_step: need >= 32 pixels per instance");
   if (I == 0) return 0;

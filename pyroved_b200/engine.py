@@ -22,8 +22,8 @@ import os
 import torch
 import torch.nn as nn
 
-from . import ops
-from ._lib import TC_WGRAD_FLOATS
+from . import ops, parallel
+from ._lib import TC_WGRAD_FLOATS, TC_WGRAD_STRIDE
 from .nets.fc import linear_layers
 
 
@@ -309,7 +309,8 @@ class SpatialVAEProgram(StepProgram):
                 n_w = TC_WGRAD_FLOATS
                 # partial layout == flat layout of (fc0.w, fc0.b, fc2.w, fc2.b, out.w, out.b)
                 base = flat.offset(L[0].weight)
-                ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], s.ctas, n_w, n_w, True)
+                ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], s.ctas, n_w,
+                                    TC_WGRAD_STRIDE, True)
                 ops.sdec_tc_gather_gUv(self.gUv_part, self.gUv, self.I, self.N)
             else:
                 hl = self.dmlp.h[-1] if self.dmlp.layers else self.h0
@@ -384,16 +385,13 @@ class SVIEngine:
 
     # ---- distributed -----------------------------------------------------
     def _attach_distributed(self):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            self.world_size = dist.get_world_size()
-            self.rank = dist.get_rank()
+        self.rank, self.world_size = parallel.rank_world()
 
     def eps_first_index(self, n_local):
         """Global index of this rank's first noise element: the noise of a
         sample depends on its GLOBAL position, so the ELBO does not depend on
         the number of GPUs."""
-        return self.rank * n_local
+        return parallel.noise_first_index(self.rank, n_local)
 
     # ---- program selection -------------------------------------------------
     def tc_eligible(self, dec, N):
@@ -431,8 +429,7 @@ class SVIEngine:
         ops.adam_flat(flat.p, flat.g, flat.m, flat.v, flat.total, self.lr, self.step_counter)
 
     def _allreduce(self):
-        import torch.distributed as dist
-        dist.all_reduce(self.flat.g, op=dist.ReduceOp.SUM, group=self.process_group)
+        parallel.allreduce_sum_(self.flat.g, self.process_group)
 
     def _execute(self, key, fn):
         """Eager on first sight of `key`, captured on the second, replayed after."""

@@ -1,0 +1,100 @@
+"""Data parallelism for the SVI step: one process per GPU, batches sharded
+across ranks, ONE all-reduce(SUM) of the flat gradient buffer (+ loss slot)
+per optimizer step over NCCL (NVLink / NVSwitch), identical fused Adam on
+every rank.
+
+The reference has no distributed code at all; the loss of
+its SVI step is a SUM over the batch (Trace_ELBO), so gradients of shards add
+up exactly -- the collective is SUM, not AVG, and no learning-rate rescaling
+is involved.  Noise is drawn from a counter-based generator keyed by the
+GLOBAL sample index, so the ELBO does not depend on the number of GPUs.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_process_group(backend=None, device=None):
+    """Initialise torch.distributed from torchrun's environment (RANK,
+    LOCAL_RANK, WORLD_SIZE, MASTER_ADDR, MASTER_PORT).  Returns (rank, world)."""
+    if dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 1
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {}
+    if backend == "nccl":
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        kw["device_id"] = torch.device("cuda:{}".format(local) if device is None else device)
+    dist.init_process_group(backend, **kw)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous slice [lo, hi) of a global batch of n samples owned by `rank`
+    (n must divide evenly: every rank runs the same static kernel shapes)."""
+    if n % world != 0:
+        raise ValueError("global batch {} is not divisible by world size {}".format(n, world))
+    per = n // world
+    return rank * per, (rank + 1) * per
+
+
+def shard(t, rank=None, world=None):
+    """This rank's contiguous slice of a global batch tensor."""
+    if rank is None or world is None:
+        rank, world = rank_world()
+    lo, hi = shard_bounds(t.shape[0], rank, world)
+    return t[lo:hi]
+
+
+def noise_first_index(rank, n_local):
+    """Global index of the first noise element of this rank's shard."""
+    return rank * n_local
+
+
+def allreduce_sum_(flat, group=None):
+    """In-place SUM all-reduce of the flat [gradients | loss] buffer."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+class ShardedLoader:
+    """Wraps a loader of GLOBAL batches; yields this rank's shard of each
+    tensor (keeps the (x,) / (x, y) tuple protocol of the trainers)."""
+
+    def __init__(self, loader, rank=None, world=None):
+        self.loader = loader
+        r, w = rank_world()
+        self.rank = r if rank is None else rank
+        self.world = w if world is None else world
+        self.dataset = _ShardedLen(loader.dataset, self.world)
+
+    def __iter__(self):
+        for batch in self.loader:
+            yield [shard(t, self.rank, self.world) for t in batch]
+
+    def __len__(self):
+        return len(self.loader)
+
+
+class _ShardedLen:
+    """len() = samples this rank sees per epoch (the trainer divides by it)."""
+
+    def __init__(self, dataset, world):
+        self.n = len(dataset) // world
+
+    def __len__(self):
+        return self.n
