@@ -291,6 +291,11 @@ def run_ours(args):
                     "bound": "tensor", "achieved": fl / t_tc / 1e12, "peak": pk["tf"],
                     "unit": "TFLOP/s", "frac": fl / t_tc / 1e12 / pk["tf"], "traffic": None,
                     "us": t_tc * 1e6}
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    roof["traffic"] = json.load(f)[roof["kernel"]]["dram_bytes_per_launch"]
+            except Exception:
+                roof["traffic"] = None
             kernels[roof["kernel"]] = roof
         roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json burst: kernel timed alone)"
         if os.environ.get("PVB_BENCH_SKIP_CPU") == "1":   # profiling runs only
