@@ -263,13 +263,13 @@ def run_ours(args):
         L = linear_layers(dec.fc_layers)
         # fused grid + affine + first layer kernel (HBM-write bound when it materialises h0)
         if not use_tc:
-            t_h0 = time_kernel_alone(lambda: ops.sdec_h0_fwd(prog.Uv, prog.h0, H, W, 2))
+            t_h0 = time_kernel_alone(lambda: ops.sdec_h0_fwd(prog.dec.Uv, prog.dec.h0, H, W, 2))
             kernels["pvb_sdec_h0_fwd"] = {
                 "bound": "hbm", "achieved": R * 128 * 4 / t_h0 / 1e9, "peak": pk["hbm_gbs"],
                 "unit": "GB/s", "frac": R * 128 * 4 / t_h0 / 1e9 / pk["hbm_gbs"], "traffic": None,
                 "us": t_h0 * 1e6}
             t_mm = time_kernel_alone(lambda: ops.linear_fwd(
-                prog.h0, L[0].weight.data, L[0].bias.data, "tanh", out=prog.dmlp.h[0]))
+                prog.dec.h0, L[0].weight.data, L[0].bias.data, "tanh", out=prog.dec.dmlp.h[0]))
             fl = 2.0 * R * 128 * 128
             kernels["sgemm_kernel(linear_fwd 128x128)"] = {
                 "bound": "tensor", "achieved": fl / t_mm / 1e12, "peak": pk["tf"],
@@ -280,10 +280,10 @@ def run_ours(args):
             roof["kernel"] = "sgemm_kernel(linear_fwd 128x128)"
         else:
             def tc_once():
-                ops.sdec_tc_step(prog.Uv, prog.x, None, L[0].weight.data, L[0].bias.data,
+                ops.sdec_tc_step(prog.dec.Uv, prog.x, None, L[0].weight.data, L[0].bias.data,
                                  L[1].weight.data, L[1].bias.data, dec.out.weight.data,
-                                 dec.out.bias.data, prog.rowll, prog.loc, prog.gUv_part,
-                                 prog.wgrad_part, prog.I, prog.B, H, W, 2, "bernoulli", True,
+                                 dec.out.bias.data, prog.dec.rowll, prog.loc, prog.dec.gUv_part,
+                                 prog.dec.wgrad_part, prog.dec.I, prog.B, H, W, 2, "bernoulli", True,
                                  0.5, True)
             t_tc = time_kernel_alone(tc_once)
             fl = float(FLOP_PER_ROW_STEP) * R

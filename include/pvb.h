@@ -144,6 +144,13 @@ int pvb_elbo_reduce(const float* rowll, const float* kl, const float* w,
                     float beta, float* ll, float* loss_out, int accumulate,
                     int64_t I, int N, void* stream);
 
+/* loss_out[0] += scale * sum_i w_i v_i   (w may be NULL; fixed order) */
+int pvb_weighted_sum(const float* v, const float* w, float scale,
+                     float* loss_out, int64_t n, void* stream);
+/* out[i] = a[i] + beta * b[i] */
+int pvb_axpy_out(const float* a, const float* b, float beta, float* out,
+                 int64_t n, void* stream);
+
 /* ---- enumerated discrete latent (TraceEnum_ELBO expectation) -----------
  * alpha = softmax(logits [B,K]); w[k*B+b] = alpha[b,k]
  * (nets/fc.py:101-108,264-271; models/jivae.py:199-220; ssivae.py:198-215) */

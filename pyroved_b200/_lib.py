@@ -50,6 +50,8 @@ SIGNATURES = {
     "pvb_sdec_h0_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_obs_loglik": [_f, _f, _f, _f, _f, _f, _i64, _i64, _i32, _i32, _i32, _fl, _st],
     "pvb_elbo_reduce": [_f, _f, _f, _fl, _f, _f, _i32, _i64, _i32, _st],
+    "pvb_weighted_sum": [_f, _f, _fl, _f, _i64, _st],
+    "pvb_axpy_out": [_f, _f, _fl, _f, _i64, _st],
     "pvb_enum_head_fwd": [_f, _f, _f, _i64, _i32, _st],
     "pvb_enum_head_bwd": [_f, _f, _fl, _f, _f, _i64, _i32, _st],
     "pvb_class_nll": [_f, _f, _fl, _f, _f, _i64, _i32, _st],

@@ -372,6 +372,38 @@ extern "C" int pvb_fold_bwd(const pvb_fold_cfg* cfg, const float* z, const float
   return pvb::launch_status();
 }
 
+namespace {
+__global__ void weighted_sum_kernel(const float* __restrict__ v, const float* __restrict__ w,
+                                    float scale, float* __restrict__ loss_out, int64_t n) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (w ? w[i] : 1.f) * v[i];
+  s = pvb::block_sum(s, sm);
+  if (threadIdx.x == 0) loss_out[0] += scale * s;
+}
+__global__ void axpy_out_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                float beta, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmaf(beta, b[i], a[i]);
+}
+}  // namespace
+
+extern "C" int pvb_weighted_sum(const float* v, const float* w, float scale, float* loss_out,
+                                int64_t n, void* stream) {
+  PVB_CHECK_ARG(v && loss_out && n >= 0, "pvb_weighted_sum: bad argument");
+  if (n == 0) return 0;
+  weighted_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(v, w, scale, loss_out, n); pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_axpy_out(const float* a, const float* b, float beta, float* out, int64_t n,
+                            void* stream) {
+  PVB_CHECK_ARG(a && b && out && n >= 0, "pvb_axpy_out: bad argument");
+  if (n == 0) return 0;
+  axpy_out_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, beta, out, n); pvb::count_launch();
+  return pvb::launch_status();
+}
+
 extern "C" int pvb_enum_head_fwd(const float* logits, float* alpha, float* w, int64_t B, int K,
                                  void* stream) {
   PVB_CHECK_ARG(logits && alpha && B >= 0 && K > 0, "pvb_enum_head_fwd: bad argument");

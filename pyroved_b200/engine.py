@@ -141,6 +141,7 @@ class MLP:
 
 class StepProgram:
     """Static buffers + kernel sequence for one (model, batch shape)."""
+    loss_const = 0.0   # host-side constant added to the returned loss (per rank)
 
     def __init__(self, engine, B, has_y):
         self.engine = engine
@@ -148,97 +149,216 @@ class StepProgram:
         self.has_y = has_y
 
 
-class SpatialVAEProgram(StepProgram):
-    """iVAE (Trace_ELBO) step: reference models/ivae.py:165-221."""
+class DecoderOps:
+    """Decoder forward/backward over I instances (I = B, or K*B when a discrete
+    latent is enumerated).  Spatial decoder: fused tcgen05 kernel when the net
+    is the default 128-128 tanh MLP, generic fp32 kernels otherwise; non-spatial
+    (`fcDecoderNet`, coord == 0): generic GEMMs on the latent code."""
 
-    def __init__(self, engine, B, has_y):
+    def __init__(self, engine, I, B, cond_dim):
+        m = engine.model
+        self.engine = engine
+        self.I, self.Bx, self.Cd = I, B, cond_dim
+        self.N = m._n_pix
+        self.Zf = m.z_dim            # full latent width (transform + content)
+        dev, flat = engine.device, engine.flat
+        f32 = dict(device=dev, dtype=torch.float32)
+        dec = m.decoder
+        self.spatial = m.coord > 0
+        N = self.N
+        R = I * N
+        self.rowll = torch.empty(R, **f32)
+        self.loc = torch.empty(R, **f32)
+        self.ll = torch.empty(I, **f32)
+        self.gz = torch.zeros(I, self.Zf, **f32)
+        self.gcond = None
+        layers = linear_layers(dec.fc_layers)
+        self.use_tc = False
+        if self.spatial:
+            cl = dec.coord_latent
+            Hd0 = cl.fc_coord.out_features
+            self.fold_cfg = ops.make_fold_cfg(m.ndim, m.invariances, m._latent_dim, cond_dim, Hd0,
+                                              m._dx_prior, m._dy_prior, m._sc_prior)
+            self.Uv = torch.empty(I, 3, Hd0, **f32)
+            self.gUv = torch.empty(I, 3, Hd0, **f32)
+            self.G_fold = ops.fold_bwd_num_partials()
+            self.fold_per = Hd0 * (m.ndim + 1 + m._latent_dim + cond_dim)
+            self.fold_part = torch.empty(self.G_fold, self.fold_per, **f32)
+            self.use_tc = engine.tc_eligible(dec, N)
+            if self.use_tc:
+                s = ops.sdec_tc_sizes(I, N)
+                self.tc_sizes = s
+                self.gUv_part = torch.empty(max(s.gUv_part_floats, 4), **f32)
+                self.wgrad_part = torch.empty(max(s.wgrad_part_floats, 4), **f32)
+            else:
+                self.h0 = torch.empty(R, Hd0, **f32)
+                self.dmlp = MLP(layers, dec.activation, R, dev, flat)
+                Hl = layers[-1].out_features if layers else Hd0
+                self.logit = torch.empty(R, 1, **f32)
+                self.dlogit = torch.empty(R, 1, **f32)
+                wmax = max([Hd0, Hl] + [l.in_features for l in layers])
+                self.dec_scratch = [torch.empty(R * wmax, **f32) for _ in range(3)]
+        else:
+            self.dec_in = torch.zeros(I, self.Zf + cond_dim, **f32)
+            self.dmlp = MLP(layers, dec.activation, I, dev, flat)
+            Hl = layers[-1].out_features
+            self.logit = torch.empty(I, N, **f32)
+            self.dlogit = torch.empty(I, N, **f32)
+            wmax = max([Hl, self.Zf + cond_dim] + [l.in_features for l in layers])
+            self.dec_scratch = [torch.empty(I * wmax, **f32) for _ in range(3)]
+
+    def forward(self, z, cond, x, w, want_grad):
+        """z [I,Zf], cond [I,Cd] or None, x [B,N], w [I] or None -> fills rowll/loc/ll."""
+        m = self.engine.model
+        dec, samp = m.decoder, m.sampler_d
+        if self.spatial:
+            cl = dec.coord_latent
+            ops.fold_fwd(self.fold_cfg, z, cond, cl.fc_coord.weight.data, cl.fc_coord.bias.data,
+                         cl.fc_latent.weight.data, self.Uv)
+            if self.use_tc:
+                L = linear_layers(dec.fc_layers)
+                ops.sdec_tc_step(self.Uv, x, w, L[0].weight.data, L[0].bias.data,
+                                 L[1].weight.data, L[1].bias.data, dec.out.weight.data,
+                                 dec.out.bias.data, self.rowll, self.loc, self.gUv_part,
+                                 self.wgrad_part, self.I, self.Bx, m._H, m._W, m.ndim, samp.name,
+                                 dec.sigmoid_out, samp.decoder_sig, want_grad)
+            else:
+                ops.sdec_h0_fwd(self.Uv, self.h0, m._H, m._W, m.ndim)
+                hl = self.dmlp.forward(self.h0)
+                ops.linear_fwd(hl, dec.out.weight.data, dec.out.bias.data, None, out=self.logit)
+                ops.obs_loglik(self.logit, x, w, self.rowll, self.dlogit if want_grad else None,
+                               self.loc, self.I, self.Bx, self.N, samp.name, dec.sigmoid_out,
+                               samp.decoder_sig)
+        else:
+            self.dec_in[:, :self.Zf].copy_(z)
+            if self.Cd > 0:
+                self.dec_in[:, self.Zf:].copy_(cond)
+            hl = self.dmlp.forward(self.dec_in)
+            ops.linear_fwd(hl, dec.out.weight.data, dec.out.bias.data, None, out=self.logit)
+            ops.obs_loglik(self.logit, x, w, self.rowll, self.dlogit if want_grad else None,
+                           self.loc, self.I, self.Bx, self.N, samp.name, dec.sigmoid_out,
+                           samp.decoder_sig)
+        ops.elbo_reduce(self.rowll, None, None, 0.0, self.ll, None, False, self.I, self.N)
+
+    def backward(self, z, cond):
+        """Accumulates decoder weight gradients; returns dloss/dz [I,Zf]."""
+        eng = self.engine
+        m, flat = eng.model, eng.flat
+        dec = m.decoder
+        if self.spatial:
+            cl = dec.coord_latent
+            if self.use_tc:
+                L = linear_layers(dec.fc_layers)
+                n_w = TC_WGRAD_FLOATS
+                # partial layout == flat layout of (fc0.w, fc0.b, fc2.w, fc2.b, out.w, out.b)
+                base = flat.offset(L[0].weight)
+                ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], self.tc_sizes.ctas,
+                                    n_w, TC_WGRAD_STRIDE, True)
+                ops.sdec_tc_gather_gUv(self.gUv_part, self.gUv, self.I, self.N)
+            else:
+                hl = self.dmlp.h[-1] if self.dmlp.layers else self.h0
+                d_hl = self.dec_scratch[2][:hl.numel()].view_as(hl)
+                ops.linear_bwd(hl, dec.out.weight.data, None, None, self.dlogit, self.dlogit, d_hl,
+                               False, flat.gv(dec.out.weight), flat.gv(dec.out.bias), None)
+                dh0 = self.dmlp.backward(d_hl, self.dec_scratch, True)
+                ops.sdec_h0_bwd(dh0, self.h0, self.gUv, m._H, m._W, m.ndim)
+            ops.fold_bwd(self.fold_cfg, z, cond, cl.fc_coord.weight.data,
+                         cl.fc_latent.weight.data, self.gUv, self.gz, self.gcond, self.fold_part)
+            Hd0 = cl.fc_coord.out_features
+            nd = m.ndim
+            LC = m._latent_dim + self.Cd
+            G, per = self.G_fold, self.fold_per
+            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.weight), G, Hd0 * nd, per, True, 0)
+            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.bias), G, Hd0, per, True, Hd0 * nd)
+            if LC > 0:
+                ops.reduce_partials(self.fold_part, flat.gv(cl.fc_latent.weight), G, Hd0 * LC, per,
+                                    True, Hd0 * (nd + 1))
+        else:
+            hl = self.dmlp.h[-1]
+            d_hl = self.dec_scratch[2][:hl.numel()].view_as(hl)
+            ops.linear_bwd(hl, dec.out.weight.data, None, None, self.dlogit, self.dlogit, d_hl,
+                           False, flat.gv(dec.out.weight), flat.gv(dec.out.bias), None)
+            d_in = self.dmlp.backward(d_hl, self.dec_scratch, True)
+            self.gz.copy_(d_in[:, :self.Zf])
+        return self.gz
+
+
+class GaussHead:
+    """fc11 / fc12 heads + reparameterised sample + their backward, for M rows."""
+
+    def __init__(self, engine, enc, M, Z):
+        f32 = dict(device=engine.device, dtype=torch.float32)
+        self.engine, self.enc, self.M, self.Z = engine, enc, M, Z
+        self.eps = torch.zeros(M, Z, **f32)
+        self.mu = torch.empty(M, Z, **f32)
+        self.s_pre = torch.empty(M, Z, **f32)
+        self.sigma = torch.empty(M, Z, **f32)
+        self.z = torch.empty(M, Z, **f32)
+        self.kl = torch.empty(M, **f32)
+        self.gmu = torch.empty(M, Z, **f32)
+        self.gs_pre = torch.empty(M, Z, **f32)
+        self.dh = torch.empty(M, enc.fc11.in_features, **f32)
+
+    def forward(self, h, gen_eps, n_rank_elems=None):
+        eng, enc = self.engine, self.enc
+        if gen_eps:
+            ops.randn(self.eps, eng.seed, eng.step_counter, eng.eps_first_index(self.eps.numel()))
+        ops.linear_fwd(h, enc.fc11.weight.data, enc.fc11.bias.data, None, out=self.mu)
+        ops.linear_fwd(h, enc.fc12.weight.data, enc.fc12.bias.data, None, out=self.s_pre)
+        ops.latent_fwd(self.mu, self.s_pre, self.eps, self.sigma, self.z, self.kl)
+
+    def backward(self, h, gz, w, beta):
+        """-> self.dh = dloss/dh through both heads."""
+        flat, enc = self.engine.flat, self.enc
+        ops.latent_bwd(gz, self.eps, self.sigma, self.s_pre, self.z, w, beta, self.gmu, self.gs_pre)
+        ops.linear_bwd(h, enc.fc11.weight.data, None, None, self.gmu, self.gmu, self.dh, False,
+                       flat.gv(enc.fc11.weight), flat.gv(enc.fc11.bias), None)
+        ops.linear_bwd(h, enc.fc12.weight.data, None, None, self.gs_pre, self.gs_pre, self.dh,
+                       True, flat.gv(enc.fc12.weight), flat.gv(enc.fc12.bias), None)
+        return self.dh
+
+
+def _mlp_scratch(layers, M, device):
+    wmax = max([l.in_features for l in layers[1:]] + [layers[-1].out_features, 1])
+    return [torch.empty(M * wmax, device=device, dtype=torch.float32) for _ in range(2)]
+
+
+class SpatialVAEProgram(StepProgram):
+    """iVAE (Trace_ELBO) step: reference models/ivae.py:165-221.  Also the
+    supervised ssiVAE step (ys observed): same trace plus the constant
+    log p(y) = log(1/K) per sample (models/ssivae.py:153-215)."""
+
+    def __init__(self, engine, B, has_y, cond_dim=None, loss_const=0.0):
         super().__init__(engine, B, has_y)
         m = engine.model
-        dev = engine.device
-        flat = engine.flat
+        dev, flat = engine.device, engine.flat
         self.N = m._n_pix
         self.Z = m.z_dim
-        self.C = m.c_dim if has_y else 0
-        if m.c_dim > 0 and not has_y:
-            raise ValueError("model was built with c_dim={} but no y was passed".format(m.c_dim))
+        c_model = m.c_dim if cond_dim is None else cond_dim
+        self.C = c_model if has_y else 0
+        if c_model > 0 and not has_y:
+            raise ValueError("model was built with c_dim={} but no y was passed".format(c_model))
+        self.loss_const = loss_const
         N, Z, C = self.N, self.Z, self.C
         f32 = dict(device=dev, dtype=torch.float32)
-        # inputs
         self.enc_in = torch.zeros(B, N + C, **f32)
         self.x = torch.zeros(B, N, **f32) if C > 0 else self.enc_in
         self.y = torch.zeros(B, C, **f32) if C > 0 else None
-        self.eps = torch.zeros(B, Z, **f32)
-        # encoder
         enc = m.encoder_z
         self.enc = MLP(linear_layers(enc.fc_layers), enc.activation, B, dev, flat)
-        He = enc.fc11.in_features
-        self.mu = torch.empty(B, Z, **f32)
-        self.s_pre = torch.empty(B, Z, **f32)
-        self.sigma = torch.empty(B, Z, **f32)
-        self.z = torch.empty(B, Z, **f32)
-        self.kl = torch.empty(B, **f32)
-        self.gz = torch.zeros(B, Z, **f32)
-        self.gmu = torch.empty(B, Z, **f32)
-        self.gs_pre = torch.empty(B, Z, **f32)
-        self.dh_e = torch.empty(B, He, **f32)
-        wmax = max([He] + [l.in_features for l in self.enc.layers[1:]] + [1])
-        self.enc_scratch = [torch.empty(B * wmax, **f32) for _ in range(2)]
-        self.ll = torch.empty(B, **f32)
-        dec = m.decoder
-        self.spatial = m.coord > 0
-        if self.spatial:
-            self._init_spatial(dec, B, dev, flat, f32)
-        else:
-            self._init_fc(dec, B, dev, flat, f32)
+        self.enc_scratch = _mlp_scratch(self.enc.layers, B, dev)
+        self.head = GaussHead(engine, enc, B, Z)
+        self.dec = DecoderOps(engine, B, B, C)
 
-    # ---- decoder buffers -------------------------------------------------
-    def _init_spatial(self, dec, I, dev, flat, f32):
-        m = self.engine.model
-        self.I = I
-        N = self.N
-        R = I * N
-        cl = dec.coord_latent
-        Hd0 = cl.fc_coord.out_features
-        self.fold_cfg = ops.make_fold_cfg(m.ndim, m.invariances, m._latent_dim, self.C, Hd0,
-                                          m._dx_prior, m._dy_prior, m._sc_prior)
-        self.Uv = torch.empty(I, 3, Hd0, **f32)
-        self.gUv = torch.empty(I, 3, Hd0, **f32)
-        self.G_fold = ops.fold_bwd_num_partials()
-        self.fold_per = Hd0 * (m.ndim + 1 + m._latent_dim + self.C)
-        self.fold_part = torch.empty(self.G_fold, self.fold_per, **f32)
-        self.gcond = torch.empty(I, max(self.C, 1), **f32) if self.C > 0 else None
-        self.rowll = torch.empty(R, **f32)
-        self.loc = torch.empty(R, **f32)
-        layers = linear_layers(dec.fc_layers)
-        self.use_tc = self.engine.tc_eligible(dec, N)
-        if self.use_tc:
-            s = ops.sdec_tc_sizes(I, N)
-            self.tc_sizes = s
-            self.gUv_part = torch.empty(max(s.gUv_part_floats, 1), **f32)
-            self.wgrad_part = torch.empty(max(s.wgrad_part_floats, 1), **f32)
-        else:
-            self.h0 = torch.empty(R, Hd0, **f32)
-            self.dmlp = MLP(layers, dec.activation, R, dev, flat)
-            Hl = layers[-1].out_features if layers else Hd0
-            self.logit = torch.empty(R, 1, **f32)
-            self.dlogit = torch.empty(R, 1, **f32)
-            wmax = max([Hd0, Hl] + [l.in_features for l in layers])
-            self.dec_scratch = [torch.empty(R * wmax, **f32) for _ in range(3)]
+    # convenient aliases (tests / inference read these)
+    eps = property(lambda s: s.head.eps)
+    mu = property(lambda s: s.head.mu)
+    sigma = property(lambda s: s.head.sigma)
+    z = property(lambda s: s.head.z)
+    loc = property(lambda s: s.dec.loc)
+    ll = property(lambda s: s.dec.ll)
+    use_tc = property(lambda s: s.dec.use_tc)
 
-    def _init_fc(self, dec, I, dev, flat, f32):
-        self.I = I
-        layers = linear_layers(dec.fc_layers)
-        self.dec_in = torch.zeros(I, self.Z + self.C, **f32)
-        self.dmlp = MLP(layers, dec.activation, I, dev, flat)
-        Hl = layers[-1].out_features
-        self.logit = torch.empty(I, self.N, **f32)
-        self.dlogit = torch.empty(I, self.N, **f32)
-        self.rowll = torch.empty(I * self.N, **f32)
-        self.loc = torch.empty(I * self.N, **f32)
-        wmax = max([Hl, self.Z + self.C] + [l.in_features for l in layers])
-        self.dec_scratch = [torch.empty(I * wmax, **f32) for _ in range(3)]
-
-    # ---- inputs ------------------------------------------------------------
     def load(self, x, y):
         B, N = self.B, self.N
         x = x.reshape(B, -1)
@@ -252,101 +372,178 @@ class SpatialVAEProgram(StepProgram):
         else:
             self.enc_in.copy_(x, non_blocking=True)
 
-    # ---- kernel sequences ----------------------------------------------------
     def forward(self, beta, want_grad, gen_eps):
-        eng = self.engine
-        m = eng.model
-        flat = eng.flat
-        enc = m.encoder_z
-        if gen_eps:
-            ops.randn(self.eps, eng.seed, eng.step_counter, eng.eps_first_index(self.B * self.Z))
+        flat = self.engine.flat
         h = self.enc.forward(self.enc_in)
-        ops.linear_fwd(h, enc.fc11.weight.data, enc.fc11.bias.data, None, out=self.mu)
-        ops.linear_fwd(h, enc.fc12.weight.data, enc.fc12.bias.data, None, out=self.s_pre)
-        ops.latent_fwd(self.mu, self.s_pre, self.eps, self.sigma, self.z, self.kl)
-        samp = m.sampler_d
-        dec = m.decoder
-        if self.spatial:
-            cl = dec.coord_latent
-            ops.fold_fwd(self.fold_cfg, self.z, self.y, cl.fc_coord.weight.data,
-                         cl.fc_coord.bias.data, cl.fc_latent.weight.data, self.Uv)
-            if self.use_tc:
-                L = linear_layers(dec.fc_layers)
-                ops.sdec_tc_step(self.Uv, self.x, None, L[0].weight.data, L[0].bias.data,
-                                 L[1].weight.data, L[1].bias.data, dec.out.weight.data,
-                                 dec.out.bias.data, self.rowll, self.loc, self.gUv_part,
-                                 self.wgrad_part, self.I, self.B, m._H, m._W, m.ndim, samp.name,
-                                 dec.sigmoid_out, samp.decoder_sig, want_grad)
-            else:
-                ops.sdec_h0_fwd(self.Uv, self.h0, m._H, m._W, m.ndim)
-                hl = self.dmlp.forward(self.h0)
-                ops.linear_fwd(hl, dec.out.weight.data, dec.out.bias.data, None, out=self.logit)
-                ops.obs_loglik(self.logit, self.x, None, self.rowll,
-                               self.dlogit if want_grad else None, self.loc, self.I, self.B,
-                               self.N, samp.name, dec.sigmoid_out, samp.decoder_sig)
-        else:
-            self.dec_in[:, :self.Z].copy_(self.z)
-            if self.C > 0:
-                self.dec_in[:, self.Z:].copy_(self.y)
-            hl = self.dmlp.forward(self.dec_in)
-            ops.linear_fwd(hl, dec.out.weight.data, dec.out.bias.data, None, out=self.logit)
-            ops.obs_loglik(self.logit, self.x, None, self.rowll,
-                           self.dlogit if want_grad else None, self.loc, self.I, self.B, self.N,
-                           samp.name, dec.sigmoid_out, samp.decoder_sig)
-        ops.elbo_reduce(self.rowll, self.kl, None, beta, self.ll, flat.loss, False, self.I, self.N)
+        self.head.forward(h, gen_eps)
+        self.dec.forward(self.head.z, self.y, self.x, None, want_grad)
+        ops.weighted_sum(self.dec.ll, None, -1.0, flat.loss)
+        ops.weighted_sum(self.head.kl, None, -float(beta), flat.loss)
 
     def backward(self, beta):
-        eng = self.engine
-        m = eng.model
-        flat = eng.flat
-        dec = m.decoder
+        gz = self.dec.backward(self.head.z, self.y)
+        dh = self.head.backward(self.enc.h[-1], gz, None, beta)
+        self.enc.backward(dh, self.enc_scratch, False)
+
+
+class EnumVAEProgram(StepProgram):
+    """TraceEnum_ELBO step with one enumerated discrete latent.
+
+    kind == "jivae"  (reference models/jivae.py:152-220): encoder(x) -> mu, sigma,
+        alpha; the continuous code is shared by the K enumerated classes.
+    kind == "ssivae" (unsupervised; reference models/ssivae.py:153-215):
+        alpha = classifier(x); encoder_z([x, onehot_k]) per class.
+    Instance i = k*B + b; alpha_bk weights every downstream cost.
+    """
+
+    def __init__(self, engine, B, kind):
+        super().__init__(engine, B, False)
+        m = engine.model
+        dev, flat = engine.device, engine.flat
+        self.kind = kind
+        self.N, self.Z = m._n_pix, m.z_dim
+        K = m.discrete_dim if kind == "jivae" else m.num_classes
+        self.K = K
+        I = K * B
+        self.I = I
+        N, Z = self.N, self.Z
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.x = torch.zeros(B, N, **f32)
+        self.onehot = torch.zeros(I, K, **f32)
+        self.onehot.view(K, B, K)[torch.arange(K), :, torch.arange(K)] = 1.0
+        self.logits = torch.empty(B, K, **f32)
+        self.alpha = torch.empty(B, K, **f32)
+        self.w = torch.empty(I, **f32)
+        self.glogits = torch.zeros(B * K + B, **f32)
+        self.cost = torch.empty(I, **f32)
         enc = m.encoder_z
-        if self.spatial:
-            cl = dec.coord_latent
-            if self.use_tc:
-                L = linear_layers(dec.fc_layers)
-                s = self.tc_sizes
-                n_w = TC_WGRAD_FLOATS
-                # partial layout == flat layout of (fc0.w, fc0.b, fc2.w, fc2.b, out.w, out.b)
-                base = flat.offset(L[0].weight)
-                ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], s.ctas, n_w,
-                                    TC_WGRAD_STRIDE, True)
-                ops.sdec_tc_gather_gUv(self.gUv_part, self.gUv, self.I, self.N)
-            else:
-                hl = self.dmlp.h[-1] if self.dmlp.layers else self.h0
-                d_hl = self.dec_scratch[2][:hl.numel()].view_as(hl)
-                ops.linear_bwd(hl, dec.out.weight.data, None, None, self.dlogit, self.dlogit, d_hl,
-                               False, flat.gv(dec.out.weight), flat.gv(dec.out.bias), None)
-                dh0 = self.dmlp.backward(d_hl, self.dec_scratch, True)
-                ops.sdec_h0_bwd(dh0, self.h0, self.gUv, m._H, m._W, m.ndim)
-            ops.fold_bwd(self.fold_cfg, self.z, self.y, cl.fc_coord.weight.data,
-                         cl.fc_latent.weight.data, self.gUv, self.gz, self.gcond, self.fold_part)
-            Hd0 = cl.fc_coord.out_features
-            nd = m.ndim
-            LC = m._latent_dim + self.C
-            G, per = self.G_fold, self.fold_per
-            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.weight), G, Hd0 * nd, per, True, 0)
-            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.bias), G, Hd0, per, True, Hd0 * nd)
-            if LC > 0:
-                ops.reduce_partials(self.fold_part, flat.gv(cl.fc_latent.weight), G, Hd0 * LC, per,
-                                    True, Hd0 * (nd + 1))
-            gz = self.gz
+        if kind == "jivae":
+            self.enc = MLP(linear_layers(enc.fc_layers), enc.activation, B, dev, flat)
+            self.enc_scratch = _mlp_scratch(self.enc.layers, B, dev)
+            self.head = GaussHead(engine, enc, B, Z)
+            self.z_rep = torch.empty(I, Z, **f32)
+            self.gz_b = torch.empty(B, Z, **f32)
         else:
-            hl = self.dmlp.h[-1]
-            d_hl = self.dec_scratch[2][:hl.numel()].view_as(hl)
-            ops.linear_bwd(hl, dec.out.weight.data, None, None, self.dlogit, self.dlogit, d_hl,
-                           False, flat.gv(dec.out.weight), flat.gv(dec.out.bias), None)
-            d_in = self.dmlp.backward(d_hl, self.dec_scratch, True)
-            self.gz.copy_(d_in[:, :self.Z])
-            gz = self.gz
-        ops.latent_bwd(gz, self.eps, self.sigma, self.s_pre, self.z, None, beta, self.gmu,
-                       self.gs_pre)
-        h = self.enc.h[-1]
-        ops.linear_bwd(h, enc.fc11.weight.data, None, None, self.gmu, self.gmu, self.dh_e, False,
-                       flat.gv(enc.fc11.weight), flat.gv(enc.fc11.bias), None)
-        ops.linear_bwd(h, enc.fc12.weight.data, None, None, self.gs_pre, self.gs_pre, self.dh_e,
-                       True, flat.gv(enc.fc12.weight), flat.gv(enc.fc12.bias), None)
-        self.enc.backward(self.dh_e, self.enc_scratch, False)
+            self.enc_in = torch.zeros(I, N + K, **f32)
+            self.enc_in[:, N:].copy_(self.onehot)
+            self.enc = MLP(linear_layers(enc.fc_layers), enc.activation, I, dev, flat)
+            self.enc_scratch = _mlp_scratch(self.enc.layers, I, dev)
+            self.head = GaussHead(engine, enc, I, Z)
+            cls = m.encoder_y
+            self.cls = MLP(linear_layers(cls.fc_layers), cls.activation, B, dev, flat)
+            self.cls_scratch = _mlp_scratch(self.cls.layers, B, dev)
+            self.dh_c = torch.empty(B, cls.out.in_features, **f32)
+        self.dec = DecoderOps(engine, I, B, K)
+
+    eps = property(lambda s: s.head.eps)
+    mu = property(lambda s: s.head.mu)
+    sigma = property(lambda s: s.head.sigma)
+    loc = property(lambda s: s.dec.loc)
+    ll = property(lambda s: s.dec.ll)
+    use_tc = property(lambda s: s.dec.use_tc)
+
+    def load(self, x, y):
+        B, N, K = self.B, self.N, self.K
+        x = x.reshape(B, -1)
+        if x.shape[1] != N:
+            raise ValueError("expected {} features per sample, got {}".format(N, x.shape[1]))
+        self.x.copy_(x, non_blocking=True)
+        if self.kind == "ssivae":
+            self.enc_in.view(K, B, N + K)[:, :, :N].copy_(self.x.unsqueeze(0).expand(K, B, N))
+
+    def forward(self, beta, want_grad, gen_eps):
+        m = self.engine.model
+        flat = self.engine.flat
+        K, B, Z = self.K, self.B, self.Z
+        if self.kind == "jivae":
+            b0, b1 = beta
+            enc = m.encoder_z
+            h = self.enc.forward(self.x)
+            self.head.forward(h, gen_eps)
+            ops.linear_fwd(h, enc.fc13.weight.data, enc.fc13.bias.data, None, out=self.logits)
+            ops.enum_head_fwd(self.logits, self.alpha, self.w)
+            self.z_rep.view(K, B, Z).copy_(self.head.z.unsqueeze(0).expand(K, B, Z))
+            self.dec.forward(self.z_rep, self.onehot, self.x, self.w, want_grad)
+            ops.weighted_sum(self.head.kl, None, -float(b0), flat.loss)
+            ops.enum_head_bwd(self.alpha, self.dec.ll, b1, self.glogits, flat.loss)
+        else:
+            cls = m.encoder_y
+            hc = self.cls.forward(self.x)
+            ops.linear_fwd(hc, cls.out.weight.data, cls.out.bias.data, None, out=self.logits)
+            ops.enum_head_fwd(self.logits, self.alpha, self.w)
+            h = self.enc.forward(self.enc_in)
+            self.head.forward(h, gen_eps)
+            self.dec.forward(self.head.z, self.onehot, self.x, self.w, want_grad)
+            ops.axpy_out(self.dec.ll, self.head.kl, float(beta), self.cost)
+            ops.enum_head_bwd(self.alpha, self.cost, 1.0, self.glogits, flat.loss)
+
+    def backward(self, beta):
+        m = self.engine.model
+        flat = self.engine.flat
+        K, B, Z = self.K, self.B, self.Z
+        if self.kind == "jivae":
+            b0, b1 = beta
+            enc = m.encoder_z
+            gz = self.dec.backward(self.z_rep, self.onehot)
+            ops.reduce_partials(gz, self.gz_b, K, B * Z, B * Z, False)
+            h = self.enc.h[-1]
+            dh = self.head.backward(h, self.gz_b, None, b0)
+            ops.linear_bwd(h, enc.fc13.weight.data, None, None, self.glogits, self.glogits, dh,
+                           True, flat.gv(enc.fc13.weight), flat.gv(enc.fc13.bias), None)
+            self.enc.backward(dh, self.enc_scratch, False)
+        else:
+            cls = m.encoder_y
+            gz = self.dec.backward(self.head.z, self.onehot)
+            dh = self.head.backward(self.enc.h[-1], gz, self.w, beta)
+            self.enc.backward(dh, self.enc_scratch, False)
+            hc = self.cls.h[-1]
+            ops.linear_bwd(hc, cls.out.weight.data, None, None, self.glogits, self.glogits,
+                           self.dh_c, False, flat.gv(cls.out.weight), flat.gv(cls.out.bias), None)
+            self.cls.backward(self.dh_c, self.cls_scratch, False)
+
+
+class ClassifierAuxProgram(StepProgram):
+    """ssiVAE auxiliary step (reference models/ssivae.py:229-248):
+    loss = -mult * sum_b log Cat(y_b | classifier(x_b)); no sites when ys is None."""
+
+    def __init__(self, engine, B, has_y):
+        super().__init__(engine, B, has_y)
+        m = engine.model
+        dev, flat = engine.device, engine.flat
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.N, self.K = m._n_pix, m.num_classes
+        self.x = torch.zeros(B, self.N, **f32)
+        self.y = torch.zeros(B, self.K, **f32)
+        cls = m.encoder_y
+        self.cls = MLP(linear_layers(cls.fc_layers), cls.activation, B, dev, flat)
+        self.cls_scratch = _mlp_scratch(self.cls.layers, B, dev)
+        self.logits = torch.empty(B, self.K, **f32)
+        self.glogits = torch.zeros(B * self.K + B, **f32)
+        self.dh_c = torch.empty(B, cls.out.in_features, **f32)
+        self.eps = torch.zeros(1, **f32)
+
+    def load(self, x, y):
+        self.x.copy_(x.reshape(self.B, -1), non_blocking=True)
+        if y is not None:
+            self.y.copy_(y.reshape(self.B, -1), non_blocking=True)
+
+    def forward(self, mult, want_grad, gen_eps):
+        if not self.has_y:
+            return
+        cls = self.engine.model.encoder_y
+        hc = self.cls.forward(self.x)
+        ops.linear_fwd(hc, cls.out.weight.data, cls.out.bias.data, None, out=self.logits)
+        ops.class_nll(self.logits, self.y, mult, self.glogits, self.engine.flat.loss)
+
+    def backward(self, mult):
+        if not self.has_y:
+            return
+        flat = self.engine.flat
+        cls = self.engine.model.encoder_y
+        hc = self.cls.h[-1]
+        ops.linear_bwd(hc, cls.out.weight.data, None, None, self.glogits, self.glogits, self.dh_c,
+                       False, flat.gv(cls.out.weight), flat.gv(cls.out.bias), None)
+        self.cls.backward(self.dh_c, self.cls_scratch, False)
 
 
 class SVIEngine:
@@ -404,11 +601,11 @@ class SVIEngine:
                 and dec.activation == "tanh" and N >= 32
                 and self.model.sampler_d.name in ("bernoulli", "gaussian"))
 
-    def _program(self, B, has_y):
-        key = (B, has_y)
+    def _program(self, B, has_y, mode="main"):
+        key = (B, has_y, mode)
         prog = self.programs.get(key)
         if prog is None:
-            prog = self.model._make_program(self, B, has_y)
+            prog = self.model._make_program(self, B, has_y, mode)
             self.programs[key] = prog
         return prog
 
@@ -417,6 +614,8 @@ class SVIEngine:
         flat = self.flat
         if train or update:
             flat.g.zero_()
+        else:
+            flat.loss.zero_()
         prog.forward(beta, train, gen_eps)
         if train:
             prog.backward(beta)
@@ -453,6 +652,11 @@ class SVIEngine:
     def step(self, *args, **kwargs):
         return self._step(args, kwargs, train=True)
 
+    def step_aux(self, *args, **kwargs):
+        """Auxiliary (supervised) loss step of semi-supervised models
+        (reference trainers/auxsvi.py:79-81,99)."""
+        return self._step(args, kwargs, train=True, mode="aux")
+
     def evaluate_loss(self, *args, **kwargs):
         return self._step(args, kwargs, train=False, update=False)
 
@@ -461,21 +665,22 @@ class SVIEngine:
         optimizer update -- used by the parity tests."""
         return self._step(args, kwargs, train=True, update=False)
 
-    def _step(self, args, kwargs, train=True, update=True):
+    def _step(self, args, kwargs, train=True, update=True, mode="main"):
         self.flat.ensure() and self._invalidate()
+        kwargs = dict(kwargs)
         x = args[0]
         y = args[1] if len(args) > 1 else None
         eps = kwargs.pop("_eps", None)
         sync = kwargs.pop("_sync", True)
-        beta = self.model._beta(kwargs)
+        beta = self.model._beta(kwargs) if mode == "main" else self.model._aux_scale(kwargs)
         B = x.shape[0]
-        prog = self._program(B, y is not None)
+        prog = self._program(B, y is not None, mode)
         prog.load(x, y)
-        if eps is not None:
+        if eps is not None and mode == "main":
             prog.eps.copy_(eps.reshape(prog.eps.shape), non_blocking=True)
         gen_eps = eps is None
         bkey = tuple(beta) if isinstance(beta, (list, tuple)) else float(beta)
-        key = (B, y is not None, bkey, train, gen_eps, update)
+        key = (B, y is not None, mode, bkey, train, gen_eps, update)
         if self.world_size > 1 and train:
             self._execute(key + ("grads",), lambda: self._run(prog, beta, True, gen_eps, False))
             self._allreduce()
@@ -485,7 +690,7 @@ class SVIEngine:
             self._execute(key, lambda: self._run(prog, beta, train, gen_eps, update))
         if not sync:
             return self.flat.loss     # device scalar, no host synchronisation
-        return float(self.flat.loss.item())
+        return float(self.flat.loss.item()) + prog.loss_const * self.world_size
 
     def _invalidate(self):
         self.programs.clear()

@@ -194,5 +194,8 @@ class baseVAE(nn.Module):
         b = kwargs.get("scale_factor", 1.)
         return float(b)
 
-    def _make_program(self, engine, B, has_y):
+    def _aux_scale(self, kwargs):
+        return 1.0
+
+    def _make_program(self, engine, B, has_y, mode="main"):
         raise NotImplementedError

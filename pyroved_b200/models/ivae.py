@@ -79,6 +79,6 @@ class iVAE(baseVAE):
                 plot_spect_grid(loc, d, **kwargs)
         return loc
 
-    def _make_program(self, engine, B, has_y):
+    def _make_program(self, engine, B, has_y, mode="main"):
         from ..engine import SpatialVAEProgram
         return SpatialVAEProgram(engine, B, has_y)

@@ -118,6 +118,16 @@ def elbo_reduce(rowll, kl, w, beta, ll, loss_out, accumulate, I, N):
                                      int(accumulate), I, N, _stream()), "pvb_elbo_reduce")
 
 
+def weighted_sum(v, w, scale, loss_out):
+    check(_lib.lib().pvb_weighted_sum(_p(v), _p(w), float(scale), _p(loss_out), v.numel(),
+                                      _stream()), "pvb_weighted_sum")
+
+
+def axpy_out(a, b, beta, out):
+    check(_lib.lib().pvb_axpy_out(_p(a), _p(b), float(beta), _p(out), a.numel(), _stream()),
+          "pvb_axpy_out")
+
+
 def enum_head_fwd(logits, alpha, w):
     B, K = logits.shape
     check(_lib.lib().pvb_enum_head_fwd(_p(logits), _p(alpha), _p(w), B, K, _stream()),

@@ -1,0 +1,107 @@
+"""auxSVItrainer: semi-supervised training loop with an auxiliary
+classification loss (reference trainers/auxsvi.py:19-225).  Each batch runs
+TWO fused CUDA optimisation steps sharing one Adam state: the (enumerated)
+ELBO step and the auxiliary classifier step -- for unlabeled batches the
+auxiliary step has no loss terms but Pyro still runs the optimizer, which is
+reproduced (Adam on zero gradients)."""
+from collections import OrderedDict
+from copy import deepcopy as dc
+from typing import Optional
+
+import torch
+
+from ..engine import SVIEngine
+from ..utils import average_weights, set_deterministic_mode
+
+
+class auxSVItrainer:
+    """
+    Args:
+        model: initialised ssiVAE
+        task: "classification" ("regression" needs ss_reg_iVAE: not in this build)
+        optimizer: None or {"lr": ...} (Adam, default lr 5e-4)
+        seed: reproducibility seed
+    Keyword Args: lr (5e-4), device
+    """
+
+    def __init__(self, model, task: str = "classification", optimizer=None, seed: int = 1,
+                 **kwargs) -> None:
+        set_deterministic_mode(seed)
+        if task not in ["classification", "regression"]:
+            raise ValueError("Choose between 'classification' and 'regression' tasks")
+        if task == "regression":
+            raise NotImplementedError("ss_reg_iVAE / regression task is outside this build's scope")
+        self.task = task
+        self.device = kwargs.get("device", 'cuda' if torch.cuda.is_available() else 'cpu')
+        lr = kwargs.get("lr", 5e-4)
+        if isinstance(optimizer, dict):
+            lr = optimizer.get("lr", lr)
+        elif optimizer is not None:
+            raise TypeError("pass optimizer=None or {'lr': ...}: Adam is fused into the CUDA step")
+        self.svi = SVIEngine(model, lr=lr, enumerate_parallel=True, seed=seed, device=self.device)
+        self.model = model
+        self.history = {"training_loss": [], "test": []}
+        self.current_epoch = 0
+        self.running_weights = {}
+
+    def compute_loss(self, xs: torch.Tensor, ys: Optional[torch.Tensor] = None, **kwargs) -> float:
+        """basic (ELBO) step + auxiliary step (reference auxsvi.py:88-100)."""
+        xs = xs.to(self.device, non_blocking=True)
+        args = (xs,)
+        if ys is not None:
+            args = (xs, ys.to(self.device, non_blocking=True))
+        loss = self.svi.step(*args, **kwargs)
+        loss_aux = self.svi.step_aux(*args, **kwargs)
+        return loss + loss_aux
+
+    def train(self, loader_unsup, loader_sup, **kwargs) -> float:
+        """One epoch; a labeled batch every p-th iteration (auxsvi.py:102-128)."""
+        sup_batches = len(loader_sup)
+        unsup_batches = len(loader_unsup)
+        p = (sup_batches + unsup_batches) // sup_batches
+        loader_sup = iter(loader_sup)
+        epoch_loss = 0.
+        unsup_count = 0
+        for i, (xs,) in enumerate(loader_unsup):
+            epoch_loss += self.compute_loss(xs, **kwargs)
+            unsup_count += xs.shape[0]
+            if i % p == 1:
+                xs, ys = next(loader_sup)
+                _ = self.compute_loss(xs, ys, **kwargs)
+        return epoch_loss / unsup_count
+
+    def evaluate(self, loader_val) -> float:
+        correct, total = 0, 0
+        for data, labels in loader_val:
+            predicted = self.model.classifier(data)
+            _, lab_idx = torch.max(labels.cpu(), 1)
+            correct += (predicted == lab_idx).sum().item()
+            total += data.size(0)
+        return correct / total
+
+    def step(self, loader_unsup, loader_sup, loader_val=None, **kwargs) -> None:
+        train_loss = self.train(loader_unsup, loader_sup, **kwargs)
+        self.history["training_loss"].append(train_loss)
+        if loader_val is not None:
+            self.history["test"].append(self.evaluate(loader_val))
+        self.current_epoch += 1
+
+    def save_running_weights(self, net: str) -> None:
+        net = getattr(self.model, net)
+        sd = OrderedDict()
+        for k, v in net.state_dict().items():
+            sd[k] = dc(v).cpu()
+        self.running_weights[self.current_epoch] = sd
+
+    def average_weights(self, net: str) -> None:
+        net = getattr(self.model, net)
+        net.load_state_dict(average_weights(self.running_weights))
+
+    def print_statistics(self) -> None:
+        e = self.current_epoch
+        if len(self.history["test"]) > 0:
+            template = 'Epoch: {} Training loss: {:.4f}, Test accuracy: {:.4f}'
+            print(template.format(e, self.history["training_loss"][-1], self.history["test"][-1]))
+        else:
+            template = 'Epoch: {} Training loss: {:.4f}'
+            print(template.format(e, self.history["training_loss"][-1]))
