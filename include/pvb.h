@@ -175,11 +175,16 @@ int pvb_class_nll(const float* logits, const float* y_onehot, float mult,
 int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,
                         int64_t part_stride, int accumulate, void* stream);
 int pvb_counter_add(int32_t* counter, int32_t v, void* stream);
-/* torch.optim.Adam defaults (Pyro optim.Adam, trainers/svi.py:79-81):
- * t = *step_counter (already incremented for this step). */
+/* torch.optim.Adam defaults (Pyro optim.Adam, trainers/svi.py:79-81).
+ * Pyro keeps one optimizer PER PARAMETER, created when the parameter first
+ * carries a gradient: element i takes its own step count
+ *   t_i = *step_counter - first_step[i]   (step_counter already incremented),
+ * and is left untouched while first_step[i] < 0 (parameter not yet seen).
+ * first_step == NULL: every element active since step 0. */
 int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
                   float lr, float beta1, float beta2, float eps,
-                  const int32_t* step_counter, void* stream);
+                  const int32_t* step_counter, const int32_t* first_step,
+                  void* stream);
 
 /* ---- spatial decoder, fused tcgen05 path (Hd = 128, two tanh layers) ----
  * One persistent kernel per step: grid -> h0 -> (128x128 tcgen05 GEMM + tanh)

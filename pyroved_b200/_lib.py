@@ -57,7 +57,7 @@ SIGNATURES = {
     "pvb_class_nll": [_f, _f, _fl, _f, _f, _i64, _i32, _st],
     "pvb_reduce_partials": [_f, _f, _i32, _i64, _i64, _i32, _st],
     "pvb_counter_add": [_f, _i32, _st],
-    "pvb_adam_flat": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _st],
+    "pvb_adam_flat": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _f, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
     "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
                          _i32, _i32, _i32, _i32, _i32, _fl, _i32, _st],

@@ -60,44 +60,34 @@ extern "C" int pvb_counter_add(int32_t* counter, int32_t v, void* stream) {
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                  float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                  float b1, float b2, float eps,
-                                 const int32_t* __restrict__ step_counter) {
-  const float t = (float)(*step_counter);
-  const float bc1 = 1.f - powf(b1, t);
-  const float bc2s = sqrtf(1.f - powf(b2, t));
-  const float step_size = lr / bc1;
-  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i + 3 < n) {
-    float4 P = *reinterpret_cast<float4*>(p + i);
-    const float4 Gv = *reinterpret_cast<const float4*>(g + i);
-    float4 Mv = *reinterpret_cast<float4*>(m + i);
-    float4 Vv = *reinterpret_cast<float4*>(v + i);
-    float* pp = reinterpret_cast<float*>(&P);
-    const float* gg = reinterpret_cast<const float*>(&Gv);
-    float* mm = reinterpret_cast<float*>(&Mv);
-    float* vv = reinterpret_cast<float*>(&Vv);
+                                 const int32_t* __restrict__ step_counter,
+                                 const int32_t* __restrict__ first_step) {
+  const int step = *step_counter;
+  int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  int last_t = -1;
+  float step_size = 0.f, bc2s = 1.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mm[k] = b1 * mm[k] + (1.f - b1) * gg[k];
-      vv[k] = b2 * vv[k] + (1.f - b2) * gg[k] * gg[k];
-      pp[k] -= step_size * mm[k] / (sqrtf(vv[k]) / bc2s + eps);
+  for (int k = 0; k < 4; ++k) {
+    int64_t j = i0 + k;
+    if (j >= n) break;
+    int t = first_step ? (first_step[j] < 0 ? 0 : step - first_step[j]) : step;
+    if (t <= 0) continue;   // parameter has never carried a gradient
+    if (t != last_t) {
+      step_size = lr / (1.f - powf(b1, (float)t));
+      bc2s = sqrtf(1.f - powf(b2, (float)t));
+      last_t = t;
     }
-    *reinterpret_cast<float4*>(p + i) = P;
-    *reinterpret_cast<float4*>(m + i) = Mv;
-    *reinterpret_cast<float4*>(v + i) = Vv;
-  } else {
-    for (int64_t j = i; j < n; ++j) {
-      float gj = g[j];
-      float mj = b1 * m[j] + (1.f - b1) * gj;
-      float vj = b2 * v[j] + (1.f - b2) * gj * gj;
-      m[j] = mj;
-      v[j] = vj;
-      p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
-    }
+    float gj = g[j];
+    float mj = b1 * m[j] + (1.f - b1) * gj;
+    float vj = b2 * v[j] + (1.f - b2) * gj * gj;
+    m[j] = mj;
+    v[j] = vj;
+    p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
   }
 }
 extern "C" int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                              float beta1, float beta2, float eps, const int32_t* step_counter,
-                             void* stream) {
+                             const int32_t* first_step, void* stream) {
   PVB_CHECK_ARG(p && g && m && v && step_counter && n >= 0, "pvb_adam_flat: bad argument");
   PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                     ((uintptr_t)v % 16 == 0),
@@ -105,6 +95,7 @@ extern "C" int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64
   if (n == 0) return 0;
   int64_t n4 = (n + 3) / 4;
   adam_flat_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1,
-                                                                         beta2, eps, step_counter); pvb::count_launch();
+                                                                         beta2, eps, step_counter,
+                                                                         first_step); pvb::count_launch();
   return pvb::launch_status();
 }

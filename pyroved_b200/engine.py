@@ -58,6 +58,10 @@ class FlatParams:
         self.g = torch.zeros(self.total + 4, device=dev, dtype=torch.float32)
         self.m = torch.zeros(self.total, device=dev, dtype=torch.float32)
         self.v = torch.zeros(self.total, device=dev, dtype=torch.float32)
+        # optimizer step at which each parameter first carried a gradient (-1: never);
+        # Pyro creates one Adam per parameter on first sight (oracle/pyro_min/pyro/optim)
+        self.first_step = torch.full((self.total,), -1, device=dev, dtype=torch.int32)
+        self.active = set()
         self._views = {}
         for n, p in named:
             o, k, shp = self.offsets[n]
@@ -76,12 +80,14 @@ class FlatParams:
 
     def ensure(self):
         if not self.intact():
-            m, v = self.m, self.v
+            m, v, fs, act = self.m, self.v, self.first_step, self.active
             old_total = self.total
             self._build()
             if self.total == old_total:   # keep optimizer state across a rebuild
                 self.m.copy_(m)
                 self.v.copy_(v)
+                self.first_step.copy_(fs)
+                self.active = act
             return True
         return False
 
@@ -95,6 +101,17 @@ class FlatParams:
 
     def offset(self, param):
         return self.offsets[self._views[id(param)]][0]
+
+    def activate(self, modules, step):
+        """Mark the parameters of `modules` as carrying gradients from optimizer
+        step `step` (0-based count of updates done so far) onwards."""
+        for mod in modules:
+            for p in mod.parameters():
+                n = self._views[id(p)]
+                if n not in self.active:
+                    o, k, _ = self.offsets[n]
+                    self.first_step[o:o + k] = step
+                    self.active.add(n)
 
 
 class MLP:
@@ -147,6 +164,11 @@ class StepProgram:
         self.engine = engine
         self.B = B
         self.has_y = has_y
+
+    def grad_modules(self):
+        """Modules whose parameters receive gradients from this program."""
+        m = self.engine.model
+        return [m.encoder_z, m.decoder]
 
 
 class DecoderOps:
@@ -442,6 +464,13 @@ class EnumVAEProgram(StepProgram):
     ll = property(lambda s: s.dec.ll)
     use_tc = property(lambda s: s.dec.use_tc)
 
+    def grad_modules(self):
+        m = self.engine.model
+        mods = [m.encoder_z, m.decoder]
+        if self.kind == "ssivae":
+            mods.append(m.encoder_y)
+        return mods
+
     def load(self, x, y):
         B, N, K = self.B, self.N, self.K
         x = x.reshape(B, -1)
@@ -522,6 +551,9 @@ class ClassifierAuxProgram(StepProgram):
         self.dh_c = torch.empty(B, cls.out.in_features, **f32)
         self.eps = torch.zeros(1, **f32)
 
+    def grad_modules(self):
+        return [self.engine.model.encoder_y] if self.has_y else []
+
     def load(self, x, y):
         self.x.copy_(x.reshape(self.B, -1), non_blocking=True)
         if y is not None:
@@ -567,6 +599,7 @@ class SVIEngine:
         self.seed = int(seed)
         self.flat = FlatParams(model, self.device)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.updates_done = 0     # host mirror of step_counter
         self.programs = {}
         self.graphs = {}
         if use_graphs is None:
@@ -625,7 +658,8 @@ class SVIEngine:
     def _update(self):
         flat = self.flat
         ops.counter_add(self.step_counter, 1)
-        ops.adam_flat(flat.p, flat.g, flat.m, flat.v, flat.total, self.lr, self.step_counter)
+        ops.adam_flat(flat.p, flat.g, flat.m, flat.v, flat.total, self.lr, self.step_counter,
+                      flat.first_step)
 
     def _allreduce(self):
         parallel.allreduce_sum_(self.flat.g, self.process_group)
@@ -679,6 +713,10 @@ class SVIEngine:
         if eps is not None and mode == "main":
             prog.eps.copy_(eps.reshape(prog.eps.shape), non_blocking=True)
         gen_eps = eps is None
+        if train:
+            self.flat.activate(prog.grad_modules(), self.updates_done)
+        if update:
+            self.updates_done += 1
         bkey = tuple(beta) if isinstance(beta, (list, tuple)) else float(beta)
         key = (B, y is not None, mode, bkey, train, gen_eps, update)
         if self.world_size > 1 and train:

@@ -158,9 +158,9 @@ def counter_add(counter, v):
     check(_lib.lib().pvb_counter_add(_p(counter), v, _stream()), "pvb_counter_add")
 
 
-def adam_flat(p, g, m, v, n, lr, step_counter, beta1=0.9, beta2=0.999, eps=1e-8):
+def adam_flat(p, g, m, v, n, lr, step_counter, first_step=None, beta1=0.9, beta2=0.999, eps=1e-8):
     check(_lib.lib().pvb_adam_flat(_p(p), _p(g), _p(m), _p(v), n, float(lr), beta1, beta2, eps,
-                                   _p(step_counter), _stream()), "pvb_adam_flat")
+                                   _p(step_counter), _p(first_step), _stream()), "pvb_adam_flat")
 
 
 def has_tcgen05():
