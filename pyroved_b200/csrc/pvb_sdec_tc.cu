@@ -6,13 +6,22 @@
 //   h0  = tanh(U g + v)                 CUDA cores  -> smem A0 (fp16)
 //   h1  = tanh(h0 W1^T + b1)            tcgen05 (TMEM acc) + epilogue -> smem A1
 //   h2  = tanh(h1 W2^T + b2)            tcgen05 + epilogue (registers, smem Db)
-//   l   = h2 . wo + bo ; log-lik ; dl   per-row epilogue (row == thread)
+//   l   = h2 . wo + bo ; log-lik ; dl   per-row epilogue
 //   D2  = dl wo (1-h2^2)                -> smem Da
 //   dh1 = D2 W2      ; dW2' += D2^T [h1|1] ; dwo += h2^T dl      tcgen05
 //   D1  = dh1 (1-h1^2)                  -> smem Db
 //   dh0 = D1 W1      ; dW1' += D1^T [h0|1]                       tcgen05
 //   D0  = dh0 (1-h0^2)                  -> smem Da
 //   dUv = D0^T [gx,gy,1 per sample slot]                          tcgen05
+//
+// Warp roles: 16 epilogue warps (thread = one tile row x 32 columns, taken as
+// four 8-column chunks interleaved over the tile width) + 1 MMA-issuing warp.
+// The epilogue of GEMM k writes the next operand 32 columns at a time and
+// signals an mbarrier per 32-column group, so the MMA warp issues the K-steps
+// of GEMM k+1 while the rest of the epilogue is still running; the
+// weight-gradient MMAs are issued behind the dh MMAs and finish under the
+// next epilogue.  (One accumulator suffices: every epilogue thread pulls its
+// 32 accumulator columns into registers before it signals the first group.)
 //
 // Weight-gradient accumulators (dW1', dW2', dwo) live in TMEM for the whole
 // kernel and are written once per CTA as partials; per-sample dUv goes out as
@@ -32,8 +41,11 @@ namespace {
 
 constexpr int HD = 128;            // hidden width (fixed for this kernel)
 constexpr int TILE = 128;          // rows per tile
-constexpr int NTHREADS = 256;      // 8 warps: (lane quarter q = warp%4) x (column half = warp/4)
-constexpr int MAX_SLOTS = 5;       // samples a tile can touch when N >= 32
+constexpr int NEPI = 512;          // 16 epilogue warps: (lane quarter q = warp%4) x (column group cg = warp/4)
+constexpr int NTHREADS = NEPI + 32;  // + one MMA-issuing warp
+constexpr int MMA_WARP = NEPI / 32;
+constexpr int MAX_SLOTS = 4;       // samples a 128-row tile can touch when N >= MIN_PIX
+constexpr int MIN_PIX = 43;        // floor(127/N) + 2 <= 4
 constexpr int CHUNK = TILE * 16;   // bytes of one chunk-column (8 fp16 columns x 128 rows)
 
 // ---- shared memory map (bytes) ------------------------------------------------
@@ -47,12 +59,22 @@ constexpr int SM_G = SM_DB + 16 * CHUNK;          // [128][16] grid coords per s
 constexpr int SM_DL = SM_G + 2 * CHUNK;           // [128][16] dl in column 0
 constexpr int SM_F32 = SM_DL + 2 * CHUNK;         // fp32 scratch, see below
 constexpr int F_B1 = 0, F_B2 = 128, F_WO = 256;   // biases / out weights
-constexpr int F_UV = 384;                         // [MAX_SLOTS][3][128]
-constexpr int F_PART = F_UV + MAX_SLOTS * 3 * HD; // [2][128] partial dots
-constexpr int F_RED = F_PART + 256;               // [8] block reduction
-constexpr int F_END = F_RED + 8;
-constexpr int SM_BAR = SM_F32 + F_END * 4;        // mbarrier (8 B) + tmem base (4 B)
-constexpr int SMEM_BYTES = SM_BAR + 16;
+constexpr int UV_FLOATS = MAX_SLOTS * 3 * HD;
+constexpr int F_UV = 384;                         // [2][MAX_SLOTS][3][128]  (double buffered)
+constexpr int F_X = F_UV + 2 * UV_FLOATS;         // [2][128] targets of the tile rows
+constexpr int F_WI = F_X + 2 * TILE;              // [2][128] instance weights of the tile rows
+constexpr int F_PART = F_WI + 2 * TILE;           // [4][128] partial dots per column group
+constexpr int F_RED = F_PART + 4 * TILE;          // [32] block reduction
+constexpr int F_END = F_RED + 32;
+constexpr int SM_BAR = SM_F32 + F_END * 4;        // mbarriers + tmem base
+constexpr int BAR_READY = 0;                      // ready[4]: TMEM A column group written (16 warps)
+constexpr int BAR_SM = 4;                         // sm[5]: smem operands of S0,S2,S4,S6,S8 published
+constexpr int BAR_ACC = 9;                        // accumulator of the current GEMM complete
+constexpr int BAR_DUV = 10;                       // all MMAs of the tile complete (dUv last)
+constexpr int BAR_DW = 11;                        // dW1' MMAs complete (A0, Db reusable)
+constexpr int BAR_DWO = 12;                       // dwo MMAs complete (Db: h2 -> D1)
+constexpr int N_BARS = 13;
+constexpr int SMEM_BYTES = SM_BAR + (N_BARS + 1) * 8;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 
 // ---- tensor memory map (columns) -------------------------------------------------
@@ -61,7 +83,22 @@ constexpr uint32_t TM_DW1 = 128;   // 144 cols : dW1 (128) | db1 (col 128)
 constexpr uint32_t TM_DW2 = 272;   // 144 cols : dW2 | db2
 constexpr uint32_t TM_DWO = 416;   // 16 cols  : dwo in column 0
 constexpr uint32_t TM_DUV = 432;   // 16 cols  : per-tile dUv
+constexpr uint32_t TM_AT = 448;    // 64 cols  : A operand of the forward / dh GEMMs (128 x 128 fp16)
 constexpr int TM_COLS = 512;
+
+#ifdef PVB_TC_TRACE
+// debug build only: per-stage timestamps of CTA 0 (epilogue warp 0 / MMA warp), tools/tc_trace.py
+__device__ long long g_trace[2][64][32];
+#define TRACE(role, ev)                                                              \
+  do {                                                                               \
+    if (blockIdx.x == 0 && lane == 0 && (role == 1 || warp == 0) && trace_it < 64)   \
+      g_trace[role][trace_it][ev] = clock64();                                       \
+  } while (0)
+#define TRACE_NEXT() ++trace_it
+#else
+#define TRACE(role, ev) do {} while (0)
+#define TRACE_NEXT() do {} while (0)
+#endif
 
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
@@ -76,6 +113,7 @@ struct Params {
   float* rowll; float* loc; float* gUv_part; float* wgrad_part;
   int64_t R; int64_t B; int N; int H; int W; int ndim;
   int sampler; int sigmoid_d; float sig; int backward; int64_t tiles;
+  int64_t step_q; int step_r; int step_qb;   // (TILE*grid) / N, % N, and step_q % B
 };
 
 // fp32 [128][128] row-major global weights -> fp16 row-chunk tile in smem
@@ -98,16 +136,151 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int k16) {  // K
   return umma::smem_desc(base + k16 * 256, 128, CHUNK);
 }
 
+// barrier among the 16 epilogue warps only (the MMA warp never joins)
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// this thread's 32 accumulator columns: chunk-columns cg, 4+cg, 8+cg, 12+cg (8 columns each)
+__device__ __forceinline__ void load_acc(uint32_t tm_lane, int cg, float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) umma::tmem_ld8(tm_lane + TM_ACC + 8 * (4 * j + cg), v + 8 * j);
+  umma::tmem_ld_wait();
+}
+
+__device__ __forceinline__ void lds8(const float* p, float* o) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// 8 columns of tanh(v + bias) -> four fp16 pairs
+__device__ __forceinline__ uint4 tanh8(const float* v, const float* bias) {
+  float b[8];
+  lds8(bias, b);
+  __half2 hh[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    hh[e] = __floats2half2_rn(fast_tanh(v[2 * e] + b[2 * e]), fast_tanh(v[2 * e + 1] + b[2 * e + 1]));
+  return *reinterpret_cast<uint4*>(hh);
+}
+
+// 8 columns of  d = v * (1 - h^2)  (h: four fp16 pairs) -> four fp16 pairs
+__device__ __forceinline__ uint4 dact8(const float* v, uint4 hraw) {
+  const __half2* hh = reinterpret_cast<const __half2*>(&hraw);
+  const __half2 one = __float2half2_rn(1.f);
+  __half2 dd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __half2 g = __hfma2(__hneg2(hh[j]), hh[j], one);   // exactly rounded 1 - h^2
+    dd[j] = __hmul2(__floats2half2_rn(v[2 * j], v[2 * j + 1]), g);
+  }
+  return *reinterpret_cast<uint4*>(dd);
+}
+
+// ---- tile geometry without per-thread 64-bit divisions -----------------------------------------
+// A CTA walks tiles blockIdx.x, +grid, +2 grid, ...; (i_first, off) = first instance of the tile
+// and the tile's first row inside it, advanced incrementally with host-computed step constants.
+struct TileCursor {
+  int64_t tile;
+  int64_t i_first;   // instance containing the first row of the tile
+  int ib_first;      // i_first % B  (row of the target image)
+  int off;           // tile*TILE - i_first*N, in [0, N)
+};
+struct RowGeo {
+  int64_t r_glob;
+  float gx, gy;
+  int slot, n_slots;
+  bool valid;
+};
+
+__device__ __forceinline__ void cursor_advance(TileCursor& c, const Params& P) {
+  c.tile += gridDim.x;
+  c.i_first += P.step_q;
+  c.ib_first += P.step_qb;
+  c.off += P.step_r;
+  if (c.off >= P.N) { c.off -= P.N; ++c.i_first; ++c.ib_first; }
+  if (c.ib_first >= (int)P.B) c.ib_first -= (int)P.B;
+}
+
+// (offset inside the first instance) -> slot, pixel; N >= MIN_PIX bounds the quotient by 3
+__device__ __forceinline__ void split_slot(int rem, int N, int& slot, int& pix) {
+  slot = 0;
+#pragma unroll
+  for (int s = 0; s < MAX_SLOTS - 1; ++s)
+    if (rem >= N) { rem -= N; ++slot; }
+  pix = rem;
+}
+
+// row geometry of the cursor's tile + asynchronous staging of its Uv rows / targets / weights
+// into buffer `buf`
+__device__ __forceinline__ RowGeo stage_tile(const Params& P, float* f32, const TileCursor& c,
+                                             int buf, int tid, int row, int cg) {
+  RowGeo g;
+  g.r_glob = c.tile * TILE + row;
+  g.valid = g.r_glob < P.R;
+  const int64_t left = P.R - c.tile * TILE;                 // rows from the tile start to R
+  const int last_row = left < TILE ? (int)left - 1 : TILE - 1;
+  int last_slot, last_pix;
+  split_slot(c.off + last_row, P.N, last_slot, last_pix);
+  g.n_slots = last_slot + 1;
+  int pix;
+  split_slot(c.off + (g.valid ? row : 0), P.N, g.slot, pix);
+  g.gx = 0.f;
+  g.gy = 0.f;
+  pvb::grid_xy(pix, P.H, P.W, P.ndim, g.gx, g.gy);
+  if (tid < g.n_slots * (3 * HD / 4))
+    cp_async16(f32 + F_UV + buf * UV_FLOATS + tid * 4, P.Uv + c.i_first * 3 * HD + tid * 4);
+  if (g.valid) {
+    if (cg == 0 && P.x) {
+      int ib = c.ib_first + g.slot;
+      while (ib >= (int)P.B) ib -= (int)P.B;
+      cp_async4(f32 + F_X + buf * TILE + row, P.x + (int64_t)ib * P.N + pix);
+    }
+    if (cg == 1 && P.w) cp_async4(f32 + F_WI + buf * TILE + row, P.w + c.i_first + g.slot);
+  }
+  return g;
+}
+
+// chunk j of this thread -> tensor-memory A operand, then signal column group j.
+// (tcgen05.st is ordered against the MMA by wait::st + fence::before_thread_sync; no
+// generic->async proxy fence is involved, which is what makes a per-chunk signal cheap.)
+__device__ __forceinline__ void publish_chunk(uint64_t* bars, uint32_t tm_lane, int cg, int j, uint4 out) {
+  umma::tmem_st4(tm_lane + TM_AT + 4 * (4 * j + cg), out);
+  umma::tmem_st_wait();
+  umma::fence_before_sync();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bars + BAR_READY + j);
+}
+// this thread's 4 chunks -> row-chunk tile in shared memory (operands of the weight-gradient
+// MMAs and of later element-wise passes), then one proxy fence + signal per warp
+__device__ __forceinline__ void store_tile4(uint8_t* tile, int row, int cg, const uint4* out) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(tile + umma::tile_off(TILE, row, 8 * (4 * j + cg))) = out[j];
+}
+__device__ __forceinline__ void signal_smem(uint64_t* bars, int stage) {
+  umma::fence_proxy_async();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bars + BAR_SM + stage);
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* f32 = reinterpret_cast<float*>(smem + SM_F32);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + N_BARS * 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hf = warp >> 2;
+  const int q = warp & 3, cg = (warp >> 2) & 3;
   const int row = q * 32 + lane;        // tile row == TMEM lane owned by this thread
-  const int col0 = hf * 64;             // this thread's 64 columns
 
   // ---- one-time setup ----------------------------------------------------------
   stage_weight(P.W1, smem + SM_W1, tid);
@@ -117,23 +290,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     f32[F_B2 + tid] = P.b2[tid];
     f32[F_WO + tid] = P.wo[tid];
   }
-  {
+  if (tid < NEPI) {
     // constant chunk-columns: [A0|A1] column 128 = 1 (bias column), 129..143 = 0;
-    // DL columns 8..15 = 0
+    // DL columns 8..15 = 0; default targets 0 / weights 1
     uint4 ones = make_uint4(0x00003C00u, 0u, 0u, 0u);  // fp16 {1,0,0,0,0,0,0,0}
     uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    if (hf == 0) {
+    if (cg == 0) {
       *reinterpret_cast<uint4*>(smem + SM_A0 + umma::tile_off(TILE, row, 128)) = ones;
       *reinterpret_cast<uint4*>(smem + SM_A0 + umma::tile_off(TILE, row, 136)) = zero;
-      *reinterpret_cast<uint4*>(smem + SM_DL + umma::tile_off(TILE, row, 8)) = zero;
-    } else {
+    } else if (cg == 1) {
       *reinterpret_cast<uint4*>(smem + SM_A1 + umma::tile_off(TILE, row, 128)) = ones;
       *reinterpret_cast<uint4*>(smem + SM_A1 + umma::tile_off(TILE, row, 136)) = zero;
+    } else if (cg == 2) {
+      *reinterpret_cast<uint4*>(smem + SM_DL + umma::tile_off(TILE, row, 8)) = zero;
+    } else {
+      f32[F_X + row] = 0.f;
+      f32[F_X + TILE + row] = 0.f;
+      f32[F_WI + row] = 1.f;
+      f32[F_WI + TILE + row] = 1.f;
     }
   }
-  if (warp == 0) umma::tmem_alloc<TM_COLS>(tmem_slot);
+  if (warp == MMA_WARP) umma::tmem_alloc<TM_COLS>(tmem_slot);
   if (tid == 0) {
-    umma::mbar_init(bar, 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) umma::mbar_init(bars + BAR_READY + j, NEPI / 32);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) umma::mbar_init(bars + BAR_SM + j, NEPI / 32);
+    umma::mbar_init(bars + BAR_ACC, 1);
+    umma::mbar_init(bars + BAR_DUV, 1);
+    umma::mbar_init(bars + BAR_DW, 1);
+    umma::mbar_init(bars + BAR_DWO, 1);
     umma::mbar_fence_init();
   }
   umma::fence_proxy_async();
@@ -142,301 +328,387 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
   umma::fence_after_sync();
   const uint32_t tm = *tmem_slot;
   const uint32_t tm_lane = tm + ((uint32_t)(q * 32) << 16);
-  const float bo = P.bo[0];
-  uint32_t phase = 0;
-  bool first_tile = true;
-  float dl_sum = 0.f;  // sum of dl over this thread's rows (column half 0 only) -> dbo
+  float dl_sum = 0.f;  // sum of dl over this thread's rows (column group 0 only) -> dbo
+  bool any_tile = false;
+#ifdef PVB_TC_TRACE
+  int trace_it = 0;
+#endif
 
-  const uint32_t sW1 = umma::smem_u32(smem + SM_W1), sW2 = umma::smem_u32(smem + SM_W2);
-  const uint32_t sA0 = umma::smem_u32(smem + SM_A0), sA1 = umma::smem_u32(smem + SM_A1);
-  const uint32_t sDA = umma::smem_u32(smem + SM_DA), sDB = umma::smem_u32(smem + SM_DB);
-  const uint32_t sG = umma::smem_u32(smem + SM_G), sDL = umma::smem_u32(smem + SM_DL);
-  constexpr uint32_t ID_FWD = umma::idesc_f16(128, 128, 0, 0);   // A K-major, B K-major
-  constexpr uint32_t ID_DH = umma::idesc_f16(128, 128, 0, 1);    // A K-major, B MN-major
-  constexpr uint32_t ID_DW = umma::idesc_f16(128, 144, 1, 1);    // both MN-major, N = 128+16
-  constexpr uint32_t ID_N16 = umma::idesc_f16(128, 16, 1, 1);    // both MN-major, N = 16
-
-  for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
-    // ---- S0: rows of this tile, sample slots, first layer ------------------------
-    const int64_t r_glob = tile * TILE + row;
-    const bool valid = r_glob < P.R;
-    const int64_t i_first = (tile * TILE) / P.N;
-    const int64_t r_last = (tile * TILE + TILE - 1 < P.R - 1) ? tile * TILE + TILE - 1 : P.R - 1;
-    const int n_slots = (int)(r_last / P.N - i_first) + 1;
-    const int64_t inst = valid ? r_glob / P.N : i_first;
-    const int pix = valid ? (int)(r_glob - inst * P.N) : 0;
-    const int slot = (int)(inst - i_first);
-    float gx = 0.f, gy = 0.f;
-    pvb::grid_xy(pix, P.H, P.W, P.ndim, gx, gy);
-    float xv = 0.f, wi = 1.f;
-    if (valid) {
-      if (P.x) xv = __ldg(P.x + (inst % P.B) * P.N + pix);
-      if (P.w) wi = __ldg(P.w + inst);
-    }
-    for (int k = tid; k < n_slots * 3 * HD; k += NTHREADS)
-      f32[F_UV + k] = __ldg(P.Uv + i_first * 3 * HD + k);
-    __syncthreads();
-    {
-      const float* u = f32 + F_UV + slot * 3 * HD;
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        __half2 hh[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int c = col0 + c8 * 8 + 2 * j;
-          float a = fast_tanh(fmaf(u[c], gx, fmaf(u[HD + c], gy, u[2 * HD + c])));
-          float b = fast_tanh(fmaf(u[c + 1], gx, fmaf(u[HD + c + 1], gy, u[2 * HD + c + 1])));
-          hh[j] = valid ? __floats2half2_rn(a, b) : __floats2half2_rn(0.f, 0.f);
-        }
-        *reinterpret_cast<uint4*>(smem + SM_A0 + umma::tile_off(TILE, row, col0 + c8 * 8)) =
-            *reinterpret_cast<uint4*>(hh);
-      }
-      if (P.backward) {
-        // G[row][3*slot + {0,1,2}] = {gx, gy, 1}; this thread fills columns [8*hf, 8*hf+8)
-        __half g8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          int n = hf * 8 + j;
-          float v = 0.f;
-          if (valid && n / 3 == slot) v = (n % 3 == 0) ? gx : (n % 3 == 1) ? gy : 1.f;
-          g8[j] = __float2half_rn(v);
-        }
-        *reinterpret_cast<uint4*>(smem + SM_G + umma::tile_off(TILE, row, hf * 8)) =
-            *reinterpret_cast<uint4*>(g8);
-      }
-    }
-    umma::fence_proxy_async();
-    umma::fence_before_sync();
-    __syncthreads();
-    // ---- S1: ACC = h0 W1^T ---------------------------------------------------------
-    if (tid == 0) {
-      umma::fence_after_sync();
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_f16_ss(tm + TM_ACC, desc_kmajor(sA0, k), desc_kmajor(sW1, k), ID_FWD, k > 0);
-      umma::commit(bar);
-    }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    // ---- S2: h1 = tanh(ACC + b1) -> A1 ----------------------------------------------
-#pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      float v[32];
-      umma::tmem_ld32(tm_lane + TM_ACC + col0 + cb * 32, v);
-      umma::tmem_ld_wait();
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        __half2 hh[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int c = col0 + cb * 32 + c8 * 8 + 2 * j;
-          hh[j] = __floats2half2_rn(fast_tanh(v[c8 * 8 + 2 * j] + f32[F_B1 + c]),
-                                    fast_tanh(v[c8 * 8 + 2 * j + 1] + f32[F_B1 + c + 1]));
-        }
-        *reinterpret_cast<uint4*>(smem + SM_A1 +
-                                  umma::tile_off(TILE, row, col0 + cb * 32 + c8 * 8)) =
-            *reinterpret_cast<uint4*>(hh);
-      }
-    }
-    umma::fence_proxy_async();
-    umma::fence_before_sync();
-    __syncthreads();
-    // ---- S3: ACC = h1 W2^T -----------------------------------------------------------
-    if (tid == 0) {
-      umma::fence_after_sync();
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_f16_ss(tm + TM_ACC, desc_kmajor(sA1, k), desc_kmajor(sW2, k), ID_FWD, k > 0);
-      umma::commit(bar);
-    }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    // ---- S4: h2, logit, log-lik, dl, D2 --------------------------------------------------
-    __half2 h2p[32];
-    float pdot = 0.f;
-#pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      float v[32];
-      umma::tmem_ld32(tm_lane + TM_ACC + col0 + cb * 32, v);
-      umma::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        int c = col0 + cb * 32 + 2 * j;
-        __half2 h = __floats2half2_rn(fast_tanh(v[2 * j] + f32[F_B2 + c]),
-                                      fast_tanh(v[2 * j + 1] + f32[F_B2 + c + 1]));
-        h2p[cb * 16 + j] = h;
-        float2 hf2 = __half22float2(h);
-        pdot = fmaf(hf2.x, f32[F_WO + c], pdot);
-        pdot = fmaf(hf2.y, f32[F_WO + c + 1], pdot);
-      }
-    }
-    f32[F_PART + hf * TILE + row] = pdot;
-    if (P.backward) {
-      // h2 -> Db (A operand of the dwo GEMM)
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8)
-        *reinterpret_cast<uint4*>(smem + SM_DB + umma::tile_off(TILE, row, col0 + c8 * 8)) =
-            *reinterpret_cast<uint4*>(&h2p[c8 * 4]);
-    }
-    __syncthreads();
-    const float logit = f32[F_PART + row] + f32[F_PART + TILE + row] + bo;
-    float ll = 0.f, dnll = 0.f, locv;
-    if (P.x) {
-      pvb::obs_terms(logit, xv, P.sampler, P.sigmoid_d, P.sig, ll, dnll, locv);
-    } else {
-      locv = P.sigmoid_d ? pvb::sigmoid_f(logit) : logit;
-    }
-    const float dl = valid ? wi * dnll : 0.f;
-    if (hf == 0 && valid) {
-      if (P.rowll) P.rowll[r_glob] = ll;
-      if (P.loc) P.loc[r_glob] = locv;
-    }
-    if (!P.backward) {
-      // forward only: the next tile may reuse A0/A1 after this barrier
-      umma::fence_before_sync();
-      __syncthreads();
-      continue;
-    }
-    if (hf == 0) {
-      dl_sum += dl;
-      __half d8[8];
-      d8[0] = __float2half_rn(dl);
-#pragma unroll
-      for (int j = 1; j < 8; ++j) d8[j] = __float2half_rn(0.f);
-      *reinterpret_cast<uint4*>(smem + SM_DL + umma::tile_off(TILE, row, 0)) =
-          *reinterpret_cast<uint4*>(d8);
-    }
-#pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-      __half2 dd[4];
+  if (warp == MMA_WARP) {
+    // =========================== MMA issuer =====================================
+    const uint32_t sW1 = umma::smem_u32(smem + SM_W1), sW2 = umma::smem_u32(smem + SM_W2);
+    const uint32_t sA0 = umma::smem_u32(smem + SM_A0), sA1 = umma::smem_u32(smem + SM_A1);
+    const uint32_t sDA = umma::smem_u32(smem + SM_DA), sDB = umma::smem_u32(smem + SM_DB);
+    const uint32_t sG = umma::smem_u32(smem + SM_G), sDL = umma::smem_u32(smem + SM_DL);
+    const uint32_t tA = tm + TM_AT;
+    constexpr uint32_t ID_FWD = umma::idesc_f16(128, 128, 0, 0);   // A (TMEM), B K-major
+    constexpr uint32_t ID_DH = umma::idesc_f16(128, 128, 0, 1);    // A (TMEM), B MN-major
+    constexpr uint32_t ID_DW = umma::idesc_f16(128, 144, 1, 1);    // both MN-major, N = 128+16
+    constexpr uint32_t ID_N16 = umma::idesc_f16(128, 16, 1, 1);    // both MN-major, N = 16
+    uint32_t rph = 0, sph = 0;
+    uint32_t acc = 0;  // 0 on this CTA's first tile: weight-gradient accumulators start fresh
+    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+      // ---- GEMM1: ACC = h0 W1^T, K-steps issued as the h0 column groups land in TMEM ----
+      TRACE(1, 0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int c = col0 + c8 * 8 + 2 * j;
-        float2 h = __half22float2(h2p[c8 * 4 + j]);
-        dd[j] = __floats2half2_rn(dl * f32[F_WO + c] * (1.f - h.x * h.x),
-                                  dl * f32[F_WO + c + 1] * (1.f - h.y * h.y));
+        umma::mbar_wait(bars + BAR_READY + j, rph);
+        TRACE(1, 1 + j);
+        umma::fence_after_sync();
+        if (lane == 0) {
+          umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_kmajor(sW1, 2 * j), ID_FWD, j > 0);
+          umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_kmajor(sW1, 2 * j + 1), ID_FWD, 1);
+          if (j == 3) umma::commit(bars + BAR_ACC);
+        }
+        __syncwarp();
       }
-      *reinterpret_cast<uint4*>(smem + SM_DA + umma::tile_off(TILE, row, col0 + c8 * 8)) =
-          *reinterpret_cast<uint4*>(dd);
-    }
-    umma::fence_proxy_async();
-    umma::fence_before_sync();
-    __syncthreads();
-    // ---- S5: dh1 = D2 W2 ; dW2' += D2^T [h1|1] ; dwo += h2^T dl ------------------------------
-    if (tid == 0) {
+      rph ^= 1;
+      // ---- GEMM2: ACC = h1 W2^T ----
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        umma::mbar_wait(bars + BAR_READY + j, rph);
+        TRACE(1, 5 + j);
+        umma::fence_after_sync();
+        if (lane == 0) {
+          umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_kmajor(sW2, 2 * j), ID_FWD, j > 0);
+          umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_kmajor(sW2, 2 * j + 1), ID_FWD, 1);
+          if (j == 3) umma::commit(bars + BAR_ACC);
+        }
+        __syncwarp();
+      }
+      rph ^= 1;
+      if (!P.backward) {
+        TRACE_NEXT();
+        continue;
+      }
+      // ---- GEMM3: ACC = D2 W2 ----
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        umma::mbar_wait(bars + BAR_READY + j, rph);
+        TRACE(1, 9 + j);
+        umma::fence_after_sync();
+        if (lane == 0) {
+          umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_mnmajor(sW2, 2 * j), ID_DH, j > 0);
+          umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_mnmajor(sW2, 2 * j + 1), ID_DH, 1);
+          if (j == 3) umma::commit(bars + BAR_ACC);
+        }
+        __syncwarp();
+      }
+      rph ^= 1;
+      // shared-memory operands of S0 (h0), S2 (h1), S4 (h2, D2, dl) are published by now or soon
+#pragma unroll
+      for (int s = 0; s < 3; ++s) umma::mbar_wait(bars + BAR_SM + s, sph);
       umma::fence_after_sync();
-      const uint32_t acc = first_tile ? 0u : 1u;
+      if (lane == 0) {
+        // dwo += h2^T dl ; Db (h2) may be overwritten with D1 once this completes
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_f16_ss(tm + TM_ACC, desc_kmajor(sDA, k), desc_mnmajor(sW2, k), ID_DH, k > 0);
+        for (int k = 0; k < 8; ++k)
+          umma::mma_f16_ss(tm + TM_DWO, desc_mnmajor(sDB, k), desc_mnmajor(sDL, k), ID_N16,
+                           (k > 0) ? 1u : acc);
+        umma::commit(bars + BAR_DWO);
+      }
+      __syncwarp();
+      // ---- GEMM4: ACC = D1 W1, with dW2' += D2^T [h1|1] slotted between its K-steps ----
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_f16_ss(tm + TM_DW2, desc_mnmajor(sDA, k), desc_mnmajor(sA1, k), ID_DW,
-                         (k > 0) ? 1u : acc);
+      for (int j = 0; j < 4; ++j) {
+        umma::mbar_wait(bars + BAR_READY + j, rph);
+        TRACE(1, 13 + j);
+        umma::fence_after_sync();
+        if (lane == 0) {
+          umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_mnmajor(sW1, 2 * j), ID_DH, j > 0);
+          umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_mnmajor(sW1, 2 * j + 1), ID_DH, 1);
+          if (j < 3) {
+            const int k0 = 3 * j, k1 = (j == 2) ? 8 : 3 * j + 3;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_f16_ss(tm + TM_DWO, desc_mnmajor(sDB, k), desc_mnmajor(sDL, k), ID_N16,
-                         (k > 0) ? 1u : acc);
-      umma::commit(bar);
+            for (int k = k0; k < k1; ++k)
+              umma::mma_f16_ss(tm + TM_DW2, desc_mnmajor(sDA, k), desc_mnmajor(sA1, k), ID_DW,
+                               (k > 0) ? 1u : acc);
+          } else {
+            umma::commit(bars + BAR_ACC);   // also covers dW2': Da may be overwritten (D0)
+          }
+        }
+        __syncwarp();
+      }
+      rph ^= 1;
+      // ---- dW1' += D1^T [h0|1] (needs the shared-memory copy of D1) ----
+      umma::mbar_wait(bars + BAR_SM + 3, sph);
+      umma::fence_after_sync();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma::mma_f16_ss(tm + TM_DW1, desc_mnmajor(sDB, k), desc_mnmajor(sA0, k), ID_DW,
+                           (k > 0) ? 1u : acc);
+        umma::commit(bars + BAR_DW);
+      }
+      __syncwarp();
+      // ---- dUv(tile) = D0^T G ----
+      umma::mbar_wait(bars + BAR_SM + 4, sph);
+      sph ^= 1;
+      TRACE(1, 17);
+      umma::fence_after_sync();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma::mma_f16_ss(tm + TM_DUV, desc_mnmajor(sDA, k), desc_mnmajor(sG, k), ID_N16, k > 0);
+        umma::commit(bars + BAR_DUV);
+      }
+      __syncwarp();
+      acc = 1;
+      TRACE_NEXT();
     }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    // ---- S6: D1 = dh1 (1 - h1^2) -> Db ----------------------------------------------------------
-#pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      float v[32];
-      umma::tmem_ld32(tm_lane + TM_ACC + col0 + cb * 32, v);
-      umma::tmem_ld_wait();
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        const uint32_t off = umma::tile_off(TILE, row, col0 + cb * 32 + c8 * 8);
-        uint4 hraw = *reinterpret_cast<const uint4*>(smem + SM_A1 + off);
-        const __half2* hh = reinterpret_cast<const __half2*>(&hraw);
-        __half2 dd[4];
+  } else {
+    // =========================== epilogue warps ====================================
+    const float bo = P.bo[0];
+    uint32_t aph = 0, dph = 0, wph = 0, oph = 0;
+    int64_t prev_tile = -1;
+    int prev_slots = 0;
+    int buf = 0;
+    TileCursor cur_c;
+    cur_c.tile = blockIdx.x;                       // grid <= tiles: every CTA owns a tile
+    cur_c.i_first = (cur_c.tile * TILE) / P.N;     // the only 64-bit divisions of the kernel
+    cur_c.off = (int)(cur_c.tile * TILE - cur_c.i_first * P.N);
+    cur_c.ib_first = (int)(cur_c.i_first % P.B);
+    RowGeo cur = stage_tile(P, f32, cur_c, 0, tid, row, cg);
+    cp_async_wait_all();
+    epi_bar();
+    while (cur_c.tile < P.tiles) {
+      const int64_t tile = cur_c.tile;
+      any_tile = true;
+      TRACE(0, 0);
+      const bool valid = cur.valid;
+      const float gx = cur.gx, gy = cur.gy;
+      const int slot = cur.slot;
+      const int64_t r_glob = cur.r_glob;
+      const int n_slots = cur.n_slots;
+      const float xv = f32[F_X + buf * TILE + row];    // staged one tile ago (or before the loop)
+      const float wi = f32[F_WI + buf * TILE + row];
+      uint4 out[4];
+      // ---- S0: first layer h0 = tanh(U g + v) -> TMEM A (+ A0) ------------------------------
+      {
+        const float* u = f32 + F_UV + buf * UV_FLOATS + slot * 3 * HD;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 h = __half22float2(hh[j]);
-          dd[j] = __floats2half2_rn(v[c8 * 8 + 2 * j] * (1.f - h.x * h.x),
-                                    v[c8 * 8 + 2 * j + 1] * (1.f - h.y * h.y));
+          const int c0 = 8 * (4 * j + cg);
+          float ux[8], uy[8], uc[8];
+          lds8(u + c0, ux);
+          lds8(u + HD + c0, uy);
+          lds8(u + 2 * HD + c0, uc);
+          __half2 hh[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = fast_tanh(fmaf(ux[2 * e], gx, fmaf(uy[2 * e], gy, uc[2 * e])));
+            float b = fast_tanh(fmaf(ux[2 * e + 1], gx, fmaf(uy[2 * e + 1], gy, uc[2 * e + 1])));
+            hh[e] = valid ? __floats2half2_rn(a, b) : __floats2half2_rn(0.f, 0.f);
+          }
+          out[j] = *reinterpret_cast<uint4*>(hh);
+          publish_chunk(bars, tm_lane, cg, j, out[j]);
+          TRACE(0, 1 + j);
         }
-        *reinterpret_cast<uint4*>(smem + SM_DB + off) = *reinterpret_cast<uint4*>(dd);
       }
-    }
-    umma::fence_proxy_async();
-    umma::fence_before_sync();
-    __syncthreads();
-    // ---- S7: dh0 = D1 W1 ; dW1' += D1^T [h0|1] -----------------------------------------------------
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t acc = first_tile ? 0u : 1u;
+      if (P.backward) {
+        if (prev_tile >= 0) {
+          // dW1' of the previous tile has finished reading A0 / Db; then every MMA of the
+          // previous tile (dUv was issued last): Da, G and the dUv accumulator are free
+          umma::mbar_wait(bars + BAR_DW, wph);
+          wph ^= 1;
+        }
+        store_tile4(smem + SM_A0, row, cg, out);
+        if (prev_tile >= 0) {
+          umma::mbar_wait(bars + BAR_DUV, dph);
+          dph ^= 1;
+          umma::fence_after_sync();
+          if (cg == 1) {
+            // per-tile dUv partials of the previous tile: lane == hidden unit
+            float v[16];
+            umma::tmem_ld16(tm_lane + TM_DUV, v);
+            umma::tmem_ld_wait();
+            float* dst = P.gUv_part + prev_tile * (MAX_SLOTS * 3 * HD);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_f16_ss(tm + TM_ACC, desc_kmajor(sDB, k), desc_mnmajor(sW1, k), ID_DH, k > 0);
+            for (int n = 0; n < MAX_SLOTS * 3; ++n)
+              if (n < prev_slots * 3) dst[n * HD + row] = v[n];   // unused slots are never read
+          }
+        }
+        if (cg >= 2) {
+          // G[row][3*slot + {0,1,2}] = {gx, gy, 1}; column groups 2 and 3 fill 8 columns each
+          const int hf = cg - 2;
+          __half g8[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_f16_ss(tm + TM_DW1, desc_mnmajor(sDB, k), desc_mnmajor(sA0, k), ID_DW,
-                         (k > 0) ? 1u : acc);
-      umma::commit(bar);
-    }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    // ---- S8: D0 = dh0 (1 - h0^2) -> Da ---------------------------------------------------------------
-#pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
+          for (int e = 0; e < 8; ++e) {
+            int n = hf * 8 + e;
+            float v = 0.f;
+            if (valid && n / 3 == slot) v = (n % 3 == 0) ? gx : (n % 3 == 1) ? gy : 1.f;
+            g8[e] = __float2half_rn(v);
+          }
+          *reinterpret_cast<uint4*>(smem + SM_G + umma::tile_off(TILE, row, hf * 8)) =
+              *reinterpret_cast<uint4*>(g8);
+        }
+        signal_smem(bars, 0);   // h0 (and G) visible to the tensor core
+      }
+      TRACE(0, 5);
+      prev_tile = tile;
+      prev_slots = n_slots;
+      // stage the next tile (geometry now; Uv / targets / weights land asynchronously in the
+      // other buffer and are made visible by the S4 barrier below)
+      TileCursor nxt_c = cur_c;
+      cursor_advance(nxt_c, P);
+      RowGeo nxt = cur;
+      if (nxt_c.tile < P.tiles) nxt = stage_tile(P, f32, nxt_c, buf ^ 1, tid, row, cg);
       float v[32];
-      umma::tmem_ld32(tm_lane + TM_ACC + col0 + cb * 32, v);
-      umma::tmem_ld_wait();
+      TRACE(0, 6);
+      // ---- S2: h1 = tanh(ACC + b1) -> TMEM A (+ A1) -------------------------------------------
+      umma::mbar_wait(bars + BAR_ACC, aph);
+      aph ^= 1;
+      TRACE(0, 7);
+      umma::fence_after_sync();
+      load_acc(tm_lane, cg, v);
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        const uint32_t off = umma::tile_off(TILE, row, col0 + cb * 32 + c8 * 8);
-        uint4 hraw = *reinterpret_cast<const uint4*>(smem + SM_A0 + off);
-        const __half2* hh = reinterpret_cast<const __half2*>(&hraw);
-        __half2 dd[4];
+      for (int j = 0; j < 4; ++j) {
+        out[j] = tanh8(v + 8 * j, f32 + F_B1 + 8 * (4 * j + cg));
+        publish_chunk(bars, tm_lane, cg, j, out[j]);
+      }
+      if (P.backward) {
+        store_tile4(smem + SM_A1, row, cg, out);
+        signal_smem(bars, 1);
+      }
+      TRACE(0, 8);
+      // ---- S4: h2, logit, dl, D2 -> TMEM A (+ Db, Da, DL) ------------------------------------------
+      umma::mbar_wait(bars + BAR_ACC, aph);
+      aph ^= 1;
+      TRACE(0, 9);
+      umma::fence_after_sync();
+      load_acc(tm_lane, cg, v);
+      float pdot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = 8 * (4 * j + cg);
+        out[j] = tanh8(v + 8 * j, f32 + F_B2 + c0);
+        float wv[8];
+        lds8(f32 + F_WO + c0, wv);
+        const __half2* hh = reinterpret_cast<const __half2*>(&out[j]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 hf2 = __half22float2(hh[e]);
+          pdot = fmaf(hf2.x, wv[2 * e], pdot);
+          pdot = fmaf(hf2.y, wv[2 * e + 1], pdot);
+        }
+      }
+      f32[F_PART + cg * TILE + row] = pdot;
+      cp_async_wait_all();   // this thread's share of the next tile's staging has landed
+      TRACE(0, 10);
+      epi_bar();
+      TRACE(0, 11);
+      const float logit = ((f32[F_PART + row] + f32[F_PART + TILE + row]) +
+                           (f32[F_PART + 2 * TILE + row] + f32[F_PART + 3 * TILE + row])) + bo;
+      // observation terms (fast intrinsics, ~1e-6 relative): dl feeds the backward pass, the
+      // per-pixel log-likelihood and reconstruction go out from column group 0
+      float ll = 0.f, dnll = 0.f, locv;
+      if (P.x) {
+        pvb::obs_terms_fast(logit, xv, P.sampler, P.sigmoid_d, P.sig, ll, dnll, locv);
+      } else {
+        locv = P.sigmoid_d ? __fdividef(1.f, 1.f + __expf(-logit)) : logit;
+      }
+      if (P.backward) {
+        // critical path first: D2 -> TMEM A
+        const float dl = valid ? wi * dnll : 0.f;
+        uint4 d2[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 h = __half22float2(hh[j]);
-          dd[j] = __floats2half2_rn(v[c8 * 8 + 2 * j] * (1.f - h.x * h.x),
-                                    v[c8 * 8 + 2 * j + 1] * (1.f - h.y * h.y));
+          float wv[8];
+          lds8(f32 + F_WO + 8 * (4 * j + cg), wv);
+          const __half2 one = __float2half2_rn(1.f);
+          const __half2* hh = reinterpret_cast<const __half2*>(&out[j]);
+          __half2 dd[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __half2 g = __hfma2(__hneg2(hh[e]), hh[e], one);
+            dd[e] = __hmul2(__floats2half2_rn(dl * wv[2 * e], dl * wv[2 * e + 1]), g);
+          }
+          d2[j] = *reinterpret_cast<uint4*>(dd);
+          publish_chunk(bars, tm_lane, cg, j, d2[j]);
         }
-        *reinterpret_cast<uint4*>(smem + SM_DA + off) = *reinterpret_cast<uint4*>(dd);
+        TRACE(0, 12);
+        // off the critical path: h2 -> Db, D2 -> Da, dl -> DL (weight-gradient operands)
+        store_tile4(smem + SM_DB, row, cg, out);
+        store_tile4(smem + SM_DA, row, cg, d2);
+        if (cg == 1) {
+          __half d8[8];
+          d8[0] = __float2half_rn(dl);
+#pragma unroll
+          for (int e = 1; e < 8; ++e) d8[e] = __float2half_rn(0.f);
+          *reinterpret_cast<uint4*>(smem + SM_DL + umma::tile_off(TILE, row, 0)) =
+              *reinterpret_cast<uint4*>(d8);
+        }
+        if (cg == 0) dl_sum += dl;
+        signal_smem(bars, 2);
+      }
+      if (cg == 0 && valid) {
+        if (P.rowll) P.rowll[r_glob] = ll;
+        if (P.loc) P.loc[r_glob] = locv;
+      }
+      TRACE(0, 13);
+      if (!P.backward) {
+        umma::fence_before_sync();   // accumulator reads done before the next tile's signals
+        cur = nxt;
+        cur_c = nxt_c;
+        buf ^= 1;
+        TRACE_NEXT();
+        continue;
+      }
+      // ---- S6: D1 = dh1 (1 - h1^2) -> TMEM A (+ Db) ---------------------------------------------------
+      umma::mbar_wait(bars + BAR_ACC, aph);
+      aph ^= 1;
+      TRACE(0, 14);
+      umma::fence_after_sync();
+      load_acc(tm_lane, cg, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = umma::tile_off(TILE, row, 8 * (4 * j + cg));
+        out[j] = dact8(v + 8 * j, *reinterpret_cast<const uint4*>(smem + SM_A1 + off));
+        publish_chunk(bars, tm_lane, cg, j, out[j]);
+      }
+      umma::mbar_wait(bars + BAR_DWO, oph);   // dwo has finished reading h2 from Db
+      oph ^= 1;
+      store_tile4(smem + SM_DB, row, cg, out);
+      signal_smem(bars, 3);
+      TRACE(0, 15);
+      // ---- S8: D0 = dh0 (1 - h0^2) -> Da ---------------------------------------------------------------
+      umma::mbar_wait(bars + BAR_ACC, aph);
+      aph ^= 1;
+      TRACE(0, 16);
+      umma::fence_after_sync();
+      load_acc(tm_lane, cg, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = umma::tile_off(TILE, row, 8 * (4 * j + cg));
+        out[j] = dact8(v + 8 * j, *reinterpret_cast<const uint4*>(smem + SM_A0 + off));
+      }
+      store_tile4(smem + SM_DA, row, cg, out);
+      umma::fence_before_sync();   // accumulator reads done before the next tile's signals
+      signal_smem(bars, 4);
+      TRACE(0, 17);
+      cur = nxt;
+      cur_c = nxt_c;
+      buf ^= 1;
+      TRACE_NEXT();
+    }
+    // last tile: wait for its MMAs, write its dUv partials
+    if (P.backward && prev_tile >= 0) {
+      umma::mbar_wait(bars + BAR_DUV, dph);
+      umma::fence_after_sync();
+      if (cg == 1) {
+        float v[16];
+        umma::tmem_ld16(tm_lane + TM_DUV, v);
+        umma::tmem_ld_wait();
+        float* dst = P.gUv_part + prev_tile * (MAX_SLOTS * 3 * HD);
+#pragma unroll
+        for (int n = 0; n < MAX_SLOTS * 3; ++n)
+          if (n < prev_slots * 3) dst[n * HD + row] = v[n];
       }
     }
-    umma::fence_proxy_async();
-    umma::fence_before_sync();
-    __syncthreads();
-    // ---- S9: dUv(tile) = D0^T G -------------------------------------------------------------------------
-    if (tid == 0) {
-      umma::fence_after_sync();
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_f16_ss(tm + TM_DUV, desc_mnmajor(sDA, k), desc_mnmajor(sG, k), ID_N16, k > 0);
-      umma::commit(bar);
-    }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    // ---- S10: per-tile dUv partials: lane == hidden unit ---------------------------------------------------
-    if (hf == 0) {
-      float v[16];
-      umma::tmem_ld16(tm_lane + TM_DUV, v);
-      umma::tmem_ld_wait();
-      float* dst = P.gUv_part + tile * (MAX_SLOTS * 3 * HD);
-#pragma unroll
-      for (int n = 0; n < MAX_SLOTS * 3; ++n)
-        if (n < n_slots * 3) dst[n * HD + row] = v[n];   // unused slots are never read
-    }
-    first_tile = false;
-    umma::fence_before_sync();
-    __syncthreads();
   }
 
   // ---- weight-gradient partials of this CTA ---------------------------------------------------------------
   if (P.backward) {
-    umma::fence_after_sync();
     float* out = P.wgrad_part + (size_t)blockIdx.x * PVB_TC_WGRAD_STRIDE;
     // layout: dW1[128][128] | db1[128] | dW2[128][128] | db2[128] | dwo[128] | dbo
     float* o_dW1 = out;
@@ -445,53 +717,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     float* o_db2 = o_dW2 + HD * HD;
     float* o_dwo = o_db2 + HD;
     float* o_dbo = o_dwo + HD;
-    const bool any = !first_tile;  // false if this CTA processed no tile
+    if (warp != MMA_WARP) {
+      umma::fence_after_sync();
+      const int col0 = cg * 32;             // this thread's 32 contiguous columns of row `row`
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t base = which == 0 ? TM_DW1 : TM_DW2;
-      float* oW = which == 0 ? o_dW1 : o_dW2;
-      float* ob = which == 0 ? o_db1 : o_db2;
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t base = which == 0 ? TM_DW1 : TM_DW2;
+        float* oW = which == 0 ? o_dW1 : o_dW2;
+        float* ob = which == 0 ? o_db1 : o_db2;
         float v[32];
-        if (any) {
-          umma::tmem_ld32(tm_lane + base + col0 + cb * 32, v);
+        if (any_tile) {
+          umma::tmem_ld32(tm_lane + base + col0, v);
           umma::tmem_ld_wait();
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-        float4* dst = reinterpret_cast<float4*>(oW + row * HD + col0 + cb * 32);
+        float4* dst = reinterpret_cast<float4*>(oW + row * HD + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (cg == 3) {
+          float b[16];
+          if (any_tile) {
+            umma::tmem_ld16(tm_lane + base + 128, b);
+            umma::tmem_ld_wait();
+          } else {
+            b[0] = 0.f;
+          }
+          ob[row] = b[0];
+        }
       }
-      if (hf == 1) {
-        float v[16];
-        if (any) {
-          umma::tmem_ld16(tm_lane + base + 128, v);
+      if (cg == 0) {
+        float b[16];
+        if (any_tile) {
+          umma::tmem_ld16(tm_lane + TM_DWO, b);
           umma::tmem_ld_wait();
         } else {
-          v[0] = 0.f;
+          b[0] = 0.f;
         }
-        ob[row] = v[0];
+        o_dwo[row] = b[0];
       }
-    }
-    if (hf == 0) {
-      float v[16];
-      if (any) {
-        umma::tmem_ld16(tm_lane + TM_DWO, v);
-        umma::tmem_ld_wait();
-      } else {
-        v[0] = 0.f;
-      }
-      o_dwo[row] = v[0];
     }
     float tot = pvb::block_sum(dl_sum, f32 + F_RED);
     if (tid == 0) o_dbo[0] = tot;
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc<TM_COLS>(tm);
+  if (warp == MMA_WARP) umma::tmem_dealloc<TM_COLS>(tm);
 }
 
 // gUv[i][c][h] = sum over the tiles touching instance i of its slot partial
@@ -524,8 +796,14 @@ int sm_count() {
 
 extern "C" int pvb_has_tcgen05(void) { return 1; }
 
+#ifdef PVB_TC_TRACE
+extern "C" int pvb_tc_trace_read(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 2 * 64 * 32);
+}
+#endif
+
 extern "C" int pvb_sdec_tc_sizes(int64_t I, int N, pvb_tc_sizes* out) {
-  PVB_CHECK_ARG(out && I >= 0 && N >= 32, "pvb_sdec_tc_sizes: need N >= 32 pixels per instance");
+  PVB_CHECK_ARG(out && I >= 0 && N >= MIN_PIX, "pvb_sdec_tc_sizes: need N >= 43 pixels per instance");
   int64_t R = I * N;
   out->tiles = (R + TILE - 1) / TILE;
   int sms = sm_count();
@@ -550,7 +828,8 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
   PVB_CHECK_ARG(((uintptr_t)W1 % 16 == 0) && ((uintptr_t)W2 % 16 == 0), "pvb_sdec_tc_step: weights must be 16-byte aligned");
   PVB_CHECK_ARG(!backward || ((uintptr_t)wgrad_part % 16 == 0), "pvb_sdec_tc_step: wgrad_part must be 16-byte aligned");
   const int N = (ndim == 1) ? H : H * W;
-  PVB_CHECK_ARG(N >= 32, "pvb_sdec_tc_step: need >= 32 pixels per instance");
+  PVB_CHECK_ARG(N >= MIN_PIX, "pvb_sdec_tc_step: need >= 43 pixels per instance");
+  PVB_CHECK_ARG(B < (1LL << 30) && I < (1LL << 40), "pvb_sdec_tc_step: batch too large");
   if (I == 0) return 0;
   pvb_tc_sizes s;
   pvb_sdec_tc_sizes(I, N, &s);
@@ -566,6 +845,10 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
   P.R = I * N; P.B = B; P.N = N; P.H = H; P.W = (ndim == 1) ? 1 : W; P.ndim = ndim;
   P.sampler = sampler; P.sigmoid_d = sigmoid_d; P.sig = decoder_sig; P.backward = backward;
   P.tiles = s.tiles;
+  const int64_t step = (int64_t)TILE * s.ctas;
+  P.step_q = step / N;
+  P.step_r = (int)(step % N);
+  P.step_qb = (int)(P.step_q % B);
   sdec_tc_kernel<<<s.ctas, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
   pvb::count_launch();
   return pvb::launch_status();
@@ -573,7 +856,7 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
 
 extern "C" int pvb_sdec_tc_gather_gUv(const float* gUv_part, float* gUv, int64_t I, int N,
                                       void* stream) {
-  PVB_CHECK_ARG(gUv_part && gUv && I >= 0 && N >= 32, "pvb_sdec_tc_gather_gUv: bad argument");
+  PVB_CHECK_ARG(gUv_part && gUv && I >= 0 && N >= MIN_PIX, "pvb_sdec_tc_gather_gUv: bad argument");
   if (I == 0) return 0;
   gather_gUv_kernel<<<(unsigned)I, 128, 0, (cudaStream_t)stream>>>(gUv_part, gUv, I, N);
   pvb::count_launch();

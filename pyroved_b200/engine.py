@@ -631,7 +631,7 @@ class SVIEngine:
         return (len(layers) == 2 and all(l.in_features == 128 and l.out_features == 128
                                          for l in layers)
                 and dec.coord_latent.fc_coord.out_features == 128
-                and dec.activation == "tanh" and N >= 32
+                and dec.activation == "tanh" and N >= 43
                 and self.model.sampler_d.name in ("bernoulli", "gaussian"))
 
     def _program(self, B, has_y, mode="main"):

@@ -70,6 +70,65 @@ __global__ void probe_kernel(const __half* __restrict__ A, const __half* __restr
   if (warp == 0) umma::tmem_dealloc<256>(tm);
 }
 
+// case: A operand in tensor memory (written with tcgen05.st, lane = row, fp16 pairs packed
+// per 32-bit column), B in shared memory: D[128][N] = sum_k A(m,k) B(n,k)
+template <int N, int KT, int B_MN>
+__global__ void probe_ts_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
+                                float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  constexpr int B_ROWS = B_MN ? KT : N;
+  uint8_t* sB = smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < N * KT; idx += blockDim.x) {
+    int n = idx / KT, k = idx % KT;
+    int r = B_MN ? k : n, c = B_MN ? n : k;
+    *reinterpret_cast<__half*>(sB + umma::tile_off(B_ROWS, r, c)) = B[idx];
+  }
+  if (warp == 0) umma::tmem_alloc<512>(&tmem_base);
+  if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = tmem_base;
+  const uint32_t TM_A = 256;   // A tile: columns [256, 256 + KT/2)
+  {
+    const int row = warp * 32 + lane;
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(A + row * KT);   // fp16 pairs
+    for (int c4 = 0; c4 < KT / 2; c4 += 4) {
+      uint4 r = make_uint4(arow[c4], arow[c4 + 1], arow[c4 + 2], arow[c4 + 3]);
+      umma::tmem_st4(tm + ((uint32_t)(warp * 32) << 16) + TM_A + c4, r);
+    }
+    umma::tmem_st_wait();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    umma::fence_after_sync();
+    constexpr uint32_t idesc = umma::idesc_f16(128, N, 0, B_MN);
+    for (int k = 0; k < KT / 16; ++k) {
+      uint64_t bd;
+      if (B_MN) bd = umma::smem_desc(umma::smem_u32(sB) + k * 256, 128, B_ROWS * 16);
+      else      bd = umma::smem_desc(umma::smem_u32(sB) + k * 2 * B_ROWS * 16, B_ROWS * 16, 128);
+      umma::mma_f16_ts(tm, tm + TM_A + k * 8, bd, idesc, k > 0);
+    }
+    umma::commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(warp * 32 + lane) * N + c0 + j] = v[j];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<512>(tm);
+}
+
 template <int N, int KT, int A_MN, int B_MN>
 bool run_case(const char* name) {
   std::vector<__half> hA(128 * KT), hB(N * KT);
@@ -89,8 +148,13 @@ bool run_case(const char* name) {
   cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
   cudaMemset(dD, 0, out.size() * 4);
   size_t smem = (128 * KT + N * KT) * 2 + 1024;
-  cudaFuncSetAttribute(probe_kernel<N, KT, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  probe_kernel<N, KT, A_MN, B_MN><<<1, 128, smem>>>(dA, dB, dD);
+  if (A_MN == 2) {   // A from tensor memory
+    cudaFuncSetAttribute(probe_ts_kernel<N, KT, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    probe_ts_kernel<N, KT, B_MN><<<1, 128, smem>>>(dA, dB, dD);
+  } else {
+    cudaFuncSetAttribute(probe_kernel<N, KT, (A_MN & 1), B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    probe_kernel<N, KT, (A_MN & 1), B_MN><<<1, 128, smem>>>(dA, dB, dD);
+  }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%-34s CUDA error: %s\n", name, cudaGetErrorString(e)); return false; }
   cudaMemcpy(out.data(), dD, out.size() * 4, cudaMemcpyDeviceToHost);
@@ -111,6 +175,8 @@ int main() {
   ok &= run_case<144, 128, 1, 1>("A MN-major, B MN-major N=144");
   ok &= run_case<16, 128, 1, 1>("A MN-major, B MN-major N=16");
   ok &= run_case<16, 128, 0, 0>("A K-major, B K-major N=16");
+  ok &= run_case<128, 128, 2, 0>("A in TMEM, B K-major");
+  ok &= run_case<128, 128, 2, 1>("A in TMEM, B MN-major");
   printf(ok ? "UMMA PROBE: ALL PASS\n" : "UMMA PROBE: FAILURES\n");
   return ok ? 0 : 1;
 }
