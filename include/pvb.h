@@ -170,6 +170,95 @@ int pvb_class_nll(const float* logits, const float* y_onehot, float mult,
                   float* glogits, float* loss_out, int64_t B, int K,
                   void* stream);
 
+/* ---- fused small-batch MLP kernels (encoder / classifier side) -----------
+ * The guide's encoder is launch-latency bound at SVI batch sizes (M <= a few
+ * thousand rows, widths <= 256): these three entry points replace the
+ * per-layer GEMM / bias / activation / column-sum launches.
+ * Reference: nets/fc.py:51-61 (fcEncoderNet), :97-108 (jfcEncoderNet),
+ * :264-271 (fcClassifierNet), models/ivae.py:204-221 (guide) and their autograd. */
+#define PVB_MLP_MAX_LAYERS 4
+#define PVB_MLP_MAX_HEADS 3
+#define PVB_MLP_MAX_WIDTH 256
+#define PVB_MLP_MAX_HEAD_DIM 64
+typedef struct {
+  int64_t M;                 /* rows */
+  /* hidden layers computed here, on h_in [M, w_in] (the output of the first,
+   * wide layer, computed by pvb_linear_fwd): y_l = act(y_{l-1} W_l^T + b_l) */
+  int32_t n_layers;          /* 0..3 */
+  int32_t w_in;
+  const float* h_in;
+  int32_t width[3];
+  const float* W[3];
+  const float* b[3];
+  float* h[3];               /* saved activations [M, width_l] */
+  float* pre[3];             /* pre-activations (gelu only; may be NULL) */
+  int32_t act;
+  /* linear heads on the last hidden activation: out_k = y W_k^T + b_k */
+  int32_t n_heads;           /* 1..3 */
+  int32_t hdim[3];
+  const float* hW[3];
+  const float* hb[3];
+  float* hout[3];
+  /* reparameterised sample from heads 0 (mu) and 1 (s_pre): as pvb_randn + pvb_latent_fwd */
+  int32_t gauss;             /* 0/1; Z = hdim[0] = hdim[1] */
+  int32_t gen_eps;           /* 1: eps from Philox (seed, *step_counter, first_index); 0: read eps */
+  float* eps;                /* [M, Z] read (gen_eps = 0) or written (gen_eps = 1) */
+  float* sigma;
+  float* z;
+  float* kl;
+  uint64_t seed;
+  const int32_t* step_counter;
+  int64_t first_index;
+  /* coordinate-transform fold of z into the first decoder layer: as pvb_fold_fwd */
+  int32_t fold;              /* 0/1 */
+  pvb_fold_cfg cfg;
+  const float* cond;
+  const float* Wc;
+  const float* bc;
+  const float* Wz;
+  float* Uv;
+} pvb_mlp_tail_args;
+int pvb_mlp_tail_fwd(const pvb_mlp_tail_args* a, void* stream);
+
+typedef struct {
+  int64_t M;
+  int32_t n_layers;          /* hidden layers 0..n-1 (1..4), widths width[l] */
+  int32_t width[4];
+  const float* W[4];         /* W[l] [width[l], width[l-1]]; W[0] unused (no input gradient) */
+  const float* h[4];         /* saved activations */
+  const float* pre[4];       /* gelu only */
+  int32_t act;
+  float* dpre[4];            /* out: gradient wrt the pre-activation of layer l, [M, width[l]] */
+  int32_t n_heads;
+  int32_t hdim[3];
+  const float* hW[3];        /* [hdim, width[n-1]] */
+  const float* g[3];         /* gradient wrt head output k, [M, hdim[k]] */
+} pvb_mlp_chain_args;
+/* gradient through the heads and the hidden stack, one launch */
+int pvb_mlp_chain_bwd(const pvb_mlp_chain_args* a, void* stream);
+
+typedef struct {
+  const float* d;            /* [M, N] gradient wrt the layer output (pre-activation) */
+  const float* x;            /* [M, K] layer input */
+  float* dW;                 /* [N, K] += d^T x */
+  float* db;                 /* [N]    += colsum(d)  (may be NULL) */
+  int32_t N, K;
+} pvb_wgrad_problem;
+/* all weight / bias gradients of a stack in one launch (deterministic: every
+ * output element is produced by one CTA in a fixed order) */
+int pvb_mlp_wgrad(const pvb_wgrad_problem* problems, int n_problems, int64_t M, void* stream);
+
+/* Per-instance backward of the latent side in one launch: gathers dUv from the
+ * fused decoder's per-tile partials (gUv_part; or reads gUv when gUv_part is
+ * NULL), pvb_fold_bwd, then pvb_latent_bwd on the resulting dz
+ * (gmu / gs_pre written when non-NULL; requires I rows of eps/sigma/s_pre). */
+int pvb_latent_side_bwd(const pvb_fold_cfg* cfg, const float* z, const float* cond,
+                        const float* Wc, const float* Wz, const float* gUv,
+                        const float* gUv_part, int N, float* gz, float* gcond,
+                        float* part, const float* eps, const float* sigma,
+                        const float* s_pre, const float* w, float beta, float* gmu,
+                        float* gs_pre, int64_t I, void* stream);
+
 /* ---- optimizer / reductions -------------------------------------------- */
 /* out[j] (+)= sum_g part[g*part_stride + j], j < n, fixed order (deterministic) */
 int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,
@@ -185,6 +274,13 @@ int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
                   float lr, float beta1, float beta2, float eps,
                   const int32_t* step_counter, const int32_t* first_step,
                   void* stream);
+/* Same update with the step increment folded in: every element uses
+ * t = *step_counter + 1 (- first_step[i]); the last CTA to finish stores
+ * *step_counter += 1 (ticket must point to a zeroed int32 owned by the caller). */
+int pvb_adam_flat_step(float* p, const float* g, float* m, float* v, int64_t n,
+                       float lr, float beta1, float beta2, float eps,
+                       int32_t* step_counter, const int32_t* first_step,
+                       int32_t* ticket, void* stream);
 
 /* ---- spatial decoder, fused tcgen05 path (Hd = 128, two tanh layers) ----
  * One persistent kernel per step: grid -> h0 -> (128x128 tcgen05 GEMM + tanh)
@@ -201,6 +297,8 @@ typedef struct {
   int64_t gUv_part_floats;
   int64_t wgrad_part_floats; /* G * PVB_TC_WGRAD_STRIDE */
 } pvb_tc_sizes;
+#define PVB_TC_TILE 128       /* rows per tile of the fused kernel */
+#define PVB_TC_MAX_SLOTS 5    /* instances a tile can touch (N >= 32) */
 #define PVB_TC_WGRAD_FLOATS (2 * 128 * 128 + 2 * 128 + 128 + 1)
 /* per-CTA stride of wgrad_part (16-byte aligned rows) */
 #define PVB_TC_WGRAD_STRIDE ((PVB_TC_WGRAD_FLOATS + 3) / 4 * 4)

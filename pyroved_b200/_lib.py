@@ -31,6 +31,34 @@ class TcSizes(C.Structure):
                 ("gUv_part_floats", C.c_int64), ("wgrad_part_floats", C.c_int64)]
 
 
+class MlpTailArgs(C.Structure):
+    """pvb_mlp_tail_args"""
+    _fields_ = [("M", C.c_int64), ("n_layers", C.c_int32), ("w_in", C.c_int32), ("h_in", C.c_void_p),
+                ("width", C.c_int32 * 3), ("W", C.c_void_p * 3), ("b", C.c_void_p * 3),
+                ("h", C.c_void_p * 3), ("pre", C.c_void_p * 3), ("act", C.c_int32),
+                ("n_heads", C.c_int32), ("hdim", C.c_int32 * 3), ("hW", C.c_void_p * 3),
+                ("hb", C.c_void_p * 3), ("hout", C.c_void_p * 3),
+                ("gauss", C.c_int32), ("gen_eps", C.c_int32), ("eps", C.c_void_p),
+                ("sigma", C.c_void_p), ("z", C.c_void_p), ("kl", C.c_void_p),
+                ("seed", C.c_uint64), ("step_counter", C.c_void_p), ("first_index", C.c_int64),
+                ("fold", C.c_int32), ("cfg", FoldCfg), ("cond", C.c_void_p), ("Wc", C.c_void_p),
+                ("bc", C.c_void_p), ("Wz", C.c_void_p), ("Uv", C.c_void_p)]
+
+
+class MlpChainArgs(C.Structure):
+    """pvb_mlp_chain_args"""
+    _fields_ = [("M", C.c_int64), ("n_layers", C.c_int32), ("width", C.c_int32 * 4),
+                ("W", C.c_void_p * 4), ("h", C.c_void_p * 4), ("pre", C.c_void_p * 4),
+                ("act", C.c_int32), ("dpre", C.c_void_p * 4), ("n_heads", C.c_int32),
+                ("hdim", C.c_int32 * 3), ("hW", C.c_void_p * 3), ("g", C.c_void_p * 3)]
+
+
+class WgradProblem(C.Structure):
+    """pvb_wgrad_problem"""
+    _fields_ = [("d", C.c_void_p), ("x", C.c_void_p), ("dW", C.c_void_p), ("db", C.c_void_p),
+                ("N", C.c_int32), ("K", C.c_int32)]
+
+
 # name -> argtypes ; every entry returns int except where noted.  This table
 # must list every symbol of include/pvb.h (tests/test_abi.py checks it).
 SIGNATURES = {
@@ -58,6 +86,12 @@ SIGNATURES = {
     "pvb_reduce_partials": [_f, _f, _i32, _i64, _i64, _i32, _st],
     "pvb_counter_add": [_f, _i32, _st],
     "pvb_adam_flat": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _f, _st],
+    "pvb_adam_flat_step": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _f, _f, _st],
+    "pvb_mlp_tail_fwd": [C.POINTER(MlpTailArgs), _st],
+    "pvb_mlp_chain_bwd": [C.POINTER(MlpChainArgs), _st],
+    "pvb_mlp_wgrad": [C.POINTER(WgradProblem), _i32, _i64, _st],
+    "pvb_latent_side_bwd": [C.POINTER(FoldCfg), _f, _f, _f, _f, _f, _f, _i32, _f, _f, _f, _f, _f, _f,
+                            _f, _fl, _f, _f, _i64, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
     "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
                          _i32, _i32, _i32, _i32, _i32, _fl, _i32, _st],

@@ -4,12 +4,12 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall"
-SRCS="pvb_core.cu pvb_gemm.cu pvb_latent.cu pvb_sdec_simt.cu"
+SRCS="pvb_core.cu pvb_gemm.cu pvb_latent.cu pvb_sdec_simt.cu pvb_mlp.cu"
 [ -f pvb_sdec_tc.cu ] && SRCS="$SRCS pvb_sdec_tc.cu"
 OBJS=""
 for s in $SRCS; do
   o="${s%.cu}.o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ pvb_common.cuh -nt "$o" ] || [ ../../include/pvb.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ pvb_common.cuh -nt "$o" ] || [ pvb_fold.cuh -nt "$o" ] || [ umma.cuh -nt "$o" ] || [ ../../include/pvb.h -nt "$o" ]; then
     $NVCC $FLAGS ${PVB_EXTRA_FLAGS} -c "$s" -o "$o" &
   fi
   OBJS="$OBJS $o"

@@ -139,6 +139,18 @@ __device__ __forceinline__ void obs_terms(float l, float x, int sampler, int sig
   }
 }
 
+// d(-log p(x|l))/dl alone: the shortest dependent chain (two MUFU ops), for the critical path
+__device__ __forceinline__ float obs_dnll_fast(float l, float x, int sampler, int sigmoid_d, float sig) {
+  if (sampler == PVB_SAMPLER_BERNOULLI) {
+    float p = sigmoid_d ? __fdividef(1.f, 1.f + __expf(-l)) : l;
+    bool in = (p >= PVB_PROB_EPS) && (p <= 1.f - PVB_PROB_EPS);
+    if (sigmoid_d) return in ? (p - x) : 0.f;
+    return in ? __fdividef(p - x, p * (1.f - p)) : 0.f;
+  }
+  float m = sigmoid_d ? __fdividef(1.f, 1.f + __expf(-l)) : l;
+  float dm = __fdividef(m - x, sig * sig);
+  return sigmoid_d ? dm * m * (1.f - m) : dm;
+}
 // obs_terms with fast intrinsics (__expf/__logf/__fdividef: ~1e-6 relative), same case analysis.
 // Used by the fused tensor-core decoder, whose operands are fp16 anyway; its log-likelihood and
 // reconstruction stay ~1e-6 relative to the exact path (tolerance of the path: 1e-3).

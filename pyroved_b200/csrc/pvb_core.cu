@@ -20,29 +20,39 @@ extern "C" int pvb_version(void) { return 100; }
 extern "C" const char* pvb_last_error_string(void) { return pvb::g_err; }
 
 // ---------------------------------------------------------------------------
-__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                       int G, int64_t n, int64_t stride, int accumulate) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  // four independent partial sums keep several loads in flight; the
-  // summation order is fixed, so the result is bitwise reproducible
+// 32 outputs per CTA; the G partials are split over 8 thread groups whose sums are combined in
+// a fixed order -> bitwise reproducible, and short dependent chains even for large G
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int G, int64_t n,
+                       int64_t stride, int accumulate) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int g = 0;
-  for (; g + 3 < G; g += 4) {
-    s0 += part[(int64_t)g * stride + i];
-    s1 += part[(int64_t)(g + 1) * stride + i];
-    s2 += part[(int64_t)(g + 2) * stride + i];
-    s3 += part[(int64_t)(g + 3) * stride + i];
+  if (i < n) {
+    int g = grp;
+    for (; g + 24 < G; g += 32) {
+      s0 += part[(int64_t)g * stride + i];
+      s1 += part[(int64_t)(g + 8) * stride + i];
+      s2 += part[(int64_t)(g + 16) * stride + i];
+      s3 += part[(int64_t)(g + 24) * stride + i];
+    }
+    for (; g < G; g += 8) s0 += part[(int64_t)g * stride + i];
   }
-  for (; g < G; ++g) s0 += part[(int64_t)g * stride + i];
-  float s = (s0 + s1) + (s2 + s3);
-  out[i] = accumulate ? out[i] + s : s;
+  sm[grp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (grp == 0 && i < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][lane];
+    out[i] = accumulate ? out[i] + s : s;
+  }
 }
 extern "C" int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,
                                    int64_t part_stride, int accumulate, void* stream) {
   PVB_CHECK_ARG(part && out && G > 0 && n >= 0 && part_stride >= n, "pvb_reduce_partials: bad argument");
   if (n == 0) return 0;
-  reduce_partials_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(part, out, G, n,
+  reduce_partials_kernel<<<pvb::cdiv(n, 32), 256, 0, (cudaStream_t)stream>>>(part, out, G, n,
                                                                               part_stride, accumulate); pvb::count_launch();
   return pvb::launch_status();
 }
@@ -57,12 +67,10 @@ extern "C" int pvb_counter_add(int32_t* counter, int32_t v, void* stream) {
 // torch.optim.Adam (defaults; no amsgrad / weight decay):
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2
 //   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
-__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                 float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
-                                 float b1, float b2, float eps,
-                                 const int32_t* __restrict__ step_counter,
-                                 const int32_t* __restrict__ first_step) {
-  const int step = *step_counter;
+__device__ __forceinline__ void adam_update4(float* __restrict__ p, const float* __restrict__ g,
+                                             float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                             float lr, float b1, float b2, float eps, int step,
+                                             const int32_t* __restrict__ first_step) {
   int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   int last_t = -1;
   float step_size = 0.f, bc2s = 1.f;
@@ -85,6 +93,32 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
     p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
   }
 }
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                 float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                 float b1, float b2, float eps,
+                                 const int32_t* __restrict__ step_counter,
+                                 const int32_t* __restrict__ first_step) {
+  adam_update4(p, g, m, v, n, lr, b1, b2, eps, *step_counter, first_step);
+}
+// same, with the step increment folded in: all CTAs read the counter before taking a ticket,
+// the last ticket holder stores counter + 1 (and re-arms the ticket)
+__global__ void adam_flat_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                      float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                      float lr, float b1, float b2, float eps,
+                                      int32_t* step_counter, const int32_t* __restrict__ first_step,
+                                      int32_t* ticket) {
+  const int step = *reinterpret_cast<volatile int32_t*>(step_counter) + 1;
+  adam_update4(p, g, m, v, n, lr, b1, b2, eps, step, first_step);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int t = atomicAdd(ticket, 1);
+    if (t == (int)gridDim.x - 1) {
+      *step_counter = step;
+      *ticket = 0;
+    }
+  }
+}
 extern "C" int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                              float beta1, float beta2, float eps, const int32_t* step_counter,
                              const int32_t* first_step, void* stream) {
@@ -97,5 +131,19 @@ extern "C" int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64
   adam_flat_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1,
                                                                          beta2, eps, step_counter,
                                                                          first_step); pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_adam_flat_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                                  float beta1, float beta2, float eps, int32_t* step_counter,
+                                  const int32_t* first_step, int32_t* ticket, void* stream) {
+  PVB_CHECK_ARG(p && g && m && v && step_counter && ticket && n >= 0, "pvb_adam_flat_step: bad argument");
+  PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                    ((uintptr_t)v % 16 == 0),
+                "pvb_adam_flat_step: buffers must be 16-byte aligned");
+  if (n == 0) return 0;   // (the counter is not advanced for an empty parameter set)
+  int64_t n4 = (n + 3) / 4;
+  adam_flat_step_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, step_counter, first_step, ticket); pvb::count_launch();
   return pvb::launch_status();
 }

@@ -230,6 +230,9 @@ int launch_sgemm_small(const float* A, const float* B, float* C, float* Cpre, co
   int64_t max_splits = K / 64;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
+  // a forward layer with a fused epilogue: one launch beats split-K + memset + second pass once
+  // a third of the SMs have a tile
+  if (tiles >= 48 && !accumulate && (bias || Cpre || act != PVB_ACT_NONE)) splits = 1;
   int64_t k_chunk = K;
   if (splits > 1) {
     k_chunk = ((K + splits - 1) / splits + SBK - 1) / SBK * SBK;

@@ -2,22 +2,12 @@
 // KL, the coordinate-transform fold into the first decoder layer (and its
 // backward), enumerated discrete heads.  All tiny ([I, Z] sized) work.
 #include "pvb_common.cuh"
+#include "pvb_fold.cuh"
 
 namespace {
-
-// ---- Philox4x32-10 ---------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
-  }
-  return c;
-}
+using pvb::philox4x32_10;
+using pvb::Split;
+using pvb::split_of;
 
 __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed,
                              const int32_t* __restrict__ step_counter, int64_t first_index) {
@@ -68,25 +58,6 @@ __global__ void latent_bwd_kernel(const float* __restrict__ gz, const float* __r
   gmu[o] = g;
   float gsig = g * eps[o] - bw / sigma[o];
   gs_pre[o] = gsig * pvb::sigmoid_f(s_pre[o]);
-}
-
-// ---- fold: (phi, dx, dy, s, zc, cond) -> Uv[i] = (U0 | U1 | v) ---------------
-struct Split {
-  int off_phi, off_t, off_s, off_c;  // offsets into z (-1 if absent)
-};
-__host__ __device__ inline Split split_of(const pvb_fold_cfg& c) {
-  Split s;
-  int o = 0;
-  s.off_phi = s.off_t = s.off_s = -1;
-  if (c.ndim == 1) {
-    if (c.inv & PVB_INV_T) { s.off_t = o; o += 1; }
-  } else {
-    if (c.inv & PVB_INV_R) { s.off_phi = o; o += 1; }
-    if (c.inv & PVB_INV_T) { s.off_t = o; o += 2; }
-    if (c.inv & PVB_INV_S) { s.off_s = o; o += 1; }
-  }
-  s.off_c = o;
-  return s;
 }
 
 __global__ void fold_fwd_kernel(pvb_fold_cfg cfg, const float* __restrict__ z,

@@ -1,0 +1,502 @@
+// Fused small-batch MLP kernels for the encoder / classifier side of the SVI step.
+//
+// At SVI batch sizes the guide's encoder (nets/fc.py:51-61, 97-108, 264-271) is
+// launch-latency bound: [M <= a few thousand] x [<= 256] activations, a dozen tiny
+// GEMM / bias / activation / column-sum launches per direction.  Here:
+//   pvb_mlp_tail_fwd    hidden layers >= 1, the linear heads, the reparameterised sample
+//                       (+ Philox noise), the sampled KL and the coordinate-transform fold
+//                       -- one launch, RB batch rows per CTA, activations stay in smem
+//   pvb_mlp_chain_bwd   heads -> hidden stack backward (gradients wrt pre-activations)
+//   pvb_mlp_wgrad       every dW / db of the stack as one grouped launch
+//   pvb_latent_side_bwd dUv gather + fold backward + latent backward per instance
+// The first (wide) layer stays a plain GEMM (pvb_linear_fwd with fused bias + activation).
+#include "pvb_common.cuh"
+#include "pvb_fold.cuh"
+
+namespace {
+
+constexpr int RB = 8;        // batch rows per CTA
+constexpr int MT = 256;      // threads per CTA
+constexpr int MAXW = PVB_MLP_MAX_WIDTH;
+constexpr int MAXHD = PVB_MLP_MAX_HEAD_DIM;
+constexpr int KC = 16;       // K chunk of the staged weight tile
+constexpr int WLD = MAXW + 1;
+
+// out_s[r][n] = act(b[n] + sum_k in_s[r][k] W[n][k]),  r < RB, n < N <= 256, K <= 256.
+// Thread (n0 = tid % 128, half = tid / 128) owns outputs n0, n0 + 128 of rows 4*half .. +3.
+// W [N][K] row-major is staged K-chunk by K-chunk, transposed, through Ws[KC][WLD].
+__device__ __forceinline__ void dense_rows(const float* __restrict__ W, const float* __restrict__ b,
+                                           int N, int K, const float* in_s, float* out_s, int act,
+                                           float* __restrict__ h_g, float* __restrict__ pre_g,
+                                           int64_t row0, int64_t M, float* Ws) {
+  const int tid = threadIdx.x, n0 = tid & 127, half = tid >> 7;
+  float acc[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    const int kmax = (K - k0 < KC) ? K - k0 : KC;
+    __syncthreads();   // previous chunk consumed (and in_s complete on the first pass)
+    for (int idx = tid; idx < N * KC; idx += MT) {
+      int n = idx / KC, kk = idx % KC;
+      Ws[kk * WLD + n] = (kk < kmax) ? __ldg(W + (size_t)n * K + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+    const bool two = n0 + 128 < N;
+    if (n0 < N) {
+#pragma unroll 4
+      for (int kk = 0; kk < kmax; ++kk) {
+        float w0 = Ws[kk * WLD + n0];
+        float w1 = two ? Ws[kk * WLD + n0 + 128] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float x = in_s[(half * 4 + i) * MAXW + k0 + kk];
+          acc[0][i] = fmaf(x, w0, acc[0][i]);
+          acc[1][i] = fmaf(x, w1, acc[1][i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    int n = n0 + 128 * j;
+    if (n >= N) continue;
+    float bn = b ? __ldg(b + n) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int r = half * 4 + i;
+      float v = acc[j][i] + bn;
+      float a = pvb::act_fwd(v, act);
+      out_s[r * MAXW + n] = a;
+      if (row0 + r < M) {
+        if (h_g) h_g[(row0 + r) * N + n] = a;
+        if (pre_g) pre_g[(row0 + r) * N + n] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MT) mlp_tail_fwd_kernel(pvb_mlp_tail_args a) {
+  __shared__ float bufA[RB * MAXW];
+  __shared__ float bufB[RB * MAXW];
+  __shared__ float Ws[KC * WLD];
+  __shared__ float heads[PVB_MLP_MAX_HEADS][RB * MAXW / 4];   // [RB][<=64]
+  __shared__ float zs[RB * MAXHD];
+  __shared__ pvb::Xform xf[RB];
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * RB;
+  // stage the input rows (zero beyond M)
+  for (int idx = tid; idx < RB * a.w_in; idx += MT) {
+    int r = idx / a.w_in, k = idx % a.w_in;
+    bufA[r * MAXW + k] = (row0 + r < a.M) ? a.h_in[(row0 + r) * a.w_in + k] : 0.f;
+  }
+  float* cur = bufA;
+  float* nxt = bufB;
+  int K = a.w_in;
+  for (int l = 0; l < a.n_layers; ++l) {
+    dense_rows(a.W[l], a.b[l], a.width[l], K, cur, nxt, a.act, a.h[l], a.pre[l], row0, a.M, Ws);
+    float* t = cur; cur = nxt; nxt = t;
+    K = a.width[l];
+  }
+  // linear heads (outputs re-use the [RB][MAXW] addressing of dense_rows: head dims <= 64,
+  // so each head buffer holds RB rows at stride MAXW only for n < 64 -> use a compact copy)
+  for (int k = 0; k < a.n_heads; ++k) {
+    dense_rows(a.hW[k], a.hb[k], a.hdim[k], K, cur, nxt, PVB_ACT_NONE, a.hout[k], nullptr, row0,
+               a.M, Ws);
+    __syncthreads();
+    for (int idx = tid; idx < RB * a.hdim[k]; idx += MT) {
+      int r = idx / a.hdim[k], n = idx % a.hdim[k];
+      heads[k][r * MAXHD + n] = nxt[r * MAXW + n];
+    }
+    __syncthreads();
+  }
+  if (!a.gauss) return;
+  // reparameterised sample + sampled KL (pvb_randn + pvb_latent_fwd)
+  const int Z = a.hdim[0];
+  if (tid < RB && row0 + tid < a.M) {
+    const int r = tid;
+    const int64_t i = row0 + r;
+    const uint32_t step = (a.gen_eps && a.step_counter) ? (uint32_t)(*a.step_counter) : 0u;
+    float acc = 0.f;
+    for (int d = 0; d < Z; ++d) {
+      const int64_t o = i * Z + d;
+      float e;
+      if (a.gen_eps) {
+        e = pvb::philox_randn((uint64_t)(a.first_index + o), step, a.seed);
+        a.eps[o] = e;
+      } else {
+        e = a.eps[o];
+      }
+      float sg = pvb::softplus_f(heads[1][r * MAXHD + d]);
+      float zz = fmaf(sg, e, heads[0][r * MAXHD + d]);
+      a.sigma[o] = sg;
+      a.z[o] = zz;
+      zs[r * MAXHD + d] = zz;
+      acc += -0.5f * zz * zz + 0.5f * e * e + logf(sg);
+    }
+    a.kl[i] = acc;
+    if (a.fold) xf[r] = pvb::xform_of(a.cfg, pvb::split_of(a.cfg), zs + r * MAXHD);
+  }
+  if (!a.fold) return;
+  __syncthreads();
+  const pvb::Split sp = pvb::split_of(a.cfg);
+  const int Hd = a.cfg.hidden;
+  for (int idx = tid; idx < RB * Hd; idx += MT) {
+    int r = idx / Hd, h = idx % Hd;
+    int64_t i = row0 + r;
+    if (i >= a.M) continue;
+    const float* cond_i = a.cond ? a.cond + i * a.cfg.cond_dim : nullptr;
+    pvb::fold_unit(a.cfg, sp, xf[r], zs + r * MAXHD, cond_i, a.Wc, a.bc, a.Wz, h,
+                   a.Uv + i * 3 * Hd);
+  }
+}
+
+// ---- heads + hidden stack backward ---------------------------------------------------------
+// dh[r][k] (k < Kw) += sum_n g_s[r][n] Wt[n][k]   with W [Nn][Kw] row-major (coalesced over k)
+__device__ __forceinline__ void back_rows(const float* __restrict__ W, int Nn, int Kw,
+                                          const float* g_s, int g_ld, float acc[2][4]) {
+  const int tid = threadIdx.x, k0 = tid & 127, half = tid >> 7;
+  if (k0 >= Kw) return;
+  const bool two = k0 + 128 < Kw;
+  for (int n = 0; n < Nn; ++n) {
+    float w0 = __ldg(W + (size_t)n * Kw + k0);
+    float w1 = two ? __ldg(W + (size_t)n * Kw + k0 + 128) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float g = g_s[(half * 4 + i) * g_ld + n];
+      acc[0][i] = fmaf(g, w0, acc[0][i]);
+      acc[1][i] = fmaf(g, w1, acc[1][i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MT) mlp_chain_bwd_kernel(pvb_mlp_chain_args a) {
+  __shared__ float gs[PVB_MLP_MAX_HEADS][RB * MAXHD];
+  __shared__ float dp[RB * MAXW];
+  const int tid = threadIdx.x, k0 = tid & 127, half = tid >> 7;
+  const int64_t row0 = (int64_t)blockIdx.x * RB;
+  for (int k = 0; k < a.n_heads; ++k)
+    for (int idx = tid; idx < RB * a.hdim[k]; idx += MT) {
+      int r = idx / a.hdim[k], n = idx % a.hdim[k];
+      gs[k][r * MAXHD + n] = (row0 + r < a.M) ? a.g[k][(row0 + r) * a.hdim[k] + n] : 0.f;
+    }
+  __syncthreads();
+  float acc[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+  int l = a.n_layers - 1;
+  for (int k = 0; k < a.n_heads; ++k) back_rows(a.hW[k], a.hdim[k], a.width[l], gs[k], MAXHD, acc);
+  for (; l >= 0; --l) {
+    const int Wd = a.width[l];
+    // dpre = dh * act'(h)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int k = k0 + 128 * j;
+      if (k >= Wd) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int r = half * 4 + i;
+        float d = 0.f;
+        if (row0 + r < a.M) {
+          int64_t o = (row0 + r) * Wd + k;
+          float p = a.pre[l] ? a.pre[l][o] : 0.f;
+          d = acc[j][i] * pvb::act_grad(a.h[l][o], p, a.act);
+          a.dpre[l][o] = d;
+        }
+        dp[r * MAXW + k] = d;
+      }
+    }
+    if (l == 0) break;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    back_rows(a.W[l], Wd, a.width[l - 1], dp, MAXW, acc);
+    __syncthreads();
+  }
+}
+
+// ---- grouped weight gradients ------------------------------------------------------------------
+constexpr int WG_T = 32, WG_NT = 128, WG_MAXP = 8;
+struct WgradArgs {
+  int64_t M;
+  int n_prob;
+  pvb_wgrad_problem p[WG_MAXP];
+  int tile0[WG_MAXP + 1];
+};
+
+__global__ void __launch_bounds__(WG_NT) mlp_wgrad_kernel(WgradArgs a) {
+  __shared__ float As[WG_T][WG_T + 4];   // [m][n]
+  __shared__ float Bs[WG_T][WG_T + 4];   // [m][k]
+  int pi = 0;
+  while (pi + 1 < a.n_prob && (int)blockIdx.x >= a.tile0[pi + 1]) ++pi;
+  const pvb_wgrad_problem pr = a.p[pi];
+  const int t = blockIdx.x - a.tile0[pi];
+  const int tk_n = (pr.K + WG_T - 1) / WG_T;
+  const int n0 = (t / tk_n) * WG_T, kk0 = (t % tk_n) * WG_T;
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;   // 8 k-quads x 16 n-pairs
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float bsum = 0.f;   // threads 0..31 of the k-tile 0 CTA: column sum of d
+  const bool do_bias = pr.db && kk0 == 0;
+  for (int64_t m0 = 0; m0 < a.M; m0 += WG_T) {
+#pragma unroll
+    for (int it = 0; it < (WG_T * WG_T) / WG_NT; ++it) {
+      int idx = tid + it * WG_NT;
+      int c = idx % WG_T, m = idx / WG_T;
+      int64_t gm = m0 + m;
+      As[m][c] = (gm < a.M && n0 + c < pr.N) ? pr.d[gm * pr.N + n0 + c] : 0.f;
+      Bs[m][c] = (gm < a.M && kk0 + c < pr.K) ? pr.x[gm * pr.K + kk0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < WG_T; ++m) {
+      float2 a2 = *reinterpret_cast<const float2*>(&As[m][ty * 2]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[m][tx * 4]);
+      acc[0][0] = fmaf(a2.x, b4.x, acc[0][0]); acc[0][1] = fmaf(a2.x, b4.y, acc[0][1]);
+      acc[0][2] = fmaf(a2.x, b4.z, acc[0][2]); acc[0][3] = fmaf(a2.x, b4.w, acc[0][3]);
+      acc[1][0] = fmaf(a2.y, b4.x, acc[1][0]); acc[1][1] = fmaf(a2.y, b4.y, acc[1][1]);
+      acc[1][2] = fmaf(a2.y, b4.z, acc[1][2]); acc[1][3] = fmaf(a2.y, b4.w, acc[1][3]);
+    }
+    if (do_bias && tid < WG_T) {
+#pragma unroll
+      for (int m = 0; m < WG_T; ++m) bsum += As[m][tid];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int n = n0 + ty * 2 + i;
+    if (n >= pr.N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = kk0 + tx * 4 + j;
+      if (k < pr.K) pr.dW[(size_t)n * pr.K + k] += acc[i][j];
+    }
+  }
+  if (do_bias && tid < WG_T && n0 + tid < pr.N) pr.db[n0 + tid] += bsum;
+}
+
+// ---- per-instance latent-side backward ---------------------------------------------------------
+constexpr int LS_G = 256, LS_T = 128, LS_MAXR = 40;
+
+__global__ void __launch_bounds__(LS_T)
+latent_side_bwd_kernel(pvb_fold_cfg cfg, const float* __restrict__ z, const float* __restrict__ cond,
+                       const float* __restrict__ Wc, const float* __restrict__ Wz,
+                       const float* __restrict__ gUv, const float* __restrict__ gUv_part, int N,
+                       float* __restrict__ gz, float* __restrict__ gcond, float* __restrict__ part,
+                       const float* __restrict__ eps, const float* __restrict__ sigma,
+                       const float* __restrict__ s_pre, const float* __restrict__ w, float beta,
+                       float* __restrict__ gmu, float* __restrict__ gs_pre, int64_t I) {
+  extern __shared__ float sh[];  // [Hd*(ndim+1+LC)] weight-grad accumulators + reduction scratch
+  const pvb::Split sp = pvb::split_of(cfg);
+  const int Z = sp.off_c + cfg.latent_dim;
+  const int LC = cfg.latent_dim + cfg.cond_dim;
+  const int Hd = cfg.hidden;
+  const int nd = cfg.ndim;
+  const int per_h = nd + 1 + LC;
+  float* acc = sh;                        // [Hd][per_h]
+  float* red = sh + (size_t)Hd * per_h;   // [4][LS_MAXR]
+  float* gzs = red + 4 * LS_MAXR;         // [LS_MAXR] dz of the current instance
+  for (int k = threadIdx.x; k < Hd * per_h; k += blockDim.x) acc[k] = 0.f;
+  __syncthreads();
+  const int NR = 4 + LC;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int TILE = PVB_TC_TILE, SLOTS = PVB_TC_MAX_SLOTS;
+
+  for (int64_t i = blockIdx.x; i < I; i += gridDim.x) {
+    const float* zi = z + i * Z;
+    const pvb::Xform t = pvb::xform_of(cfg, sp, zi);
+    const float c = t.c, sn = t.sn, s = t.s, dx = t.dx, dy = t.dy;
+    float r[LS_MAXR];
+#pragma unroll
+    for (int k = 0; k < LS_MAXR; ++k) r[k] = 0.f;
+    const int64_t t0 = gUv_part ? (i * N) / TILE : 0, t1 = gUv_part ? ((i + 1) * N - 1) / TILE : 0;
+    for (int h = threadIdx.x; h < Hd; h += blockDim.x) {
+      float g0, g1, gv;
+      if (gUv_part) {
+        // sum over the tiles touching instance i of its slot partial (fixed order)
+        g0 = g1 = gv = 0.f;
+        for (int64_t tt = t0; tt <= t1; ++tt) {
+          int slot = (int)(i - (tt * TILE) / N);
+          const float* p = gUv_part + tt * (SLOTS * 3 * Hd) + slot * 3 * Hd;
+          g0 += p[h];
+          g1 += p[Hd + h];
+          gv += p[2 * Hd + h];
+        }
+      } else {
+        const float* g = gUv + i * 3 * Hd;
+        g0 = g[h]; g1 = g[Hd + h]; gv = g[2 * Hd + h];
+      }
+      float* a = acc + (size_t)h * per_h;
+      if (nd == 2) {
+        float w0 = Wc[h * 2], w1 = Wc[h * 2 + 1];
+        a[0] += gv * dx + s * (g0 * c - g1 * sn);
+        a[1] += gv * dy + s * (g0 * sn + g1 * c);
+        r[0] += s * (g0 * (-w0 * sn + w1 * c) + g1 * (-w0 * c - w1 * sn));  // d/dphi
+        r[1] += gv * w0;                                                      // d/d(dx)
+        r[2] += gv * w1;                                                      // d/d(dy)
+        r[3] += g0 * (w0 * c + w1 * sn) + g1 * (-w0 * sn + w1 * c);           // d/ds
+      } else {
+        float w0 = Wc[h];
+        a[0] += gv * dx + g0;
+        r[1] += gv * w0;
+      }
+      a[nd] += gv;  // bias
+      for (int j = 0; j < cfg.latent_dim; ++j) {
+        a[nd + 1 + j] += gv * zi[sp.off_c + j];
+        if (4 + j < LS_MAXR) r[4 + j] += gv * Wz[h * LC + j];
+      }
+      for (int j = 0; j < cfg.cond_dim; ++j) {
+        int jj = cfg.latent_dim + j;
+        a[nd + 1 + jj] += gv * cond[i * cfg.cond_dim + j];
+        if (4 + jj < LS_MAXR) r[4 + jj] += gv * Wz[h * LC + jj];
+      }
+    }
+    __syncthreads();
+    for (int k = 0; k < NR; ++k) {
+      float v = pvb::warp_sum(r[k]);
+      if (lane == 0) red[wid * LS_MAXR + k] = v;
+    }
+    if (threadIdx.x < Z) gzs[threadIdx.x] = 0.f;
+    __syncthreads();
+    if (threadIdx.x < NR) {
+      int k = threadIdx.x;
+      float v = 0.f;
+      for (int ww = 0; ww < LS_T / 32; ++ww) v += red[ww * LS_MAXR + k];
+      int zo = -1;
+      if (k == 0) { if (sp.off_phi >= 0) zo = sp.off_phi; }
+      else if (k == 1) { if (sp.off_t >= 0) { zo = sp.off_t; v *= cfg.dx_prior; } }
+      else if (k == 2) { if (sp.off_t >= 0 && nd == 2) { zo = sp.off_t + 1; v *= cfg.dy_prior; } }
+      else if (k == 3) { if (sp.off_s >= 0) { zo = sp.off_s; v *= cfg.sc_prior; } }
+      else if (k - 4 < cfg.latent_dim) zo = sp.off_c + (k - 4);
+      else if (gcond) gcond[i * cfg.cond_dim + (k - 4 - cfg.latent_dim)] = v;
+      if (zo >= 0) {
+        gz[i * Z + zo] = v;
+        gzs[zo] = v;
+      }
+    }
+    __syncthreads();
+    if (gmu && threadIdx.x < Z) {
+      // pvb_latent_bwd: loss = -sum w (ll + beta kl)
+      const int64_t o = i * Z + threadIdx.x;
+      const float bw = beta * (w ? w[i] : 1.f);
+      const float zz = z[o];
+      const float g = gzs[threadIdx.x] + bw * zz;
+      gmu[o] = g;
+      const float gsig = g * eps[o] - bw / sigma[o];
+      gs_pre[o] = gsig * pvb::sigmoid_f(s_pre[o]);
+    }
+    __syncthreads();
+  }
+  float* p = part + (size_t)blockIdx.x * Hd * per_h;
+  // partial layout: gWc[Hd][nd] | gbc[Hd] | gWz[Hd][LC]
+  for (int k = threadIdx.x; k < Hd * per_h; k += blockDim.x) {
+    int h = k / per_h, q = k % per_h;
+    float v = acc[k];
+    if (q < nd) p[h * nd + q] = v;
+    else if (q == nd) p[Hd * nd + h] = v;
+    else p[Hd * (nd + 1) + h * LC + (q - nd - 1)] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int pvb_mlp_tail_fwd(const pvb_mlp_tail_args* a, void* stream) {
+  PVB_CHECK_ARG(a && a->M >= 0 && a->h_in, "pvb_mlp_tail_fwd: bad argument");
+  PVB_CHECK_ARG(a->n_layers >= 0 && a->n_layers <= 3 && a->n_heads >= 1 && a->n_heads <= PVB_MLP_MAX_HEADS,
+                "pvb_mlp_tail_fwd: up to 3 hidden layers and 1..3 heads");
+  PVB_CHECK_ARG(a->w_in > 0 && a->w_in <= MAXW, "pvb_mlp_tail_fwd: input width %d > %d", a->w_in, MAXW);
+  for (int l = 0; l < a->n_layers; ++l)
+    PVB_CHECK_ARG(a->width[l] > 0 && a->width[l] <= MAXW && a->W[l] && a->h[l],
+                  "pvb_mlp_tail_fwd: bad layer %d", l);
+  for (int k = 0; k < a->n_heads; ++k)
+    PVB_CHECK_ARG(a->hdim[k] > 0 && a->hdim[k] <= MAXHD && a->hW[k] && a->hout[k],
+                  "pvb_mlp_tail_fwd: bad head %d", k);
+  PVB_CHECK_ARG(a->act >= 0 && a->act <= PVB_ACT_SIGMOID, "pvb_mlp_tail_fwd: unknown activation");
+  if (a->gauss) {
+    PVB_CHECK_ARG(a->n_heads >= 2 && a->hdim[0] == a->hdim[1] && a->eps && a->sigma && a->z && a->kl,
+                  "pvb_mlp_tail_fwd: gaussian head needs mu / s_pre heads and output buffers");
+  }
+  if (a->fold) {
+    PVB_CHECK_ARG(a->gauss && a->Wc && a->bc && a->Uv, "pvb_mlp_tail_fwd: fold needs the sample");
+    PVB_CHECK_ARG(a->cfg.cond_dim == 0 || a->cond, "pvb_mlp_tail_fwd: cond required");
+    pvb::Split sp = pvb::split_of(a->cfg);
+    PVB_CHECK_ARG(sp.off_c + a->cfg.latent_dim == a->hdim[0], "pvb_mlp_tail_fwd: latent split != Z");
+  }
+  if (a->M == 0) return 0;
+  mlp_tail_fwd_kernel<<<pvb::cdiv(a->M, RB), MT, 0, (cudaStream_t)stream>>>(*a);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_mlp_chain_bwd(const pvb_mlp_chain_args* a, void* stream) {
+  PVB_CHECK_ARG(a && a->M >= 0, "pvb_mlp_chain_bwd: bad argument");
+  PVB_CHECK_ARG(a->n_layers >= 1 && a->n_layers <= PVB_MLP_MAX_LAYERS && a->n_heads >= 1 &&
+                    a->n_heads <= PVB_MLP_MAX_HEADS,
+                "pvb_mlp_chain_bwd: 1..4 layers and 1..3 heads");
+  for (int l = 0; l < a->n_layers; ++l)
+    PVB_CHECK_ARG(a->width[l] > 0 && a->width[l] <= MAXW && a->h[l] && a->dpre[l] && (l == 0 || a->W[l]),
+                  "pvb_mlp_chain_bwd: bad layer %d", l);
+  for (int k = 0; k < a->n_heads; ++k)
+    PVB_CHECK_ARG(a->hdim[k] > 0 && a->hdim[k] <= MAXHD && a->hW[k] && a->g[k],
+                  "pvb_mlp_chain_bwd: bad head %d", k);
+  PVB_CHECK_ARG(a->act != PVB_ACT_GELU || a->pre[0], "pvb_mlp_chain_bwd: gelu needs the pre-activations");
+  if (a->M == 0) return 0;
+  mlp_chain_bwd_kernel<<<pvb::cdiv(a->M, RB), MT, 0, (cudaStream_t)stream>>>(*a);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_mlp_wgrad(const pvb_wgrad_problem* problems, int n_problems, int64_t M,
+                             void* stream) {
+  PVB_CHECK_ARG(problems && n_problems >= 1 && n_problems <= WG_MAXP && M >= 0,
+                "pvb_mlp_wgrad: 1..8 problems");
+  if (M == 0) return 0;
+  WgradArgs a;
+  a.M = M;
+  a.n_prob = n_problems;
+  int tiles = 0;
+  for (int i = 0; i < n_problems; ++i) {
+    PVB_CHECK_ARG(problems[i].d && problems[i].x && problems[i].dW && problems[i].N > 0 && problems[i].K > 0,
+                  "pvb_mlp_wgrad: bad problem %d", i);
+    a.p[i] = problems[i];
+    a.tile0[i] = tiles;
+    tiles += ((problems[i].N + WG_T - 1) / WG_T) * ((problems[i].K + WG_T - 1) / WG_T);
+  }
+  a.tile0[n_problems] = tiles;
+  mlp_wgrad_kernel<<<tiles, WG_NT, 0, (cudaStream_t)stream>>>(a);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_latent_side_bwd(const pvb_fold_cfg* cfg, const float* z, const float* cond,
+                                   const float* Wc, const float* Wz, const float* gUv,
+                                   const float* gUv_part, int N, float* gz, float* gcond,
+                                   float* part, const float* eps, const float* sigma,
+                                   const float* s_pre, const float* w, float beta, float* gmu,
+                                   float* gs_pre, int64_t I, void* stream) {
+  PVB_CHECK_ARG(cfg && z && Wc && (gUv || gUv_part) && gz && part && I >= 0,
+                "pvb_latent_side_bwd: bad argument");
+  PVB_CHECK_ARG(cfg->ndim == 1 || cfg->ndim == 2, "pvb_latent_side_bwd: ndim must be 1 or 2");
+  PVB_CHECK_ARG(cfg->latent_dim + cfg->cond_dim + 4 <= LS_MAXR, "pvb_latent_side_bwd: latent_dim + cond_dim > 36");
+  PVB_CHECK_ARG(!gUv_part || N >= 32, "pvb_latent_side_bwd: tile partials need N >= 32");
+  PVB_CHECK_ARG(!gmu || (gs_pre && eps && sigma && s_pre), "pvb_latent_side_bwd: latent backward needs eps/sigma/s_pre");
+  if (I == 0) return 0;
+  int per_h = cfg->ndim + 1 + cfg->latent_dim + cfg->cond_dim;
+  size_t smem = ((size_t)cfg->hidden * per_h + 5 * LS_MAXR) * sizeof(float);
+  PVB_CHECK_ARG(smem <= 200 * 1024, "pvb_latent_side_bwd: hidden*(dims) too large");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(latent_side_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  latent_side_bwd_kernel<<<LS_G, LS_T, smem, (cudaStream_t)stream>>>(
+      *cfg, z, cond, Wc, Wz, gUv, gUv_part, N, gz, gcond, part, eps, sigma, s_pre, w, beta, gmu,
+      gs_pre, I);
+  pvb::count_launch();
+  return pvb::launch_status();
+}

@@ -44,8 +44,9 @@ constexpr int TILE = 128;          // rows per tile
 constexpr int NEPI = 512;          // 16 epilogue warps: (lane quarter q = warp%4) x (column group cg = warp/4)
 constexpr int NTHREADS = NEPI + 32;  // + one MMA-issuing warp
 constexpr int MMA_WARP = NEPI / 32;
-constexpr int MAX_SLOTS = 4;       // samples a 128-row tile can touch when N >= MIN_PIX
-constexpr int MIN_PIX = 43;        // floor(127/N) + 2 <= 4
+constexpr int MAX_SLOTS = 5;       // samples a 128-row tile can touch when N >= MIN_PIX
+constexpr int MIN_PIX = 32;        // floor(127/N) + 2 <= 5
+static_assert(TILE == PVB_TC_TILE && MAX_SLOTS == PVB_TC_MAX_SLOTS, "pvb.h constants out of sync");
 constexpr int CHUNK = TILE * 16;   // bytes of one chunk-column (8 fp16 columns x 128 rows)
 
 // ---- shared memory map (bytes) ------------------------------------------------
@@ -60,10 +61,15 @@ constexpr int SM_DL = SM_G + 2 * CHUNK;           // [128][16] dl in column 0
 constexpr int SM_F32 = SM_DL + 2 * CHUNK;         // fp32 scratch, see below
 constexpr int F_B1 = 0, F_B2 = 128, F_WO = 256;   // biases / out weights
 constexpr int UV_FLOATS = MAX_SLOTS * 3 * HD;
-constexpr int F_UV = 384;                         // [2][MAX_SLOTS][3][128]  (double buffered)
-constexpr int F_X = F_UV + 2 * UV_FLOATS;         // [2][128] targets of the tile rows
-constexpr int F_WI = F_X + 2 * TILE;              // [2][128] instance weights of the tile rows
-constexpr int F_PART = F_WI + 2 * TILE;           // [4][128] partial dots per column group
+// per-tile staging (single-buffered: staged for tile t+1 once GEMM1 of tile t has completed,
+// i.e. after every warp has consumed tile t's copy; published by the S4 barrier of tile t)
+constexpr int F_UV = 384;                         // [MAX_SLOTS][3][128] first-layer coefficients
+constexpr int F_X = F_UV + UV_FLOATS;             // [128] targets of the tile rows
+constexpr int F_WI = F_X + TILE;                  // [128] instance weights of the tile rows
+constexpr int F_GX = F_WI + TILE;                 // [128] grid x of the tile rows
+constexpr int F_GY = F_GX + TILE;                 // [128] grid y
+constexpr int F_GI = F_GY + TILE;                 // [128] int: slot | valid << 8 | n_slots << 16
+constexpr int F_PART = F_GI + TILE;               // [4][128] partial dots per column group
 constexpr int F_RED = F_PART + 4 * TILE;          // [32] block reduction
 constexpr int F_END = F_RED + 32;
 constexpr int SM_BAR = SM_F32 + F_END * 4;        // mbarriers + tmem base
@@ -95,7 +101,13 @@ __device__ long long g_trace[2][64][32];
       g_trace[role][trace_it][ev] = clock64();                                       \
   } while (0)
 #define TRACE_NEXT() ++trace_it
+__device__ long long g_wtrace[16][16];
+#define WTRACE(ev)                                                                    \
+  do {                                                                               \
+    if (blockIdx.x == 0 && lane == 0 && trace_it == 3) g_wtrace[warp][ev] = clock64(); \
+  } while (0)
 #else
+#define WTRACE(ev) do {} while (0)
 #define TRACE(role, ev) do {} while (0)
 #define TRACE_NEXT() do {} while (0)
 #endif
@@ -194,13 +206,6 @@ struct TileCursor {
   int ib_first;      // i_first % B  (row of the target image)
   int off;           // tile*TILE - i_first*N, in [0, N)
 };
-struct RowGeo {
-  int64_t r_glob;
-  float gx, gy;
-  int slot, n_slots;
-  bool valid;
-};
-
 __device__ __forceinline__ void cursor_advance(TileCursor& c, const Params& P) {
   c.tile += gridDim.x;
   c.i_first += P.step_q;
@@ -219,34 +224,35 @@ __device__ __forceinline__ void split_slot(int rem, int N, int& slot, int& pix) 
   pix = rem;
 }
 
-// row geometry of the cursor's tile + asynchronous staging of its Uv rows / targets / weights
-// into buffer `buf`
-__device__ __forceinline__ RowGeo stage_tile(const Params& P, float* f32, const TileCursor& c,
-                                             int buf, int tid, int row, int cg) {
-  RowGeo g;
-  g.r_glob = c.tile * TILE + row;
-  g.valid = g.r_glob < P.R;
+// asynchronous staging of the cursor's tile: Uv rows (all threads), targets (column group 0),
+// instance weights (group 1), row geometry (group 3)
+__device__ __forceinline__ void stage_tile(const Params& P, float* f32, const TileCursor& c,
+                                           int tid, int row, int cg) {
   const int64_t left = P.R - c.tile * TILE;                 // rows from the tile start to R
   const int last_row = left < TILE ? (int)left - 1 : TILE - 1;
   int last_slot, last_pix;
   split_slot(c.off + last_row, P.N, last_slot, last_pix);
-  g.n_slots = last_slot + 1;
-  int pix;
-  split_slot(c.off + (g.valid ? row : 0), P.N, g.slot, pix);
-  g.gx = 0.f;
-  g.gy = 0.f;
-  pvb::grid_xy(pix, P.H, P.W, P.ndim, g.gx, g.gy);
-  if (tid < g.n_slots * (3 * HD / 4))
-    cp_async16(f32 + F_UV + buf * UV_FLOATS + tid * 4, P.Uv + c.i_first * 3 * HD + tid * 4);
-  if (g.valid) {
-    if (cg == 0 && P.x) {
-      int ib = c.ib_first + g.slot;
+  const int n_slots = last_slot + 1;
+  if (tid < n_slots * (3 * HD / 4))
+    cp_async16(f32 + F_UV + tid * 4, P.Uv + c.i_first * 3 * HD + tid * 4);
+  const bool valid = row <= last_row;
+  int slot, pix;
+  split_slot(c.off + (valid ? row : 0), P.N, slot, pix);
+  if (cg == 0) {
+    if (valid && P.x) {
+      int ib = c.ib_first + slot;
       while (ib >= (int)P.B) ib -= (int)P.B;
-      cp_async4(f32 + F_X + buf * TILE + row, P.x + (int64_t)ib * P.N + pix);
+      cp_async4(f32 + F_X + row, P.x + (int64_t)ib * P.N + pix);
     }
-    if (cg == 1 && P.w) cp_async4(f32 + F_WI + buf * TILE + row, P.w + c.i_first + g.slot);
+  } else if (cg == 1) {
+    if (valid && P.w) cp_async4(f32 + F_WI + row, P.w + c.i_first + slot);
+  } else if (cg == 3) {
+    float gx = 0.f, gy = 0.f;
+    pvb::grid_xy(pix, P.H, P.W, P.ndim, gx, gy);
+    f32[F_GX + row] = gx;
+    f32[F_GY + row] = gy;
+    reinterpret_cast<int*>(f32)[F_GI + row] = slot | ((int)valid << 8) | (n_slots << 16);
   }
-  return g;
 }
 
 // chunk j of this thread -> tensor-memory A operand, then signal column group j.
@@ -305,9 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       *reinterpret_cast<uint4*>(smem + SM_DL + umma::tile_off(TILE, row, 8)) = zero;
     } else {
       f32[F_X + row] = 0.f;
-      f32[F_X + TILE + row] = 0.f;
       f32[F_WI + row] = 1.f;
-      f32[F_WI + TILE + row] = 1.f;
     }
   }
   if (warp == MMA_WARP) umma::tmem_alloc<TM_COLS>(tmem_slot);
@@ -462,30 +466,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     uint32_t aph = 0, dph = 0, wph = 0, oph = 0;
     int64_t prev_tile = -1;
     int prev_slots = 0;
-    int buf = 0;
     TileCursor cur_c;
     cur_c.tile = blockIdx.x;                       // grid <= tiles: every CTA owns a tile
     cur_c.i_first = (cur_c.tile * TILE) / P.N;     // the only 64-bit divisions of the kernel
     cur_c.off = (int)(cur_c.tile * TILE - cur_c.i_first * P.N);
     cur_c.ib_first = (int)(cur_c.i_first % P.B);
-    RowGeo cur = stage_tile(P, f32, cur_c, 0, tid, row, cg);
+    stage_tile(P, f32, cur_c, tid, row, cg);
     cp_async_wait_all();
     epi_bar();
     while (cur_c.tile < P.tiles) {
       const int64_t tile = cur_c.tile;
       any_tile = true;
       TRACE(0, 0);
-      const bool valid = cur.valid;
-      const float gx = cur.gx, gy = cur.gy;
-      const int slot = cur.slot;
-      const int64_t r_glob = cur.r_glob;
-      const int n_slots = cur.n_slots;
-      const float xv = f32[F_X + buf * TILE + row];    // staged one tile ago (or before the loop)
-      const float wi = f32[F_WI + buf * TILE + row];
+      // this row's staged geometry / target / weight (published by the previous S4 barrier)
+      const int gi = reinterpret_cast<const int*>(f32)[F_GI + row];
+      const bool valid = (gi >> 8) & 1;
+      const int slot = gi & 0xff, n_slots = gi >> 16;
+      const float gx = f32[F_GX + row], gy = f32[F_GY + row];
+      const int64_t r_glob = tile * TILE + row;
+      const float xv = f32[F_X + row];
+      const float wi = f32[F_WI + row];
       uint4 out[4];
       // ---- S0: first layer h0 = tanh(U g + v) -> TMEM A (+ A0) ------------------------------
       {
-        const float* u = f32 + F_UV + buf * UV_FLOATS + slot * 3 * HD;
+        const float* u = f32 + F_UV + slot * 3 * HD;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c0 = 8 * (4 * j + cg);
@@ -517,16 +521,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           umma::mbar_wait(bars + BAR_DUV, dph);
           dph ^= 1;
           umma::fence_after_sync();
-          if (cg == 1) {
-            // per-tile dUv partials of the previous tile: lane == hidden unit
-            float v[16];
-            umma::tmem_ld16(tm_lane + TM_DUV, v);
-            umma::tmem_ld_wait();
-            float* dst = P.gUv_part + prev_tile * (MAX_SLOTS * 3 * HD);
-#pragma unroll
-            for (int n = 0; n < MAX_SLOTS * 3; ++n)
-              if (n < prev_slots * 3) dst[n * HD + row] = v[n];   // unused slots are never read
-          }
         }
         if (cg >= 2) {
           // G[row][3*slot + {0,1,2}] = {gx, gy, 1}; column groups 2 and 3 fill 8 columns each
@@ -543,16 +537,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
               *reinterpret_cast<uint4*>(g8);
         }
         signal_smem(bars, 0);   // h0 (and G) visible to the tensor core
+        if (prev_tile >= 0 && cg == 1) {
+          // per-tile dUv partials of the previous tile: lane == hidden unit (after the fence:
+          // a MEMBAR would otherwise wait for these global stores)
+          float v[16];
+          umma::tmem_ld16(tm_lane + TM_DUV, v);
+          umma::tmem_ld_wait();
+          float* dst = P.gUv_part + prev_tile * (MAX_SLOTS * 3 * HD);
+#pragma unroll
+          for (int n = 0; n < MAX_SLOTS * 3; ++n)
+            if (n < prev_slots * 3) dst[n * HD + row] = v[n];   // unused slots are never read
+        }
       }
       TRACE(0, 5);
       prev_tile = tile;
       prev_slots = n_slots;
-      // stage the next tile (geometry now; Uv / targets / weights land asynchronously in the
-      // other buffer and are made visible by the S4 barrier below)
-      TileCursor nxt_c = cur_c;
-      cursor_advance(nxt_c, P);
-      RowGeo nxt = cur;
-      if (nxt_c.tile < P.tiles) nxt = stage_tile(P, f32, nxt_c, buf ^ 1, tid, row, cg);
       float v[32];
       TRACE(0, 6);
       // ---- S2: h1 = tanh(ACC + b1) -> TMEM A (+ A1) -------------------------------------------
@@ -570,6 +569,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         store_tile4(smem + SM_A1, row, cg, out);
         signal_smem(bars, 1);
       }
+      // next tile's staging: any time after GEMM1 of this tile (every warp has then consumed the
+      // current copy).  Forward-only: here, published by the S4 barrier.  With backward: in the
+      // shadow of GEMM4 + dW2' (tensor-bound phase), published by a barrier at the tile end.
+      TileCursor nxt_c = cur_c;
+      cursor_advance(nxt_c, P);
+      if (!P.backward && nxt_c.tile < P.tiles) stage_tile(P, f32, nxt_c, tid, row, cg);
       TRACE(0, 8);
       // ---- S4: h2, logit, dl, D2 -> TMEM A (+ Db, Da, DL) ------------------------------------------
       umma::mbar_wait(bars + BAR_ACC, aph);
@@ -601,14 +606,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
                            (f32[F_PART + 2 * TILE + row] + f32[F_PART + 3 * TILE + row])) + bo;
       // observation terms (fast intrinsics, ~1e-6 relative): dl feeds the backward pass, the
       // per-pixel log-likelihood and reconstruction go out from column group 0
-      float ll = 0.f, dnll = 0.f, locv;
-      if (P.x) {
-        pvb::obs_terms_fast(logit, xv, P.sampler, P.sigmoid_d, P.sig, ll, dnll, locv);
-      } else {
-        locv = P.sigmoid_d ? __fdividef(1.f, 1.f + __expf(-logit)) : logit;
-      }
       if (P.backward) {
-        // critical path first: D2 -> TMEM A
+        // critical path first: dl by the shortest chain, D2 -> TMEM A
+        const float dnll = P.x ? pvb::obs_dnll_fast(logit, xv, P.sampler, P.sigmoid_d, P.sig) : 0.f;
         const float dl = valid ? wi * dnll : 0.f;
         uint4 d2[4];
 #pragma unroll
@@ -642,15 +642,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         signal_smem(bars, 2);
       }
       if (cg == 0 && valid) {
+        // per-pixel log-likelihood and reconstruction (fast intrinsics, ~1e-6 relative)
+        float ll = 0.f, dn_unused, locv;
+        if (P.x) {
+          pvb::obs_terms_fast(logit, xv, P.sampler, P.sigmoid_d, P.sig, ll, dn_unused, locv);
+        } else {
+          locv = P.sigmoid_d ? __fdividef(1.f, 1.f + __expf(-logit)) : logit;
+        }
         if (P.rowll) P.rowll[r_glob] = ll;
         if (P.loc) P.loc[r_glob] = locv;
       }
       TRACE(0, 13);
       if (!P.backward) {
         umma::fence_before_sync();   // accumulator reads done before the next tile's signals
-        cur = nxt;
         cur_c = nxt_c;
-        buf ^= 1;
         TRACE_NEXT();
         continue;
       }
@@ -666,6 +671,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         out[j] = dact8(v + 8 * j, *reinterpret_cast<const uint4*>(smem + SM_A1 + off));
         publish_chunk(bars, tm_lane, cg, j, out[j]);
       }
+      if (nxt_c.tile < P.tiles) stage_tile(P, f32, nxt_c, tid, row, cg);
       umma::mbar_wait(bars + BAR_DWO, oph);   // dwo has finished reading h2 from Db
       oph ^= 1;
       store_tile4(smem + SM_DB, row, cg, out);
@@ -685,10 +691,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       store_tile4(smem + SM_DA, row, cg, out);
       umma::fence_before_sync();   // accumulator reads done before the next tile's signals
       signal_smem(bars, 4);
+      cp_async_wait_all();
+      epi_bar();             // publishes the staging of the next tile
       TRACE(0, 17);
-      cur = nxt;
       cur_c = nxt_c;
-      buf ^= 1;
       TRACE_NEXT();
     }
     // last tile: wait for its MMAs, write its dUv partials
@@ -800,10 +806,13 @@ extern "C" int pvb_has_tcgen05(void) { return 1; }
 extern "C" int pvb_tc_trace_read(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 2 * 64 * 32);
 }
+extern "C" int pvb_tc_wtrace_read(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_wtrace, sizeof(long long) * 16 * 16);
+}
 #endif
 
 extern "C" int pvb_sdec_tc_sizes(int64_t I, int N, pvb_tc_sizes* out) {
-  PVB_CHECK_ARG(out && I >= 0 && N >= MIN_PIX, "pvb_sdec_tc_sizes: need N >= 43 pixels per instance");
+  PVB_CHECK_ARG(out && I >= 0 && N >= MIN_PIX, "pvb_sdec_tc_sizes: need N >= 32 pixels per instance");
   int64_t R = I * N;
   out->tiles = (R + TILE - 1) / TILE;
   int sms = sm_count();
@@ -828,7 +837,7 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
   PVB_CHECK_ARG(((uintptr_t)W1 % 16 == 0) && ((uintptr_t)W2 % 16 == 0), "pvb_sdec_tc_step: weights must be 16-byte aligned");
   PVB_CHECK_ARG(!backward || ((uintptr_t)wgrad_part % 16 == 0), "pvb_sdec_tc_step: wgrad_part must be 16-byte aligned");
   const int N = (ndim == 1) ? H : H * W;
-  PVB_CHECK_ARG(N >= MIN_PIX, "pvb_sdec_tc_step: need >= 43 pixels per instance");
+  PVB_CHECK_ARG(N >= MIN_PIX, "pvb_sdec_tc_step: need >= 32 pixels per instance");
   PVB_CHECK_ARG(B < (1LL << 30) && I < (1LL << 40), "pvb_sdec_tc_step: batch too large");
   if (I == 0) return 0;
   pvb_tc_sizes s;

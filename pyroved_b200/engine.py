@@ -156,6 +156,85 @@ class MLP:
         return d
 
 
+class FusedStack:
+    """A Linear+activation stack with linear heads on the fused small-batch kernels
+    (pvb_mlp_tail_fwd / pvb_mlp_chain_bwd / pvb_mlp_wgrad): the first, wide layer is one GEMM
+    with fused bias + activation, everything behind it (hidden layers, heads, the
+    reparameterised sample and the coordinate-transform fold) is one launch; backward is two.
+    Same arithmetic as `MLP` + `GaussHead` (+ `ops.fold_fwd`)."""
+    MAX_ROWS = 4096
+
+    @staticmethod
+    def eligible(layers, heads, M):
+        return (1 <= len(layers) <= 4 and 1 <= len(heads) <= 3 and M <= FusedStack.MAX_ROWS
+                and all(l.out_features <= 256 for l in layers)
+                and all(h.out_features <= 64 and h.in_features == layers[-1].out_features
+                        for h in heads))
+
+    def __init__(self, engine, layers, act, heads, M, gauss_head=None, fold=None):
+        dev, flat = engine.device, engine.flat
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.engine, self.layers, self.act, self.heads, self.M = engine, layers, act, heads, M
+        self.h = [torch.empty(M, l.out_features, **f32) for l in layers]
+        self.pre = ([torch.empty(M, l.out_features, **f32) for l in layers]
+                    if act == "gelu" else [None] * len(layers))
+        self.dpre = [torch.empty(M, l.out_features, **f32) for l in layers]
+        self.gauss = gauss_head            # GaussHead: buffers mu/s_pre/eps/sigma/z/kl/gmu/gs_pre
+        if gauss_head is not None:
+            self.hout = [gauss_head.mu, gauss_head.s_pre] + [
+                torch.empty(M, h.out_features, **f32) for h in heads[2:]]
+        else:
+            self.hout = [torch.empty(M, h.out_features, **f32) for h in heads]
+        self.fold = fold
+        self.x = None
+        self._tail = {}
+        self._chain = None
+        self._wgrad = None
+
+    def forward(self, x, gen_eps=False):
+        eng = self.engine
+        self.x = x
+        l0 = self.layers[0]
+        ops.linear_fwd(x, l0.weight.data, l0.bias.data if l0.bias is not None else None, self.act,
+                       out=self.h[0], pre=self.pre[0])
+        key = bool(gen_eps)
+        args = self._tail.get(key)
+        if args is None:
+            gauss = None
+            if self.gauss is not None:
+                g = self.gauss
+                gauss = dict(eps=g.eps, sigma=g.sigma, z=g.z, kl=g.kl, gen_eps=gen_eps,
+                             seed=eng.seed, step_counter=eng.step_counter,
+                             first_index=eng.eps_first_index(g.eps.numel()))
+            args = ops.make_mlp_tail_args(self.M, self.h[0], self.layers[1:], self.h[1:],
+                                          self.pre[1:], self.act, self.heads, self.hout, gauss,
+                                          self.fold)
+            self._tail[key] = args
+        ops.mlp_tail_fwd(args)
+        return self.h[-1]
+
+    def backward(self, head_grads):
+        """head_grads[k]: gradient wrt the output of head k, [M, hdim_k].  Accumulates every
+        weight / bias gradient of the stack and its heads into the flat gradient buffer."""
+        flat = self.engine.flat
+        if self._chain is None:
+            self._chain = ops.make_mlp_chain_args(self.M, self.layers, self.h, self.pre, self.act,
+                                                  self.dpre, self.heads, head_grads)
+            items = []
+            for k, l in enumerate(self.layers):
+                xin = self.x if k == 0 else self.h[k - 1]
+                items.append((self.dpre[k], xin, flat.gv(l.weight),
+                              flat.gv(l.bias) if l.bias is not None else None))
+            for k, hd in enumerate(self.heads):
+                items.append((head_grads[k], self.h[-1], flat.gv(hd.weight),
+                              flat.gv(hd.bias) if hd.bias is not None else None))
+            self._wgrad = ops.make_wgrad_problems(items)
+            self._grads_id = [g.data_ptr() for g in head_grads] + [self.x.data_ptr()]
+        assert self._grads_id == [g.data_ptr() for g in head_grads] + [self.x.data_ptr()]
+        ops.mlp_chain_bwd(self._chain)
+        ops.mlp_wgrad(self._wgrad, self.M)
+
+
 class StepProgram:
     """Static buffers + kernel sequence for one (model, batch shape)."""
     loss_const = 0.0   # host-side constant added to the returned loss (per rank)
@@ -229,14 +308,22 @@ class DecoderOps:
             wmax = max([Hl, self.Zf + cond_dim] + [l.in_features for l in layers])
             self.dec_scratch = [torch.empty(I * wmax, **f32) for _ in range(3)]
 
-    def forward(self, z, cond, x, w, want_grad):
-        """z [I,Zf], cond [I,Cd] or None, x [B,N], w [I] or None -> fills rowll/loc/ll."""
+    def fold_ctx(self, cond):
+        """Arguments of the coordinate-transform fold, for kernels that fuse it."""
+        cl = self.engine.model.decoder.coord_latent
+        return dict(cfg=self.fold_cfg, cond=cond, Wc=cl.fc_coord.weight.data,
+                    bc=cl.fc_coord.bias.data, Wz=cl.fc_latent.weight.data, Uv=self.Uv)
+
+    def forward(self, z, cond, x, w, want_grad, kl=None, beta=0.0, loss_out=None, uv_ready=False):
+        """z [I,Zf], cond [I,Cd] or None, x [B,N], w [I] or None -> fills rowll/loc/ll.
+        With loss_out: also loss_out += -sum_i (ll_i + beta kl_i) in the same reduction."""
         m = self.engine.model
         dec, samp = m.decoder, m.sampler_d
         if self.spatial:
             cl = dec.coord_latent
-            ops.fold_fwd(self.fold_cfg, z, cond, cl.fc_coord.weight.data, cl.fc_coord.bias.data,
-                         cl.fc_latent.weight.data, self.Uv)
+            if not uv_ready:
+                ops.fold_fwd(self.fold_cfg, z, cond, cl.fc_coord.weight.data,
+                             cl.fc_coord.bias.data, cl.fc_latent.weight.data, self.Uv)
             if self.use_tc:
                 L = linear_layers(dec.fc_layers)
                 ops.sdec_tc_step(self.Uv, x, w, L[0].weight.data, L[0].bias.data,
@@ -260,7 +347,50 @@ class DecoderOps:
             ops.obs_loglik(self.logit, x, w, self.rowll, self.dlogit if want_grad else None,
                            self.loc, self.I, self.Bx, self.N, samp.name, dec.sigmoid_out,
                            samp.decoder_sig)
-        ops.elbo_reduce(self.rowll, None, None, 0.0, self.ll, None, False, self.I, self.N)
+        if loss_out is not None:
+            ops.elbo_reduce(self.rowll, kl, w, beta, self.ll, loss_out, True, self.I, self.N)
+        else:
+            ops.elbo_reduce(self.rowll, None, None, 0.0, self.ll, None, False, self.I, self.N)
+
+    def _reduce_fold_partials(self):
+        eng = self.engine
+        m, flat = eng.model, eng.flat
+        cl = m.decoder.coord_latent
+        Hd0 = cl.fc_coord.out_features
+        nd = m.ndim
+        LC = m._latent_dim + self.Cd
+        G, per = self.G_fold, self.fold_per
+        o_w, o_b = flat.offset(cl.fc_coord.weight), flat.offset(cl.fc_coord.bias)
+        o_z = flat.offset(cl.fc_latent.weight) if LC > 0 else o_b + Hd0
+        if o_b == o_w + Hd0 * nd and o_z == o_b + Hd0:
+            # the three gradients are contiguous in the flat buffer, in partial order: one launch
+            ops.reduce_partials(self.fold_part, flat.g[o_w:o_w + per], G, per, per, True, 0)
+            return
+        ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.weight), G, Hd0 * nd, per, True, 0)
+        ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.bias), G, Hd0, per, True, Hd0 * nd)
+        if LC > 0:
+            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_latent.weight), G, Hd0 * LC, per,
+                                True, Hd0 * (nd + 1))
+
+    def backward_fused(self, head, cond, w, beta):
+        """Fused-decoder variant of backward() that also runs the latent backward:
+        weight-gradient partial reduction, then ONE launch for dUv gather + fold backward +
+        latent backward (-> head.gmu / head.gs_pre), then the fold-weight partial reduction."""
+        assert self.spatial and self.use_tc
+        eng = self.engine
+        m, flat = eng.model, eng.flat
+        dec = m.decoder
+        cl = dec.coord_latent
+        L = linear_layers(dec.fc_layers)
+        n_w = TC_WGRAD_FLOATS
+        base = flat.offset(L[0].weight)
+        ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], self.tc_sizes.ctas,
+                            n_w, TC_WGRAD_STRIDE, True)
+        ops.latent_side_bwd(self.fold_cfg, head.z, cond, cl.fc_coord.weight.data,
+                            cl.fc_latent.weight.data, None, self.gUv_part, self.N, self.gz,
+                            self.gcond, self.fold_part, head.eps, head.sigma, head.s_pre, w, beta,
+                            head.gmu, head.gs_pre)
+        self._reduce_fold_partials()
 
     def backward(self, z, cond):
         """Accumulates decoder weight gradients; returns dloss/dz [I,Zf]."""
@@ -286,15 +416,7 @@ class DecoderOps:
                 ops.sdec_h0_bwd(dh0, self.h0, self.gUv, m._H, m._W, m.ndim)
             ops.fold_bwd(self.fold_cfg, z, cond, cl.fc_coord.weight.data,
                          cl.fc_latent.weight.data, self.gUv, self.gz, self.gcond, self.fold_part)
-            Hd0 = cl.fc_coord.out_features
-            nd = m.ndim
-            LC = m._latent_dim + self.Cd
-            G, per = self.G_fold, self.fold_per
-            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.weight), G, Hd0 * nd, per, True, 0)
-            ops.reduce_partials(self.fold_part, flat.gv(cl.fc_coord.bias), G, Hd0, per, True, Hd0 * nd)
-            if LC > 0:
-                ops.reduce_partials(self.fold_part, flat.gv(cl.fc_latent.weight), G, Hd0 * LC, per,
-                                    True, Hd0 * (nd + 1))
+            self._reduce_fold_partials()
         else:
             hl = self.dmlp.h[-1]
             d_hl = self.dec_scratch[2][:hl.numel()].view_as(hl)
@@ -367,10 +489,18 @@ class SpatialVAEProgram(StepProgram):
         self.x = torch.zeros(B, N, **f32) if C > 0 else self.enc_in
         self.y = torch.zeros(B, C, **f32) if C > 0 else None
         enc = m.encoder_z
-        self.enc = MLP(linear_layers(enc.fc_layers), enc.activation, B, dev, flat)
-        self.enc_scratch = _mlp_scratch(self.enc.layers, B, dev)
         self.head = GaussHead(engine, enc, B, Z)
         self.dec = DecoderOps(engine, B, B, C)
+        enc_layers = linear_layers(enc.fc_layers)
+        self.fused = (not engine.force_generic and
+                      FusedStack.eligible(enc_layers, [enc.fc11, enc.fc12], B))
+        if self.fused:
+            fold = self.dec.fold_ctx(self.y) if self.dec.spatial else None
+            self.enc = FusedStack(engine, enc_layers, enc.activation, [enc.fc11, enc.fc12], B,
+                                  gauss_head=self.head, fold=fold)
+        else:
+            self.enc = MLP(enc_layers, enc.activation, B, dev, flat)
+            self.enc_scratch = _mlp_scratch(self.enc.layers, B, dev)
 
     # convenient aliases (tests / inference read these)
     eps = property(lambda s: s.head.eps)
@@ -396,14 +526,27 @@ class SpatialVAEProgram(StepProgram):
 
     def forward(self, beta, want_grad, gen_eps):
         flat = self.engine.flat
+        if self.fused:
+            self.enc.forward(self.enc_in, gen_eps)
+            self.dec.forward(self.head.z, self.y, self.x, None, want_grad, kl=self.head.kl,
+                             beta=float(beta), loss_out=flat.loss, uv_ready=self.dec.spatial)
+            return
         h = self.enc.forward(self.enc_in)
         self.head.forward(h, gen_eps)
-        self.dec.forward(self.head.z, self.y, self.x, None, want_grad)
-        ops.weighted_sum(self.dec.ll, None, -1.0, flat.loss)
-        ops.weighted_sum(self.head.kl, None, -float(beta), flat.loss)
+        self.dec.forward(self.head.z, self.y, self.x, None, want_grad, kl=self.head.kl,
+                         beta=float(beta), loss_out=flat.loss)
 
     def backward(self, beta):
+        if self.fused and self.dec.spatial and self.dec.use_tc:
+            self.dec.backward_fused(self.head, self.y, None, beta)
+            self.enc.backward([self.head.gmu, self.head.gs_pre])
+            return
         gz = self.dec.backward(self.head.z, self.y)
+        if self.fused:
+            ops.latent_bwd(gz, self.head.eps, self.head.sigma, self.head.s_pre, self.head.z, None,
+                           beta, self.head.gmu, self.head.gs_pre)
+            self.enc.backward([self.head.gmu, self.head.gs_pre])
+            return
         dh = self.head.backward(self.enc.h[-1], gz, None, beta)
         self.enc.backward(dh, self.enc_scratch, False)
 
@@ -599,6 +742,7 @@ class SVIEngine:
         self.seed = int(seed)
         self.flat = FlatParams(model, self.device)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.adam_ticket = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.updates_done = 0     # host mirror of step_counter
         self.programs = {}
         self.graphs = {}
@@ -631,7 +775,7 @@ class SVIEngine:
         return (len(layers) == 2 and all(l.in_features == 128 and l.out_features == 128
                                          for l in layers)
                 and dec.coord_latent.fc_coord.out_features == 128
-                and dec.activation == "tanh" and N >= 43
+                and dec.activation == "tanh" and N >= 32
                 and self.model.sampler_d.name in ("bernoulli", "gaussian"))
 
     def _program(self, B, has_y, mode="main"):
@@ -657,9 +801,8 @@ class SVIEngine:
 
     def _update(self):
         flat = self.flat
-        ops.counter_add(self.step_counter, 1)
-        ops.adam_flat(flat.p, flat.g, flat.m, flat.v, flat.total, self.lr, self.step_counter,
-                      flat.first_step)
+        ops.adam_flat_step(flat.p, flat.g, flat.m, flat.v, flat.total, self.lr, self.step_counter,
+                           self.adam_ticket, flat.first_step)
 
     def _allreduce(self):
         parallel.allreduce_sum_(self.flat.g, self.process_group)

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import FoldCfg, TcSizes, check
+from ._lib import FoldCfg, MlpChainArgs, MlpTailArgs, TcSizes, WgradProblem, check
 
 ACT = {None: 0, "none": 0, "tanh": 1, "relu": 2, "lrelu": 3, "softplus": 4, "gelu": 5,
        "sigmoid": 6}
@@ -185,3 +185,102 @@ def sdec_tc_step(Uv, x, w, W1, b1, W2, b2, wo, bo, rowll, loc, gUv_part, wgrad_p
 def sdec_tc_gather_gUv(gUv_part, gUv, I, N):
     check(_lib.lib().pvb_sdec_tc_gather_gUv(_p(gUv_part), _p(gUv), I, N, _stream()),
           "pvb_sdec_tc_gather_gUv")
+
+
+def adam_flat_step(p, g, m, v, n, lr, step_counter, ticket, first_step=None, beta1=0.9, beta2=0.999,
+                   eps=1e-8):
+    """Adam update + step-counter increment in one launch."""
+    check(_lib.lib().pvb_adam_flat_step(_p(p), _p(g), _p(m), _p(v), n, float(lr), beta1, beta2, eps,
+                                        _p(step_counter), _p(first_step), _p(ticket), _stream()),
+          "pvb_adam_flat_step")
+
+
+# ---- fused small-batch MLP kernels (argument blocks are built once per program) ---------
+def _ptrs(ctype_array, tensors):
+    for i, t in enumerate(tensors):
+        ctype_array[i] = _p(t)
+
+
+def make_mlp_tail_args(M, h_in, layers, hs, pres, act, heads, houts, gauss=None, fold=None):
+    """layers / heads: lists of nn.Linear; hs / pres / houts: preallocated outputs.
+    gauss: dict(eps, sigma, z, kl, gen_eps, seed, step_counter, first_index) or None.
+    fold : dict(cfg, cond, Wc, bc, Wz, Uv) or None."""
+    a = MlpTailArgs()
+    a.M = M
+    a.n_layers = len(layers)
+    a.w_in = h_in.shape[1]
+    a.h_in = _p(h_in)
+    for i, l in enumerate(layers):
+        a.width[i] = l.out_features
+        a.W[i] = _p(l.weight.data)
+        a.b[i] = _p(l.bias.data) if l.bias is not None else None
+        a.h[i] = _p(hs[i])
+        a.pre[i] = _p(pres[i])
+    a.act = ACT[act]
+    a.n_heads = len(heads)
+    for i, l in enumerate(heads):
+        a.hdim[i] = l.out_features
+        a.hW[i] = _p(l.weight.data)
+        a.hb[i] = _p(l.bias.data) if l.bias is not None else None
+        a.hout[i] = _p(houts[i])
+    a.gauss = 0 if gauss is None else 1
+    if gauss is not None:
+        a.gen_eps = int(bool(gauss["gen_eps"]))
+        a.eps, a.sigma, a.z, a.kl = (_p(gauss[k]) for k in ("eps", "sigma", "z", "kl"))
+        a.seed = gauss["seed"] & 0xFFFFFFFFFFFFFFFF
+        a.step_counter = _p(gauss["step_counter"])
+        a.first_index = gauss["first_index"]
+    a.fold = 0 if fold is None else 1
+    if fold is not None:
+        a.cfg = fold["cfg"]
+        a.cond, a.Wc, a.bc, a.Wz, a.Uv = (_p(fold[k]) for k in ("cond", "Wc", "bc", "Wz", "Uv"))
+    return a
+
+
+def mlp_tail_fwd(args):
+    check(_lib.lib().pvb_mlp_tail_fwd(C.byref(args), _stream()), "pvb_mlp_tail_fwd")
+
+
+def make_mlp_chain_args(M, layers, hs, pres, act, dpres, heads, gs):
+    a = MlpChainArgs()
+    a.M = M
+    a.n_layers = len(layers)
+    for i, l in enumerate(layers):
+        a.width[i] = l.out_features
+        a.W[i] = _p(l.weight.data)
+        a.h[i] = _p(hs[i])
+        a.pre[i] = _p(pres[i])
+        a.dpre[i] = _p(dpres[i])
+    a.act = ACT[act]
+    a.n_heads = len(heads)
+    for i, l in enumerate(heads):
+        a.hdim[i] = l.out_features
+        a.hW[i] = _p(l.weight.data)
+        a.g[i] = _p(gs[i])
+    return a
+
+
+def mlp_chain_bwd(args):
+    check(_lib.lib().pvb_mlp_chain_bwd(C.byref(args), _stream()), "pvb_mlp_chain_bwd")
+
+
+def make_wgrad_problems(items):
+    """items: list of (d [M,N], x [M,K], dW [N,K], db [N] or None)"""
+    arr = (WgradProblem * len(items))()
+    for i, (d, x, dW, db) in enumerate(items):
+        arr[i].d, arr[i].x, arr[i].dW, arr[i].db = _p(d), _p(x), _p(dW), _p(db)
+        arr[i].N, arr[i].K = dW.shape
+    return arr
+
+
+def mlp_wgrad(problems, M):
+    check(_lib.lib().pvb_mlp_wgrad(problems, len(problems), M, _stream()), "pvb_mlp_wgrad")
+
+
+def latent_side_bwd(cfg, z, cond, Wc, Wz, gUv, gUv_part, N, gz, gcond, part, eps, sigma, s_pre, w,
+                    beta, gmu, gs_pre):
+    I = z.shape[0]
+    check(_lib.lib().pvb_latent_side_bwd(C.byref(cfg), _p(z), _p(cond), _p(Wc), _p(Wz), _p(gUv),
+                                         _p(gUv_part), N, _p(gz), _p(gcond), _p(part), _p(eps),
+                                         _p(sigma), _p(s_pre), _p(w), float(beta), _p(gmu),
+                                         _p(gs_pre), I, _stream()), "pvb_latent_side_bwd")

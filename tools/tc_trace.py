@@ -34,3 +34,11 @@ for it in range(2, 7):
 print("MMA warp: top, ready x4 for GEMM1..4, dUv operands ready (relative to the epilogue tile start)")
 for it in range(2, 7):
     print(it, (M[it, :18] - E[it, 0]).tolist())
+
+wb = np.zeros((16, 16), dtype=np.int64)
+rc = lib.pvb_tc_wtrace_read(wb.ctypes.data_as(C.POINTER(C.c_longlong)))
+assert rc == 0, rc
+base = wb[:, 0].min()
+print("per-warp S4B of tile 3: [bar-arrive, bar, dl, c0-computed, c0..c3 published, stores done, smem signalled]")
+for w in range(16):
+    print(w, (wb[w, :10] - base).tolist())
