@@ -136,6 +136,14 @@ int launch_sgemm(const float* A, const float* B, float* C, float* Cpre, const fl
 // atomically added into C (pre-zeroed unless accumulating) and bias +
 // activation run in a second, elementwise pass.
 constexpr int SBM = 32, SBN = 32, SBK = 32, SNT = 128;
+constexpr int SST = 4;   // cp.async stages: these GEMMs are latency-, not throughput-bound
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc, bool pred) {
+  // 4-byte async copy with zero fill when !pred (src-size 0)
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
 
 template <int TA, int TB>
 __global__ void __launch_bounds__(SNT)
@@ -143,15 +151,19 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
                    float* __restrict__ Cpre, const float* __restrict__ bias, int M, int N,
                    int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int act, int accumulate,
                    int64_t k_chunk) {
-  __shared__ float As[SBK][SBM + 4];
-  __shared__ float Bs[SBK][SBN + 4];
+  __shared__ float As[SST][SBK][SBM + 4];
+  __shared__ float Bs[SST][SBK][SBN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 7, ty = tid >> 3;   // 8 column quads x 16 row pairs
   const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
   const int64_t kb = (int64_t)blockIdx.z * k_chunk;
   const int64_t ke = (kb + k_chunk < K) ? kb + k_chunk : K;
+  const int n_chunks = (int)((ke - kb + SBK - 1) / SBK);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int64_t k0 = kb; k0 < ke; k0 += SBK) {
+
+  auto stage = [&](int chunk) {
+    const int buf = chunk % SST;
+    const int64_t k0 = kb + (int64_t)chunk * SBK;
 #pragma unroll
     for (int it = 0; it < (SBM * SBK) / SNT; ++it) {
       int idx = tid + it * SNT;
@@ -160,9 +172,9 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
       else         { m = idx % SBM; k = idx / SBM; }
       int gm = m0 + m;
       int64_t gk = k0 + k;
-      float v = 0.f;
-      if (gm < M && gk < ke) v = (TA == 0) ? A[(int64_t)gm * lda + gk] : A[gk * lda + gm];
-      As[k][m] = v;
+      bool ok = gm < M && gk < ke;
+      const float* src = ok ? ((TA == 0) ? A + (int64_t)gm * lda + gk : A + gk * lda + gm) : A;
+      cp_async_f32(&As[buf][k][m], src, ok);
     }
 #pragma unroll
     for (int it = 0; it < (SBN * SBK) / SNT; ++it) {
@@ -172,21 +184,33 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
       else         { k = idx % SBK; n = idx / SBK; }
       int gn = n0 + n;
       int64_t gk = k0 + k;
-      float v = 0.f;
-      if (gn < N && gk < ke) v = (TB == 0) ? B[gk * ldb + gn] : B[(int64_t)gn * ldb + gk];
-      Bs[k][n] = v;
+      bool ok = gn < N && gk < ke;
+      const float* src = ok ? ((TB == 0) ? B + gk * ldb + gn : B + (int64_t)gn * ldb + gk) : B;
+      cp_async_f32(&Bs[buf][k][n], src, ok);
     }
-    __syncthreads();
+  };
+
+  // prologue: SST-1 chunks in flight (empty commit groups keep the accounting uniform)
+#pragma unroll
+  for (int c = 0; c < SST - 1; ++c) {
+    if (c < n_chunks) stage(c);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(SST - 2) : "memory");
+    __syncthreads();   // chunk c landed for everyone; buffer (c-1)%SST is free again
+    if (c + SST - 1 < n_chunks) stage(c + SST - 1);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const int buf = c % SST;
 #pragma unroll
     for (int k = 0; k < SBK; ++k) {
-      float2 a2 = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
-      float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float2 a2 = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
       acc[0][0] = fmaf(a2.x, b4.x, acc[0][0]); acc[0][1] = fmaf(a2.x, b4.y, acc[0][1]);
       acc[0][2] = fmaf(a2.x, b4.z, acc[0][2]); acc[0][3] = fmaf(a2.x, b4.w, acc[0][3]);
       acc[1][0] = fmaf(a2.y, b4.x, acc[1][0]); acc[1][1] = fmaf(a2.y, b4.y, acc[1][1]);
       acc[1][2] = fmaf(a2.y, b4.z, acc[1][2]); acc[1][3] = fmaf(a2.y, b4.w, acc[1][3]);
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -206,6 +230,85 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
         v = pvb::act_fwd(v, act);
         *c = accumulate ? *c + v : v;
       }
+    }
+  }
+}
+
+// ---- forward layer for small batches: C = act(A[M,K] B[N,K]^T + bias) ------------------------
+// Both operands are K-contiguous, so tiles are staged with 16-byte cp.async (4 per thread and
+// chunk instead of 32 scalar ones) into K-major smem; 4 stages keep the loads ahead of the math.
+// Thread (ty, tx): rows {2ty, 2ty+1}, columns {tx, tx+8, tx+16, tx+24} (conflict-free float4 reads).
+constexpr int FLD = SBK + 4;
+__global__ void __launch_bounds__(SNT)
+linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                    float* __restrict__ Cpre, const float* __restrict__ bias, int M, int N, int K,
+                    int act) {
+  __shared__ __align__(16) float As[SST][SBM][FLD];
+  __shared__ __align__(16) float Bs[SST][SBN][FLD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int n_chunks = (K + SBK - 1) / SBK;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  auto stage = [&](int chunk) {
+    const int buf = chunk % SST;
+    const int k0 = chunk * SBK;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      int idx = tid + it * SNT;          // 256 16-byte pieces per operand tile
+      int r = idx >> 3, q = idx & 7;
+      int gk = k0 + 4 * q;
+      {
+        bool ok = (m0 + r < M) && (gk < K);   // K % 4 == 0: a piece is all-in or all-out
+        unsigned d = (unsigned)__cvta_generic_to_shared(&As[buf][r][4 * q]);
+        const float* src = ok ? A + (int64_t)(m0 + r) * K + gk : A;
+        int sz = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
+      }
+      {
+        bool ok = (n0 + r < N) && (gk < K);
+        unsigned d = (unsigned)__cvta_generic_to_shared(&Bs[buf][r][4 * q]);
+        const float* src = ok ? B + (int64_t)(n0 + r) * K + gk : B;
+        int sz = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
+      }
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < SST - 1; ++c) {
+    if (c < n_chunks) stage(c);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(SST - 2) : "memory");
+    __syncthreads();
+    if (c + SST - 1 < n_chunks) stage(c + SST - 1);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const int buf = c % SST;
+#pragma unroll
+    for (int k = 0; k < SBK; k += 4) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][2 * ty][k]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][2 * ty + 1][k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 b = *reinterpret_cast<const float4*>(&Bs[buf][tx + 8 * j][k]);
+        acc[0][j] = fmaf(a0.x, b.x, fmaf(a0.y, b.y, fmaf(a0.z, b.z, fmaf(a0.w, b.w, acc[0][j]))));
+        acc[1][j] = fmaf(a1.x, b.x, fmaf(a1.y, b.y, fmaf(a1.z, b.z, fmaf(a1.w, b.w, acc[1][j]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int gm = m0 + 2 * ty + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx + 8 * j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (Cpre) Cpre[(int64_t)gm * N + gn] = v;
+      C[(int64_t)gm * N + gn] = pvb::act_fwd(v, act);
     }
   }
 }
@@ -298,6 +401,18 @@ extern "C" int pvb_linear_fwd(const float* x, const float* W, const float* b, fl
                               int64_t M, int N, int K, int act, void* stream) {
   PVB_CHECK_ARG(x && W && y && M >= 0 && N > 0 && K > 0, "pvb_linear_fwd: bad argument");
   PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID, "pvb_linear_fwd: unknown activation %d", act);
+  // small batch, 16-byte aligned K-contiguous rows: pipelined single-launch kernel once a third
+  // of the SMs get a tile
+  if (M <= 8192 && (K % 4) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)W % 16) == 0) {
+    int tiles = (int)(((M + SBM - 1) / SBM) * ((N + SBN - 1) / SBN));
+    if (tiles >= 48 && tiles < 4 * 148) {
+      if (M == 0) return 0;
+      dim3 grid((N + SBN - 1) / SBN, (unsigned)((M + SBM - 1) / SBM));
+      linear_small_kernel<<<grid, SNT, 0, (cudaStream_t)stream>>>(x, W, y, pre, b, (int)M, N, K, act);
+      pvb::count_launch();
+      return pvb::launch_status();
+    }
+  }
   return launch_sgemm<0, 1>(x, W, y, pre, b, M, N, K, K, K, N, act, 0, 1, (cudaStream_t)stream);
 }
 

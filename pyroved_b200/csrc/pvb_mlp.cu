@@ -15,58 +15,79 @@
 
 namespace {
 
-constexpr int RB = 8;        // batch rows per CTA
-constexpr int MT = 256;      // threads per CTA
+constexpr int RB = 4;        // batch rows per CTA
+constexpr int MT = 256;      // threads per CTA (thread n owns output column n of all RB rows)
 constexpr int MAXW = PVB_MLP_MAX_WIDTH;
 constexpr int MAXHD = PVB_MLP_MAX_HEAD_DIM;
-constexpr int KC = 16;       // K chunk of the staged weight tile
-constexpr int WLD = MAXW + 1;
+constexpr int KS = 128;      // K extent of the staged weight block
+constexpr int WLD = KS + 4;  // row stride of the staged block (16-byte rows, conflict-free float4 reads)
+constexpr int WS_BYTES = MAXW * WLD * 4;
 
-// out_s[r][n] = act(b[n] + sum_k in_s[r][k] W[n][k]),  r < RB, n < N <= 256, K <= 256.
-// Thread (n0 = tid % 128, half = tid / 128) owns outputs n0, n0 + 128 of rows 4*half .. +3.
-// W [N][K] row-major is staged K-chunk by K-chunk, transposed, through Ws[KC][WLD].
+__device__ __forceinline__ void cpa16(float* smem_dst, const float* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpa4(float* smem_dst, const float* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Ws[n][0..kc) = W[n][k0..k0+kc) for n < N (W [N][K] row-major): every copy of the block is in
+// flight at once, so the block costs one memory latency
+__device__ __forceinline__ void stage_rows(const float* __restrict__ W, int N, int K, int k0, int kc,
+                                           float* Ws) {
+  const int tid = threadIdx.x;
+  if ((K & 3) == 0 && (kc & 3) == 0) {
+    const int q4 = kc >> 2;
+    for (int idx = tid; idx < N * q4; idx += MT) {
+      int n = idx / q4, q = idx - n * q4;
+      cpa16(Ws + n * WLD + 4 * q, W + (size_t)n * K + k0 + 4 * q);
+    }
+  } else {
+    for (int idx = tid; idx < N * kc; idx += MT) {
+      int n = idx / kc, k = idx - n * kc;
+      cpa4(Ws + n * WLD + k, W + (size_t)n * K + k0 + k);
+    }
+  }
+  cpa_wait_all();
+}
+
+// out_s[r][n] = act(b[n] + sum_k in_s[r][k] W[n][k]),  r < RB, n < N <= 256, K <= 256
 __device__ __forceinline__ void dense_rows(const float* __restrict__ W, const float* __restrict__ b,
                                            int N, int K, const float* in_s, float* out_s, int act,
                                            float* __restrict__ h_g, float* __restrict__ pre_g,
                                            int64_t row0, int64_t M, float* Ws) {
-  const int tid = threadIdx.x, n0 = tid & 127, half = tid >> 7;
-  float acc[2][4];
+  const int n = threadIdx.x;
+  float acc[RB];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += KC) {
-    const int kmax = (K - k0 < KC) ? K - k0 : KC;
-    __syncthreads();   // previous chunk consumed (and in_s complete on the first pass)
-    for (int idx = tid; idx < N * KC; idx += MT) {
-      int n = idx / KC, kk = idx % KC;
-      Ws[kk * WLD + n] = (kk < kmax) ? __ldg(W + (size_t)n * K + k0 + kk) : 0.f;
-    }
+  for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += KS) {
+    const int kc = (K - k0 < KS) ? K - k0 : KS;
+    __syncthreads();   // previous block consumed; in_s complete
+    stage_rows(W, N, K, k0, kc, Ws);
     __syncthreads();
-    const bool two = n0 + 128 < N;
-    if (n0 < N) {
-#pragma unroll 4
-      for (int kk = 0; kk < kmax; ++kk) {
-        float w0 = Ws[kk * WLD + n0];
-        float w1 = two ? Ws[kk * WLD + n0 + 128] : 0.f;
+    if (n < N) {
+      const float* w = Ws + n * WLD;
+      int k = 0;
+      for (; k + 4 <= kc; k += 4) {
+        float4 w4 = *reinterpret_cast<const float4*>(w + k);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float x = in_s[(half * 4 + i) * MAXW + k0 + kk];
-          acc[0][i] = fmaf(x, w0, acc[0][i]);
-          acc[1][i] = fmaf(x, w1, acc[1][i]);
+        for (int r = 0; r < RB; ++r) {
+          float4 x4 = *reinterpret_cast<const float4*>(in_s + r * MAXW + k0 + k);
+          acc[r] = fmaf(x4.x, w4.x, fmaf(x4.y, w4.y, fmaf(x4.z, w4.z, fmaf(x4.w, w4.w, acc[r]))));
         }
       }
+      for (; k < kc; ++k)
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = fmaf(in_s[r * MAXW + k0 + k], w[k], acc[r]);
     }
   }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    int n = n0 + 128 * j;
-    if (n >= N) continue;
+  if (n < N) {
     float bn = b ? __ldg(b + n) : 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int r = half * 4 + i;
-      float v = acc[j][i] + bn;
+    for (int r = 0; r < RB; ++r) {
+      float v = acc[r] + bn;
       float a = pvb::act_fwd(v, act);
       out_s[r * MAXW + n] = a;
       if (row0 + r < M) {
@@ -77,11 +98,29 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ W, const fl
   }
 }
 
+// small linear head: out_s[r][n] = b[n] + in_s[r][:] . W[n][:]  -- one warp per (row, output)
+__device__ __forceinline__ void head_rows(const float* __restrict__ W, const float* __restrict__ b,
+                                          int N, int K, const float* in_s, float* out_s,
+                                          float* __restrict__ out_g, int64_t row0, int64_t M) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int idx = warp; idx < RB * N; idx += MT / 32) {
+    int r = idx / N, n = idx - r * N;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(in_s[r * MAXW + k], __ldg(W + (size_t)n * K + k), s);
+    s = pvb::warp_sum(s);
+    if (lane == 0) {
+      float v = s + (b ? __ldg(b + n) : 0.f);
+      out_s[r * MAXHD + n] = v;
+      if (row0 + r < M && out_g) out_g[(row0 + r) * N + n] = v;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(MT) mlp_tail_fwd_kernel(pvb_mlp_tail_args a) {
-  __shared__ float bufA[RB * MAXW];
-  __shared__ float bufB[RB * MAXW];
-  __shared__ float Ws[KC * WLD];
-  __shared__ float heads[PVB_MLP_MAX_HEADS][RB * MAXW / 4];   // [RB][<=64]
+  extern __shared__ __align__(16) float Ws[];   // [MAXW][WLD]
+  __shared__ __align__(16) float bufA[RB * MAXW];
+  __shared__ __align__(16) float bufB[RB * MAXW];
+  __shared__ float heads[PVB_MLP_MAX_HEADS][RB * MAXHD];
   __shared__ float zs[RB * MAXHD];
   __shared__ pvb::Xform xf[RB];
   const int tid = threadIdx.x;
@@ -99,19 +138,11 @@ __global__ void __launch_bounds__(MT) mlp_tail_fwd_kernel(pvb_mlp_tail_args a) {
     float* t = cur; cur = nxt; nxt = t;
     K = a.width[l];
   }
-  // linear heads (outputs re-use the [RB][MAXW] addressing of dense_rows: head dims <= 64,
-  // so each head buffer holds RB rows at stride MAXW only for n < 64 -> use a compact copy)
-  for (int k = 0; k < a.n_heads; ++k) {
-    dense_rows(a.hW[k], a.hb[k], a.hdim[k], K, cur, nxt, PVB_ACT_NONE, a.hout[k], nullptr, row0,
-               a.M, Ws);
-    __syncthreads();
-    for (int idx = tid; idx < RB * a.hdim[k]; idx += MT) {
-      int r = idx / a.hdim[k], n = idx % a.hdim[k];
-      heads[k][r * MAXHD + n] = nxt[r * MAXW + n];
-    }
-    __syncthreads();
-  }
+  __syncthreads();
+  for (int k = 0; k < a.n_heads; ++k)
+    head_rows(a.hW[k], a.hb[k], a.hdim[k], K, cur, heads[k], a.hout[k], row0, a.M);
   if (!a.gauss) return;
+  __syncthreads();
   // reparameterised sample + sampled KL (pvb_randn + pvb_latent_fwd)
   const int Z = a.hdim[0];
   if (tid < RB && row0 + tid < a.M) {
@@ -153,28 +184,11 @@ __global__ void __launch_bounds__(MT) mlp_tail_fwd_kernel(pvb_mlp_tail_args a) {
 }
 
 // ---- heads + hidden stack backward ---------------------------------------------------------
-// dh[r][k] (k < Kw) += sum_n g_s[r][n] Wt[n][k]   with W [Nn][Kw] row-major (coalesced over k)
-__device__ __forceinline__ void back_rows(const float* __restrict__ W, int Nn, int Kw,
-                                          const float* g_s, int g_ld, float acc[2][4]) {
-  const int tid = threadIdx.x, k0 = tid & 127, half = tid >> 7;
-  if (k0 >= Kw) return;
-  const bool two = k0 + 128 < Kw;
-  for (int n = 0; n < Nn; ++n) {
-    float w0 = __ldg(W + (size_t)n * Kw + k0);
-    float w1 = two ? __ldg(W + (size_t)n * Kw + k0 + 128) : 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float g = g_s[(half * 4 + i) * g_ld + n];
-      acc[0][i] = fmaf(g, w0, acc[0][i]);
-      acc[1][i] = fmaf(g, w1, acc[1][i]);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(MT) mlp_chain_bwd_kernel(pvb_mlp_chain_args a) {
+  extern __shared__ __align__(16) float Ws[];   // [MAXW][WLD]: rows n of W[l], K block
   __shared__ float gs[PVB_MLP_MAX_HEADS][RB * MAXHD];
-  __shared__ float dp[RB * MAXW];
-  const int tid = threadIdx.x, k0 = tid & 127, half = tid >> 7;
+  __shared__ __align__(16) float dp[RB * MAXW];
+  const int tid = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.x * RB;
   for (int k = 0; k < a.n_heads; ++k)
     for (int idx = tid; idx < RB * a.hdim[k]; idx += MT) {
@@ -182,46 +196,72 @@ __global__ void __launch_bounds__(MT) mlp_chain_bwd_kernel(pvb_mlp_chain_args a)
       gs[k][r * MAXHD + n] = (row0 + r < a.M) ? a.g[k][(row0 + r) * a.hdim[k] + n] : 0.f;
     }
   __syncthreads();
-  float acc[2][4];
+  float acc[RB];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+  for (int r = 0; r < RB; ++r) acc[r] = 0.f;
   int l = a.n_layers - 1;
-  for (int k = 0; k < a.n_heads; ++k) back_rows(a.hW[k], a.hdim[k], a.width[l], gs[k], MAXHD, acc);
+  // through the heads: dh[r][k] = sum_heads sum_n g[r][n] hW[n][k]   (coalesced over k)
+  if (tid < a.width[l]) {
+    for (int k = 0; k < a.n_heads; ++k) {
+      const float* W = a.hW[k];
+      const int Kw = a.width[l];
+#pragma unroll 8
+      for (int n = 0; n < a.hdim[k]; ++n) {
+        float w = __ldg(W + (size_t)n * Kw + tid);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = fmaf(gs[k][r * MAXHD + n], w, acc[r]);
+      }
+    }
+  }
   for (; l >= 0; --l) {
     const int Wd = a.width[l];
     // dpre = dh * act'(h)
+    if (tid < Wd) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      int k = k0 + 128 * j;
-      if (k >= Wd) continue;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int r = half * 4 + i;
+      for (int r = 0; r < RB; ++r) {
         float d = 0.f;
         if (row0 + r < a.M) {
-          int64_t o = (row0 + r) * Wd + k;
+          int64_t o = (row0 + r) * Wd + tid;
           float p = a.pre[l] ? a.pre[l][o] : 0.f;
-          d = acc[j][i] * pvb::act_grad(a.h[l][o], p, a.act);
+          d = acc[r] * pvb::act_grad(a.h[l][o], p, a.act);
           a.dpre[l][o] = d;
         }
-        dp[r * MAXW + k] = d;
+        dp[r * MAXW + tid] = d;
       }
     }
     if (l == 0) break;
-    __syncthreads();
+    // dh_prev[r][k] = sum_n dpre[r][n] W[l][n][k]: W rows staged once per K block
+    const int Kp = a.width[l - 1];
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+    for (int k0 = 0; k0 < Kp; k0 += KS) {
+      const int kc = (Kp - k0 < KS) ? Kp - k0 : KS;
+      __syncthreads();   // dp complete; previous block consumed
+      stage_rows(a.W[l], Wd, Kp, k0, kc, Ws);
+      __syncthreads();
+      const int k = tid - k0;
+      if (k >= 0 && k < kc) {
+        int n = 0;
+        for (; n + 4 <= Wd; n += 4) {
+          float w0 = Ws[n * WLD + k], w1 = Ws[(n + 1) * WLD + k];
+          float w2 = Ws[(n + 2) * WLD + k], w3 = Ws[(n + 3) * WLD + k];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-    back_rows(a.W[l], Wd, a.width[l - 1], dp, MAXW, acc);
-    __syncthreads();
+          for (int r = 0; r < RB; ++r) {
+            float4 d4 = *reinterpret_cast<const float4*>(dp + r * MAXW + n);
+            acc[r] = fmaf(d4.x, w0, fmaf(d4.y, w1, fmaf(d4.z, w2, fmaf(d4.w, w3, acc[r]))));
+          }
+        }
+        for (; n < Wd; ++n)
+#pragma unroll
+          for (int r = 0; r < RB; ++r) acc[r] = fmaf(dp[r * MAXW + n], Ws[n * WLD + k], acc[r]);
+      }
+    }
+    __syncthreads();   // dp consumed before the next layer overwrites it
   }
 }
 
 // ---- grouped weight gradients ------------------------------------------------------------------
-constexpr int WG_T = 32, WG_NT = 128, WG_MAXP = 8;
+constexpr int WG_T = 32, WG_NT = 128, WG_MAXP = 8, WG_ST = 3;
 struct WgradArgs {
   int64_t M;
   int n_prob;
@@ -229,9 +269,15 @@ struct WgradArgs {
   int tile0[WG_MAXP + 1];
 };
 
+__device__ __forceinline__ void cpa4z(float* smem_dst, const float* gsrc, bool pred) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
 __global__ void __launch_bounds__(WG_NT) mlp_wgrad_kernel(WgradArgs a) {
-  __shared__ float As[WG_T][WG_T + 4];   // [m][n]
-  __shared__ float Bs[WG_T][WG_T + 4];   // [m][k]
+  __shared__ __align__(16) float As[WG_ST][WG_T][WG_T + 4];   // [m][n]
+  __shared__ __align__(16) float Bs[WG_ST][WG_T][WG_T + 4];   // [m][k]
   int pi = 0;
   while (pi + 1 < a.n_prob && (int)blockIdx.x >= a.tile0[pi + 1]) ++pi;
   const pvb_wgrad_problem pr = a.p[pi];
@@ -242,20 +288,55 @@ __global__ void __launch_bounds__(WG_NT) mlp_wgrad_kernel(WgradArgs a) {
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   float bsum = 0.f;   // threads 0..31 of the k-tile 0 CTA: column sum of d
   const bool do_bias = pr.db && kk0 == 0;
-  for (int64_t m0 = 0; m0 < a.M; m0 += WG_T) {
+  const int n_chunks = (int)((a.M + WG_T - 1) / WG_T);
+  const bool vec = ((pr.N & 3) == 0) && ((pr.K & 3) == 0) && (((uintptr_t)pr.d & 15) == 0) &&
+                   (((uintptr_t)pr.x & 15) == 0);
+  auto stage = [&](int chunk) {
+    const int buf = chunk % WG_ST;
+    const int64_t m0 = (int64_t)chunk * WG_T;
+    if (vec) {
+      // 256 16-byte pieces per operand tile, 2 per thread (a piece is all-in or all-out)
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        int idx = tid + it * WG_NT;
+        int m = idx >> 3, q = idx & 7;
+        int64_t gm = m0 + m;
+        bool oka = gm < a.M && n0 + 4 * q < pr.N, okb = gm < a.M && kk0 + 4 * q < pr.K;
+        unsigned da = (unsigned)__cvta_generic_to_shared(&As[buf][m][4 * q]);
+        unsigned db = (unsigned)__cvta_generic_to_shared(&Bs[buf][m][4 * q]);
+        const float* sa = oka ? pr.d + gm * pr.N + n0 + 4 * q : pr.d;
+        const float* sb = okb ? pr.x + gm * pr.K + kk0 + 4 * q : pr.x;
+        int za = oka ? 16 : 0, zb = okb ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(da), "l"(sa), "r"(za) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(db), "l"(sb), "r"(zb) : "memory");
+      }
+      return;
+    }
 #pragma unroll
     for (int it = 0; it < (WG_T * WG_T) / WG_NT; ++it) {
       int idx = tid + it * WG_NT;
       int c = idx % WG_T, m = idx / WG_T;
       int64_t gm = m0 + m;
-      As[m][c] = (gm < a.M && n0 + c < pr.N) ? pr.d[gm * pr.N + n0 + c] : 0.f;
-      Bs[m][c] = (gm < a.M && kk0 + c < pr.K) ? pr.x[gm * pr.K + kk0 + c] : 0.f;
+      bool oka = gm < a.M && n0 + c < pr.N, okb = gm < a.M && kk0 + c < pr.K;
+      cpa4z(&As[buf][m][c], oka ? pr.d + gm * pr.N + n0 + c : pr.d, oka);
+      cpa4z(&Bs[buf][m][c], okb ? pr.x + gm * pr.K + kk0 + c : pr.x, okb);
     }
+  };
+#pragma unroll
+  for (int c = 0; c < WG_ST - 1; ++c) {
+    if (c < n_chunks) stage(c);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(WG_ST - 2) : "memory");
     __syncthreads();
+    if (c + WG_ST - 1 < n_chunks) stage(c + WG_ST - 1);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const int buf = c % WG_ST;
 #pragma unroll
     for (int m = 0; m < WG_T; ++m) {
-      float2 a2 = *reinterpret_cast<const float2*>(&As[m][ty * 2]);
-      float4 b4 = *reinterpret_cast<const float4*>(&Bs[m][tx * 4]);
+      float2 a2 = *reinterpret_cast<const float2*>(&As[buf][m][ty * 2]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][m][tx * 4]);
       acc[0][0] = fmaf(a2.x, b4.x, acc[0][0]); acc[0][1] = fmaf(a2.x, b4.y, acc[0][1]);
       acc[0][2] = fmaf(a2.x, b4.z, acc[0][2]); acc[0][3] = fmaf(a2.x, b4.w, acc[0][3]);
       acc[1][0] = fmaf(a2.y, b4.x, acc[1][0]); acc[1][1] = fmaf(a2.y, b4.y, acc[1][1]);
@@ -263,9 +344,8 @@ __global__ void __launch_bounds__(WG_NT) mlp_wgrad_kernel(WgradArgs a) {
     }
     if (do_bias && tid < WG_T) {
 #pragma unroll
-      for (int m = 0; m < WG_T; ++m) bsum += As[m][tid];
+      for (int m = 0; m < WG_T; ++m) bsum += As[buf][m][tid];
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -428,7 +508,12 @@ extern "C" int pvb_mlp_tail_fwd(const pvb_mlp_tail_args* a, void* stream) {
     PVB_CHECK_ARG(sp.off_c + a->cfg.latent_dim == a->hdim[0], "pvb_mlp_tail_fwd: latent split != Z");
   }
   if (a->M == 0) return 0;
-  mlp_tail_fwd_kernel<<<pvb::cdiv(a->M, RB), MT, 0, (cudaStream_t)stream>>>(*a);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mlp_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_BYTES);
+    attr = true;
+  }
+  mlp_tail_fwd_kernel<<<pvb::cdiv(a->M, RB), MT, WS_BYTES, (cudaStream_t)stream>>>(*a);
   pvb::count_launch();
   return pvb::launch_status();
 }
@@ -446,7 +531,12 @@ extern "C" int pvb_mlp_chain_bwd(const pvb_mlp_chain_args* a, void* stream) {
                   "pvb_mlp_chain_bwd: bad head %d", k);
   PVB_CHECK_ARG(a->act != PVB_ACT_GELU || a->pre[0], "pvb_mlp_chain_bwd: gelu needs the pre-activations");
   if (a->M == 0) return 0;
-  mlp_chain_bwd_kernel<<<pvb::cdiv(a->M, RB), MT, 0, (cudaStream_t)stream>>>(*a);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mlp_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_BYTES);
+    attr = true;
+  }
+  mlp_chain_bwd_kernel<<<pvb::cdiv(a->M, RB), MT, WS_BYTES, (cudaStream_t)stream>>>(*a);
   pvb::count_launch();
   return pvb::launch_status();
 }
