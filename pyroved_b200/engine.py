@@ -751,6 +751,7 @@ class SVIEngine:
         self.use_graphs = use_graphs
         self.force_generic = os.environ.get("PVB_FORCE_GENERIC", "0") == "1"
         self.launches_per_step = 0
+        self.last_loss_const = 0.0
         # data-parallel state (pyroved_b200.parallel)
         self.world_size = 1
         self.rank = 0
@@ -869,6 +870,7 @@ class SVIEngine:
                 self._execute(("update",), self._update)
         else:
             self._execute(key, lambda: self._run(prog, beta, train, gen_eps, update))
+        self.last_loss_const = prog.loss_const * self.world_size
         if not sync:
             return self.flat.loss     # device scalar, no host synchronisation
         return float(self.flat.loss.item()) + prog.loss_const * self.world_size

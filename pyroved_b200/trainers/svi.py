@@ -1,5 +1,6 @@
 """SVItrainer: epoch loop around the fused CUDA SVI step
 (reference trainers/svi.py:11-175)."""
+from collections import deque
 from typing import Optional
 
 import torch
@@ -39,16 +40,67 @@ class SVItrainer:
         self.current_epoch = 0
 
     def train(self, train_loader, **kwargs) -> float:
-        """One epoch; returns loss / number of samples (reference svi.py:95-115)."""
+        """One epoch; returns loss / number of samples (reference svi.py:95-115).
+
+        Same per-batch work as the reference loop (host batch -> device, one SVI step, the
+        step's loss back to the host), software-pipelined: the H2D copy of batch i+1 runs on a
+        copy stream under the kernels of batch i, and the 4-byte loss of step i is read from a
+        pinned ring two steps later, so neither transfer stalls the launch thread."""
+        eng = self.svi
+        dev = eng.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage = {}
+            self._stage_free = [None, None]
+            self._loss_ring = torch.zeros(4, dtype=torch.float32).pin_memory()
+        cs = self._copy_stream
+
+        def upload(data, slot):
+            bufs = []
+            with torch.cuda.stream(cs):
+                if self._stage_free[slot] is not None:
+                    cs.wait_event(self._stage_free[slot])    # step that read this slot is done
+                for j, t in enumerate(data):
+                    key = (slot, j, tuple(t.shape), t.dtype)
+                    b = self._stage.get(key)
+                    if b is None:
+                        b = self._stage[key] = torch.empty(t.shape, dtype=t.dtype, device=dev)
+                    b.copy_(t, non_blocking=True)
+                    bufs.append(b)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return bufs, ev
+
         epoch_loss = 0.
-        for data in train_loader:
-            if len(data) == 1:
-                loss = self.svi.step(data[0].to(self.device, non_blocking=True), **kwargs)
-            else:
-                x, y = data
-                loss = self.svi.step(x.to(self.device, non_blocking=True),
-                                     y.to(self.device, non_blocking=True), **kwargs)
-            epoch_loss += loss
+        pending = deque()     # (ring index, event, host constant)
+        it = iter(train_loader)
+        nxt = next(it, None)
+        staged = upload(nxt, 0) if nxt is not None else None
+        i = 0
+        while staged is not None:
+            bufs, ev = staged
+            nxt = next(it, None)
+            staged = upload(nxt, (i + 1) % 2) if nxt is not None else None
+            main.wait_event(ev)
+            eng.step(*bufs, _sync=False, **kwargs)
+            free = torch.cuda.Event()
+            free.record(main)
+            self._stage_free[i % 2] = free
+            if len(pending) >= 3:                       # ring slot about to be reused
+                k, e, c = pending.popleft()
+                e.synchronize()
+                epoch_loss += float(self._loss_ring[k]) + c
+            k = i % 4
+            self._loss_ring[k:k + 1].copy_(eng.flat.loss, non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(main)
+            pending.append((k, e, eng.last_loss_const))
+            i += 1
+        while pending:
+            k, e, c = pending.popleft()
+            e.synchronize()
+            epoch_loss += float(self._loss_ring[k]) + c
         return epoch_loss / len(train_loader.dataset)
 
     def evaluate(self, test_loader, **kwargs) -> float:
