@@ -259,6 +259,36 @@ int pvb_latent_side_bwd(const pvb_fold_cfg* cfg, const float* z, const float* co
                         const float* s_pre, const float* w, float beta, float* gmu,
                         float* gs_pre, int64_t I, void* stream);
 
+/* ---- convolutional layers (VED: nets/conv.py:146-249; torch Conv{1,2}d, MaxPool,
+ * F.interpolate and their autograd) -------------------------------------------
+ * NCHW fp32.  k = 1 or 3, stride 1, zero padding k/2 ("same").  1-D signals
+ * [B, C, L]: pass H = 1, kh = 1, W = L, kw = k.  W [Cout, Cin, kh, kw]. */
+/* y = act(conv(x, W) + b); pre (optional) receives the pre-activation (gelu) */
+int pvb_conv_fwd(const float* x, const float* W, const float* b, float* y,
+                 float* pre, int B, int Cin, int Cout, int H, int Wd, int kh,
+                 int kw, int act, void* stream);
+/* dx = conv_transpose(dpre, W)  (gradient wrt the layer input) */
+int pvb_conv_bwd_data(const float* dpre, const float* W, float* dx, int B,
+                      int Cin, int Cout, int H, int Wd, int kh, int kw,
+                      void* stream);
+/* dW += dpre (*) x ; db[co] += sum dpre   (accumulate; db may be NULL) */
+int pvb_conv_bwd_weight(const float* dpre, const float* x, float* dW, float* db,
+                        int B, int Cin, int Cout, int H, int Wd, int kh, int kw,
+                        void* stream);
+/* dpre = dy * act'(y)  (elementwise; may run in place) */
+int pvb_act_bwd(const float* dy, const float* y, const float* pre, float* dpre,
+                int64_t n, int act, void* stream);
+/* nn.MaxPool{1,2}d(2, 2): x [BC, H, W] -> y [BC, H/2 (2-D) or H, W/2] */
+int pvb_maxpool2_fwd(const float* x, float* y, int64_t BC, int H, int Wd,
+                     int two_d, void* stream);
+int pvb_maxpool2_bwd(const float* x, const float* dy, float* dx, int64_t BC,
+                     int H, int Wd, int two_d, void* stream);
+/* F.interpolate(scale_factor=2): nearest, or bilinear (2-D only, align_corners=False) */
+int pvb_upsample2_fwd(const float* x, float* y, int64_t BC, int H, int Wd,
+                      int two_d, int bilinear, void* stream);
+int pvb_upsample2_bwd(const float* dy, float* dx, int64_t BC, int H, int Wd,
+                      int two_d, int bilinear, void* stream);
+
 /* ---- optimizer / reductions -------------------------------------------- */
 /* out[j] (+)= sum_g part[g*part_stride + j], j < n, fixed order (deterministic) */
 int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,

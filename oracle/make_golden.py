@@ -150,7 +150,7 @@ def gen(seed):
     return torch.Generator().manual_seed(seed)
 
 
-def main():
+def main_ivae():
     dev = dict(device="cpu")
     # cfg1: 1-D shift-invariant iVAE (BASELINE configs[0], reduced batch)
     x = spectra(16, 64)[:, None, :]  # [B,1,64] as in the notebook
@@ -207,14 +207,47 @@ def main():
              {"z": torch.randn(8, 3, generator=gen(15))},
              {"aux_loss_multiplier": 50.0}, aux=True)
 
-    if "--ved" not in sys.argv:
-        return
-    # cfg5 (reduced): VED image -> spectrum (large fixture: generated on demand)
-    x = blobs(4, 32, 32, seed=16, binary=False)[:, None]
-    ysp = spectra(4, 64, seed=17)[:, None]
-    m = pv.models.VED((32, 32), (64,), latent_dim=2, seed=1)
-    run_case("ved_32_64", m, dev, (x, ysp),
-             {"z": torch.randn(4, 2, generator=gen(18))}, {"scale_factor": 4.0})
+
+
+def main_ved():
+    """cfg5 (reduced channels / sizes so the fixtures stay small): VED, reference
+    models/ved.py:122-163, nets/conv.py."""
+    dev = dict(device="cpu")
+    # image -> spectrum: conv2d encoder (two max-pools), conv1d decoder (nearest upsampling)
+    x = blobs(6, 32, 32, seed=16, binary=False)[:, None]
+    ysp = spectra(6, 64, seed=17)[:, None]
+    m = pv.models.VED((32, 32), (64,), latent_dim=2, seed=1,
+                      hidden_dim_e=[(8,), (16, 16), (32, 32)],
+                      hidden_dim_d=[(32, 32), (16, 16), (8,)])
+    m.to("cpu")
+    run_case("ved_im2spec_32_64", m, dev, (x, ysp),
+             {"z": torch.randn(6, 2, generator=gen(18))}, {"scale_factor": 4.0})
+    # spectrum -> image: conv1d encoder, conv2d decoder (bilinear upsampling), tanh, gaussian
+    xs = spectra(5, 32, seed=19)[:, None]
+    yim = blobs(5, 16, 16, seed=20, binary=False)[:, None]
+    m = pv.models.VED((32,), (16, 16), latent_dim=3, seed=2, activation="tanh",
+                      sampler_d="gaussian", sigmoid_d=False, decoder_sig=0.3,
+                      hidden_dim_e=[(8,), (16, 16)], hidden_dim_d=[(16, 16), (8,)])
+    m.to("cpu")
+    run_case("ved_spec2im_32_16", m, dev, (xs, yim),
+             {"z": torch.randn(5, 3, generator=gen(21))}, {})
+    # default architecture, two input channels, small spatial size (weights subsampled? no:
+    # kept whole, the fixture is ~2 MB) -- skipped by default, enable with --ved-full
+    if "--ved-full" in sys.argv:
+        x = blobs(2, 16, 16, seed=22, binary=False)[:, None]
+        ysp = spectra(2, 32, seed=23)[:, None]
+        m = pv.models.VED((16, 16), (32,), latent_dim=2, seed=1)
+        m.to("cpu")
+        run_case("ved_default_16_32", m, dev, (x, ysp),
+                 {"z": torch.randn(2, 2, generator=gen(24))}, {})
+
+
+def main():
+    if "--ved" in sys.argv or "--ved-full" in sys.argv:
+        main_ved()
+        if "--all" not in sys.argv:
+            return
+    main_ivae()
 
 
 if __name__ == "__main__":

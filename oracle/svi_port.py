@@ -341,56 +341,86 @@ def ssivae_aux_loss(sd, cfg, xs, ys=None, aux_loss_multiplier=20.0):
 
 
 # --------------------------------------------------------------------------
-# VED  (models/ved.py:122-163, nets/conv.py)
+# VED  (models/ved.py:122-163 under Trace_ELBO; nets/conv.py)
 # --------------------------------------------------------------------------
-VED_ENC_CONVS = (0, 3, 5, 8, 10)          # feature_extractor.layers indices
-VED_ENC_POOL_AFTER = (0, 5)               # maxpool follows these conv+act
+class VedCfg:
+    """Shape / option record of a VED (constructor arguments of models/ved.py:89-103)."""
+
+    def __init__(self, input_dim, output_dim, latent_dim=2, hidden_dim_e=None, hidden_dim_d=None,
+                 activation="lrelu", sampler_d="bernoulli", sigmoid_d=True, decoder_sig=0.5,
+                 input_channels=1, output_channels=1):
+        self.input_dim, self.output_dim = tuple(input_dim), tuple(output_dim)
+        self.latent_dim = latent_dim
+        self.hidden_e = hidden_dim_e or [(32,), (64, 64), (128, 128)]
+        self.hidden_d = hidden_dim_d or [(128, 128), (64, 64), (32,)]
+        self.activation, self.sampler_d = activation, sampler_d
+        self.sigmoid_d, self.decoder_sig = sigmoid_d, decoder_sig
+        self.input_channels, self.output_channels = input_channels, output_channels
 
 
-def ved_encoder(sd, x, latent_dim):
-    """convEncoderNet.forward for the default [(32,),(64,64),(128,128)], 2-D,
-    lrelu, no batchnorm (nets/conv.py:56-64,146-196)."""
-    h = x
-    for i in VED_ENC_CONVS:
-        p = "encoder_z.feature_extractor.layers.{}".format(i)
-        h = F.leaky_relu(F.conv2d(h, sd[p + ".weight"], sd[p + ".bias"], padding=1), 0.01)
-        if i in VED_ENC_POOL_AFTER:
-            h = F.max_pool2d(h, 2, 2)
-    enc = F.linear(h.reshape(h.shape[0], -1),
-                   sd["encoder_z.features2latent.fc_latent.weight"],
+def _conv_nd(ndim):
+    return F.conv1d if ndim == 1 else F.conv2d
+
+
+def ved_encoder(sd, cfg, x):
+    """convEncoderNet.forward (nets/conv.py:56-64): FeatureExtractor (conv+act blocks, a 2x
+    max-pool after a block while more convolutions remain, conv.py:173-195) -> flatten ->
+    fc_latent -> split -> softplus on the second half."""
+    nd = len(cfg.input_dim)
+    conv, pool = _conv_nd(nd), (F.max_pool1d if nd == 1 else F.max_pool2d)
+    act = activation_fn(cfg.activation)
+    h = x.reshape(x.shape[0], cfg.input_channels, *cfg.input_dim)
+    total = sum(len(b) for b in cfg.hidden_e)
+    idx, done = 0, 0
+    for block in cfg.hidden_e:
+        for _ in block:
+            p = "encoder_z.feature_extractor.layers.{}".format(idx)
+            h = act(conv(h, sd[p + ".weight"], sd[p + ".bias"], padding=1))
+            idx += 2
+            done += 1
+        if done + 1 < total:
+            h = pool(h, 2, 2)
+            idx += 1
+    enc = F.linear(h.reshape(h.shape[0], -1), sd["encoder_z.features2latent.fc_latent.weight"],
                    sd["encoder_z.features2latent.fc_latent.bias"])
-    mu, s = enc.split(latent_dim, 1)
+    mu, s = enc.split(cfg.latent_dim, 1)
     return mu, F.softplus(s)
 
 
-def ved_decoder(sd, z, out_len, sigmoid_out=True):
-    """convDecoderNet.forward for the default [(128,128),(64,64),(32,)], 1-D
-    output, lrelu, nearest upsampling (nets/conv.py:96-102,137-143,199-249)."""
-    w = sd["decoder.latent2features.fc.weight"]
-    h = F.linear(z, w, sd["decoder.latent2features.fc.bias"])
-    h = h.reshape(z.shape[0], 128, out_len // 8)
-    convs = {0: True, 2: True, 5: True, 7: True, 10: True}
-    ups = (4, 9, 12)
-    for i in range(0, 14):
-        p = "decoder.upsampler.layers.{}".format(i)
-        if i in convs:
-            h = F.leaky_relu(F.conv1d(h, sd[p + ".weight"], sd[p + ".bias"], padding=1), 0.01)
-        elif i in ups:
-            h = F.interpolate(h, scale_factor=2, mode="nearest")
-            h = F.conv1d(h, sd[p + ".conv.weight"], sd[p + ".conv.bias"])
-        elif i == 13:
-            h = F.conv1d(h, sd[p + ".weight"], sd[p + ".bias"])
-    return torch.sigmoid(h) if sigmoid_out else h
+def ved_decoder(sd, cfg, z):
+    """convDecoderNet.forward (nets/conv.py:96-102): latent2features -> Upsampler (conv+act
+    blocks, each closed by an UpsampleBlock = x2 interpolation ('bilinear' in 2-D, 'nearest'
+    in 1-D, conv.py:127-143) + 1x1 conv; final 1x1 conv, conv.py:228-246) -> sigmoid."""
+    nd = len(cfg.output_dim)
+    conv = _conv_nd(nd)
+    act = activation_fn(cfg.activation)
+    in_dim = [int(d) // 2 ** len(cfg.hidden_d) for d in cfg.output_dim]
+    h = F.linear(z, sd["decoder.latent2features.fc.weight"], sd["decoder.latent2features.fc.bias"])
+    h = h.view(-1, cfg.hidden_d[0][0], *in_dim)
+    idx = 0
+    for block in cfg.hidden_d:
+        for _ in block:
+            p = "decoder.upsampler.layers.{}".format(idx)
+            h = act(conv(h, sd[p + ".weight"], sd[p + ".bias"], padding=1))
+            idx += 2
+        p = "decoder.upsampler.layers.{}.conv".format(idx)
+        h = F.interpolate(h, scale_factor=2, mode="bilinear" if nd == 2 else "nearest")
+        h = conv(h, sd[p + ".weight"], sd[p + ".bias"])
+        idx += 1
+    p = "decoder.upsampler.layers.{}".format(idx)
+    h = conv(h, sd[p + ".weight"], sd[p + ".bias"])
+    return torch.sigmoid(h) if cfg.sigmoid_d else h
 
 
-def ved_loss(sd, x, y, eps, latent_dim=2, beta=1.0, sampler="bernoulli",
-             sigmoid_d=True, decoder_sig=0.5):
-    mu, sig = ved_encoder(sd, x, latent_dim)
+def ved_loss(sd, cfg, x, y, eps, beta=1.0):
+    """Returns dict(loss, ll[B], loc[B,N], z, mu, sigma);
+    loss = -( sum_b log p(y_b | decoder(z_b)) + beta sum_b (log p(z_b) - log q(z_b)) )."""
+    mu, sig = ved_encoder(sd, cfg, x)
     z = mu + sig * eps
     log_q = normal_logprob(z, mu, sig)
     log_p = normal_logprob(z, torch.zeros_like(z), torch.ones_like(z))
-    loc = ved_decoder(sd, z, y.shape[-1], sigmoid_d).flatten(1)
-    ll = log_lik(loc, y.flatten(1), sampler, decoder_sig)
+    loc = ved_decoder(sd, cfg, z).flatten(1)
+    ll = log_lik(loc, y.flatten(1), cfg.sampler_d, cfg.decoder_sig)
     elbo = ll.sum() + beta * (log_p - log_q).sum()
     return {"loss": -elbo, "ll": ll, "loc": loc, "z": z, "mu": mu, "sigma": sig}
 

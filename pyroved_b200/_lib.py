@@ -92,6 +92,14 @@ SIGNATURES = {
     "pvb_mlp_wgrad": [C.POINTER(WgradProblem), _i32, _i64, _st],
     "pvb_latent_side_bwd": [C.POINTER(FoldCfg), _f, _f, _f, _f, _f, _f, _i32, _f, _f, _f, _f, _f, _f,
                             _f, _fl, _f, _f, _i64, _st],
+    "pvb_conv_fwd": [_f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_conv_bwd_data": [_f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_conv_bwd_weight": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_act_bwd": [_f, _f, _f, _f, _i64, _i32, _st],
+    "pvb_maxpool2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
+    "pvb_maxpool2_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _st],
+    "pvb_upsample2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
+    "pvb_upsample2_bwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
     "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
                          _i32, _i32, _i32, _i32, _i32, _fl, _i32, _st],

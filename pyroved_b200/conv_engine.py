@@ -1,0 +1,180 @@
+"""SVI step program for VED (reference models/ved.py:122-163 under Trace_ELBO): convolutional
+encoder -> reparameterised sample -> convolutional decoder -> per-pixel log-likelihood + KL,
+forward and hand-written backward on the kernels of csrc/pvb_conv.cu, sequenced layer by layer
+with preallocated activations (replayed as a CUDA graph by engine.SVIEngine)."""
+import torch
+
+from . import ops
+from .engine import StepProgram
+from .nets.conv import layer_plan, out_shape
+
+
+class ConvStack:
+    """A conv / pool / upsample sequence with saved activations and its backward."""
+
+    def __init__(self, engine, layers, activation, B, in_shape):
+        self.engine, self.act, self.B = engine, activation, B
+        dev = engine.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.steps = []
+        shape = tuple(in_shape)
+        self.in_shape = shape
+        biggest = B * _numel(shape)
+        for kind, mod, act in layer_plan(layers, activation):
+            oshape = out_shape(kind, mod, shape)
+            st = dict(kind=kind, mod=mod, act=act, y=torch.empty((B, *oshape), **f32),
+                      pre=(torch.empty((B, *oshape), **f32) if act == "gelu" else None))
+            self.steps.append(st)
+            shape = oshape
+            biggest = max(biggest, B * _numel(shape))
+        self.out_shape = shape
+        self.gbuf = [torch.empty(biggest, **f32) for _ in range(2)]
+        self.x = None
+
+    def forward(self, x):
+        self.x = x
+        cur = x
+        for st in self.steps:
+            m = st["mod"]
+            if st["kind"] == "conv":
+                ops.conv_fwd(cur, m.weight.data, m.bias.data if m.bias is not None else None,
+                             st["act"], st["y"], st["pre"])
+            elif st["kind"] == "pool":
+                ops.maxpool2_fwd(cur, st["y"])
+            else:
+                ops.upsample2_fwd(cur, st["y"], m.mode == "bilinear")
+            cur = st["y"]
+        return cur
+
+    def backward(self, dy, need_dx):
+        """dy: gradient wrt the stack output (clobbered).  Accumulates weight / bias gradients
+        into the flat gradient buffer; returns the gradient wrt the stack input (or None)."""
+        flat = self.engine.flat
+        d = dy
+        for k in range(len(self.steps) - 1, -1, -1):
+            st = self.steps[k]
+            m = st["mod"]
+            xin = self.steps[k - 1]["y"] if k > 0 else self.x
+            want_dx = k > 0 or need_dx
+            dx = None
+            if want_dx:
+                buf = self.gbuf[0] if d.data_ptr() != self.gbuf[0].data_ptr() else self.gbuf[1]
+                dx = buf[:xin.numel()].view_as(xin)
+            if st["kind"] == "conv":
+                if st["act"] is not None:
+                    ops.act_bwd(d, st["y"], st["pre"], d, st["act"])     # in place: d = dpre
+                ops.conv_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight),
+                                    flat.gv(m.bias) if m.bias is not None else None)
+                if want_dx:
+                    ops.conv_bwd_data(d, m.weight.data, dx)
+            elif st["kind"] == "pool":
+                if want_dx:
+                    ops.maxpool2_bwd(xin, d, dx)
+            else:
+                if want_dx:
+                    ops.upsample2_bwd(d, dx, m.mode == "bilinear")
+            d = dx
+        return d
+
+
+def _numel(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+class VEDProgram(StepProgram):
+    """One Trace_ELBO step of VED on a batch (x, y):
+    loss = -sum_b [ log p(y_b | decoder(z_b)) + beta (log p(z_b) - log q(z_b | x_b)) ]."""
+
+    def __init__(self, engine, B):
+        super().__init__(engine, B, True)
+        m = engine.model
+        dev, flat = engine.device, engine.flat
+        f32 = dict(device=dev, dtype=torch.float32)
+        enc, dec = m.encoder_z, m.decoder
+        L = m.z_dim
+        self.L = L
+        self.in_shape = (m.input_channels, *m.input_dim)
+        self.N_out = m.output_channels * _numel(m.output_dim)
+        self.x = torch.zeros((B, *self.in_shape), **f32)
+        self.y = torch.zeros(B, self.N_out, **f32)
+        self.enc = ConvStack(engine, enc.feature_extractor.layers, m.activation, B, self.in_shape)
+        self.feat_dim = _numel(self.enc.out_shape)
+        fcl = enc.features2latent.fc_latent
+        if fcl.in_features != self.feat_dim:
+            raise ValueError("encoder feature map has {} elements but features2latent expects {} "
+                             "(reference nets/conv.py:44-45 assumes len(hidden_dim)-1 poolings)"
+                             .format(self.feat_dim, fcl.in_features))
+        # fc_latent rows [0, L) -> mu, [L, 2L) -> pre-softplus sigma: two heads on weight views
+        self.W_mu, self.W_s = fcl.weight.data[:L], fcl.weight.data[L:]
+        self.b_mu, self.b_s = fcl.bias.data[:L], fcl.bias.data[L:]
+        self.eps = torch.zeros(B, L, **f32)
+        self.mu = torch.empty(B, L, **f32)
+        self.s_pre = torch.empty(B, L, **f32)
+        self.sigma = torch.empty(B, L, **f32)
+        self.z = torch.empty(B, L, **f32)
+        self.kl = torch.empty(B, **f32)
+        self.gz = torch.empty(B, L, **f32)
+        self.gmu = torch.empty(B, L, **f32)
+        self.gs_pre = torch.empty(B, L, **f32)
+        l2f = dec.latent2features
+        self.dec_in_shape = tuple(l2f.reshape_)
+        self.feat0 = torch.empty(B, _numel(self.dec_in_shape), **f32)
+        self.dec = ConvStack(engine, dec.upsampler.layers, m.activation, B, self.dec_in_shape)
+        if _numel(self.dec.out_shape) != self.N_out:
+            raise ValueError("decoder output {} does not match output_dim {}".format(
+                self.dec.out_shape, m.output_dim))
+        self.rowll = torch.empty(B * self.N_out, **f32)
+        self.dlogit = torch.empty(B * self.N_out, **f32)
+        self._loc = torch.empty(B * self.N_out, **f32)
+        self.ll = torch.empty(B, **f32)
+        self.dfeat = torch.empty(B, self.feat_dim, **f32)
+
+    loc = property(lambda s: s._loc)
+    use_tc = False
+
+    def load(self, x, y):
+        B = self.B
+        self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
+        self.y.copy_(y.reshape(B, -1), non_blocking=True)
+
+    def forward(self, beta, want_grad, gen_eps):
+        eng = self.engine
+        m = eng.model
+        samp = m.sampler_d
+        feat = self.enc.forward(self.x).view(self.B, self.feat_dim)
+        if gen_eps:
+            ops.randn(self.eps, eng.seed, eng.step_counter, eng.eps_first_index(self.eps.numel()))
+        ops.linear_fwd(feat, self.W_mu, self.b_mu, None, out=self.mu)
+        ops.linear_fwd(feat, self.W_s, self.b_s, None, out=self.s_pre)
+        ops.latent_fwd(self.mu, self.s_pre, self.eps, self.sigma, self.z, self.kl)
+        fc = m.decoder.latent2features.fc
+        ops.linear_fwd(self.z, fc.weight.data, fc.bias.data, None, out=self.feat0)
+        logit = self.dec.forward(self.feat0.view(self.B, *self.dec_in_shape))
+        ops.obs_loglik(logit.view(-1), self.y, None, self.rowll,
+                       self.dlogit if want_grad else None, self._loc, self.B, self.B, self.N_out,
+                       samp.name, m.decoder.sigmoid_out, samp.decoder_sig)
+        ops.elbo_reduce(self.rowll, self.kl, None, float(beta), self.ll, eng.flat.loss, True,
+                        self.B, self.N_out)
+
+    def backward(self, beta):
+        eng = self.engine
+        m, flat = eng.model, eng.flat
+        dfeat0 = self.dec.backward(self.dlogit.view(self.B, *self.dec.out_shape), True)
+        fc = m.decoder.latent2features.fc
+        ops.linear_bwd(self.z, fc.weight.data, None, None, dfeat0.reshape(self.B, -1),
+                       dfeat0.reshape(self.B, -1), self.gz, False, flat.gv(fc.weight),
+                       flat.gv(fc.bias), None)
+        ops.latent_bwd(self.gz, self.eps, self.sigma, self.s_pre, self.z, None, beta, self.gmu,
+                       self.gs_pre)
+        fcl = m.encoder_z.features2latent.fc_latent
+        gW, gb = flat.gv(fcl.weight), flat.gv(fcl.bias)
+        L = self.L
+        feat = self.enc.steps[-1]["y"].view(self.B, self.feat_dim)
+        ops.linear_bwd(feat, self.W_mu, None, None, self.gmu, self.gmu, self.dfeat, False,
+                       gW[:L], gb[:L], None)
+        ops.linear_bwd(feat, self.W_s, None, None, self.gs_pre, self.gs_pre, self.dfeat, True,
+                       gW[L:], gb[L:], None)
+        self.enc.backward(self.dfeat.view(self.B, *self.enc.out_shape), False)

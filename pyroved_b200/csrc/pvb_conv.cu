@@ -1,0 +1,450 @@
+// Convolutional layers of the VED encoder / decoder (reference nets/conv.py:146-249):
+// k x k (k = 1 or 3, stride 1, "same" zero padding) convolutions in 1-D / 2-D as implicit
+// GEMMs with on-the-fly gathers (no im2col buffer), 2x max-pooling, 2x nearest / bilinear
+// up-sampling, each with its hand-written backward.  NCHW fp32 like the reference; a 1-D
+// signal [B, C, L] is the 2-D case H = 1 (kernel taps along W only).
+//
+//   forward        y[b,co,h,w] = act(bias[co] + sum_{ci,kh,kw} x[b,ci,h+kh-p,w+kw-p] W[co,ci,kh,kw])
+//   backward data  dx[b,ci,h,w] = sum_{co,kh,kw} dpre[b,co,h-kh+p,w-kw+p] W[co,ci,kh,kw]
+//   backward weight dW[co,ci,kh,kw] += sum_{b,h,w} dpre[b,co,h,w] x[b,ci,h+kh-p,w+kw-p];  db[co] += sum dpre
+//
+// GEMM view: 64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread (same inner loop as
+// pvb_gemm.cu).  A per-CTA look-up table maps the flattened (channel, tap) index to its
+// address offset and tap displacement, so a gather costs two adds and a bounds test.
+#include "pvb_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int MAX_CK = 2304;   // max (channels * taps) on the gathered side: 256 channels x 9
+
+struct ConvDims {
+  int B, Cin, Cout, H, W, kh, kw;   // kh = 1 for 1-D signals; pads = kh/2, kw/2
+};
+
+struct Tap { int off; short dh, dw; };
+
+// element (channel c, tap t) of the gathered tensor with C channels: offset c*H*W + dh*W + dw
+__device__ __forceinline__ void build_lut(Tap* lut, int n_ck, const ConvDims& d, int sign) {
+  const int taps = d.kh * d.kw, ph = d.kh / 2, pw = d.kw / 2;
+  for (int k = threadIdx.x; k < n_ck; k += blockDim.x) {
+    int c = k / taps, t = k - c * taps;
+    int dh = sign * (t / d.kw - ph), dw = sign * (t % d.kw - pw);
+    lut[k].off = c * d.H * d.W + dh * d.W + dw;
+    lut[k].dh = (short)dh;
+    lut[k].dw = (short)dw;
+  }
+}
+
+__device__ __forceinline__ void mma_tile(const float (*As)[BM + 4], const float (*Bs)[BN + 4], int tx,
+                                         int ty, float acc[4][4]) {
+#pragma unroll
+  for (int k = 0; k < BK; ++k) {
+    float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+    float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+// MODE 0: forward.   M = B*H*W pixels, N = Cout, K = Cin*taps; A gathered from x, B = W[n][k]
+// MODE 1: backward data. M = pixels, N = Cin, K = Cout*taps; A gathered from dpre with mirrored
+//         taps, B[k = (co,t)][n = ci] = W[co][ci][t]
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+conv_pix_kernel(const float* __restrict__ src, const float* __restrict__ Wt,
+                const float* __restrict__ bias, float* __restrict__ dst, float* __restrict__ pre,
+                ConvDims d, int act) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tap* lut = reinterpret_cast<Tap*>(smem_raw);
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int taps = d.kh * d.kw;
+  const int Cg = (MODE == 0) ? d.Cin : d.Cout;      // channels of the gathered tensor
+  const int Nn = (MODE == 0) ? d.Cout : d.Cin;      // output channels of this GEMM
+  const int K = Cg * taps;
+  const int HW = d.H * d.W;
+  const int64_t Mtot = (int64_t)d.B * HW;
+  build_lut(lut, K, d, MODE == 0 ? 1 : -1);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  // this thread's gather pixel (A loader: m fixed, k = tid/64 + 4*it)
+  const int64_t gm = m0 + (tid & 63);
+  const bool m_ok = gm < Mtot;
+  const int gb = m_ok ? (int)(gm / HW) : 0;
+  const int gr = m_ok ? (int)(gm - (int64_t)gb * HW) : 0;
+  const int gh = gr / d.W, gw = gr - gh * d.W;
+  const float* gbase = src + (int64_t)gb * Cg * HW + gr;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      int kl = (tid >> 6) + 4 * it;
+      int k = k0 + kl;
+      float v = 0.f;
+      if (m_ok && k < K) {
+        Tap t = lut[k];
+        int hh = gh + t.dh, ww = gw + t.dw;
+        if (hh >= 0 && hh < d.H && ww >= 0 && ww < d.W) v = __ldg(gbase + t.off);
+      }
+      As[kl][tid & 63] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      int idx = tid + it * NT;
+      int kl = idx & 15, nl = idx >> 4;
+      int k = k0 + kl, n = n0 + nl;
+      float v = 0.f;
+      if (k < K && n < Nn) {
+        if (MODE == 0) {
+          v = __ldg(Wt + (int64_t)n * K + k);
+        } else {
+          int co = k / taps, t = k - co * taps;
+          v = __ldg(Wt + ((int64_t)co * d.Cin + n) * taps + t);
+        }
+      }
+      Bs[kl][nl] = v;
+    }
+    __syncthreads();
+    mma_tile(As, Bs, tx, ty, acc);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = m0 + ty * 4 + i;
+    if (m >= Mtot) continue;
+    int b = (int)(m / HW);
+    int r = (int)(m - (int64_t)b * HW);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= Nn) continue;
+      float v = acc[i][j];
+      int64_t o = ((int64_t)b * Nn + n) * HW + r;
+      if (MODE == 0) {
+        if (bias) v += __ldg(bias + n);
+        if (pre) pre[o] = v;
+        v = pvb::act_fwd(v, act);
+      }
+      dst[o] = v;
+    }
+  }
+}
+
+// backward weight: dW[co][(ci,t)] += sum over pixels; M' = Cout, N' = Cin*taps, K' = B*H*W,
+// split over gridDim.z pixel ranges (atomic accumulation); db from the n-tile-0 CTAs.
+__global__ void __launch_bounds__(NT)
+conv_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dW,
+                  float* __restrict__ db, ConvDims d, int64_t pix_per_split) {
+  __shared__ Tap lut[BN];
+  __shared__ float As[BK][BM + 4];   // [pixel][co]
+  __shared__ float Bs[BK][BN + 4];   // [pixel][(ci,t)]
+  const int taps = d.kh * d.kw, ph = d.kh / 2, pw = d.kw / 2;
+  const int Np = d.Cin * taps;
+  const int HW = d.H * d.W;
+  const int64_t Mtot = (int64_t)d.B * HW;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * BN, co0 = blockIdx.y * BM;
+  if (tid < BN) {
+    int n = n0 + tid;
+    Tap t;
+    t.off = 0; t.dh = 0; t.dw = 0;
+    if (n < Np) {
+      int c = n / taps, tt = n - c * taps;
+      int dh = tt / d.kw - ph, dw = tt % d.kw - pw;
+      t.off = c * HW + dh * d.W + dw;
+      t.dh = (short)dh;
+      t.dw = (short)dw;
+    }
+    lut[tid] = t;
+  }
+  __syncthreads();
+  const int64_t p_begin = (int64_t)blockIdx.z * pix_per_split;
+  const int64_t p_end = (p_begin + pix_per_split < Mtot) ? p_begin + pix_per_split : Mtot;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  const bool do_bias = db && blockIdx.x == 0;
+  const int kl = tid & 15;        // this thread's pixel within the chunk (fixed)
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += BK) {
+    const int64_t pm = p0 + kl;
+    const bool p_ok = pm < p_end;
+    const int b = p_ok ? (int)(pm / HW) : 0;
+    const int r = p_ok ? (int)(pm - (int64_t)b * HW) : 0;
+    const int h = r / d.W, w = r - h * d.W;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      int ml = (tid >> 4) + 16 * it;            // co within tile
+      int co = co0 + ml;
+      float v = 0.f;
+      if (p_ok && co < d.Cout) v = __ldg(dpre + ((int64_t)b * d.Cout + co) * HW + r);
+      As[kl][ml] = v;
+    }
+    const float* xb = x + (int64_t)b * d.Cin * HW + r;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      int nl = (tid >> 4) + 16 * it;
+      float v = 0.f;
+      if (p_ok && n0 + nl < Np) {
+        Tap t = lut[nl];
+        int hh = h + t.dh, ww = w + t.dw;
+        if (hh >= 0 && hh < d.H && ww >= 0 && ww < d.W) v = __ldg(xb + t.off);
+      }
+      Bs[kl][nl] = v;
+    }
+    __syncthreads();
+    mma_tile(As, Bs, tx, ty, acc);
+    if (do_bias && tid < BM) {
+#pragma unroll
+      for (int k = 0; k < BK; ++k) bsum += As[k][tid];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int co = co0 + ty * 4 + i;
+    if (co >= d.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < Np) atomicAdd(dW + (int64_t)co * Np + n, acc[i][j]);
+    }
+  }
+  if (do_bias && tid < BM && co0 + tid < d.Cout) atomicAdd(db + co0 + tid, bsum);
+}
+
+// ---- 2x max-pool (nn.MaxPool{1,2}d(2, 2), floor mode) ------------------------------------------
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t BC,
+                                    int H, int W, int Ho, int Wo, int two_d) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BC * Ho * Wo) return;
+  int wo = (int)(i % Wo);
+  int ho = (int)((i / Wo) % Ho);
+  int64_t bc = i / ((int64_t)Wo * Ho);
+  const float* p = x + (bc * H + (two_d ? 2 * ho : ho)) * W + 2 * wo;
+  float m = fmaxf(p[0], p[1]);
+  if (two_d) m = fmaxf(m, fmaxf(p[W], p[W + 1]));
+  y[i] = m;
+}
+// dx = dy routed to the first maximal element of each window (torch tie-breaking: first in
+// row-major window order); elements outside any window (odd sizes) get 0
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                    float* __restrict__ dx, int64_t BC, int H, int W, int Ho, int Wo,
+                                    int two_d) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BC * H * W) return;
+  int w = (int)(i % W);
+  int h = (int)((i / W) % H);
+  int64_t bc = i / ((int64_t)W * H);
+  int wo = w >> 1, ho = two_d ? h >> 1 : h;
+  float g = 0.f;
+  if (wo < Wo && ho < Ho) {
+    const float* p = x + (bc * H + (two_d ? 2 * ho : ho)) * W + 2 * wo;
+    float v[4] = {p[0], p[1], two_d ? p[W] : -INFINITY, two_d ? p[W + 1] : -INFINITY};
+    int best = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+      if (v[k] > v[best]) best = k;
+    int me = (w & 1) + (two_d ? 2 * (h & 1) : 0);
+    if (me == best) g = dy[(bc * Ho + ho) * Wo + wo];
+  }
+  dx[i] = g;
+}
+
+// ---- 2x up-sampling (F.interpolate(scale_factor=2), nearest; bilinear for 2-D, align_corners=False)
+__device__ __forceinline__ void bilin_src(int o, int n_in, int& i0, int& i1, float& l1) {
+  float s = fmaxf(((float)o + 0.5f) * 0.5f - 0.5f, 0.f);   // area_pixel_compute_source_index
+  i0 = (int)s;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+__global__ void upsample2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t BC,
+                                     int H, int W, int two_d, int bilinear) {
+  const int Ho = two_d ? 2 * H : H, Wo = 2 * W;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BC * Ho * Wo) return;
+  int wo = (int)(i % Wo);
+  int ho = (int)((i / Wo) % Ho);
+  int64_t bc = i / ((int64_t)Wo * Ho);
+  const float* p = x + bc * H * W;
+  if (!bilinear) {
+    y[i] = p[(two_d ? ho >> 1 : ho) * W + (wo >> 1)];
+    return;
+  }
+  int h0, h1, w0, w1;
+  float lh, lw;
+  bilin_src(ho, H, h0, h1, lh);
+  bilin_src(wo, W, w0, w1, lw);
+  y[i] = (1.f - lh) * ((1.f - lw) * p[h0 * W + w0] + lw * p[h0 * W + w1]) +
+         lh * ((1.f - lw) * p[h1 * W + w0] + lw * p[h1 * W + w1]);
+}
+// gather form of the adjoint: each input element collects from the <= 3 x 3 outputs that read it
+__global__ void upsample2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t BC,
+                                     int H, int W, int two_d, int bilinear) {
+  const int Ho = two_d ? 2 * H : H, Wo = 2 * W;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BC * H * W) return;
+  int w = (int)(i % W);
+  int h = (int)((i / W) % H);
+  int64_t bc = i / ((int64_t)W * H);
+  const float* g = dy + bc * Ho * Wo;
+  float s = 0.f;
+  if (!bilinear) {
+    if (two_d) s = g[(2 * h) * Wo + 2 * w] + g[(2 * h) * Wo + 2 * w + 1] +
+                   g[(2 * h + 1) * Wo + 2 * w] + g[(2 * h + 1) * Wo + 2 * w + 1];
+    else s = g[h * Wo + 2 * w] + g[h * Wo + 2 * w + 1];
+    dx[i] = s;
+    return;
+  }
+  for (int ho = max(2 * h - 2, 0); ho <= min(2 * h + 2, Ho - 1); ++ho) {
+    int h0, h1;
+    float lh;
+    bilin_src(ho, H, h0, h1, lh);
+    float ch = (h0 == h ? 1.f - lh : 0.f) + (h1 == h ? lh : 0.f);
+    if (ch == 0.f) continue;
+    for (int wo = max(2 * w - 2, 0); wo <= min(2 * w + 2, Wo - 1); ++wo) {
+      int w0, w1;
+      float lw;
+      bilin_src(wo, W, w0, w1, lw);
+      float cw = (w0 == w ? 1.f - lw : 0.f) + (w1 == w ? lw : 0.f);
+      if (cw != 0.f) s = fmaf(ch * cw, g[ho * Wo + wo], s);
+    }
+  }
+  dx[i] = s;
+}
+
+__global__ void act_bwd_flat_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                    const float* __restrict__ pre, float* __restrict__ dpre, int64_t n,
+                                    int act) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dpre[i] = dy[i] * pvb::act_grad(y[i], pre ? pre[i] : 0.f, act);
+}
+
+int check_dims(const ConvDims& d, const char* who) {
+  PVB_CHECK_ARG(d.B >= 0 && d.Cin > 0 && d.Cout > 0 && d.H > 0 && d.W > 0, "%s: bad dims", who);
+  PVB_CHECK_ARG((d.kh == 1 || d.kh == 3) && (d.kw == 1 || d.kw == 3), "%s: kernel size must be 1 or 3", who);
+  PVB_CHECK_ARG(d.Cin * d.kh * d.kw <= MAX_CK && d.Cout * d.kh * d.kw <= MAX_CK,
+                "%s: channels * taps > %d", who, MAX_CK);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int pvb_conv_fwd(const float* x, const float* W, const float* b, float* y, float* pre,
+                            int B, int Cin, int Cout, int H, int Wd, int kh, int kw, int act,
+                            void* stream) {
+  ConvDims d{B, Cin, Cout, H, Wd, kh, kw};
+  if (check_dims(d, "pvb_conv_fwd")) return -1;
+  PVB_CHECK_ARG(x && W && y, "pvb_conv_fwd: null pointer");
+  PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID, "pvb_conv_fwd: unknown activation %d", act);
+  if (B == 0) return 0;
+  int64_t M = (int64_t)B * H * Wd;
+  dim3 grid((unsigned)((M + BM - 1) / BM), (Cout + BN - 1) / BN);
+  size_t smem = (size_t)Cin * kh * kw * sizeof(Tap);
+  conv_pix_kernel<0><<<grid, NT, smem, (cudaStream_t)stream>>>(x, W, b, y, pre, d, act);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_conv_bwd_data(const float* dpre, const float* W, float* dx, int B, int Cin,
+                                 int Cout, int H, int Wd, int kh, int kw, void* stream) {
+  ConvDims d{B, Cin, Cout, H, Wd, kh, kw};
+  if (check_dims(d, "pvb_conv_bwd_data")) return -1;
+  PVB_CHECK_ARG(dpre && W && dx, "pvb_conv_bwd_data: null pointer");
+  if (B == 0) return 0;
+  int64_t M = (int64_t)B * H * Wd;
+  dim3 grid((unsigned)((M + BM - 1) / BM), (Cin + BN - 1) / BN);
+  size_t smem = (size_t)Cout * kh * kw * sizeof(Tap);
+  conv_pix_kernel<1><<<grid, NT, smem, (cudaStream_t)stream>>>(dpre, W, nullptr, dx, nullptr, d, 0);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_conv_bwd_weight(const float* dpre, const float* x, float* dW, float* db, int B,
+                                   int Cin, int Cout, int H, int Wd, int kh, int kw, void* stream) {
+  ConvDims d{B, Cin, Cout, H, Wd, kh, kw};
+  if (check_dims(d, "pvb_conv_bwd_weight")) return -1;
+  PVB_CHECK_ARG(dpre && x && dW, "pvb_conv_bwd_weight: null pointer");
+  if (B == 0) return 0;
+  int64_t M = (int64_t)B * H * Wd;
+  int tiles = ((Cin * kh * kw + BN - 1) / BN) * ((Cout + BM - 1) / BM);
+  int64_t splits = (148 * 4 + tiles - 1) / tiles;
+  int64_t max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int64_t per = ((M + splits - 1) / splits + BK - 1) / BK * BK;
+  splits = (M + per - 1) / per;
+  dim3 grid((Cin * kh * kw + BN - 1) / BN, (Cout + BM - 1) / BM, (unsigned)splits);
+  conv_wgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(dpre, x, dW, db, d, per);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_act_bwd(const float* dy, const float* y, const float* pre, float* dpre, int64_t n,
+                           int act, void* stream) {
+  PVB_CHECK_ARG(dy && y && dpre && n >= 0, "pvb_act_bwd: bad argument");
+  PVB_CHECK_ARG(act != PVB_ACT_GELU || pre, "pvb_act_bwd: gelu needs the pre-activation");
+  if (n == 0) return 0;
+  int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  act_bwd_flat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, y, pre, dpre, n, act);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_maxpool2_fwd(const float* x, float* y, int64_t BC, int H, int Wd, int two_d,
+                                void* stream) {
+  PVB_CHECK_ARG(x && y && BC >= 0 && H > 0 && Wd > 1 && (!two_d || H > 1), "pvb_maxpool2_fwd: bad argument");
+  int Ho = two_d ? H / 2 : H, Wo = Wd / 2;
+  int64_t n = BC * Ho * Wo;
+  if (n == 0) return 0;
+  maxpool2_fwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, BC, H, Wd, Ho, Wo, two_d);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_maxpool2_bwd(const float* x, const float* dy, float* dx, int64_t BC, int H, int Wd,
+                                int two_d, void* stream) {
+  PVB_CHECK_ARG(x && dy && dx && BC >= 0 && H > 0 && Wd > 1 && (!two_d || H > 1), "pvb_maxpool2_bwd: bad argument");
+  int Ho = two_d ? H / 2 : H, Wo = Wd / 2;
+  int64_t n = BC * H * Wd;
+  if (n == 0) return 0;
+  maxpool2_bwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, BC, H, Wd, Ho, Wo, two_d);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_upsample2_fwd(const float* x, float* y, int64_t BC, int H, int Wd, int two_d,
+                                 int bilinear, void* stream) {
+  PVB_CHECK_ARG(x && y && BC >= 0 && H > 0 && Wd > 0, "pvb_upsample2_fwd: bad argument");
+  PVB_CHECK_ARG(!bilinear || two_d, "pvb_upsample2_fwd: bilinear is 2-D only (reference nets/conv.py:128-130)");
+  int64_t n = BC * (two_d ? 2 * H : H) * 2 * Wd;
+  if (n == 0) return 0;
+  upsample2_fwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, BC, H, Wd, two_d, bilinear);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_upsample2_bwd(const float* dy, float* dx, int64_t BC, int H, int Wd, int two_d,
+                                 int bilinear, void* stream) {
+  PVB_CHECK_ARG(dy && dx && BC >= 0 && H > 0 && Wd > 0, "pvb_upsample2_bwd: bad argument");
+  PVB_CHECK_ARG(!bilinear || two_d, "pvb_upsample2_bwd: bilinear is 2-D only");
+  int64_t n = BC * H * Wd;
+  if (n == 0) return 0;
+  upsample2_bwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, BC, H, Wd, two_d, bilinear);
+  pvb::count_launch();
+  return pvb::launch_status();
+}

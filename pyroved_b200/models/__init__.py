@@ -2,5 +2,6 @@
 from .ivae import iVAE
 from .jivae import jiVAE
 from .ssivae import ssiVAE
+from .ved import VED
 
-__all__ = ['iVAE', 'jiVAE', 'ssiVAE']
+__all__ = ['iVAE', 'jiVAE', 'ssiVAE', 'VED']

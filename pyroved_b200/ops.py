@@ -284,3 +284,61 @@ def latent_side_bwd(cfg, z, cond, Wc, Wz, gUv, gUv_part, N, gz, gcond, part, eps
                                          _p(gUv_part), N, _p(gz), _p(gcond), _p(part), _p(eps),
                                          _p(sigma), _p(s_pre), _p(w), float(beta), _p(gmu),
                                          _p(gs_pre), I, _stream()), "pvb_latent_side_bwd")
+
+
+# ---- convolutional layers (NCHW; 1-D signals as H = 1) ------------------------------------
+def _conv_dims(x, W):
+    """(B, Cin, Cout, H, Wd, kh, kw) from x [B,Cin,(H,)Wd] and W [Cout,Cin,(kh,)kw]"""
+    B, Cin = x.shape[0], x.shape[1]
+    if x.dim() == 3:
+        H, Wd, kh, kw = 1, x.shape[2], 1, W.shape[2]
+    else:
+        H, Wd, kh, kw = x.shape[2], x.shape[3], W.shape[2], W.shape[3]
+    return B, Cin, W.shape[0], H, Wd, kh, kw
+
+
+def conv_fwd(x, W, b, act, out, pre=None):
+    check(_lib.lib().pvb_conv_fwd(_p(x), _p(W), _p(b), _p(out), _p(pre), *_conv_dims(x, W),
+                                  ACT[act], _stream()), "pvb_conv_fwd")
+    return out
+
+
+def conv_bwd_data(dpre, W, dx):
+    check(_lib.lib().pvb_conv_bwd_data(_p(dpre), _p(W), _p(dx), *_conv_dims(dx, W), _stream()),
+          "pvb_conv_bwd_data")
+
+
+def conv_bwd_weight(dpre, x, W, dW, db):
+    check(_lib.lib().pvb_conv_bwd_weight(_p(dpre), _p(x), _p(dW), _p(db), *_conv_dims(x, W),
+                                         _stream()), "pvb_conv_bwd_weight")
+
+
+def act_bwd(dy, y, pre, dpre, act):
+    check(_lib.lib().pvb_act_bwd(_p(dy), _p(y), _p(pre), _p(dpre), y.numel(), ACT[act], _stream()),
+          "pvb_act_bwd")
+
+
+def _plane(x):
+    """(BC, H, Wd, two_d) of an NC(H)W tensor"""
+    if x.dim() == 3:
+        return x.shape[0] * x.shape[1], 1, x.shape[2], 0
+    return x.shape[0] * x.shape[1], x.shape[2], x.shape[3], 1
+
+
+def maxpool2_fwd(x, y):
+    check(_lib.lib().pvb_maxpool2_fwd(_p(x), _p(y), *_plane(x), _stream()), "pvb_maxpool2_fwd")
+
+
+def maxpool2_bwd(x, dy, dx):
+    check(_lib.lib().pvb_maxpool2_bwd(_p(x), _p(dy), _p(dx), *_plane(x), _stream()),
+          "pvb_maxpool2_bwd")
+
+
+def upsample2_fwd(x, y, bilinear):
+    check(_lib.lib().pvb_upsample2_fwd(_p(x), _p(y), *_plane(x), int(bool(bilinear)), _stream()),
+          "pvb_upsample2_fwd")
+
+
+def upsample2_bwd(dy, dx, bilinear):
+    check(_lib.lib().pvb_upsample2_bwd(_p(dy), _p(dx), *_plane(dx), int(bool(bilinear)), _stream()),
+          "pvb_upsample2_bwd")

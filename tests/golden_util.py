@@ -27,6 +27,14 @@ CASES = {
                                          invariances=["r"])),
     "ssivae_16_r_sup": ("ssivae", dict(data_dim=(16, 16), latent_dim=2, num_classes=4,
                                        invariances=["r"])),
+    # VED (reduced channel counts keep the fixtures small)
+    "ved_im2spec_32_64": ("ved", dict(
+        input_dim=(32, 32), output_dim=(64,), latent_dim=2,
+        hidden_dim_e=[(8,), (16, 16), (32, 32)], hidden_dim_d=[(32, 32), (16, 16), (8,)])),
+    "ved_spec2im_32_16": ("ved", dict(
+        input_dim=(32,), output_dim=(16, 16), latent_dim=3, activation="tanh",
+        sampler_d="gaussian", sigmoid_d=False, decoder_sig=0.3,
+        hidden_dim_e=[(8,), (16, 16)], hidden_dim_d=[(16, 16), (8,)])),
 }
 
 

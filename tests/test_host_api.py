@@ -110,3 +110,24 @@ def test_dataloader_protocol():
     assert [len(b) for b in l1] == [1, 1, 1] and len(l1.dataset) == 10
     l2 = pv.utils.init_dataloader(x, y, batch_size=5)
     assert all(len(b) == 2 for b in l2)
+
+
+def test_ved_state_dict_keys_and_seeded_init_match_reference():
+    """VED(seed) builds the reference's parameter names, shapes AND initial values."""
+    for name in ("ved_im2spec_32_64", "ved_spec2im_32_16"):
+        g = Golden(name)
+        m = pv.models.VED(seed={"ved_spec2im_32_16": 2}.get(name, 1), device="cpu", **g.kwargs)
+        w0 = g.group("w0")
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(w0.keys())
+        for k in sd:
+            assert torch.equal(sd[k], w0[k]), k
+    m = pv.models.VED((64, 64), (128,), device="cpu")
+    keys = list(m.state_dict().keys())
+    for i in (0, 3, 5, 8, 10):
+        assert "encoder_z.feature_extractor.layers.{}.weight".format(i) in keys
+    for i in (4, 9, 12):
+        assert "decoder.upsampler.layers.{}.conv.weight".format(i) in keys
+    assert m.state_dict()["encoder_z.features2latent.fc_latent.weight"].shape == (4, 32768)
+    assert m.state_dict()["decoder.latent2features.fc.weight"].shape == (2048, 2)
+    assert sum(p.numel() for p in m.parameters()) == 577893   # SURVEY 8a16

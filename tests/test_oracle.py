@@ -15,6 +15,10 @@ torch.set_num_threads(4)
 def port_loss_fn(g, dtype=torch.float32):
     """Returns (loss_fn, args, kwargs) for svi_port.loss_and_grads."""
     kw = dict(g.kwargs)
+    if g.kind == "ved":
+        cfg = sp.VedCfg(**kw)
+        x, y = g.args(dtype)
+        return sp.ved_loss, (cfg, x, y, g.eps(dtype), float(g.kw().get("scale_factor", 1.0))), cfg
     kw.pop("hidden_dim_e", None)
     kw.pop("hidden_dim_d", None)
     cfg = sp.Cfg(**kw)
@@ -63,7 +67,7 @@ def test_port_fp64_close_to_reference(name):
     assert abs(float(out["loss"]) - g.loss) <= 1e-5 * abs(g.loss)
 
 
-@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n][0] in ("ivae", "jivae")])
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n][0] in ("ivae", "jivae", "ved")])
 def test_port_adam_step_matches_reference(name):
     g = Golden(name)
     fn, args, cfg = port_loss_fn(g)
