@@ -272,6 +272,9 @@ __device__ __forceinline__ void store_tile4(uint8_t* tile, int row, int cg, cons
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<uint4*>(tile + umma::tile_off(TILE, row, 8 * (4 * j + cg))) = out[j];
 }
+__device__ __forceinline__ void store_chunk(uint8_t* tile, int row, int cg, int j, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + umma::tile_off(TILE, row, 8 * (4 * j + cg))) = v;
+}
 __device__ __forceinline__ void signal_smem(uint64_t* bars, int stage) {
   umma::fence_proxy_async();
   __syncwarp();
@@ -410,9 +413,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           umma::mma_f16_ss(tm + TM_DWO, desc_mnmajor(sDB, k), desc_mnmajor(sDL, k), ID_N16,
                            (k > 0) ? 1u : acc);
         umma::commit(bars + BAR_DWO);
+        // dW2' += D2^T [h1|1]: in the shadow of the S6 epilogue start (the tensor pipe is idle
+        // until its first column group lands)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma::mma_f16_ss(tm + TM_DW2, desc_mnmajor(sDA, k), desc_mnmajor(sA1, k), ID_DW,
+                           (k > 0) ? 1u : acc);
       }
       __syncwarp();
-      // ---- GEMM4: ACC = D1 W1, with dW2' += D2^T [h1|1] slotted between its K-steps ----
+      // ---- GEMM4: ACC = D1 W1 ----
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         umma::mbar_wait(bars + BAR_READY + j, rph);
@@ -421,15 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         if (lane == 0) {
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_mnmajor(sW1, 2 * j), ID_DH, j > 0);
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_mnmajor(sW1, 2 * j + 1), ID_DH, 1);
-          if (j < 3) {
-            const int k0 = 3 * j, k1 = (j == 2) ? 8 : 3 * j + 3;
-#pragma unroll
-            for (int k = k0; k < k1; ++k)
-              umma::mma_f16_ss(tm + TM_DW2, desc_mnmajor(sDA, k), desc_mnmajor(sA1, k), ID_DW,
-                               (k > 0) ? 1u : acc);
-          } else {
-            umma::commit(bars + BAR_ACC);   // also covers dW2': Da may be overwritten (D0)
-          }
+          if (j == 3) umma::commit(bars + BAR_ACC);   // also covers dW2': Da may be overwritten (D0)
         }
         __syncwarp();
       }
@@ -488,6 +489,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       const float wi = f32[F_WI + row];
       uint4 out[4];
       // ---- S0: first layer h0 = tanh(U g + v) -> TMEM A (+ A0) ------------------------------
+      if (P.backward && prev_tile >= 0) {
+        // dW1' of the previous tile has finished reading A0 / Db (long done: no stall)
+        umma::mbar_wait(bars + BAR_DW, wph);
+        wph ^= 1;
+      }
       {
         const float* u = f32 + F_UV + slot * 3 * HD;
 #pragma unroll
@@ -506,18 +512,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           }
           out[j] = *reinterpret_cast<uint4*>(hh);
           publish_chunk(bars, tm_lane, cg, j, out[j]);
+          // smem copy right behind the signal: by the end of the stage only the last store
+          // is still in flight when the proxy fence drains them
+          if (P.backward) store_chunk(smem + SM_A0, row, cg, j, out[j]);
           TRACE(0, 1 + j);
         }
       }
       if (P.backward) {
         if (prev_tile >= 0) {
-          // dW1' of the previous tile has finished reading A0 / Db; then every MMA of the
-          // previous tile (dUv was issued last): Da, G and the dUv accumulator are free
-          umma::mbar_wait(bars + BAR_DW, wph);
-          wph ^= 1;
-        }
-        store_tile4(smem + SM_A0, row, cg, out);
-        if (prev_tile >= 0) {
+          // every MMA of the previous tile (dUv was issued last) is complete: Da, G and the
+          // dUv accumulator are free
           umma::mbar_wait(bars + BAR_DUV, dph);
           dph ^= 1;
           umma::fence_after_sync();
@@ -564,11 +568,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       for (int j = 0; j < 4; ++j) {
         out[j] = tanh8(v + 8 * j, f32 + F_B1 + 8 * (4 * j + cg));
         publish_chunk(bars, tm_lane, cg, j, out[j]);
+        if (P.backward) store_chunk(smem + SM_A1, row, cg, j, out[j]);
       }
-      if (P.backward) {
-        store_tile4(smem + SM_A1, row, cg, out);
-        signal_smem(bars, 1);
-      }
+      if (P.backward) signal_smem(bars, 1);
       // next tile's staging: any time after GEMM1 of this tile (every warp has then consumed the
       // current copy).  Forward-only: here, published by the S4 barrier.  With backward: in the
       // shadow of GEMM4 + dW2' (tensor-bound phase), published by a barrier at the tile end.
@@ -596,6 +598,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           pdot = fmaf(hf2.x, wv[2 * e], pdot);
           pdot = fmaf(hf2.y, wv[2 * e + 1], pdot);
         }
+        if (P.backward) store_chunk(smem + SM_DB, row, cg, j, out[j]);   // h2: dwo operand
       }
       f32[F_PART + cg * TILE + row] = pdot;
       cp_async_wait_all();   // this thread's share of the next tile's staging has landed
@@ -625,11 +628,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           }
           d2[j] = *reinterpret_cast<uint4*>(dd);
           publish_chunk(bars, tm_lane, cg, j, d2[j]);
+          store_chunk(smem + SM_DA, row, cg, j, d2[j]);
         }
         TRACE(0, 12);
-        // off the critical path: h2 -> Db, D2 -> Da, dl -> DL (weight-gradient operands)
-        store_tile4(smem + SM_DB, row, cg, out);
-        store_tile4(smem + SM_DA, row, cg, d2);
+        // dl -> DL (dwo operand)
         if (cg == 1) {
           __half d8[8];
           d8[0] = __float2half_rn(dl);
@@ -687,8 +689,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       for (int j = 0; j < 4; ++j) {
         const uint32_t off = umma::tile_off(TILE, row, 8 * (4 * j + cg));
         out[j] = dact8(v + 8 * j, *reinterpret_cast<const uint4*>(smem + SM_A0 + off));
+        *reinterpret_cast<uint4*>(smem + SM_DA + off) = out[j];
       }
-      store_tile4(smem + SM_DA, row, cg, out);
       umma::fence_before_sync();   // accumulator reads done before the next tile's signals
       signal_smem(bars, 4);
       cp_async_wait_all();
