@@ -242,7 +242,21 @@ def main_ved():
                  {"z": torch.randn(2, 2, generator=gen(24))}, {})
 
 
+def main_cb():
+    """continuous_bernoulli sampler (utils/prob.py:27) on real-valued targets in [0, 1]"""
+    dev = dict(device="cpu")
+    x = blobs(8, 12, 12, seed=30, binary=False).clamp(0.02, 0.98)
+    x[0, 0, :6] = 0.5            # exercises the Taylor branch of the log-normaliser
+    m = pv.models.iVAE((12, 12), latent_dim=2, invariances=["r"], seed=5,
+                       sampler_d="continuous_bernoulli", **dev)
+    run_case("ivae_12_r_cbern", m, dev, (x,),
+             {"latent": torch.randn(8, 3, generator=gen(31))}, {})
+
+
 def main():
+    if "--cb" in sys.argv:
+        main_cb()
+        return
     if "--ved" in sys.argv or "--ved-full" in sys.argv:
         main_ved()
         if "--all" not in sys.argv:

@@ -105,6 +105,27 @@ __device__ __forceinline__ void grid_xy(int p, int H, int W, int ndim, float& gx
 // torch clamp_probs eps for fp32 and the matching logit bound log((1-eps)/eps)
 #define PVB_PROB_EPS 1.1920928955078125e-07f
 
+// ContinuousBernoulli(probs = p).log_prob(x) and its derivative wrt p, as torch computes them
+// (torch/distributions/continuous_bernoulli.py: clamp_probs, _cont_bern_log_norm with the
+// Taylor branch inside (0.499, 0.501], xlogy / xlog1py).  FAST selects the fast intrinsics.
+template <bool FAST>
+__device__ __forceinline__ void cont_bernoulli(float p, float x, float& ll, float& dll_dp) {
+  auto lg = [](float v) { return FAST ? __logf(v) : logf(v); };
+  auto l1p = [](float v) { return FAST ? __logf(1.f + v) : log1pf(v); };
+  auto rcp = [](float v) { return FAST ? __fdividef(1.f, v) : 1.f / v; };
+  const bool unst = (p <= 0.499f) || (p > 0.501f);
+  const float cp = unst ? p : 0.499f;
+  const float A = l1p(-cp) - lg(cp);
+  const float ln_unst = lg(fabsf(A)) - (cp <= 0.5f ? l1p(-2.f * cp) : lg(2.f * cp - 1.f));
+  const float u = p - 0.5f, x2 = u * u;
+  const float taylor = 0.6931471805599453f + (4.f / 3.f + 104.f / 45.f * x2) * x2;
+  const float logC = unst ? ln_unst : taylor;
+  ll = (x == 0.f ? 0.f : x * lg(p)) + (x == 1.f ? 0.f : (1.f - x) * l1p(-p)) + logC;
+  const float dC = unst ? (-rcp(1.f - p) - rcp(p)) * rcp(A) + 2.f * rcp(1.f - 2.f * p)
+                        : 2.f * u * (4.f / 3.f + 208.f / 45.f * x2);
+  dll_dp = x * rcp(p) - (1.f - x) * rcp(1.f - p) + dC;
+}
+
 __device__ __forceinline__ void obs_terms(float l, float x, int sampler, int sigmoid_d, float sig,
                                           float& ll, float& dnll_dl, float& loc) {
   if (sampler == PVB_SAMPLER_BERNOULLI) {
@@ -128,6 +149,14 @@ __device__ __forceinline__ void obs_terms(float l, float x, int sampler, int sig
       ll = x * lg - sp;
       dnll_dl = in ? (pc - x) / (pc * (1.f - pc)) : 0.f;
     }
+  } else if (sampler == PVB_SAMPLER_CONT_BERNOULLI) {
+    float p0 = sigmoid_d ? pvb::sigmoid_f(l) : l;
+    loc = p0;
+    bool in = (p0 >= PVB_PROB_EPS) && (p0 <= 1.f - PVB_PROB_EPS);
+    float p = fminf(fmaxf(p0, PVB_PROB_EPS), 1.f - PVB_PROB_EPS);
+    float dll_dp;
+    cont_bernoulli<false>(p, x, ll, dll_dp);
+    dnll_dl = in ? -dll_dp * (sigmoid_d ? p * (1.f - p) : 1.f) : 0.f;
   } else {  // gaussian, Normal(loc, sig).log_prob(x)
     float m = sigmoid_d ? pvb::sigmoid_f(l) : l;
     loc = m;
@@ -146,6 +175,14 @@ __device__ __forceinline__ float obs_dnll_fast(float l, float x, int sampler, in
     bool in = (p >= PVB_PROB_EPS) && (p <= 1.f - PVB_PROB_EPS);
     if (sigmoid_d) return in ? (p - x) : 0.f;
     return in ? __fdividef(p - x, p * (1.f - p)) : 0.f;
+  }
+  if (sampler == PVB_SAMPLER_CONT_BERNOULLI) {
+    float p0 = sigmoid_d ? __fdividef(1.f, 1.f + __expf(-l)) : l;
+    bool in = (p0 >= PVB_PROB_EPS) && (p0 <= 1.f - PVB_PROB_EPS);
+    float p = fminf(fmaxf(p0, PVB_PROB_EPS), 1.f - PVB_PROB_EPS);
+    float ll_unused, dll_dp;
+    cont_bernoulli<true>(p, x, ll_unused, dll_dp);
+    return in ? -dll_dp * (sigmoid_d ? p * (1.f - p) : 1.f) : 0.f;
   }
   float m = sigmoid_d ? __fdividef(1.f, 1.f + __expf(-l)) : l;
   float dm = __fdividef(m - x, sig * sig);
@@ -168,6 +205,14 @@ __device__ __forceinline__ void obs_terms_fast(float l, float x, int sampler, in
     ll = x * lg - softplus_fast(lg);
     if (sigmoid_d) dnll_dl = in ? (p - x) : 0.f;
     else dnll_dl = in ? __fdividef(pc - x, pc * (1.f - pc)) : 0.f;
+  } else if (sampler == PVB_SAMPLER_CONT_BERNOULLI) {
+    float p0 = sigmoid_d ? __fdividef(1.f, 1.f + __expf(-l)) : l;
+    loc = p0;
+    bool in = (p0 >= PVB_PROB_EPS) && (p0 <= 1.f - PVB_PROB_EPS);
+    float p = fminf(fmaxf(p0, PVB_PROB_EPS), 1.f - PVB_PROB_EPS);
+    float dll_dp;
+    cont_bernoulli<true>(p, x, ll, dll_dp);
+    dnll_dl = in ? -dll_dp * (sigmoid_d ? p * (1.f - p) : 1.f) : 0.f;
   } else {
     float m = sigmoid_d ? __fdividef(1.f, 1.f + __expf(-l)) : l;
     loc = m;

@@ -160,8 +160,8 @@ extern "C" int pvb_obs_loglik(const float* logit, const float* x, const float* w
                               float* dlogit, float* loc, int64_t I, int64_t B, int N, int sampler,
                               int sigmoid_d, float decoder_sig, void* stream) {
   PVB_CHECK_ARG(logit && x && rowll && I >= 0 && B > 0 && N > 0, "pvb_obs_loglik: bad argument");
-  PVB_CHECK_ARG(sampler == PVB_SAMPLER_BERNOULLI || sampler == PVB_SAMPLER_GAUSSIAN,
-                "pvb_obs_loglik: sampler %d not supported (bernoulli, gaussian)", sampler);
+  PVB_CHECK_ARG(sampler >= PVB_SAMPLER_BERNOULLI && sampler <= PVB_SAMPLER_CONT_BERNOULLI,
+                "pvb_obs_loglik: unknown sampler %d", sampler);
   PVB_CHECK_ARG(sampler != PVB_SAMPLER_GAUSSIAN || decoder_sig > 0.f, "pvb_obs_loglik: decoder_sig must be > 0");
   int64_t R = I * N;
   if (R == 0) return 0;

@@ -833,8 +833,8 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
   PVB_CHECK_ARG(Uv && W1 && b1 && W2 && b2 && wo && bo, "pvb_sdec_tc_step: null weights");
   PVB_CHECK_ARG(ndim == 1 || ndim == 2, "pvb_sdec_tc_step: ndim must be 1 or 2");
   PVB_CHECK_ARG(I >= 0 && B > 0 && H > 0 && W > 0, "pvb_sdec_tc_step: bad dims");
-  PVB_CHECK_ARG(sampler == PVB_SAMPLER_BERNOULLI || sampler == PVB_SAMPLER_GAUSSIAN,
-                "pvb_sdec_tc_step: sampler %d not supported", sampler);
+  PVB_CHECK_ARG(sampler >= PVB_SAMPLER_BERNOULLI && sampler <= PVB_SAMPLER_CONT_BERNOULLI,
+                "pvb_sdec_tc_step: unknown sampler %d", sampler);
   PVB_CHECK_ARG(!backward || (x && gUv_part && wgrad_part), "pvb_sdec_tc_step: backward needs x and workspaces");
   PVB_CHECK_ARG(((uintptr_t)W1 % 16 == 0) && ((uintptr_t)W2 % 16 == 0), "pvb_sdec_tc_step: weights must be 16-byte aligned");
   PVB_CHECK_ARG(!backward || ((uintptr_t)wgrad_part % 16 == 0), "pvb_sdec_tc_step: wgrad_part must be 16-byte aligned");

@@ -777,7 +777,7 @@ class SVIEngine:
                                          for l in layers)
                 and dec.coord_latent.fc_coord.out_features == 128
                 and dec.activation == "tanh" and N >= 32
-                and self.model.sampler_d.name in ("bernoulli", "gaussian"))
+                and self.model.sampler_d.name in ("bernoulli", "gaussian", "continuous_bernoulli"))
 
     def _program(self, B, has_y, mode="main"):
         key = (B, has_y, mode)

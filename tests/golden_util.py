@@ -21,6 +21,8 @@ CASES = {
     "ivae_16_s_softplus": ("ivae", dict(
         data_dim=(16, 16), latent_dim=2, invariances=["s"], activation="softplus",
         hidden_dim_e=[64, 32], hidden_dim_d=[64, 64, 64])),
+    "ivae_12_r_cbern": ("ivae", dict(data_dim=(12, 12), latent_dim=2, invariances=["r"],
+                                     sampler_d="continuous_bernoulli")),
     "jivae_28_r": ("jivae", dict(data_dim=(28, 28), latent_dim=2, discrete_dim=3,
                                  invariances=["r"])),
     "ssivae_16_r_unsup": ("ssivae", dict(data_dim=(16, 16), latent_dim=2, num_classes=4,

@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 
 LOSS_RTOL = 1e-3
 LOC_ATOL = 1e-3
-SEEDS = {"ivae_12_rts_cond_gauss": 2, "ivae_12_vanilla": 3, "ivae_16_s_softplus": 4}
+SEEDS = {"ivae_12_rts_cond_gauss": 2, "ivae_12_vanilla": 3, "ivae_16_s_softplus": 4,
+         "ivae_12_r_cbern": 5}
 IVAE_CASES = [n for n in sorted(CASES) if CASES[n][0] == "ivae"]
 
 
