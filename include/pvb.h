@@ -252,6 +252,8 @@ int pvb_mlp_wgrad(const pvb_wgrad_problem* problems, int n_problems, int64_t M, 
  * fused decoder's per-tile partials (gUv_part; or reads gUv when gUv_part is
  * NULL), pvb_fold_bwd, then pvb_latent_bwd on the resulting dz
  * (gmu / gs_pre written when non-NULL; requires I rows of eps/sigma/s_pre). */
+/* part must hold pvb_latent_side_num_partials(I) rows of Hd*(ndim+1+L+C) floats */
+int pvb_latent_side_num_partials(int64_t I);
 int pvb_latent_side_bwd(const pvb_fold_cfg* cfg, const float* z, const float* cond,
                         const float* Wc, const float* Wz, const float* gUv,
                         const float* gUv_part, int N, float* gz, float* gcond,

@@ -90,6 +90,7 @@ SIGNATURES = {
     "pvb_mlp_tail_fwd": [C.POINTER(MlpTailArgs), _st],
     "pvb_mlp_chain_bwd": [C.POINTER(MlpChainArgs), _st],
     "pvb_mlp_wgrad": [C.POINTER(WgradProblem), _i32, _i64, _st],
+    "pvb_latent_side_num_partials": [_i64],
     "pvb_latent_side_bwd": [C.POINTER(FoldCfg), _f, _f, _f, _f, _f, _f, _i32, _f, _f, _f, _f, _f, _f,
                             _f, _fl, _f, _f, _i64, _st],
     "pvb_conv_fwd": [_f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],

@@ -235,24 +235,36 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
 }
 
 // ---- forward layer for small batches: C = act(A[M,K] B[N,K]^T + bias) ------------------------
-// Both operands are K-contiguous, so tiles are staged with 16-byte cp.async (4 per thread and
-// chunk instead of 32 scalar ones) into K-major smem; 4 stages keep the loads ahead of the math.
-// Thread (ty, tx): rows {2ty, 2ty+1}, columns {tx, tx+8, tx+16, tx+24} (conflict-free float4 reads).
+// Both operands are K-contiguous: tiles are staged with 16-byte cp.async into K-major smem.
+// A 32 x 32 output tile per CTA leaves one warp per scheduler, which cannot hide FMA / LDS
+// latency, so the K loop is split over LKG = 4 thread groups of the same CTA (group g takes
+// chunks g, g+4, ... through its own cp.async ring and named barrier); the four partial tiles
+// are summed in a fixed order (deterministic), then bias + activation.
+// Thread (ty, tx) of a group: rows {2ty, 2ty+1}, columns {tx, tx+8, tx+16, tx+24}.
 constexpr int FLD = SBK + 4;
-__global__ void __launch_bounds__(SNT)
+constexpr int LKG = 4;       // K groups per CTA
+constexpr int LGS = 3;       // cp.async stages per group
+constexpr int LS_THREADS = LKG * SNT;
+constexpr int LS_SMEM = LKG * LGS * (SBM + SBN) * FLD * 4;
+static_assert(LKG * SBM * (SBN + 1) * 4 <= LS_SMEM, "reduction scratch aliases the stage buffers");
+
+__global__ void __launch_bounds__(LS_THREADS)
 linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                     float* __restrict__ Cpre, const float* __restrict__ bias, int M, int N, int K,
                     int act) {
-  __shared__ __align__(16) float As[SST][SBM][FLD];
-  __shared__ __align__(16) float Bs[SST][SBN][FLD];
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) float ls_smem[];
+  const int g = threadIdx.x >> 7, tid = threadIdx.x & 127;
+  float (*As)[SBM][FLD] = reinterpret_cast<float (*)[SBM][FLD]>(ls_smem + g * LGS * (SBM + SBN) * FLD);
+  float (*Bs)[SBN][FLD] = reinterpret_cast<float (*)[SBN][FLD]>(ls_smem + g * LGS * (SBM + SBN) * FLD +
+                                                                 LGS * SBM * FLD);
   const int tx = tid & 7, ty = tid >> 3;
   const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
   const int n_chunks = (K + SBK - 1) / SBK;
+  const int my_n = (n_chunks - g + LKG - 1) / LKG;   // chunks g, g + LKG, ...
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  auto stage = [&](int chunk) {
-    const int buf = chunk % SST;
-    const int k0 = chunk * SBK;
+  auto stage = [&](int ci) {
+    const int buf = ci % LGS;
+    const int k0 = (g + ci * LKG) * SBK;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       int idx = tid + it * SNT;          // 256 16-byte pieces per operand tile
@@ -275,16 +287,16 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
     }
   };
 #pragma unroll
-  for (int c = 0; c < SST - 1; ++c) {
-    if (c < n_chunks) stage(c);
+  for (int c = 0; c < LGS - 1; ++c) {
+    if (c < my_n) stage(c);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
-  for (int c = 0; c < n_chunks; ++c) {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(SST - 2) : "memory");
-    __syncthreads();
-    if (c + SST - 1 < n_chunks) stage(c + SST - 1);
+  for (int c = 0; c < my_n; ++c) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(LGS - 2) : "memory");
+    asm volatile("bar.sync %0, 128;\n" ::"r"(g + 1) : "memory");   // this group's chunk c landed
+    if (c + LGS - 1 < my_n) stage(c + LGS - 1);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    const int buf = c % SST;
+    const int buf = c % LGS;
 #pragma unroll
     for (int k = 0; k < SBK; k += 4) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[buf][2 * ty][k]);
@@ -297,19 +309,26 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
       }
     }
   }
+  // cross-group reduction through smem (aliases the stage buffers: everyone is done with them)
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+  float* red = ls_smem;   // [LKG][SBM][SBN + 1]
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    int gm = m0 + 2 * ty + i;
-    if (gm >= M) continue;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int gn = n0 + tx + 8 * j;
-      if (gn >= N) continue;
-      float v = acc[i][j];
-      if (bias) v += bias[gn];
-      if (Cpre) Cpre[(int64_t)gm * N + gn] = v;
-      C[(int64_t)gm * N + gn] = pvb::act_fwd(v, act);
-    }
+    for (int j = 0; j < 4; ++j)
+      red[(g * SBM + 2 * ty + i) * (SBN + 1) + tx + 8 * j] = acc[i][j];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < SBM * SBN; idx += LS_THREADS) {
+    int r = idx / SBN, c = idx - r * SBN;
+    int gm = m0 + r, gn = n0 + c;
+    if (gm >= M || gn >= N) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < LKG; ++q) v += red[(q * SBM + r) * (SBN + 1) + c];
+    if (bias) v += bias[gn];
+    if (Cpre) Cpre[(int64_t)gm * N + gn] = v;
+    C[(int64_t)gm * N + gn] = pvb::act_fwd(v, act);
   }
 }
 
@@ -408,7 +427,12 @@ extern "C" int pvb_linear_fwd(const float* x, const float* W, const float* b, fl
     if (tiles >= 48 && tiles < 4 * 148) {
       if (M == 0) return 0;
       dim3 grid((N + SBN - 1) / SBN, (unsigned)((M + SBM - 1) / SBM));
-      linear_small_kernel<<<grid, SNT, 0, (cudaStream_t)stream>>>(x, W, y, pre, b, (int)M, N, K, act);
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM);
+        attr = true;
+      }
+      linear_small_kernel<<<grid, LS_THREADS, LS_SMEM, (cudaStream_t)stream>>>(x, W, y, pre, b, (int)M, N, K, act);
       pvb::count_launch();
       return pvb::launch_status();
     }

@@ -261,7 +261,13 @@ __global__ void __launch_bounds__(MT) mlp_chain_bwd_kernel(pvb_mlp_chain_args a)
 }
 
 // ---- grouped weight gradients ------------------------------------------------------------------
-constexpr int WG_T = 32, WG_NT = 128, WG_MAXP = 8, WG_ST = 3;
+// One 32 x 32 tile of one dW per CTA; the reduction over the M batch rows is split over WG_G = 4
+// thread groups of the CTA (own cp.async ring + named barrier each), partial tiles summed in a
+// fixed order.
+constexpr int WG_T = 32, WG_NT = 128, WG_MAXP = 8, WG_ST = 3, WG_G = 4;
+constexpr int WG_THREADS = WG_G * WG_NT;
+constexpr int WG_LD = WG_T + 4;
+constexpr int WG_SMEM = WG_G * WG_ST * 2 * WG_T * WG_LD * 4;
 struct WgradArgs {
   int64_t M;
   int n_prob;
@@ -275,25 +281,29 @@ __device__ __forceinline__ void cpa4z(float* smem_dst, const float* gsrc, bool p
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 
-__global__ void __launch_bounds__(WG_NT) mlp_wgrad_kernel(WgradArgs a) {
-  __shared__ __align__(16) float As[WG_ST][WG_T][WG_T + 4];   // [m][n]
-  __shared__ __align__(16) float Bs[WG_ST][WG_T][WG_T + 4];   // [m][k]
+__global__ void __launch_bounds__(WG_THREADS) mlp_wgrad_kernel(WgradArgs a) {
+  extern __shared__ __align__(16) float wg_smem[];
+  const int g = threadIdx.x >> 7, tid = threadIdx.x & 127;
+  float (*As)[WG_T][WG_LD] = reinterpret_cast<float (*)[WG_T][WG_LD]>(wg_smem + g * WG_ST * 2 * WG_T * WG_LD);
+  float (*Bs)[WG_T][WG_LD] = reinterpret_cast<float (*)[WG_T][WG_LD]>(wg_smem + g * WG_ST * 2 * WG_T * WG_LD +
+                                                                     WG_ST * WG_T * WG_LD);
   int pi = 0;
   while (pi + 1 < a.n_prob && (int)blockIdx.x >= a.tile0[pi + 1]) ++pi;
   const pvb_wgrad_problem pr = a.p[pi];
   const int t = blockIdx.x - a.tile0[pi];
   const int tk_n = (pr.K + WG_T - 1) / WG_T;
   const int n0 = (t / tk_n) * WG_T, kk0 = (t % tk_n) * WG_T;
-  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;   // 8 k-quads x 16 n-pairs
+  const int tx = tid & 7, ty = tid >> 3;   // 8 k-quads x 16 n-pairs
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  float bsum = 0.f;   // threads 0..31 of the k-tile 0 CTA: column sum of d
+  float bsum = 0.f;   // threads 0..31 of each group in the k-tile 0 CTA: column sum of d
   const bool do_bias = pr.db && kk0 == 0;
   const int n_chunks = (int)((a.M + WG_T - 1) / WG_T);
+  const int my_n = (n_chunks - g + WG_G - 1) / WG_G;
   const bool vec = ((pr.N & 3) == 0) && ((pr.K & 3) == 0) && (((uintptr_t)pr.d & 15) == 0) &&
                    (((uintptr_t)pr.x & 15) == 0);
-  auto stage = [&](int chunk) {
-    const int buf = chunk % WG_ST;
-    const int64_t m0 = (int64_t)chunk * WG_T;
+  auto stage = [&](int ci) {
+    const int buf = ci % WG_ST;
+    const int64_t m0 = (int64_t)(g + ci * WG_G) * WG_T;
     if (vec) {
       // 256 16-byte pieces per operand tile, 2 per thread (a piece is all-in or all-out)
 #pragma unroll
@@ -324,13 +334,13 @@ __global__ void __launch_bounds__(WG_NT) mlp_wgrad_kernel(WgradArgs a) {
   };
 #pragma unroll
   for (int c = 0; c < WG_ST - 1; ++c) {
-    if (c < n_chunks) stage(c);
+    if (c < my_n) stage(c);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
-  for (int c = 0; c < n_chunks; ++c) {
+  for (int c = 0; c < my_n; ++c) {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(WG_ST - 2) : "memory");
-    __syncthreads();
-    if (c + WG_ST - 1 < n_chunks) stage(c + WG_ST - 1);
+    asm volatile("bar.sync %0, 128;\n" ::"r"(g + 1) : "memory");
+    if (c + WG_ST - 1 < my_n) stage(c + WG_ST - 1);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     const int buf = c % WG_ST;
 #pragma unroll
@@ -347,21 +357,36 @@ __global__ void __launch_bounds__(WG_NT) mlp_wgrad_kernel(WgradArgs a) {
       for (int m = 0; m < WG_T; ++m) bsum += As[buf][m][tid];
     }
   }
+  // cross-group reduction (aliases the stage buffers)
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+  float* red = wg_smem;                       // [WG_G][32][33]
+  float* bred = wg_smem + WG_G * WG_T * (WG_T + 1);   // [WG_G][32]
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    int n = n0 + ty * 2 + i;
-    if (n >= pr.N) continue;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int k = kk0 + tx * 4 + j;
-      if (k < pr.K) pr.dW[(size_t)n * pr.K + k] += acc[i][j];
-    }
+    for (int j = 0; j < 4; ++j) red[(g * WG_T + ty * 2 + i) * (WG_T + 1) + tx * 4 + j] = acc[i][j];
+  if (do_bias && tid < WG_T) bred[g * WG_T + tid] = bsum;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < WG_T * WG_T; idx += WG_THREADS) {
+    int r = idx / WG_T, c = idx - r * WG_T;
+    int n = n0 + r, k = kk0 + c;
+    if (n >= pr.N || k >= pr.K) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < WG_G; ++q) v += red[(q * WG_T + r) * (WG_T + 1) + c];
+    pr.dW[(size_t)n * pr.K + k] += v;
   }
-  if (do_bias && tid < WG_T && n0 + tid < pr.N) pr.db[n0 + tid] += bsum;
+  if (do_bias && threadIdx.x < WG_T && n0 + threadIdx.x < pr.N) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < WG_G; ++q) v += bred[q * WG_T + threadIdx.x];
+    pr.db[n0 + threadIdx.x] += v;
+  }
 }
 
 // ---- per-instance latent-side backward ---------------------------------------------------------
-constexpr int LS_G = 256, LS_T = 128, LS_MAXR = 40;
+constexpr int LS_G = 512, LS_T = 128, LS_MAXR = 40;   // up to LS_G CTAs, one instance at a time
 
 __global__ void __launch_bounds__(LS_T)
 latent_side_bwd_kernel(pvb_fold_cfg cfg, const float* __restrict__ z, const float* __restrict__ cond,
@@ -558,10 +583,17 @@ extern "C" int pvb_mlp_wgrad(const pvb_wgrad_problem* problems, int n_problems, 
     tiles += ((problems[i].N + WG_T - 1) / WG_T) * ((problems[i].K + WG_T - 1) / WG_T);
   }
   a.tile0[n_problems] = tiles;
-  mlp_wgrad_kernel<<<tiles, WG_NT, 0, (cudaStream_t)stream>>>(a);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    attr = true;
+  }
+  mlp_wgrad_kernel<<<tiles, WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(a);
   pvb::count_launch();
   return pvb::launch_status();
 }
+
+extern "C" int pvb_latent_side_num_partials(int64_t I) { return (int)(I < LS_G ? (I > 0 ? I : 1) : LS_G); }
 
 extern "C" int pvb_latent_side_bwd(const pvb_fold_cfg* cfg, const float* z, const float* cond,
                                    const float* Wc, const float* Wz, const float* gUv,
@@ -584,7 +616,8 @@ extern "C" int pvb_latent_side_bwd(const pvb_fold_cfg* cfg, const float* z, cons
     cudaFuncSetAttribute(latent_side_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  latent_side_bwd_kernel<<<LS_G, LS_T, smem, (cudaStream_t)stream>>>(
+  const int grid = (int)(I < LS_G ? I : LS_G);
+  latent_side_bwd_kernel<<<grid, LS_T, smem, (cudaStream_t)stream>>>(
       *cfg, z, cond, Wc, Wz, gUv, gUv_part, N, gz, gcond, part, eps, sigma, s_pre, w, beta, gmu,
       gs_pre, I);
   pvb::count_launch();

@@ -282,7 +282,8 @@ class DecoderOps:
                                               m._dx_prior, m._dy_prior, m._sc_prior)
             self.Uv = torch.empty(I, 3, Hd0, **f32)
             self.gUv = torch.empty(I, 3, Hd0, **f32)
-            self.G_fold = ops.fold_bwd_num_partials()
+            self.G_fold = max(ops.fold_bwd_num_partials(), ops.latent_side_num_partials(I))
+            self.G_side = ops.latent_side_num_partials(I)
             self.fold_per = Hd0 * (m.ndim + 1 + m._latent_dim + cond_dim)
             self.fold_part = torch.empty(self.G_fold, self.fold_per, **f32)
             self.use_tc = engine.tc_eligible(dec, N)
@@ -352,14 +353,15 @@ class DecoderOps:
         else:
             ops.elbo_reduce(self.rowll, None, None, 0.0, self.ll, None, False, self.I, self.N)
 
-    def _reduce_fold_partials(self):
+    def _reduce_fold_partials(self, G=None):
         eng = self.engine
         m, flat = eng.model, eng.flat
         cl = m.decoder.coord_latent
         Hd0 = cl.fc_coord.out_features
         nd = m.ndim
         LC = m._latent_dim + self.Cd
-        G, per = self.G_fold, self.fold_per
+        G = ops.fold_bwd_num_partials() if G is None else G
+        per = self.fold_per
         o_w, o_b = flat.offset(cl.fc_coord.weight), flat.offset(cl.fc_coord.bias)
         o_z = flat.offset(cl.fc_latent.weight) if LC > 0 else o_b + Hd0
         if o_b == o_w + Hd0 * nd and o_z == o_b + Hd0:
@@ -390,7 +392,7 @@ class DecoderOps:
                             cl.fc_latent.weight.data, None, self.gUv_part, self.N, self.gz,
                             self.gcond, self.fold_part, head.eps, head.sigma, head.s_pre, w, beta,
                             head.gmu, head.gs_pre)
-        self._reduce_fold_partials()
+        self._reduce_fold_partials(self.G_side)
 
     def backward(self, z, cond):
         """Accumulates decoder weight gradients; returns dloss/dz [I,Zf]."""

@@ -277,6 +277,10 @@ def mlp_wgrad(problems, M):
     check(_lib.lib().pvb_mlp_wgrad(problems, len(problems), M, _stream()), "pvb_mlp_wgrad")
 
 
+def latent_side_num_partials(I):
+    return _lib.lib().pvb_latent_side_num_partials(I)
+
+
 def latent_side_bwd(cfg, z, cond, Wc, Wz, gUv, gUv_part, N, gz, gcond, part, eps, sigma, s_pre, w,
                     beta, gmu, gs_pre):
     I = z.shape[0]
