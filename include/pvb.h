@@ -291,6 +291,16 @@ int pvb_upsample2_fwd(const float* x, float* y, int64_t BC, int H, int Wd,
 int pvb_upsample2_bwd(const float* dy, float* dx, int64_t BC, int H, int Wd,
                       int two_d, int bilinear, void* stream);
 
+/* ---- regression variant (models/ss_reg_ivae.py:172-175,205-207,240-242) ----
+ * loss_out[0] += scale * sum_i log N(y_i; loc_i, sigma)   (loc may be NULL = 0;
+ * loss_out may be NULL); gloc[i] = scale (y_i - loc_i) / sigma^2 when non-NULL
+ * (the gradient of that term wrt loc; scale = -multiplier for a loss term). */
+int pvb_normal_logprob(const float* y, const float* loc, float sigma, float scale,
+                       float* loss_out, float* gloc, int64_t n, void* stream);
+/* dx_cols[M, ncols] (+)= dpre[M, N] W[N, K][:, col0 : col0 + ncols] */
+int pvb_linear_dx_cols(const float* dpre, const float* W, float* dx_cols, int64_t M,
+                       int N, int K, int col0, int ncols, int accumulate, void* stream);
+
 /* ---- optimizer / reductions -------------------------------------------- */
 /* out[j] (+)= sum_g part[g*part_stride + j], j < n, fixed order (deterministic) */
 int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,

@@ -253,7 +253,26 @@ def main_cb():
              {"latent": torch.randn(8, 3, generator=gen(31))}, {})
 
 
+def main_ssreg():
+    """ss_reg_iVAE (regression variant, Trace_ELBO): unsupervised (sampled y) and supervised"""
+    dev = dict(device="cpu")
+    tkw = dict(task="regression", **dev)
+    x = blobs(8, 16, 16, seed=40).flatten(1)
+    m = pv.models.ss_reg_iVAE((16, 16), latent_dim=2, reg_dim=2, invariances=["r", "t"], seed=1, **dev)
+    run_case("ssreg_16_rt_unsup", m, tkw, (x, None),
+             {"z": torch.randn(8, 5, generator=gen(41)), "y": torch.randn(8, 2, generator=gen(42))},
+             {"aux_loss_multiplier": 30.0, "scale_factor": 2.0}, aux=True)
+    ys = torch.randn(8, 2, generator=gen(43)) * 0.7
+    m = pv.models.ss_reg_iVAE((16, 16), latent_dim=2, reg_dim=2, invariances=["r", "t"], seed=1, **dev)
+    run_case("ssreg_16_rt_sup", m, tkw, (x, ys),
+             {"z": torch.randn(8, 5, generator=gen(44))},
+             {"aux_loss_multiplier": 30.0, "scale_factor": 2.0}, aux=True)
+
+
 def main():
+    if "--ssreg" in sys.argv:
+        main_ssreg()
+        return
     if "--cb" in sys.argv:
         main_cb()
         return

@@ -341,6 +341,53 @@ def ssivae_aux_loss(sd, cfg, xs, ys=None, aux_loss_multiplier=20.0):
 
 
 # --------------------------------------------------------------------------
+# ss_reg_iVAE  (models/ss_reg_ivae.py:152-242 under Trace_ELBO)
+# --------------------------------------------------------------------------
+def regressor(sd, cfg, x, prefix="encoder_y"):
+    """fcRegressorNet.forward (nets/fc.py:298-304)."""
+    h = fc_stack(sd, prefix, x.reshape(-1, cfg.n_pix), cfg.activation)
+    return F.linear(h, sd[prefix + ".out.weight"], sd[prefix + ".out.bias"])
+
+
+def ss_reg_loss(sd, cfg, xs, eps, ys=None, beta=1.0, eps_y=None, reg_sig=0.5):
+    """cfg.c_dim = reg_dim.  Supervised: ys observed under p(y) = N(0, reg_sig).
+    Unsupervised: y = c(x) + reg_sig * eps_y sampled from q(y|x) = N(c(x), reg_sig)
+    (ss_reg_ivae.py:205-207), scored under the prior (:172-175); the "y" sites are NOT scaled."""
+    bsz = xs.shape[0]
+    xf = xs.reshape(bsz, cfg.n_pix)
+    grid = generate_grid(cfg.data_dim, xs.dtype) if cfg.coord > 0 else None
+    sig_t = xs.new_full((bsz, cfg.c_dim), reg_sig)
+    out = {}
+    if ys is None:
+        c = regressor(sd, cfg, xs)
+        y = c + reg_sig * eps_y
+        log_qy = normal_logprob(y, c, sig_t).sum()
+        out["c"] = c
+    else:
+        y = ys
+        log_qy = 0.0
+    mu, sig, _ = fc_encoder(sd, [xf, y], cfg.activation, None, flat=False)
+    z = mu + sig * eps
+    log_q = normal_logprob(z, mu, sig)
+    log_p = normal_logprob(z, torch.zeros_like(z), torch.ones_like(z))
+    log_py = normal_logprob(y, torch.zeros_like(y), sig_t).sum()
+    loc = _decode_spatial(sd, cfg, z, y, grid).reshape(bsz, -1)
+    ll = log_lik(loc, xf, cfg.sampler_d, cfg.decoder_sig)
+    elbo = (ll + beta * (log_p - log_q)).sum() + log_py - log_qy
+    out.update({"loss": -elbo, "ll": ll, "loc": loc, "z": z, "mu": mu, "sigma": sig, "y": y})
+    return out
+
+
+def ss_reg_aux_loss(sd, cfg, xs, ys=None, aux_loss_multiplier=20.0, reg_sig=0.5):
+    """model_aux (ss_reg_ivae.py:229-242): -mult * sum_b log N(y_b; c(x_b), reg_sig)."""
+    if ys is None:
+        return {"loss": xs.new_zeros(())}
+    c = regressor(sd, cfg, xs)
+    lp = normal_logprob(ys, c, torch.full_like(c, reg_sig))
+    return {"loss": -(aux_loss_multiplier * lp).sum(), "c": c}
+
+
+# --------------------------------------------------------------------------
 # VED  (models/ved.py:122-163 under Trace_ELBO; nets/conv.py)
 # --------------------------------------------------------------------------
 class VedCfg:

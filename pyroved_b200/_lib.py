@@ -101,6 +101,8 @@ SIGNATURES = {
     "pvb_maxpool2_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_upsample2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_upsample2_bwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
+    "pvb_normal_logprob": [_f, _f, _fl, _fl, _f, _f, _i64, _st],
+    "pvb_linear_dx_cols": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
     "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
                          _i32, _i32, _i32, _i32, _i32, _fl, _i32, _st],

@@ -406,3 +406,61 @@ extern "C" int pvb_class_nll(const float* logits, const float* y_onehot, float m
   sum_into_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(nll_b, B, 1.f, loss_out); pvb::count_launch();
   return pvb::launch_status();
 }
+
+// ---- Normal(loc, sigma) observation terms of the regression variant (ss_reg_iVAE) ------------
+namespace {
+// loss_out[0] += scale * sum_i log N(y_i; loc_i, sigma)  (single block, fixed order);
+// optional gloc[i] = scale (y_i - loc_i) / sigma^2 = d(that term)/dloc_i
+__global__ void normal_logprob_kernel(const float* __restrict__ y, const float* __restrict__ loc,
+                                      float sigma, float scale, float* __restrict__ loss_out,
+                                      float* __restrict__ gloc, int64_t n) {
+  __shared__ float sm[32];
+  const float inv_var = 1.f / (sigma * sigma);
+  const float c = -logf(sigma) - 0.91893853320467274f;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float d = y[i] - (loc ? loc[i] : 0.f);
+    s += -0.5f * d * d * inv_var + c;
+    if (gloc) gloc[i] = scale * d * inv_var;
+  }
+  s = pvb::block_sum(s, sm);
+  if (threadIdx.x == 0 && loss_out) loss_out[0] += scale * s;
+}
+// dx_cols[m][j] (+)= sum_n dpre[m][n] W[n][col0 + j]: the slice of a layer's input gradient that
+// belongs to a concatenated conditioning vector; one warp per output
+__global__ void linear_dx_cols_kernel(const float* __restrict__ dpre, const float* __restrict__ W,
+                                      float* __restrict__ dx, int64_t M, int N, int K, int col0,
+                                      int ncols, int accumulate) {
+  int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (o >= M * ncols) return;
+  int64_t m = o / ncols;
+  int j = (int)(o - m * ncols);
+  float s = 0.f;
+  for (int n = lane; n < N; n += 32) s = fmaf(dpre[m * N + n], W[(int64_t)n * K + col0 + j], s);
+  s = pvb::warp_sum(s);
+  if (lane == 0) dx[o] = accumulate ? dx[o] + s : s;
+}
+}  // namespace
+
+extern "C" int pvb_normal_logprob(const float* y, const float* loc, float sigma, float scale,
+                                  float* loss_out, float* gloc, int64_t n, void* stream) {
+  PVB_CHECK_ARG(y && n >= 0 && sigma > 0.f && (loss_out || gloc), "pvb_normal_logprob: bad argument");
+  if (n == 0) return 0;
+  normal_logprob_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(y, loc, sigma, scale, loss_out, gloc, n);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
+extern "C" int pvb_linear_dx_cols(const float* dpre, const float* W, float* dx_cols, int64_t M, int N,
+                                  int K, int col0, int ncols, int accumulate, void* stream) {
+  PVB_CHECK_ARG(dpre && W && dx_cols && M >= 0 && N > 0 && K > 0 && col0 >= 0 && ncols > 0 &&
+                    col0 + ncols <= K,
+                "pvb_linear_dx_cols: bad argument");
+  if (M == 0) return 0;
+  int64_t threads = M * ncols * 32;
+  linear_dx_cols_kernel<<<pvb::cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+      dpre, W, dx_cols, M, N, K, col0, ncols, accumulate);
+  pvb::count_launch();
+  return pvb::launch_status();
+}

@@ -249,6 +249,10 @@ class StepProgram:
         m = self.engine.model
         return [m.encoder_z, m.decoder]
 
+    def set_eps(self, eps):
+        """Inject the noise of the reparameterised sites (parity tests)."""
+        self.eps.copy_(eps.reshape(self.eps.shape), non_blocking=True)
+
 
 class DecoderOps:
     """Decoder forward/backward over I instances (I = B, or K*B when a discrete
@@ -426,6 +430,8 @@ class DecoderOps:
                            False, flat.gv(dec.out.weight), flat.gv(dec.out.bias), None)
             d_in = self.dmlp.backward(d_hl, self.dec_scratch, True)
             self.gz.copy_(d_in[:, :self.Zf])
+            if self.gcond is not None:
+                self.gcond.copy_(d_in[:, self.Zf:])
         return self.gz
 
 
@@ -464,8 +470,10 @@ class GaussHead:
         return self.dh
 
 
-def _mlp_scratch(layers, M, device):
-    wmax = max([l.in_features for l in layers[1:]] + [layers[-1].out_features, 1])
+def _mlp_scratch(layers, M, device, with_input=False):
+    """ping-pong buffers for MLP.backward (with_input: room for the input gradient too)"""
+    first = 0 if with_input else 1
+    wmax = max([l.in_features for l in layers[first:]] + [layers[-1].out_features, 1])
     return [torch.empty(M * wmax, device=device, dtype=torch.float32) for _ in range(2)]
 
 
@@ -550,7 +558,166 @@ class SpatialVAEProgram(StepProgram):
             self.enc.backward([self.head.gmu, self.head.gs_pre])
             return
         dh = self.head.backward(self.enc.h[-1], gz, None, beta)
-        self.enc.backward(dh, self.enc_scratch, False)
+        self.enc_dx = self.enc.backward(dh, self.enc_scratch, getattr(self, "need_enc_dx", False))
+
+
+class SsRegProgram(SpatialVAEProgram):
+    """ss_reg_iVAE under Trace_ELBO (reference models/ss_reg_ivae.py:152-219).
+    Supervised (ys observed): the conditional iVAE trace plus log N(ys; 0, s).
+    Unsupervised: y = c(x) + s eps_y is a reparameterised sample of q(y|x) = N(c(x), s); it
+    conditions encoder_z and the decoder, is scored under the prior N(0, s), and its gradient
+    (decoder + encoder_z + prior) flows back into the regressor."""
+
+    def __init__(self, engine, B, has_y):
+        m = engine.model
+        super().__init__(engine, B, True, cond_dim=m.reg_dim)
+        self.sup = has_y
+        self.sig = float(m.reg_sig)
+        self.has_y = has_y
+        if has_y:
+            return
+        dev, flat = engine.device, engine.flat
+        f32 = dict(device=dev, dtype=torch.float32)
+        C = m.reg_dim
+        reg = m.encoder_y
+        layers = linear_layers(reg.fc_layers)
+        self.eps_y = torch.zeros(B, C, **f32)
+        self.gy = torch.empty(B, C, **f32)
+        self.dec.gcond = torch.empty(B, C, **f32)
+        self.need_enc_dx = True
+        if not self.fused:
+            self.enc_scratch = _mlp_scratch(self.enc.layers, B, dev, with_input=True)
+        self.reg_fused = (not engine.force_generic) and FusedStack.eligible(layers, [reg.out], B)
+        if self.reg_fused:
+            self.reg = FusedStack(engine, layers, reg.activation, [reg.out], B)
+            self.c = self.reg.hout[0]
+        else:
+            self.reg = MLP(layers, reg.activation, B, dev, flat)
+            self.reg_scratch = _mlp_scratch(layers, B, dev)
+            self.c = torch.empty(B, C, **f32)
+            self.dh_r = torch.empty(B, reg.out.in_features, **f32)
+
+    def grad_modules(self):
+        m = self.engine.model
+        return [m.encoder_z, m.decoder] + ([] if self.sup else [m.encoder_y])
+
+    def set_eps(self, eps):
+        if isinstance(eps, dict):
+            self.eps.copy_(eps["z"].reshape(self.eps.shape), non_blocking=True)
+            if not self.sup:
+                self.eps_y.copy_(eps["y"].reshape(self.eps_y.shape), non_blocking=True)
+        else:
+            super().set_eps(eps)
+
+    def load(self, x, y):
+        if self.sup:
+            return super().load(x, y)
+        B, N = self.B, self.N
+        self.x.copy_(x.reshape(B, -1), non_blocking=True)
+        self.enc_in[:, :N].copy_(self.x)
+
+    def forward(self, beta, want_grad, gen_eps):
+        eng = self.engine
+        flat = eng.flat
+        if not self.sup:
+            reg = eng.model.encoder_y
+            if self.reg_fused:
+                self.reg.forward(self.x)
+            else:
+                h = self.reg.forward(self.x)
+                ops.linear_fwd(h, reg.out.weight.data, reg.out.bias.data, None, out=self.c)
+            if gen_eps:
+                ops.randn(self.eps_y, eng.seed + 0x5bd1e995, eng.step_counter,
+                          eng.eps_first_index(self.eps_y.numel()))
+            ops.axpy_out(self.c, self.eps_y, self.sig, self.y)        # y = c + s eps_y
+            self.enc_in[:, self.N:].copy_(self.y)
+        super().forward(beta, want_grad, gen_eps)
+        ops.normal_logprob(self.y, None, self.sig, -1.0, flat.loss)   # - log p(y)
+        if not self.sup:
+            ops.normal_logprob(self.y, self.c, self.sig, 1.0, flat.loss)   # + log q(y|x)
+
+    def backward(self, beta):
+        super().backward(beta)
+        if self.sup:
+            return
+        eng = self.engine
+        flat = eng.flat
+        reg = eng.model.encoder_y
+        # dloss/dy = decoder path + encoder_z path + prior term y / s^2
+        if self.fused:
+            W0 = self.enc.layers[0].weight.data
+            ops.linear_dx_cols(self.enc.dpre[0], W0, self.gy, self.N)
+        else:
+            self.gy.copy_(self.enc_dx[:, self.N:])
+        ops.axpy_out(self.gy, self.dec.gcond, 1.0, self.gy)
+        ops.axpy_out(self.gy, self.y, 1.0 / (self.sig * self.sig), self.gy)
+        if self.reg_fused:
+            self.reg.backward([self.gy])
+        else:
+            hr = self.reg.h[-1]
+            ops.linear_bwd(hr, reg.out.weight.data, None, None, self.gy, self.gy, self.dh_r, False,
+                           flat.gv(reg.out.weight), flat.gv(reg.out.bias), None)
+            self.reg.backward(self.dh_r, self.reg_scratch, False)
+
+
+class RegressorAuxProgram(StepProgram):
+    """ss_reg_iVAE auxiliary step (reference models/ss_reg_ivae.py:229-242):
+    loss = -mult * sum log N(ys; c(x), s); no sites when ys is None."""
+
+    def __init__(self, engine, B, has_y):
+        super().__init__(engine, B, has_y)
+        m = engine.model
+        dev, flat = engine.device, engine.flat
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.N, self.C = m._n_pix, m.reg_dim
+        self.sig = float(m.reg_sig)
+        self.x = torch.zeros(B, self.N, **f32)
+        self.y = torch.zeros(B, self.C, **f32)
+        self.gc = torch.empty(B, self.C, **f32)
+        self.eps = torch.zeros(1, **f32)
+        reg = m.encoder_y
+        layers = linear_layers(reg.fc_layers)
+        self.reg_fused = (not engine.force_generic) and FusedStack.eligible(layers, [reg.out], B)
+        if self.reg_fused:
+            self.reg = FusedStack(engine, layers, reg.activation, [reg.out], B)
+            self.c = self.reg.hout[0]
+        else:
+            self.reg = MLP(layers, reg.activation, B, dev, flat)
+            self.reg_scratch = _mlp_scratch(layers, B, dev)
+            self.c = torch.empty(B, self.C, **f32)
+            self.dh_r = torch.empty(B, reg.out.in_features, **f32)
+
+    def grad_modules(self):
+        return [self.engine.model.encoder_y] if self.has_y else []
+
+    def load(self, x, y):
+        self.x.copy_(x.reshape(self.B, -1), non_blocking=True)
+        if y is not None:
+            self.y.copy_(y.reshape(self.B, -1), non_blocking=True)
+
+    def forward(self, mult, want_grad, gen_eps):
+        if not self.has_y:
+            return
+        reg = self.engine.model.encoder_y
+        if self.reg_fused:
+            self.reg.forward(self.x)
+        else:
+            h = self.reg.forward(self.x)
+            ops.linear_fwd(h, reg.out.weight.data, reg.out.bias.data, None, out=self.c)
+        ops.normal_logprob(self.y, self.c, self.sig, -float(mult), self.engine.flat.loss, self.gc)
+
+    def backward(self, mult):
+        if not self.has_y:
+            return
+        flat = self.engine.flat
+        reg = self.engine.model.encoder_y
+        if self.reg_fused:
+            self.reg.backward([self.gc])
+        else:
+            hr = self.reg.h[-1]
+            ops.linear_bwd(hr, reg.out.weight.data, None, None, self.gc, self.gc, self.dh_r, False,
+                           flat.gv(reg.out.weight), flat.gv(reg.out.bias), None)
+            self.reg.backward(self.dh_r, self.reg_scratch, False)
 
 
 class EnumVAEProgram(StepProgram):
@@ -857,7 +1024,7 @@ class SVIEngine:
         prog = self._program(B, y is not None, mode)
         prog.load(x, y)
         if eps is not None and mode == "main":
-            prog.eps.copy_(eps.reshape(prog.eps.shape), non_blocking=True)
+            prog.set_eps(eps)
         gen_eps = eps is None
         if train:
             self.flat.activate(prog.grad_modules(), self.updates_done)

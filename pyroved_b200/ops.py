@@ -346,3 +346,16 @@ def upsample2_fwd(x, y, bilinear):
 def upsample2_bwd(dy, dx, bilinear):
     check(_lib.lib().pvb_upsample2_bwd(_p(dy), _p(dx), *_plane(dx), int(bool(bilinear)), _stream()),
           "pvb_upsample2_bwd")
+
+
+def normal_logprob(y, loc, sigma, scale, loss_out, gloc=None):
+    check(_lib.lib().pvb_normal_logprob(_p(y), _p(loc), float(sigma), float(scale), _p(loss_out),
+                                        _p(gloc), y.numel(), _stream()), "pvb_normal_logprob")
+
+
+def linear_dx_cols(dpre, W, dx_cols, col0, accumulate=False):
+    M, N = dpre.shape
+    K = W.shape[1]
+    check(_lib.lib().pvb_linear_dx_cols(_p(dpre), _p(W), _p(dx_cols), M, N, K, col0,
+                                        dx_cols.shape[1], int(accumulate), _stream()),
+          "pvb_linear_dx_cols")

@@ -18,7 +18,7 @@ class auxSVItrainer:
     """
     Args:
         model: initialised ssiVAE
-        task: "classification" ("regression" needs ss_reg_iVAE: not in this build)
+        task: "classification" (ssiVAE, enumerated labels) or "regression" (ss_reg_iVAE)
         optimizer: None or {"lr": ...} (Adam, default lr 5e-4)
         seed: reproducibility seed
     Keyword Args: lr (5e-4), device
@@ -29,8 +29,6 @@ class auxSVItrainer:
         set_deterministic_mode(seed)
         if task not in ["classification", "regression"]:
             raise ValueError("Choose between 'classification' and 'regression' tasks")
-        if task == "regression":
-            raise NotImplementedError("ss_reg_iVAE / regression task is outside this build's scope")
         self.task = task
         self.device = kwargs.get("device", 'cuda' if torch.cuda.is_available() else 'cpu')
         lr = kwargs.get("lr", 5e-4)
@@ -38,7 +36,8 @@ class auxSVItrainer:
             lr = optimizer.get("lr", lr)
         elif optimizer is not None:
             raise TypeError("pass optimizer=None or {'lr': ...}: Adam is fused into the CUDA step")
-        self.svi = SVIEngine(model, lr=lr, enumerate_parallel=True, seed=seed, device=self.device)
+        self.svi = SVIEngine(model, lr=lr, enumerate_parallel=(task == "classification"), seed=seed,
+                             device=self.device)
         self.model = model
         self.history = {"training_loss": [], "test": []}
         self.current_epoch = 0
@@ -71,6 +70,14 @@ class auxSVItrainer:
         return epoch_loss / unsup_count
 
     def evaluate(self, loader_val) -> float:
+        if self.task == "regression":
+            # mean over validation batches of the per-batch MSE (reference auxsvi.py:151-162)
+            acc, n = 0., 0
+            for data, gt in loader_val:
+                pred = self.model.regressor(data)
+                acc += torch.nn.functional.mse_loss(pred, gt.cpu()).item()
+                n += 1
+            return acc / n
         correct, total = 0, 0
         for data, labels in loader_val:
             predicted = self.model.classifier(data)
@@ -100,7 +107,9 @@ class auxSVItrainer:
     def print_statistics(self) -> None:
         e = self.current_epoch
         if len(self.history["test"]) > 0:
-            template = 'Epoch: {} Training loss: {:.4f}, Test accuracy: {:.4f}'
+            template = ('Epoch: {} Training loss: {:.4f}, Test accuracy: {:.4f}'
+                        if self.task == "classification" else
+                        'Epoch: {} Training loss: {:.4f}, Test MSE: {:.4f}')
             print(template.format(e, self.history["training_loss"][-1], self.history["test"][-1]))
         else:
             template = 'Epoch: {} Training loss: {:.4f}'

@@ -29,6 +29,10 @@ CASES = {
                                          invariances=["r"])),
     "ssivae_16_r_sup": ("ssivae", dict(data_dim=(16, 16), latent_dim=2, num_classes=4,
                                        invariances=["r"])),
+    "ssreg_16_rt_unsup": ("ssreg", dict(data_dim=(16, 16), latent_dim=2, reg_dim=2,
+                                        invariances=["r", "t"])),
+    "ssreg_16_rt_sup": ("ssreg", dict(data_dim=(16, 16), latent_dim=2, reg_dim=2,
+                                      invariances=["r", "t"])),
     # VED (reduced channel counts keep the fixtures small)
     "ved_im2spec_32_64": ("ved", dict(
         input_dim=(32, 32), output_dim=(64,), latent_dim=2,
@@ -69,7 +73,8 @@ class Golden:
 
     def eps(self, dtype=torch.float32):
         e = self.group("eps", dtype)
-        assert len(e) == 1
+        if len(e) > 1:          # several reparameterised sites (ss_reg_iVAE: "y" and "z")
+            return dict(e)
         return next(iter(e.values()))
 
     def kw(self):

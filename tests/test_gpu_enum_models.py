@@ -128,3 +128,56 @@ def test_jivae_trainer_and_inference_api(inv):
     assert man.shape == (9, 8, 8)
     trav = vae.manifold_traversal(3, 0, plot=False)
     assert trav.shape == (9, 8, 8)
+
+
+# ---- ss_reg_iVAE (regression variant, Trace_ELBO with a reparameterised y) ---------------------
+@pytest.mark.parametrize("generic", [True, False], ids=["fp32-generic", "default"])
+@pytest.mark.parametrize("name", ["ssreg_16_rt_unsup", "ssreg_16_rt_sup"])
+def test_ss_reg_ivae_vs_reference_golden(name, generic):
+    os.environ["PVB_FORCE_GENERIC"] = "1" if generic else "0"
+    g = Golden(name)
+    m = pv.models.ss_reg_iVAE(seed=1, device="cuda:0", **g.kwargs)
+    m.load_state_dict(g.group("w0"))
+    tr = pv.trainers.auxSVItrainer(m, task="regression", device="cuda:0")
+    x, y = g.args()
+    args = (x.cuda(),) if y is None else (x.cuda(), y.cuda())
+    e = g.eps()
+    eps = {k: v.cuda() for k, v in e.items()} if isinstance(e, dict) else e.cuda()
+    kw = {k: float(v) for k, v in g.kw().items()}
+    loss = tr.svi.loss_and_grads(*args, _eps=eps, **kw)
+    assert abs(loss - g.loss) <= LOSS_RTOL * abs(g.loss), (loss, g.loss)
+    prog = next(iter(tr.svi.programs.values()))
+    assert (prog.loc.cpu() - g.t("loc").reshape(-1)).abs().max().item() <= LOC_ATOL
+    assert torch.allclose(prog.mu.cpu(), g.t("mu"), atol=1e-4)
+    check_grads(m, g, 2e-3 if generic else 2e-2)
+    if y is not None and generic:
+        # compute_loss = ELBO step + auxiliary regression step (two Adam updates)
+        m.load_state_dict(g.group("w0"))
+        tr2 = pv.trainers.auxSVItrainer(m, task="regression", device="cuda:0")
+        tr2.svi.step(x.cuda(), y.cuda(), _eps=eps, **kw)
+        tr2.svi.step_aux(x.cuda(), y.cuda(), **kw)
+        check_w1(m, g)
+
+
+def test_ss_reg_trainer_loop_and_inference_api():
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(1)
+    xu = (torch.rand(96, 16, 16, generator=gen) < 0.3).float().flatten(1)
+    xs = (torch.rand(32, 16, 16, generator=gen) < 0.3).float().flatten(1)
+    ys = xs.mean(1, keepdim=True) * 4 - 1
+    m = pv.models.ss_reg_iVAE((16, 16), latent_dim=2, reg_dim=1, invariances=['r'], seed=1,
+                              device="cuda:0")
+    tr = pv.trainers.auxSVItrainer(m, task="regression", device="cuda:0")
+    lu, ls, lv = pv.utils.init_ssvae_dataloaders(xu, (xs, ys), (xs, ys), batch_size=16)
+    for _ in range(3):
+        tr.step(lu, ls, lv, aux_loss_multiplier=20)
+    assert len(tr.history["training_loss"]) == 3 and all(v == v for v in tr.history["training_loss"])
+    assert len(tr.history["test"]) == 3 and tr.history["test"][-1] >= 0
+    tr.print_statistics()
+    pred = m.regressor(xs)
+    assert pred.shape == (32, 1)
+    zm, zs, yy = m.encode(xs)
+    assert zm.shape == (32, 3) and zs.shape == (32, 3) and yy.shape == (32, 1)
+    img = m.decode(torch.randn(4, 2), torch.zeros(4, 1))
+    assert img.shape == (4, 16, 16)
+    assert m.manifold2d(3, torch.zeros(1), plot=False).shape == (9, 16, 16)

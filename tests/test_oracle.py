@@ -19,6 +19,12 @@ def port_loss_fn(g, dtype=torch.float32):
         cfg = sp.VedCfg(**kw)
         x, y = g.args(dtype)
         return sp.ved_loss, (cfg, x, y, g.eps(dtype), float(g.kw().get("scale_factor", 1.0))), cfg
+    if g.kind == "ssreg":
+        cfg = sp.Cfg(kw["data_dim"], kw["latent_dim"], kw["invariances"], c_dim=kw["reg_dim"])
+        x, y = g.args(dtype)
+        e = g.eps(dtype)
+        ez, ey = (e["z"], e["y"]) if isinstance(e, dict) else (e, None)
+        return sp.ss_reg_loss, (cfg, x, ez, y, float(g.kw().get("scale_factor", 1.0)), ey), cfg
     kw.pop("hidden_dim_e", None)
     kw.pop("hidden_dim_d", None)
     cfg = sp.Cfg(**kw)
@@ -139,3 +145,21 @@ def test_init_matches_reference_weights():
     assert list(sd.keys()) == list(w0.keys())
     for k in sd:
         assert torch.equal(sd[k], w0[k]), k
+
+
+def test_ss_reg_aux_and_two_optimizer_steps():
+    """auxSVItrainer(task="regression").compute_loss on a labeled batch: ELBO step, then the
+    auxiliary regression step, two Adam updates sharing per-parameter state."""
+    g = Golden("ssreg_16_rt_sup")
+    fn, args, cfg = port_loss_fn(g)
+    sd = g.group("w0")
+    x, y = g.args()
+    opt = sp.AdamState(lr=5e-4)
+    out, grads = sp.loss_and_grads(fn, sd, *args)
+    sd1 = opt.step(dict(sd), grads)
+    out2, grads2 = sp.loss_and_grads(sp.ss_reg_aux_loss, sd1, cfg, x, y, 30.0)
+    grads2 = {k: (v if v is not None else torch.zeros_like(sd1[k])) for k, v in grads2.items()}
+    sd2 = opt.step(sd1, grads2)
+    assert abs(float(out["loss"]) + float(out2["loss"]) - g.loss_step) <= 1e-5 * abs(g.loss_step)
+    for k, v in g.group("w1").items():
+        assert torch.allclose(sd2[k], v, atol=2e-5), k
