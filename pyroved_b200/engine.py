@@ -378,10 +378,12 @@ class DecoderOps:
             ops.reduce_partials(self.fold_part, flat.gv(cl.fc_latent.weight), G, Hd0 * LC, per,
                                 True, Hd0 * (nd + 1))
 
-    def backward_fused(self, head, cond, w, beta):
+    def backward_fused(self, head, cond, w, beta, z=None):
         """Fused-decoder variant of backward() that also runs the latent backward:
         weight-gradient partial reduction, then ONE launch for dUv gather + fold backward +
-        latent backward (-> head.gmu / head.gs_pre), then the fold-weight partial reduction."""
+        latent backward (-> head.gmu / head.gs_pre), then the fold-weight partial reduction.
+        head=None (latent shared by several instances, jiVAE): only dz (self.gz) is produced
+        from the instance codes `z`."""
         assert self.spatial and self.use_tc
         eng = self.engine
         m, flat = eng.model, eng.flat
@@ -392,11 +394,17 @@ class DecoderOps:
         base = flat.offset(L[0].weight)
         ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], self.tc_sizes.ctas,
                             n_w, TC_WGRAD_STRIDE, True)
-        ops.latent_side_bwd(self.fold_cfg, head.z, cond, cl.fc_coord.weight.data,
-                            cl.fc_latent.weight.data, None, self.gUv_part, self.N, self.gz,
-                            self.gcond, self.fold_part, head.eps, head.sigma, head.s_pre, w, beta,
-                            head.gmu, head.gs_pre)
+        if head is None:
+            ops.latent_side_bwd(self.fold_cfg, z, cond, cl.fc_coord.weight.data,
+                                cl.fc_latent.weight.data, None, self.gUv_part, self.N, self.gz,
+                                self.gcond, self.fold_part, None, None, None, None, 0.0, None, None)
+        else:
+            ops.latent_side_bwd(self.fold_cfg, head.z, cond, cl.fc_coord.weight.data,
+                                cl.fc_latent.weight.data, None, self.gUv_part, self.N, self.gz,
+                                self.gcond, self.fold_part, head.eps, head.sigma, head.s_pre, w,
+                                beta, head.gmu, head.gs_pre)
         self._reduce_fold_partials(self.G_side)
+        return self.gz
 
     def backward(self, z, cond):
         """Accumulates decoder weight gradients; returns dloss/dz [I,Zf]."""
@@ -751,23 +759,43 @@ class EnumVAEProgram(StepProgram):
         self.glogits = torch.zeros(B * K + B, **f32)
         self.cost = torch.empty(I, **f32)
         enc = m.encoder_z
+        enc_layers = linear_layers(enc.fc_layers)
+        self.dec = DecoderOps(engine, I, B, K)
+        ok = not engine.force_generic
+        self.glog_view = self.glogits[:B * K].view(B, K)
         if kind == "jivae":
-            self.enc = MLP(linear_layers(enc.fc_layers), enc.activation, B, dev, flat)
-            self.enc_scratch = _mlp_scratch(self.enc.layers, B, dev)
             self.head = GaussHead(engine, enc, B, Z)
             self.z_rep = torch.empty(I, Z, **f32)
             self.gz_b = torch.empty(B, Z, **f32)
+            heads = [enc.fc11, enc.fc12, enc.fc13]
+            self.fused = ok and FusedStack.eligible(enc_layers, heads, B)
+            if self.fused:
+                self.enc = FusedStack(engine, enc_layers, enc.activation, heads, B,
+                                      gauss_head=self.head)
+                self.logits = self.enc.hout[2]
+            else:
+                self.enc = MLP(enc_layers, enc.activation, B, dev, flat)
+                self.enc_scratch = _mlp_scratch(self.enc.layers, B, dev)
         else:
             self.enc_in = torch.zeros(I, N + K, **f32)
             self.enc_in[:, N:].copy_(self.onehot)
-            self.enc = MLP(linear_layers(enc.fc_layers), enc.activation, I, dev, flat)
-            self.enc_scratch = _mlp_scratch(self.enc.layers, I, dev)
             self.head = GaussHead(engine, enc, I, Z)
             cls = m.encoder_y
-            self.cls = MLP(linear_layers(cls.fc_layers), cls.activation, B, dev, flat)
-            self.cls_scratch = _mlp_scratch(self.cls.layers, B, dev)
-            self.dh_c = torch.empty(B, cls.out.in_features, **f32)
-        self.dec = DecoderOps(engine, I, B, K)
+            cls_layers = linear_layers(cls.fc_layers)
+            self.fused = (ok and FusedStack.eligible(enc_layers, [enc.fc11, enc.fc12], I)
+                          and FusedStack.eligible(cls_layers, [cls.out], B))
+            if self.fused:
+                fold = self.dec.fold_ctx(self.onehot) if self.dec.spatial else None
+                self.enc = FusedStack(engine, enc_layers, enc.activation, [enc.fc11, enc.fc12], I,
+                                      gauss_head=self.head, fold=fold)
+                self.cls = FusedStack(engine, cls_layers, cls.activation, [cls.out], B)
+                self.logits = self.cls.hout[0]
+            else:
+                self.enc = MLP(enc_layers, enc.activation, I, dev, flat)
+                self.enc_scratch = _mlp_scratch(self.enc.layers, I, dev)
+                self.cls = MLP(cls_layers, cls.activation, B, dev, flat)
+                self.cls_scratch = _mlp_scratch(self.cls.layers, B, dev)
+                self.dh_c = torch.empty(B, cls.out.in_features, **f32)
 
     eps = property(lambda s: s.head.eps)
     mu = property(lambda s: s.head.mu)
@@ -799,9 +827,12 @@ class EnumVAEProgram(StepProgram):
         if self.kind == "jivae":
             b0, b1 = beta
             enc = m.encoder_z
-            h = self.enc.forward(self.x)
-            self.head.forward(h, gen_eps)
-            ops.linear_fwd(h, enc.fc13.weight.data, enc.fc13.bias.data, None, out=self.logits)
+            if self.fused:
+                self.enc.forward(self.x, gen_eps)      # hidden stack + 3 heads + sample: 2 launches
+            else:
+                h = self.enc.forward(self.x)
+                self.head.forward(h, gen_eps)
+                ops.linear_fwd(h, enc.fc13.weight.data, enc.fc13.bias.data, None, out=self.logits)
             ops.enum_head_fwd(self.logits, self.alpha, self.w)
             self.z_rep.view(K, B, Z).copy_(self.head.z.unsqueeze(0).expand(K, B, Z))
             self.dec.forward(self.z_rep, self.onehot, self.x, self.w, want_grad)
@@ -809,12 +840,19 @@ class EnumVAEProgram(StepProgram):
             ops.enum_head_bwd(self.alpha, self.dec.ll, b1, self.glogits, flat.loss)
         else:
             cls = m.encoder_y
-            hc = self.cls.forward(self.x)
-            ops.linear_fwd(hc, cls.out.weight.data, cls.out.bias.data, None, out=self.logits)
-            ops.enum_head_fwd(self.logits, self.alpha, self.w)
-            h = self.enc.forward(self.enc_in)
-            self.head.forward(h, gen_eps)
-            self.dec.forward(self.head.z, self.onehot, self.x, self.w, want_grad)
+            if self.fused:
+                self.cls.forward(self.x)
+                ops.enum_head_fwd(self.logits, self.alpha, self.w)
+                self.enc.forward(self.enc_in, gen_eps)
+                self.dec.forward(self.head.z, self.onehot, self.x, self.w, want_grad,
+                                 uv_ready=self.dec.spatial)
+            else:
+                hc = self.cls.forward(self.x)
+                ops.linear_fwd(hc, cls.out.weight.data, cls.out.bias.data, None, out=self.logits)
+                ops.enum_head_fwd(self.logits, self.alpha, self.w)
+                h = self.enc.forward(self.enc_in)
+                self.head.forward(h, gen_eps)
+                self.dec.forward(self.head.z, self.onehot, self.x, self.w, want_grad)
             ops.axpy_out(self.dec.ll, self.head.kl, float(beta), self.cost)
             ops.enum_head_bwd(self.alpha, self.cost, 1.0, self.glogits, flat.loss)
 
@@ -825,8 +863,18 @@ class EnumVAEProgram(StepProgram):
         if self.kind == "jivae":
             b0, b1 = beta
             enc = m.encoder_z
-            gz = self.dec.backward(self.z_rep, self.onehot)
+            tc = self.dec.spatial and self.dec.use_tc
+            if self.fused and tc:
+                gz = self.dec.backward_fused(None, self.onehot, None, 0.0, z=self.z_rep)
+            else:
+                gz = self.dec.backward(self.z_rep, self.onehot)
             ops.reduce_partials(gz, self.gz_b, K, B * Z, B * Z, False)
+            if self.fused:
+                hd = self.head
+                ops.latent_bwd(self.gz_b, hd.eps, hd.sigma, hd.s_pre, hd.z, None, b0, hd.gmu,
+                               hd.gs_pre)
+                self.enc.backward([hd.gmu, hd.gs_pre, self.glog_view])
+                return
             h = self.enc.h[-1]
             dh = self.head.backward(h, self.gz_b, None, b0)
             ops.linear_bwd(h, enc.fc13.weight.data, None, None, self.glogits, self.glogits, dh,
@@ -834,6 +882,17 @@ class EnumVAEProgram(StepProgram):
             self.enc.backward(dh, self.enc_scratch, False)
         else:
             cls = m.encoder_y
+            if self.fused:
+                hd = self.head
+                if self.dec.spatial and self.dec.use_tc:
+                    self.dec.backward_fused(hd, self.onehot, self.w, beta)
+                else:
+                    gz = self.dec.backward(hd.z, self.onehot)
+                    ops.latent_bwd(gz, hd.eps, hd.sigma, hd.s_pre, hd.z, self.w, beta, hd.gmu,
+                                   hd.gs_pre)
+                self.enc.backward([hd.gmu, hd.gs_pre])
+                self.cls.backward([self.glog_view])
+                return
             gz = self.dec.backward(self.head.z, self.onehot)
             dh = self.head.backward(self.enc.h[-1], gz, self.w, beta)
             self.enc.backward(dh, self.enc_scratch, False)
@@ -856,12 +915,19 @@ class ClassifierAuxProgram(StepProgram):
         self.x = torch.zeros(B, self.N, **f32)
         self.y = torch.zeros(B, self.K, **f32)
         cls = m.encoder_y
-        self.cls = MLP(linear_layers(cls.fc_layers), cls.activation, B, dev, flat)
-        self.cls_scratch = _mlp_scratch(self.cls.layers, B, dev)
-        self.logits = torch.empty(B, self.K, **f32)
+        layers = linear_layers(cls.fc_layers)
         self.glogits = torch.zeros(B * self.K + B, **f32)
-        self.dh_c = torch.empty(B, cls.out.in_features, **f32)
+        self.glog_view = self.glogits[:B * self.K].view(B, self.K)
         self.eps = torch.zeros(1, **f32)
+        self.fused = (not engine.force_generic) and FusedStack.eligible(layers, [cls.out], B)
+        if self.fused:
+            self.cls = FusedStack(engine, layers, cls.activation, [cls.out], B)
+            self.logits = self.cls.hout[0]
+        else:
+            self.cls = MLP(layers, cls.activation, B, dev, flat)
+            self.cls_scratch = _mlp_scratch(self.cls.layers, B, dev)
+            self.logits = torch.empty(B, self.K, **f32)
+            self.dh_c = torch.empty(B, cls.out.in_features, **f32)
 
     def grad_modules(self):
         return [self.engine.model.encoder_y] if self.has_y else []
@@ -875,8 +941,11 @@ class ClassifierAuxProgram(StepProgram):
         if not self.has_y:
             return
         cls = self.engine.model.encoder_y
-        hc = self.cls.forward(self.x)
-        ops.linear_fwd(hc, cls.out.weight.data, cls.out.bias.data, None, out=self.logits)
+        if self.fused:
+            self.cls.forward(self.x)
+        else:
+            hc = self.cls.forward(self.x)
+            ops.linear_fwd(hc, cls.out.weight.data, cls.out.bias.data, None, out=self.logits)
         ops.class_nll(self.logits, self.y, mult, self.glogits, self.engine.flat.loss)
 
     def backward(self, mult):
@@ -884,6 +953,9 @@ class ClassifierAuxProgram(StepProgram):
             return
         flat = self.engine.flat
         cls = self.engine.model.encoder_y
+        if self.fused:
+            self.cls.backward([self.glog_view])
+            return
         hc = self.cls.h[-1]
         ops.linear_bwd(hc, cls.out.weight.data, None, None, self.glogits, self.glogits, self.dh_c,
                        False, flat.gv(cls.out.weight), flat.gv(cls.out.bias), None)
