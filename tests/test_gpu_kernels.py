@@ -1,0 +1,173 @@
+"""Kernel-level GPU tests: the fused small-batch MLP kernels, the pipelined forward layer, the
+reductions and the optimizer against plain PyTorch fp32 ops (awkward sizes on purpose)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from pyroved_b200 import ops
+
+pytestmark = pytest.mark.gpu
+torch.backends.cuda.matmul.allow_tf32 = False
+ACTS = {"tanh": torch.tanh, "lrelu": lambda t: F.leaky_relu(t, 0.01), "gelu": F.gelu,
+        "softplus": F.softplus, "relu": F.relu}
+
+
+def _lin(i, o, gen):
+    l = nn.Linear(i, o)
+    with torch.no_grad():
+        l.weight.copy_(torch.randn(o, i, generator=gen) / i ** 0.5)
+        l.bias.copy_(torch.randn(o, generator=gen) * 0.1)
+    return l.cuda()
+
+
+@pytest.mark.parametrize("M,w_in,widths,hdims,act", [
+    (13, 96, [160, 72], [5, 5, 7], "gelu"),
+    (512, 128, [128], [5, 5], "tanh"),
+    (7, 256, [], [3, 3], "lrelu"),
+    (33, 64, [256, 36, 128], [64], "softplus"),
+])
+def test_mlp_tail_chain_wgrad_vs_torch(M, w_in, widths, hdims, act):
+    gen = torch.Generator().manual_seed(M + w_in)
+    f = ACTS[act]
+    dims = [w_in] + widths
+    layers = [_lin(dims[i], dims[i + 1], gen) for i in range(len(widths))]
+    heads = [_lin(dims[-1], h, gen) for h in hdims]
+    h_in = torch.randn(M, w_in, generator=gen).cuda()
+    gauss = len(hdims) >= 2 and hdims[0] == hdims[1]
+    # reference
+    hs, pres, cur = [], [], h_in
+    for l in layers:
+        p = F.linear(cur, l.weight, l.bias)
+        pres.append(p)
+        cur = f(p)
+        hs.append(cur)
+    outs = [F.linear(cur, hd.weight, hd.bias) for hd in heads]
+    # kernels
+    kh = [torch.empty(M, w, device="cuda") for w in widths]
+    kp = [torch.empty(M, w, device="cuda") if act == "gelu" else None for w in widths]
+    ko = [torch.empty(M, h, device="cuda") for h in hdims]
+    g = None
+    if gauss:
+        Z = hdims[0]
+        eps = torch.randn(M, Z, generator=gen).cuda()
+        g = dict(eps=eps, sigma=torch.empty(M, Z, device="cuda"), z=torch.empty(M, Z, device="cuda"),
+                 kl=torch.empty(M, device="cuda"), gen_eps=False, seed=1,
+                 step_counter=torch.zeros(1, dtype=torch.int32, device="cuda"), first_index=0)
+    args = ops.make_mlp_tail_args(M, h_in, layers, kh, kp, act, heads, ko, g, None)
+    ops.mlp_tail_fwd(args)
+    for a, b in zip(kh, hs):
+        assert torch.allclose(a, b, atol=2e-5, rtol=1e-4)
+    for a, b in zip(ko, outs):
+        assert torch.allclose(a, b, atol=5e-5, rtol=1e-4)
+    if gauss:
+        sig = F.softplus(outs[1])
+        z = outs[0] + sig * eps
+        kl = (-0.5 * z * z + 0.5 * eps * eps + torch.log(sig)).sum(1)
+        assert torch.allclose(g["sigma"], sig, atol=2e-5) and torch.allclose(g["z"], z, atol=5e-5)
+        assert torch.allclose(g["kl"], kl, atol=2e-4, rtol=1e-4)
+    if not widths:
+        return
+    # backward: random head gradients through heads + stack (layer 0 input gradient not needed)
+    gh = [torch.randn(M, h, generator=gen).cuda() for h in hdims]
+    x0 = torch.randn(M, 24, generator=gen).cuda()       # pretend input of layer 0 for its dW
+    l0 = _lin(24, w_in, gen)
+    params = [p for l in [l0] + layers + heads for p in (l.weight, l.bias)]
+    for p in params:
+        p.grad = None
+    pre0 = F.linear(x0, l0.weight, l0.bias)
+    cur = f(pre0)
+    h0 = cur.detach()
+    hs2, pres2 = [h0], [pre0.detach()]
+    for l in layers:
+        p = F.linear(cur, l.weight, l.bias)
+        pres2.append(p.detach())
+        cur = f(p)
+        hs2.append(cur.detach())
+    loss = sum((F.linear(cur, hd.weight, hd.bias) * gk).sum() for hd, gk in zip(heads, gh))
+    loss.backward()
+    all_layers = [l0] + layers
+    dpre = [torch.empty(M, l.out_features, device="cuda") for l in all_layers]
+    cargs = ops.make_mlp_chain_args(M, all_layers, hs2, pres2 if act == "gelu" else [None] * len(all_layers),
+                                    act, dpre, heads, gh)
+    ops.mlp_chain_bwd(cargs)
+    items = []
+    gW = [torch.zeros_like(l.weight) for l in all_layers + heads]
+    gb = [torch.zeros_like(l.bias) for l in all_layers + heads]
+    for k, l in enumerate(all_layers):
+        items.append((dpre[k], x0 if k == 0 else hs2[k - 1], gW[k], gb[k]))
+    for k, hd in enumerate(heads):
+        items.append((gh[k], hs2[-1], gW[len(all_layers) + k], gb[len(all_layers) + k]))
+    ops.mlp_wgrad(ops.make_wgrad_problems(items), M)
+    for k, l in enumerate(all_layers + heads):
+        sw = l.weight.grad.abs().max().item() + 1e-6
+        assert (gW[k] - l.weight.grad).abs().max().item() <= 2e-4 * sw + 1e-5, k
+        assert torch.allclose(gb[k], l.bias.grad, atol=2e-4, rtol=1e-4), k
+
+
+@pytest.mark.parametrize("M,N,K,act", [(512, 128, 784, "tanh"), (100, 96, 260, "gelu"),
+                                       (1024, 128, 4100, None), (64, 48, 30, "relu")])
+def test_linear_fwd_bwd_vs_torch(M, N, K, act):
+    gen = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=gen).cuda()
+    l = _lin(K, N, gen)
+    f = ACTS[act] if act else (lambda t: t)
+    xr = x.clone().requires_grad_(True)
+    pre_r = F.linear(xr, l.weight, l.bias)
+    yr = f(pre_r)
+    dy = torch.randn(M, N, generator=gen).cuda()
+    yr.backward(dy)
+    y = torch.empty(M, N, device="cuda")
+    pre = torch.empty(M, N, device="cuda")
+    ops.linear_fwd(x, l.weight.data, l.bias.data, act, out=y, pre=pre)
+    assert torch.allclose(y, yr.detach(), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(pre, pre_r.detach(), atol=1e-4, rtol=1e-4)
+    dx = torch.empty(M, K, device="cuda")
+    dW, db = torch.zeros_like(l.weight), torch.zeros_like(l.bias)
+    ws = torch.empty(M, N, device="cuda")
+    ops.linear_bwd(x, l.weight.data, y, pre, dy, ws, dx, False, dW, db, act)
+    assert torch.allclose(dx, xr.grad, atol=2e-4, rtol=1e-4)
+    assert (dW - l.weight.grad).abs().max().item() <= 2e-4 * l.weight.grad.abs().max().item() + 1e-5
+    assert torch.allclose(db, l.bias.grad, atol=5e-4, rtol=1e-4)
+
+
+def test_reductions_adam_and_regression_terms():
+    gen = torch.Generator().manual_seed(0)
+    part = torch.randn(148, 1000, generator=gen).cuda()
+    out = torch.ones(777, device="cuda")
+    ops.reduce_partials(part, out, 148, 777, 1000, True)
+    assert torch.allclose(out, 1 + part[:, :777].sum(0), atol=1e-4)
+    # Adam with the folded step counter == torch.optim.Adam over three steps
+    p0 = torch.randn(1003, generator=gen)
+    ref = nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p = p0.clone().cuda()
+    pad = torch.zeros(1004, device="cuda")
+    pad[:1003] = p
+    m, v = torch.zeros(1004, device="cuda"), torch.zeros(1004, device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for step in range(3):
+        gr = torch.randn(1003, generator=gen)
+        ref.grad = gr.clone()
+        opt.step()
+        gpad = torch.zeros(1004, device="cuda")
+        gpad[:1003] = gr.cuda()
+        ops.adam_flat_step(pad, gpad, m, v, 1003, 1e-3, ctr, ticket)
+        assert ctr.item() == step + 1 and ticket.item() == 0
+    assert torch.allclose(pad[:1003].cpu(), ref.detach(), atol=2e-6)
+    # Normal log-prob sum and its gradient; input-gradient column slice
+    y = torch.randn(50, 3, generator=gen).cuda()
+    c = torch.randn(50, 3, generator=gen).cuda().requires_grad_(True)
+    lp = torch.distributions.Normal(c, 0.4).log_prob(y).sum()
+    (-7.0 * lp).backward()
+    loss = torch.zeros(1, device="cuda")
+    gc = torch.empty(50, 3, device="cuda")
+    ops.normal_logprob(y, c.detach(), 0.4, -7.0, loss, gc)
+    assert abs(loss.item() + 7.0 * lp.item()) <= 1e-4 * abs(7.0 * lp.item())
+    assert torch.allclose(gc, c.grad, atol=1e-4, rtol=1e-4)
+    dpre = torch.randn(37, 64, generator=gen).cuda()
+    W = torch.randn(64, 103, generator=gen).cuda()
+    dxc = torch.empty(37, 3, device="cuda")
+    ops.linear_dx_cols(dpre, W, dxc, 100)
+    assert torch.allclose(dxc, (dpre @ W)[:, 100:], atol=1e-4, rtol=1e-4)
