@@ -301,6 +301,21 @@ int pvb_normal_logprob(const float* y, const float* loc, float sigma, float scal
 int pvb_linear_dx_cols(const float* dpre, const float* W, float* dx_cols, int64_t M,
                        int N, int K, int col0, int ncols, int accumulate, void* stream);
 
+/* ---- the same convolutions on tcgen05 tensor cores (csrc/pvb_conv_tc.cu) --------
+ * For layers with Cin, Cout multiples of 16 (<= 128 outputs per GEMM, <= 256 gathered
+ * channels).  Same NCHW fp32 tensors as pvb_conv_*; operands are converted on the fly to
+ * fp16, fp32 accumulation in tensor memory.
+ * workspace: pvb_conv_tc_workspace_bytes(...) bytes, 16-byte aligned (repacked weights). */
+int pvb_conv_tc_supported(int Cin, int Cout, int kh, int kw);
+int64_t pvb_conv_tc_workspace_bytes(int Cin, int Cout, int kh, int kw);
+/* mode 0: dst = act(conv(src = x, W) + b), pre optional; mode 1: dst = dx from src = dpre */
+int pvb_conv_tc_pix(const float* src, const float* W, const float* b, float* dst,
+                    float* pre, void* workspace, int B, int Cin, int Cout, int H,
+                    int Wd, int kh, int kw, int act, int mode, void* stream);
+/* dW += dpre (*) x ; db += sum dpre  (atomic accumulation) */
+int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, float* db, int B,
+                      int Cin, int Cout, int H, int Wd, int kh, int kw, void* stream);
+
 /* ---- optimizer / reductions -------------------------------------------- */
 /* out[j] (+)= sum_g part[g*part_stride + j], j < n, fixed order (deterministic) */
 int pvb_reduce_partials(const float* part, float* out, int G, int64_t n,

@@ -103,6 +103,10 @@ SIGNATURES = {
     "pvb_upsample2_bwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_normal_logprob": [_f, _f, _fl, _fl, _f, _f, _i64, _st],
     "pvb_linear_dx_cols": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_conv_tc_supported": [_i32, _i32, _i32, _i32],
+    "pvb_conv_tc_workspace_bytes": [_i32, _i32, _i32, _i32],
+    "pvb_conv_tc_pix": [_f, _f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_conv_tc_wgrad": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
     "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
                          _i32, _i32, _i32, _i32, _i32, _fl, _i32, _st],
@@ -133,7 +137,8 @@ def lib():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = (C.c_char_p if name == "pvb_last_error_string" else
-                          C.c_longlong if name == "pvb_launch_count" else C.c_int)
+                          C.c_longlong if name in ("pvb_launch_count",
+                                                   "pvb_conv_tc_workspace_bytes") else C.c_int)
         _LIB = handle
     return _LIB
 

@@ -24,6 +24,12 @@ class ConvStack:
             oshape = out_shape(kind, mod, shape)
             st = dict(kind=kind, mod=mod, act=act, y=torch.empty((B, *oshape), **f32),
                       pre=(torch.empty((B, *oshape), **f32) if act == "gelu" else None))
+            # tensor-core path for layers with >= 16 channels on both sides (tcgen05, fp16 / bf16
+            # operands); the others (first / last layer) stay on the fp32 kernels
+            st["tc"] = (kind == "conv" and not engine.force_generic
+                        and ops.conv_tc_supported(mod.weight))
+            if st["tc"]:
+                st["ws"] = ops.conv_tc_workspace(mod.weight)
             self.steps.append(st)
             shape = oshape
             biggest = max(biggest, B * _numel(shape))
@@ -37,8 +43,11 @@ class ConvStack:
         for st in self.steps:
             m = st["mod"]
             if st["kind"] == "conv":
-                ops.conv_fwd(cur, m.weight.data, m.bias.data if m.bias is not None else None,
-                             st["act"], st["y"], st["pre"])
+                bias = m.bias.data if m.bias is not None else None
+                if st["tc"]:
+                    ops.conv_tc_fwd(cur, m.weight.data, bias, st["act"], st["y"], st["ws"], st["pre"])
+                else:
+                    ops.conv_fwd(cur, m.weight.data, bias, st["act"], st["y"], st["pre"])
             elif st["kind"] == "pool":
                 ops.maxpool2_fwd(cur, st["y"])
             else:
@@ -63,10 +72,15 @@ class ConvStack:
             if st["kind"] == "conv":
                 if st["act"] is not None:
                     ops.act_bwd(d, st["y"], st["pre"], d, st["act"])     # in place: d = dpre
-                ops.conv_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight),
-                                    flat.gv(m.bias) if m.bias is not None else None)
-                if want_dx:
-                    ops.conv_bwd_data(d, m.weight.data, dx)
+                gb = flat.gv(m.bias) if m.bias is not None else None
+                if st["tc"]:
+                    ops.conv_tc_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
+                    if want_dx:
+                        ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"])
+                else:
+                    ops.conv_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
+                    if want_dx:
+                        ops.conv_bwd_data(d, m.weight.data, dx)
             elif st["kind"] == "pool":
                 if want_dx:
                     ops.maxpool2_bwd(xin, d, dx)
@@ -133,7 +147,7 @@ class VEDProgram(StepProgram):
         self.dfeat = torch.empty(B, self.feat_dim, **f32)
 
     loc = property(lambda s: s._loc)
-    use_tc = False
+    use_tc = property(lambda s: any(st["tc"] for st in s.enc.steps + s.dec.steps))
 
     def load(self, x, y):
         B = self.B

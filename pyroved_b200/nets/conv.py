@@ -7,6 +7,7 @@ seed gives the same initial weights.  The modules only OWN parameters and descri
 sequence; `forward` (inference) and training (conv_engine.VEDProgram) run the hand-written CUDA
 kernels of csrc/pvb_conv.cu through the C ABI.  Not supported here: batchnorm=True and 3-D data.
 """
+import os
 from typing import List, Tuple
 from warnings import warn
 
@@ -262,7 +263,11 @@ def run_layers(layers, x, activation):
         shp = out_shape(kind, mod, tuple(x.shape[1:]))
         y = torch.empty((x.shape[0], *shp), device=x.device, dtype=torch.float32)
         if kind == "conv":
-            ops.conv_fwd(x, mod.weight.data, mod.bias.data if mod.bias is not None else None, act, y)
+            bias = mod.bias.data if mod.bias is not None else None
+            if os.environ.get("PVB_FORCE_GENERIC", "0") != "1" and ops.conv_tc_supported(mod.weight):
+                ops.conv_tc_fwd(x, mod.weight.data, bias, act, y, ops.conv_tc_workspace(mod.weight))
+            else:
+                ops.conv_fwd(x, mod.weight.data, bias, act, y)
         elif kind == "pool":
             ops.maxpool2_fwd(x, y)
         else:

@@ -359,3 +359,31 @@ def linear_dx_cols(dpre, W, dx_cols, col0, accumulate=False):
     check(_lib.lib().pvb_linear_dx_cols(_p(dpre), _p(W), _p(dx_cols), M, N, K, col0,
                                         dx_cols.shape[1], int(accumulate), _stream()),
           "pvb_linear_dx_cols")
+
+
+# ---- tensor-core convolutions (same tensors; operands converted on the fly) ----------------
+def conv_tc_supported(W):
+    kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
+    return bool(_lib.lib().pvb_conv_tc_supported(W.shape[1], W.shape[0], kh, kw))
+
+
+def conv_tc_workspace(W):
+    kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
+    n = _lib.lib().pvb_conv_tc_workspace_bytes(W.shape[1], W.shape[0], kh, kw)
+    return torch.empty((n + 3) // 4, device=W.device, dtype=torch.float32)
+
+
+def conv_tc_fwd(x, W, b, act, out, ws, pre=None):
+    check(_lib.lib().pvb_conv_tc_pix(_p(x), _p(W), _p(b), _p(out), _p(pre), _p(ws),
+                                     *_conv_dims(x, W), ACT[act], 0, _stream()), "pvb_conv_tc_pix")
+    return out
+
+
+def conv_tc_bwd_data(dpre, W, dx, ws):
+    check(_lib.lib().pvb_conv_tc_pix(_p(dpre), _p(W), None, _p(dx), None, _p(ws),
+                                     *_conv_dims(dx, W), 0, 1, _stream()), "pvb_conv_tc_pix")
+
+
+def conv_tc_bwd_weight(dpre, x, W, dW, db):
+    check(_lib.lib().pvb_conv_tc_wgrad(_p(dpre), _p(x), _p(dW), _p(db), *_conv_dims(x, W),
+                                       _stream()), "pvb_conv_tc_wgrad")

@@ -3,6 +3,8 @@ the CUDA kernels through the C ABI against (a) golden vectors of the unmodified 
 (b) the CPU oracle port on fresh inputs, (c) plain PyTorch fp32 ops for every conv-side kernel.
 Tolerances: ELBO <= 1e-3 relative, reconstruction max-abs <= 1e-3 (north_star); the fp32 kernels
 are in fact ~1e-6."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -20,28 +22,53 @@ VED_CASES = [n for n in sorted(CASES) if CASES[n][0] == "ved"]
 SEEDS = {"ved_spec2im_32_16": 2}
 
 
-def build(name, g):
+def grad_check(m, gref, generic):
+    """fp32 path: every parameter gradient within 2e-3 (max-norm and L2).  tcgen05 path (fp16
+    operands): per-tensor bounds of 1e-1 (max-norm) / 6e-2 (L2) -- small tensors whose entries are
+    heavily cancelling sums (e.g. the 5e-4-sized latent2features bias gradient) amplify the 5e-4
+    operand rounding -- plus a global bound: the whole gradient vector within 1e-2 in L2."""
+    mtol, l2tol = (2e-3, 2e-3) if generic else (1e-1, 6e-2)
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        ref = gref[k]
+        err = (p.grad - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+        l2 = (p.grad - ref).norm().item() / (ref.norm().item() + 1e-6)
+        assert err <= mtol and l2 <= l2tol, (k, err, l2)
+        num += (p.grad - ref).pow(2).sum().item()
+        den += ref.pow(2).sum().item()
+    assert (num / den) ** 0.5 <= (2e-3 if generic else 1e-2), (num / den) ** 0.5
+
+
+def build(name, g, generic=True):
+    os.environ["PVB_FORCE_GENERIC"] = "1" if generic else "0"
     m = pv.models.VED(seed=SEEDS.get(name, 1), device="cuda:0", **g.kwargs)
     m.load_state_dict(g.group("w0"))
     return m, pv.trainers.SVItrainer(m, seed=1, device="cuda:0")
 
 
+@pytest.mark.parametrize("generic", [True, False], ids=["fp32-generic", "default"])
 @pytest.mark.parametrize("name", VED_CASES)
-def test_ved_loss_recon_grads_vs_reference_golden(name):
+def test_ved_loss_recon_grads_vs_reference_golden(name, generic):
+    """fp32 kernels: ~1e-6; default path (tcgen05 convolutions with fp16 operands where the channel
+    counts allow): ELBO / reconstruction inside the 1e-3 tolerance of the path (measured: forward
+    activations within 8e-5, decoder gradients within 5e-4).  Encoder gradients get a looser
+    max-norm bound there: a leaky-ReLU whose pre-activation sits within that 8e-5 of zero takes
+    the other slope (1 flip in 12,288 on this fixture), which moves the few weight-gradient entries
+    it feeds by ~3 % of the largest entry at batch 6 -- a property of the non-smooth net, not of the
+    backward kernels (`grad_check` therefore also bounds the relative L2 error)."""
     g = Golden(name)
-    m, tr = build(name, g)
+    m, tr = build(name, g, generic)
     x, y = g.args()
     kw = {k: float(v) for k, v in g.kw().items()}
     loss = tr.svi.loss_and_grads(x.cuda(), y.cuda(), _eps=g.eps().cuda(), **kw)
-    assert abs(loss - g.loss) <= 1e-4 * abs(g.loss), (loss, g.loss)
     prog = next(iter(tr.svi.programs.values()))
-    assert (prog.loc.cpu() - g.t("loc").reshape(-1)).abs().max().item() <= 1e-4
-    assert torch.allclose(prog.mu.cpu(), g.t("mu"), atol=1e-4)
-    assert torch.allclose(prog.sigma.cpu(), g.t("sigma"), atol=1e-4)
-    for k, p in m.named_parameters():
-        ref = g.group("grad")[k].cuda()
-        err = (p.grad - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
-        assert err <= 2e-3, (k, err)
+    assert prog.use_tc == (not generic)
+    ltol, atol = (1e-4, 1e-4) if generic else (1e-3, 1e-3)
+    assert abs(loss - g.loss) <= ltol * abs(g.loss), (loss, g.loss)
+    assert (prog.loc.cpu() - g.t("loc").reshape(-1)).abs().max().item() <= atol
+    assert torch.allclose(prog.mu.cpu(), g.t("mu"), atol=10 * atol)
+    assert torch.allclose(prog.sigma.cpu(), g.t("sigma"), atol=10 * atol)
+    grad_check(m, {k: v.cuda() for k, v in g.group("grad").items()}, generic)
 
 
 @pytest.mark.parametrize("name", VED_CASES)
@@ -59,8 +86,10 @@ def test_ved_full_step_matches_reference_adam(name):
         assert torch.allclose(sd[k].reshape(-1)[idx], g.t("w1sub." + k), atol=5e-5), k
 
 
-def test_ved_default_architecture_vs_oracle_and_training():
+@pytest.mark.parametrize("generic", [True, False], ids=["fp32-generic", "default"])
+def test_ved_default_architecture_vs_oracle_and_training(generic):
     """cfg5 shapes (64x64 image -> 128-point spectrum, default filters) at a small batch."""
+    os.environ["PVB_FORCE_GENERIC"] = "1" if generic else "0"
     torch.manual_seed(0)
     B = 6
     m = pv.models.VED((64, 64), (128,), latent_dim=2, seed=3, device="cuda:0")
@@ -73,13 +102,12 @@ def test_ved_default_architecture_vs_oracle_and_training():
     loss = tr.svi.loss_and_grads(x.cuda(), y.cuda(), _eps=eps.cuda(), scale_factor=4.0)
     cfg = sp.VedCfg((64, 64), (128,), 2)
     ref, grads = sp.loss_and_grads(sp.ved_loss, sd, cfg, x, y, eps, 4.0)
-    assert abs(loss - float(ref["loss"])) <= 1e-4 * abs(float(ref["loss"]))
+    ltol, atol = (1e-4, 1e-4) if generic else (1e-3, 1e-3)
+    assert abs(loss - float(ref["loss"])) <= ltol * abs(float(ref["loss"]))
     prog = next(iter(tr.svi.programs.values()))
-    assert (prog.loc.cpu().reshape(B, -1) - ref["loc"]).abs().max().item() <= 1e-4
-    for k, p in m.named_parameters():
-        r = grads[k].cuda()
-        err = (p.grad - r).abs().max().item() / (r.abs().max().item() + 1e-6)
-        assert err <= 2e-3, (k, err)
+    assert prog.use_tc == (not generic)
+    assert (prog.loc.cpu().reshape(B, -1) - ref["loc"]).abs().max().item() <= atol
+    grad_check(m, {k: v.cuda() for k, v in grads.items()}, generic)
     # optimisation steps on a fixed batch / fixed noise reduce the loss (CUDA-graph replay
     # included), and the epoch loop of the trainer runs on (x, y) loaders
     xc, yc, ec = x.cuda(), y.cuda(), eps.cuda()
@@ -91,6 +119,7 @@ def test_ved_default_architecture_vs_oracle_and_training():
 
 
 def test_ved_inference_api():
+    os.environ["PVB_FORCE_GENERIC"] = "0"
     m = pv.models.VED((32, 32), (64,), latent_dim=2, seed=1, device="cuda:0",
                       hidden_dim_e=[(8,), (16, 16)], hidden_dim_d=[(16,), (8,)])
     x = torch.rand(5, 32, 32)
@@ -177,3 +206,44 @@ def test_pool_and_upsample_kernels_vs_torch(shape):
         dx = torch.empty_like(x)
         ops.upsample2_bwd(dy, dx, mode == "bilinear")
         assert torch.allclose(dx, xr.grad, atol=1e-5)
+
+
+# ---- tensor-core convolutions (fp16 operands, fp32 accumulate) vs PyTorch fp32 ----------
+@pytest.mark.parametrize("shape", [
+    (3, 32, 64, 16, 16, 3, 2),     # B, Cin, Cout, H, W, k, ndim
+    (2, 128, 128, 8, 8, 3, 2),
+    (5, 64, 128, 7, 9, 3, 2),      # odd spatial sizes, partial last tile
+    (4, 128, 64, 1, 32, 3, 1),     # 1-D
+    (3, 64, 64, 1, 20, 1, 1),      # 1x1
+    (2, 16, 48, 6, 6, 3, 2),       # small channel counts
+])
+def test_tc_conv_kernels_vs_torch(shape):
+    B, Cin, Cout, H, W, k, nd = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    if nd == 2:
+        x = torch.randn(B, Cin, H, W, generator=g).cuda()
+        wt = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+        conv = F.conv2d
+    else:
+        x = torch.randn(B, Cin, W, generator=g).cuda()
+        wt = (torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5).cuda()
+        conv = F.conv1d
+    assert ops.conv_tc_supported(wt)
+    b = torch.randn(Cout, generator=g).cuda()
+    ws = ops.conv_tc_workspace(wt)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, wt, b))
+    yr = F.leaky_relu(conv(xr, wr, br, padding=k // 2), 0.01)
+    dy = torch.randn(yr.shape, generator=g).cuda()
+    yr.backward(dy)
+    y = torch.empty_like(yr)
+    ops.conv_tc_fwd(x, wt, b, "lrelu", y, ws)
+    assert (y - yr.detach()).abs().max().item() <= 4e-3 * yr.abs().max().item()
+    dpre = dy.clone()
+    ops.act_bwd(dpre, yr.detach(), None, dpre, "lrelu")
+    dx = torch.empty_like(x)
+    ops.conv_tc_bwd_data(dpre, wt, dx, ws)
+    assert (dx - xr.grad).abs().max().item() <= 4e-3 * xr.grad.abs().max().item()
+    dW, db = torch.zeros_like(wt), torch.zeros_like(b)
+    ops.conv_tc_bwd_weight(dpre, x, wt, dW, db)
+    assert (dW - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
+    assert (db - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
