@@ -307,6 +307,7 @@ int pvb_linear_dx_cols(const float* dpre, const float* W, float* dx_cols, int64_
  * fp16, fp32 accumulation in tensor memory.
  * workspace: pvb_conv_tc_workspace_bytes(...) bytes, 16-byte aligned (repacked weights). */
 int pvb_conv_tc_supported(int Cin, int Cout, int kh, int kw);
+int pvb_conv_tc_wgrad_supported(int Cin, int Cout, int kh, int kw);  /* also Cin < 16 (padded) */
 int64_t pvb_conv_tc_workspace_bytes(int Cin, int Cout, int kh, int kw);
 /* mode 0: dst = act(conv(src = x, W) + b), pre optional; mode 1: dst = dx from src = dpre */
 int pvb_conv_tc_pix(const float* src, const float* W, const float* b, float* dst,

@@ -104,6 +104,7 @@ SIGNATURES = {
     "pvb_normal_logprob": [_f, _f, _fl, _fl, _f, _f, _i64, _st],
     "pvb_linear_dx_cols": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_tc_supported": [_i32, _i32, _i32, _i32],
+    "pvb_conv_tc_wgrad_supported": [_i32, _i32, _i32, _i32],
     "pvb_conv_tc_workspace_bytes": [_i32, _i32, _i32, _i32],
     "pvb_conv_tc_pix": [_f, _f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_tc_wgrad": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],

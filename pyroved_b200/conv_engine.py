@@ -30,6 +30,8 @@ class ConvStack:
                         and ops.conv_tc_supported(mod.weight))
             if st["tc"]:
                 st["ws"] = ops.conv_tc_workspace(mod.weight)
+            st["tc_wgrad"] = (kind == "conv" and not engine.force_generic
+                              and ops.conv_tc_wgrad_supported(mod.weight))
             self.steps.append(st)
             shape = oshape
             biggest = max(biggest, B * _numel(shape))
@@ -73,13 +75,14 @@ class ConvStack:
                 if st["act"] is not None:
                     ops.act_bwd(d, st["y"], st["pre"], d, st["act"])     # in place: d = dpre
                 gb = flat.gv(m.bias) if m.bias is not None else None
-                if st["tc"]:
+                if st["tc_wgrad"]:
                     ops.conv_tc_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
-                    if want_dx:
-                        ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"])
                 else:
                     ops.conv_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
-                    if want_dx:
+                if want_dx:
+                    if st["tc"]:
+                        ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"])
+                    else:
                         ops.conv_bwd_data(d, m.weight.data, dx)
             elif st["kind"] == "pool":
                 if want_dx:

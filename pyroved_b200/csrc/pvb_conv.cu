@@ -240,28 +240,53 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restri
   y[i] = m;
 }
 // dx = dy routed to the first maximal element of each window (torch tie-breaking: first in
-// row-major window order); elements outside any window (odd sizes) get 0
+// row-major window order).  One thread per output window (reads its 2 / 4 inputs once, writes the
+// whole window); elements outside any window (odd sizes) are zeroed by the trailing threads.
 __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                     float* __restrict__ dx, int64_t BC, int H, int W, int Ho, int Wo,
                                     int two_d) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BC * H * W) return;
-  int w = (int)(i % W);
-  int h = (int)((i / W) % H);
-  int64_t bc = i / ((int64_t)W * H);
-  int wo = w >> 1, ho = two_d ? h >> 1 : h;
-  float g = 0.f;
-  if (wo < Wo && ho < Ho) {
-    const float* p = x + (bc * H + (two_d ? 2 * ho : ho)) * W + 2 * wo;
-    float v[4] = {p[0], p[1], two_d ? p[W] : -INFINITY, two_d ? p[W + 1] : -INFINITY};
+  const int64_t n_win = BC * Ho * Wo;
+  if (i < n_win) {
+    int wo = (int)(i % Wo);
+    int ho = (int)((i / Wo) % Ho);
+    int64_t bc = i / ((int64_t)Wo * Ho);
+    const int64_t o = (bc * H + (two_d ? 2 * ho : ho)) * W + 2 * wo;
+    float v[4] = {x[o], x[o + 1], two_d ? x[o + W] : -INFINITY, two_d ? x[o + W + 1] : -INFINITY};
     int best = 0;
 #pragma unroll
     for (int k = 1; k < 4; ++k)
       if (v[k] > v[best]) best = k;
-    int me = (w & 1) + (two_d ? 2 * (h & 1) : 0);
-    if (me == best) g = dy[(bc * Ho + ho) * Wo + wo];
+    const float g = dy[i];
+    float2 top = make_float2(best == 0 ? g : 0.f, best == 1 ? g : 0.f);
+    if ((o & 1) == 0) {
+      *reinterpret_cast<float2*>(dx + o) = top;
+    } else {
+      dx[o] = top.x;
+      dx[o + 1] = top.y;
+    }
+    if (two_d) {
+      float2 bot = make_float2(best == 2 ? g : 0.f, best == 3 ? g : 0.f);
+      if (((o + W) & 1) == 0) {
+        *reinterpret_cast<float2*>(dx + o + W) = bot;
+      } else {
+        dx[o + W] = bot.x;
+        dx[o + W + 1] = bot.y;
+      }
+    }
+    return;
   }
-  dx[i] = g;
+  // odd sizes: the last column / row belongs to no window
+  i -= n_win;
+  const int odd_w = W & 1, odd_h = two_d ? (H & 1) : 0;
+  const int64_t per_plane = (int64_t)odd_w * H + (int64_t)odd_h * (W - odd_w);
+  if (per_plane == 0 || i >= BC * per_plane) return;
+  int64_t bc = i / per_plane;
+  int r = (int)(i - bc * per_plane);
+  int h, w;
+  if (r < odd_w * H) { h = r; w = W - 1; }
+  else { h = H - 1; w = r - odd_w * H; }
+  dx[(bc * H + h) * W + w] = 0.f;
 }
 
 // ---- 2x up-sampling (F.interpolate(scale_factor=2), nearest; bilinear for 2-D, align_corners=False)
@@ -334,6 +359,44 @@ __global__ void act_bwd_flat_kernel(const float* __restrict__ dy, const float* _
   for (; i < n; i += stride) dpre[i] = dy[i] * pvb::act_grad(y[i], pre ? pre[i] : 0.f, act);
 }
 
+// Cin == 1 (the first encoder layer): HBM-write bound, so no GEMM machinery -- one thread per
+// pixel keeps its <= 9 inputs in registers and streams the Cout outputs (coalesced per channel)
+__global__ void __launch_bounds__(256)
+conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
+                   const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ pre,
+                   ConvDims d, int act) {
+  extern __shared__ float wsm[];   // [Cout][taps] + [Cout]
+  const int taps = d.kh * d.kw, ph = d.kh / 2, pw = d.kw / 2;
+  for (int k = threadIdx.x; k < d.Cout * taps; k += blockDim.x) wsm[k] = Wt[k];
+  for (int k = threadIdx.x; k < d.Cout; k += blockDim.x) wsm[d.Cout * taps + k] = bias ? bias[k] : 0.f;
+  __syncthreads();
+  const int HW = d.H * d.W;
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= (int64_t)d.B * HW) return;
+  const int b = (int)(m / HW), r = (int)(m - (int64_t)b * HW);
+  const int h = r / d.W, w = r - h * d.W;
+  float in[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    in[t] = 0.f;
+    if (t < taps) {
+      int hh = h + t / d.kw - ph, ww = w + t % d.kw - pw;
+      if (hh >= 0 && hh < d.H && ww >= 0 && ww < d.W) in[t] = __ldg(x + (int64_t)b * HW + hh * d.W + ww);
+    }
+  }
+  float* o = y + (int64_t)b * d.Cout * HW + r;
+  float* po = pre ? pre + (int64_t)b * d.Cout * HW + r : nullptr;
+  for (int co = 0; co < d.Cout; ++co) {
+    float v = wsm[d.Cout * taps + co];
+    const float* wr = wsm + co * taps;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      if (t < taps) v = fmaf(in[t], wr[t], v);
+    if (po) po[(int64_t)co * HW] = v;
+    o[(int64_t)co * HW] = pvb::act_fwd(v, act);
+  }
+}
+
 int check_dims(const ConvDims& d, const char* who) {
   PVB_CHECK_ARG(d.B >= 0 && d.Cin > 0 && d.Cout > 0 && d.H > 0 && d.W > 0, "%s: bad dims", who);
   PVB_CHECK_ARG((d.kh == 1 || d.kh == 3) && (d.kw == 1 || d.kw == 3), "%s: kernel size must be 1 or 3", who);
@@ -353,6 +416,12 @@ extern "C" int pvb_conv_fwd(const float* x, const float* W, const float* b, floa
   PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID, "pvb_conv_fwd: unknown activation %d", act);
   if (B == 0) return 0;
   int64_t M = (int64_t)B * H * Wd;
+  if (Cin == 1 && Cout * (kh * kw + 1) * sizeof(float) <= 40 * 1024) {
+    size_t smem1 = (size_t)Cout * (kh * kw + 1) * sizeof(float);
+    conv_c1_fwd_kernel<<<pvb::cdiv(M, 256), 256, smem1, (cudaStream_t)stream>>>(x, W, b, y, pre, d, act);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   dim3 grid((unsigned)((M + BM - 1) / BM), (Cout + BN - 1) / BN);
   size_t smem = (size_t)Cin * kh * kw * sizeof(Tap);
   conv_pix_kernel<0><<<grid, NT, smem, (cudaStream_t)stream>>>(x, W, b, y, pre, d, act);
@@ -420,7 +489,8 @@ extern "C" int pvb_maxpool2_bwd(const float* x, const float* dy, float* dx, int6
                                 int two_d, void* stream) {
   PVB_CHECK_ARG(x && dy && dx && BC >= 0 && H > 0 && Wd > 1 && (!two_d || H > 1), "pvb_maxpool2_bwd: bad argument");
   int Ho = two_d ? H / 2 : H, Wo = Wd / 2;
-  int64_t n = BC * H * Wd;
+  const int odd_w = Wd & 1, odd_h = two_d ? (H & 1) : 0;
+  int64_t n = BC * Ho * Wo + BC * ((int64_t)odd_w * H + (int64_t)odd_h * (Wd - odd_w));
   if (n == 0) return 0;
   maxpool2_bwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, BC, H, Wd, Ho, Wo, two_d);
   pvb::count_launch();

@@ -284,14 +284,16 @@ conv_tc_pix_kernel(const float* __restrict__ src, const uint16_t* __restrict__ W
 // tap t [128 px][Cin] (MN-major), one N = Cin MMA chain (8 K-steps of 16 pixels) per tap.
 constexpr int WG_THREADS = 160;
 constexpr int WG_A = TP * 128 * 2;               // 32 KB: dpre tile, 16 chunk-columns
-constexpr int WG_MAX_TAPS = 4;                   // taps per CTA (<= 512 / Cin)
+constexpr int WG_MAX_TAPS = 9;                   // taps per CTA (<= (512 - 16) / Cin)
 constexpr int WG_STAGES = 2;
 
 template <bool BF16>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dW,
-                     float* __restrict__ db, int B, int Cin, int Cout, int H, int W, int kh, int kw,
+                     float* __restrict__ db, int B, int Cin_real, int Cout, int H, int W, int kh, int kw,
                      int taps_per_cta, int64_t tiles_per_split) {
+  // fewer than 16 input channels (the first layer): the x tile is zero-padded to 16 columns
+  const int Cin = Cin_real < 16 ? 16 : Cin_real;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int b_tile = TP * Cin * 2;                       // one shifted x tile
   const int stage_bytes = WG_A + taps_per_cta * b_tile + TP * ROWB * 2;   // + ones tile (16 columns)
@@ -381,7 +383,7 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
         }
       }
       // shifted x tiles, one per tap of this CTA
-      const float* xb = x + (int64_t)gb * Cin * HW + gr;
+      const float* xb = x + (int64_t)gb * Cin_real * HW + gr;
       for (int t = 0; t < ntap; ++t) {
         const int tap = tap0 + t;
         const int dh = tap / kw - ph, dw = tap % kw - pw;
@@ -389,9 +391,20 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
         const bool ok = m_ok && hh >= 0 && hh < H && ww >= 0 && ww < W;
         const float* p = xb + (ok ? dh * W + dw : 0);
         uint8_t* bt = st + WG_A + t * b_tile + row * ROWB;
-        for (int c0 = 0; c0 < Cin; c0 += 64)
-          gather_row<BF16, false>(p + (int64_t)c0 * HW, HW, min(64, Cin - c0), ok, 1.f,
-                                  bt + (c0 / 8) * (TP * ROWB));
+        if (Cin_real < 16) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (ok && j < Cin_real) ? __ldg(p + (int64_t)j * HW) : 0.f;
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8)
+            *reinterpret_cast<uint4*>(bt + c8 * (TP * ROWB)) =
+                make_uint4(pack2<BF16>(v[c8 * 8], v[c8 * 8 + 1]), pack2<BF16>(v[c8 * 8 + 2], v[c8 * 8 + 3]),
+                           pack2<BF16>(v[c8 * 8 + 4], v[c8 * 8 + 5]), pack2<BF16>(v[c8 * 8 + 6], v[c8 * 8 + 7]));
+        } else {
+          for (int c0 = 0; c0 < Cin; c0 += 64)
+            gather_row<BF16, false>(p + (int64_t)c0 * HW, HW, min(64, Cin - c0), ok, 1.f,
+                                    bt + (c0 / 8) * (TP * ROWB));
+        }
       }
       if (do_bias) {
         // ones tile [128 px][16]: column 0 = 1 for valid pixels -> bias sums in one N = 16 chain
@@ -418,7 +431,8 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
           if (co < Cout) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              atomicAdd(dW + ((int64_t)co * Cin + n0 + j) * taps + tap, v[j] * (1.f / GRAD_SCALE));
+              if (n0 + j < Cin_real)
+                atomicAdd(dW + ((int64_t)co * Cin_real + n0 + j) * taps + tap, v[j] * (1.f / GRAD_SCALE));
           }
         }
       }
@@ -450,6 +464,10 @@ bool tc_ok(int Cg, int Nout, int kh, int kw) {
 
 extern "C" int pvb_conv_tc_supported(int Cin, int Cout, int kh, int kw) {
   return tc_ok(Cin, Cout, kh, kw) && tc_ok(Cout, Cin, kh, kw) ? 1 : 0;
+}
+// the weight-gradient kernel alone also takes layers with fewer than 16 input channels
+extern "C" int pvb_conv_tc_wgrad_supported(int Cin, int Cout, int kh, int kw) {
+  return tc_ok(Cin < 16 ? 16 : Cin, Cout, kh, kw) && Cout <= 128 ? 1 : 0;
 }
 
 extern "C" int64_t pvb_conv_tc_workspace_bytes(int Cin, int Cout, int kh, int kw) {
@@ -497,7 +515,9 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
 extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, float* db, int B, int Cin,
                                  int Cout, int H, int Wd, int kh, int kw, void* stream) {
   PVB_CHECK_ARG(dpre && x && dW, "pvb_conv_tc_wgrad: null pointer");
-  PVB_CHECK_ARG(tc_ok(Cin, Cout, kh, kw) && tc_ok(Cout, Cin, kh, kw), "pvb_conv_tc_wgrad: unsupported shape");
+  const int Cin_real = Cin;
+  if (Cin < 16) Cin = 16;                        // zero-padded x tile
+  PVB_CHECK_ARG(tc_ok(Cin, Cout, kh, kw) && Cout <= 128, "pvb_conv_tc_wgrad: unsupported shape");
   if (B == 0) return 0;
   const int taps = kh * kw;
   int tpc = (512 - 16) / Cin;                    // taps per CTA: accumulators + 16 bias columns <= 512
@@ -526,7 +546,7 @@ extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, f
   }
   dim3 grid(groups, (unsigned)splits);
   conv_tc_wgrad_kernel<BWD_BF16><<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(
-      dpre, x, dW, db, B, Cin, Cout, H, Wd, kh, kw, tpc, per);
+      dpre, x, dW, db, B, Cin_real, Cout, H, Wd, kh, kw, tpc, per);
   pvb::count_launch();
   return pvb::launch_status();
 }

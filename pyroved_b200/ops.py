@@ -367,6 +367,11 @@ def conv_tc_supported(W):
     return bool(_lib.lib().pvb_conv_tc_supported(W.shape[1], W.shape[0], kh, kw))
 
 
+def conv_tc_wgrad_supported(W):
+    kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
+    return bool(_lib.lib().pvb_conv_tc_wgrad_supported(W.shape[1], W.shape[0], kh, kw))
+
+
 def conv_tc_workspace(W):
     kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
     n = _lib.lib().pvb_conv_tc_workspace_bytes(W.shape[1], W.shape[0], kh, kw)

@@ -247,3 +247,28 @@ def test_tc_conv_kernels_vs_torch(shape):
     ops.conv_tc_bwd_weight(dpre, x, wt, dW, db)
     assert (dW - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
     assert (db - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 32, 16, 16, 3, 2), (2, 3, 64, 1, 40, 3, 1), (4, 5, 16, 7, 5, 1, 2)])
+def test_tc_weight_gradient_with_few_input_channels(shape):
+    """first-layer case: Cin < 16 is zero-padded inside the tensor-core weight-gradient kernel"""
+    B, Cin, Cout, H, W, k, nd = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    if nd == 2:
+        x = torch.randn(B, Cin, H, W, generator=g).cuda()
+        wt = torch.randn(Cout, Cin, k, k, generator=g).cuda()
+        conv = F.conv2d
+    else:
+        x = torch.randn(B, Cin, W, generator=g).cuda()
+        wt = torch.randn(Cout, Cin, k, generator=g).cuda()
+        conv = F.conv1d
+    assert ops.conv_tc_wgrad_supported(wt) and not ops.conv_tc_supported(wt)
+    b = torch.zeros(Cout).cuda()
+    wr, br = wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = conv(x, wr, br, padding=k // 2)
+    dy = torch.randn(yr.shape, generator=g).cuda()
+    yr.backward(dy)
+    dW, db = torch.zeros_like(wt), torch.zeros_like(b)
+    ops.conv_tc_bwd_weight(dy, x, wt, dW, db)
+    assert (dW - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
+    assert (db - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
