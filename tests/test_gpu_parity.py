@@ -178,3 +178,24 @@ def test_rng_is_counter_based_and_reproducible():
     c = torch.empty(100000, device="cuda")
     ops.randn(c, 1234, ctr, 0)
     assert not torch.equal(a, c)
+
+
+@pytest.mark.parametrize("dim,inv,B", [((6, 6), ['r', 't'], 37), ((33,), ['t'], 50), ((5, 9), ['s'], 3)])
+def test_fused_decoder_small_images_many_slots_per_tile(dim, inv, B):
+    """N = 36 / 33 / 45 pixels: a 128-row tile of the fused kernel touches up to 5 instances, tiles
+    straddle instance boundaries and the last tile is partial (ragged R)."""
+    os.environ["PVB_FORCE_GENERIC"] = "0"
+    m = pv.models.iVAE(dim, 2, inv, seed=7, device="cuda:0")
+    tr = pv.trainers.SVItrainer(m, device="cuda:0")
+    gen = torch.Generator().manual_seed(B)
+    x = (torch.rand(B, *dim, generator=gen) < 0.4).float()
+    eps = torch.randn(B, m.z_dim, generator=gen)
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    loss = tr.svi.loss_and_grads(x.cuda(), _eps=eps.cuda())
+    prog = next(iter(tr.svi.programs.values()))
+    assert prog.use_tc
+    cfg = sp.Cfg(dim, 2, inv)
+    ref, grads = sp.loss_and_grads(sp.ivae_loss, sd, cfg, x, eps)
+    assert abs(loss - float(ref["loss"])) <= LOSS_RTOL * abs(float(ref["loss"]))
+    assert (prog.loc.cpu().reshape(B, -1) - ref["loc"]).abs().max().item() <= LOC_ATOL
+    grad_check(m, grads, 2e-2)
