@@ -322,6 +322,9 @@ def run_ours(args):
                        "global_batch": BATCH * world, "parallelism": "dp{}".format(world),
                        "decoder_path": "tcgen05-fused" if use_tc else "fp32-generic",
                        "cuda_graphs": bool(svi.use_graphs),
+                       "exchange": ("none (1 GPU)" if world == 1 else
+                                    "fused all-reduce + Adam kernel over NVLink peer memory"
+                                    if svi.peer is not None else "NCCL all-reduce"),
                        "l2": "inputs rotate through a pool of {} batches ({} MB) > 126 MB L2"
                              .format(POOL, POOL * BATCH * H * W * 4 // 2 ** 20)},
             "e2e": {"value": total / t_e2e, "unit": "samples/s",

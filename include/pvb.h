@@ -291,6 +291,42 @@ int pvb_upsample2_fwd(const float* x, float* y, int64_t BC, int H, int Wd,
 int pvb_upsample2_bwd(const float* dy, float* dx, int64_t BC, int H, int Wd,
                       int two_d, int bilinear, void* stream);
 
+/* ---- data-parallel exchange over NVLink peer memory (csrc/pvb_peer.cu) ----
+ * Fused SUM all-reduce of the flat [n gradients | loss] buffers of all ranks + the Adam
+ * update of pvb_adam_flat_step, one kernel, deterministic (rank-order sums, identical on
+ * every rank).  peer_g: DEVICE array of `world` pointers, entry r = rank r's gradient
+ * buffer (n + 4 floats, symmetric memory mapped into this process; entry `rank` = own_g);
+ * peer_flags: DEVICE array of `world` pointers to each rank's flag block of
+ * pvb_peer_flag_words() zero-initialised uint32 (symmetric memory); state: 4 zero-initialised
+ * int32 of this rank.  On return (stream order) p/m/v are updated, own_g[n] holds the global
+ * loss, *step_counter is advanced, and every peer has finished reading own_g.
+ * Every rank must launch it the same number of times (SPMD); n % 4 == 0. */
+int pvb_peer_flag_words(void);
+int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* own_g, int64_t n,
+                            const void* peer_g, const void* peer_flags, int32_t* state,
+                            int rank, int world, float lr, float beta1, float beta2,
+                            float eps, int32_t* step_counter, const int32_t* first_step,
+                            void* stream);
+
+/* ---- nn.BatchNorm{1,2}d of the convolutional nets (csrc/pvb_norm.cu; reference
+ * nets/conv.py:187,240 with batchnorm=True, utils/nn.py:103-105) ----------------
+ * x, y [B, C, HW] fp32.  training != 0: batch statistics (biased variance) normalise,
+ * running_mean / running_var (unbiased) move by `momentum` and *num_batches_tracked
+ * (int64; each may be NULL) += 1; training == 0: the running statistics normalise.
+ * save_mean / save_invstd [C] receive the statistics used (input of pvb_bn_bwd).
+ * workspace: pvb_bn_workspace_bytes(C) bytes, 16-byte aligned. */
+int64_t pvb_bn_workspace_bytes(int C);
+int pvb_bn_fwd(const float* x, const float* gamma, const float* beta,
+               float* running_mean, float* running_var, int64_t* num_batches_tracked,
+               float* y, float* save_mean, float* save_invstd, void* workspace, int B,
+               int C, int64_t HW, float eps, float momentum, int training, void* stream);
+/* training-mode backward: dgamma[c] += sum dy xhat, dbeta[c] += sum dy (either may be
+ * NULL), dx = gamma invstd (dy - mean(dy) - xhat mean(dy xhat)); dx may alias dy */
+int pvb_bn_bwd(const float* dy, const float* x, const float* gamma,
+               const float* save_mean, const float* save_invstd, float* dx,
+               float* dgamma, float* dbeta, void* workspace, int B, int C, int64_t HW,
+               void* stream);
+
 /* ---- regression variant (models/ss_reg_ivae.py:172-175,205-207,240-242) ----
  * loss_out[0] += scale * sum_i log N(y_i; loc_i, sigma)   (loc may be NULL = 0;
  * loss_out may be NULL); gloc[i] = scale (y_i - loc_i) / sigma^2 when non-NULL

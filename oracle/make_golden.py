@@ -231,6 +231,22 @@ def main_ved():
     m.to("cpu")
     run_case("ved_spec2im_32_16", m, dev, (xs, yim),
              {"z": torch.randn(5, 3, generator=gen(21))}, {})
+    # batchnorm=True (nets/conv.py:186-187, 239-240): BatchNorm2d encoder / BatchNorm1d decoder and
+    # the other way round; w1.* then also pins the running statistics after one step
+    x = blobs(6, 16, 16, seed=25, binary=False)[:, None]
+    ysp = spectra(6, 32, seed=26)[:, None]
+    m = pv.models.VED((16, 16), (32,), latent_dim=2, seed=3, batchnorm=True,
+                      hidden_dim_e=[(8,), (16, 16)], hidden_dim_d=[(16, 16), (8,)])
+    m.to("cpu")
+    run_case("ved_bn_im2spec_16_32", m, dev, (x, ysp),
+             {"z": torch.randn(6, 2, generator=gen(27))}, {"scale_factor": 2.0})
+    xs = spectra(5, 32, seed=28)[:, None]
+    yim = blobs(5, 16, 16, seed=29, binary=False)[:, None]
+    m = pv.models.VED((32,), (16, 16), latent_dim=2, seed=4, batchnorm=True, activation="tanh",
+                      hidden_dim_e=[(8,), (16, 16)], hidden_dim_d=[(16, 16), (8,)])
+    m.to("cpu")
+    run_case("ved_bn_spec2im_32_16", m, dev, (xs, yim),
+             {"z": torch.randn(5, 2, generator=gen(30))}, {})
     # default architecture, two input channels, small spatial size (weights subsampled? no:
     # kept whole, the fixture is ~2 MB) -- skipped by default, enable with --ved-full
     if "--ved-full" in sys.argv:

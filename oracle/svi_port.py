@@ -395,7 +395,8 @@ class VedCfg:
 
     def __init__(self, input_dim, output_dim, latent_dim=2, hidden_dim_e=None, hidden_dim_d=None,
                  activation="lrelu", sampler_d="bernoulli", sigmoid_d=True, decoder_sig=0.5,
-                 input_channels=1, output_channels=1):
+                 input_channels=1, output_channels=1, batchnorm=False):
+        self.batchnorm = batchnorm
         self.input_dim, self.output_dim = tuple(input_dim), tuple(output_dim)
         self.latent_dim = latent_dim
         self.hidden_e = hidden_dim_e or [(32,), (64, 64), (128, 128)]
@@ -409,7 +410,25 @@ def _conv_nd(ndim):
     return F.conv1d if ndim == 1 else F.conv2d
 
 
-def ved_encoder(sd, cfg, x):
+def _bnorm(sd, p, h, stats):
+    """nn.BatchNorm{1,2}d in training mode (the reference never calls .eval()): batch statistics,
+    biased variance, eps 1e-5.  `stats` (optional dict) receives the running statistics after
+    torch's momentum-0.1 update (unbiased variance), keyed like the state_dict."""
+    red = [0] + list(range(2, h.dim()))
+    mean = h.mean(red, keepdim=True)
+    var = ((h - mean) ** 2).mean(red, keepdim=True)
+    if stats is not None:
+        n = h.numel() // h.shape[1]
+        with torch.no_grad():
+            stats[p + ".running_mean"] = 0.9 * sd[p + ".running_mean"] + 0.1 * mean.flatten()
+            stats[p + ".running_var"] = (0.9 * sd[p + ".running_var"]
+                                         + 0.1 * var.flatten() * n / max(n - 1, 1))
+            stats[p + ".num_batches_tracked"] = sd[p + ".num_batches_tracked"] + 1
+    shape = [1, -1] + [1] * (h.dim() - 2)
+    return (h - mean) / torch.sqrt(var + 1e-5) * sd[p + ".weight"].view(shape) + sd[p + ".bias"].view(shape)
+
+
+def ved_encoder(sd, cfg, x, stats=None):
     """convEncoderNet.forward (nets/conv.py:56-64): FeatureExtractor (conv+act blocks, a 2x
     max-pool after a block while more convolutions remain, conv.py:173-195) -> flatten ->
     fc_latent -> split -> softplus on the second half."""
@@ -424,6 +443,9 @@ def ved_encoder(sd, cfg, x):
             p = "encoder_z.feature_extractor.layers.{}".format(idx)
             h = act(conv(h, sd[p + ".weight"], sd[p + ".bias"], padding=1))
             idx += 2
+            if cfg.batchnorm:
+                h = _bnorm(sd, "encoder_z.feature_extractor.layers.{}".format(idx), h, stats)
+                idx += 1
             done += 1
         if done + 1 < total:
             h = pool(h, 2, 2)
@@ -434,7 +456,7 @@ def ved_encoder(sd, cfg, x):
     return mu, F.softplus(s)
 
 
-def ved_decoder(sd, cfg, z):
+def ved_decoder(sd, cfg, z, stats=None):
     """convDecoderNet.forward (nets/conv.py:96-102): latent2features -> Upsampler (conv+act
     blocks, each closed by an UpsampleBlock = x2 interpolation ('bilinear' in 2-D, 'nearest'
     in 1-D, conv.py:127-143) + 1x1 conv; final 1x1 conv, conv.py:228-246) -> sigmoid."""
@@ -450,6 +472,9 @@ def ved_decoder(sd, cfg, z):
             p = "decoder.upsampler.layers.{}".format(idx)
             h = act(conv(h, sd[p + ".weight"], sd[p + ".bias"], padding=1))
             idx += 2
+            if cfg.batchnorm:
+                h = _bnorm(sd, "decoder.upsampler.layers.{}".format(idx), h, stats)
+                idx += 1
         p = "decoder.upsampler.layers.{}.conv".format(idx)
         h = F.interpolate(h, scale_factor=2, mode="bilinear" if nd == 2 else "nearest")
         h = conv(h, sd[p + ".weight"], sd[p + ".bias"])
@@ -459,14 +484,15 @@ def ved_decoder(sd, cfg, z):
     return torch.sigmoid(h) if cfg.sigmoid_d else h
 
 
-def ved_loss(sd, cfg, x, y, eps, beta=1.0):
+def ved_loss(sd, cfg, x, y, eps, beta=1.0, stats=None):
     """Returns dict(loss, ll[B], loc[B,N], z, mu, sigma);
-    loss = -( sum_b log p(y_b | decoder(z_b)) + beta sum_b (log p(z_b) - log q(z_b)) )."""
-    mu, sig = ved_encoder(sd, cfg, x)
+    loss = -( sum_b log p(y_b | decoder(z_b)) + beta sum_b (log p(z_b) - log q(z_b)) ).
+    The model replays the guide's z, so each net runs once per step (one batch-norm update)."""
+    mu, sig = ved_encoder(sd, cfg, x, stats)
     z = mu + sig * eps
     log_q = normal_logprob(z, mu, sig)
     log_p = normal_logprob(z, torch.zeros_like(z), torch.ones_like(z))
-    loc = ved_decoder(sd, cfg, z).flatten(1)
+    loc = ved_decoder(sd, cfg, z, stats).flatten(1)
     ll = log_lik(loc, y.flatten(1), cfg.sampler_d, cfg.decoder_sig)
     elbo = ll.sum() + beta * (log_p - log_q).sum()
     return {"loss": -elbo, "ll": ll, "loc": loc, "z": z, "mu": mu, "sigma": sig}
@@ -478,9 +504,10 @@ def ved_loss(sd, cfg, x, y, eps, beta=1.0):
 def loss_and_grads(loss_fn, sd, *args, **kwargs):
     """Runs loss_fn with autograd over every tensor of `sd`; returns
     (outputs dict, grads dict keyed like sd; params unused by the loss -> None)."""
-    leaf = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in sd.items())
+    leaf = OrderedDict((k, v.detach().clone().requires_grad_(True) if v.is_floating_point()
+                        else v.detach().clone()) for k, v in sd.items())
     out = loss_fn(leaf, *args, **kwargs)
-    names = list(leaf.keys())
+    names = [k for k, v in leaf.items() if v.requires_grad]
     if out["loss"].requires_grad:
         g = torch.autograd.grad(out["loss"], [leaf[n] for n in names], allow_unused=True)
     else:

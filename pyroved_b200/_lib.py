@@ -97,6 +97,12 @@ SIGNATURES = {
     "pvb_conv_bwd_data": [_f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_bwd_weight": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_act_bwd": [_f, _f, _f, _f, _i64, _i32, _st],
+    "pvb_peer_flag_words": [],
+    "pvb_peer_allreduce_adam": [_f, _f, _f, _f, _i64, _f, _f, _f, _i32, _i32, _fl, _fl, _fl, _fl,
+                                _f, _f, _st],
+    "pvb_bn_workspace_bytes": [_i32],
+    "pvb_bn_fwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _fl, _fl, _i32, _st],
+    "pvb_bn_bwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _st],
     "pvb_maxpool2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_maxpool2_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_upsample2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
@@ -139,7 +145,8 @@ def lib():
             fn.argtypes = argtypes
             fn.restype = (C.c_char_p if name == "pvb_last_error_string" else
                           C.c_longlong if name in ("pvb_launch_count",
-                                                   "pvb_conv_tc_workspace_bytes") else C.c_int)
+                                                   "pvb_conv_tc_workspace_bytes",
+                                                   "pvb_bn_workspace_bytes") else C.c_int)
         _LIB = handle
     return _LIB
 

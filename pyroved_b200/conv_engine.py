@@ -32,6 +32,9 @@ class ConvStack:
                 st["ws"] = ops.conv_tc_workspace(mod.weight)
             st["tc_wgrad"] = (kind == "conv" and not engine.force_generic
                               and ops.conv_tc_wgrad_supported(mod.weight))
+            if kind == "bn":
+                st["stats"] = torch.empty(2, oshape[0], **f32)       # batch mean, 1/std
+                st["ws"] = ops.bn_workspace(oshape[0], dev)
             self.steps.append(st)
             shape = oshape
             biggest = max(biggest, B * _numel(shape))
@@ -50,6 +53,10 @@ class ConvStack:
                     ops.conv_tc_fwd(cur, m.weight.data, bias, st["act"], st["y"], st["ws"], st["pre"])
                 else:
                     ops.conv_fwd(cur, m.weight.data, bias, st["act"], st["y"], st["pre"])
+            elif st["kind"] == "bn":
+                # batch statistics + running-statistics update (the reference trains with the
+                # modules in their default training mode)
+                ops.bn_fwd(cur, m, st["y"], st["stats"][0], st["stats"][1], st["ws"], training=True)
             elif st["kind"] == "pool":
                 ops.maxpool2_fwd(cur, st["y"])
             else:
@@ -84,6 +91,11 @@ class ConvStack:
                         ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"])
                     else:
                         ops.conv_bwd_data(d, m.weight.data, dx)
+            elif st["kind"] == "bn":
+                # the step below is always the convolution whose output feeds this layer
+                gg = flat.gv(m.weight) if m.affine else None
+                gb = flat.gv(m.bias) if m.affine else None
+                ops.bn_bwd(d, xin, m, st["stats"][0], st["stats"][1], dx, gg, gb, st["ws"])
             elif st["kind"] == "pool":
                 if want_dx:
                     ops.maxpool2_bwd(xin, d, dx)

@@ -18,6 +18,7 @@ Layout in HBM
 """
 import math
 import os
+import warnings
 
 import torch
 import torch.nn as nn
@@ -34,9 +35,11 @@ def _align4(n):
 class FlatParams:
     """Flat parameter / gradient / Adam-state buffers with per-parameter views."""
 
-    def __init__(self, module: nn.Module, device):
+    def __init__(self, module: nn.Module, device, g_alloc=None):
         self.module = module
         self.device = torch.device(device)
+        # g_alloc(n_floats) -> zeroed fp32 buffer (symmetric memory for the NVLink exchange)
+        self.g_alloc = g_alloc
         self._build()
 
     def _build(self):
@@ -55,7 +58,8 @@ class FlatParams:
             new_p[o:o + k].copy_(p.data.reshape(-1).to(dev, torch.float32))
         self.p = new_p
         # gradient buffer: [grads | loss, pad3]
-        self.g = torch.zeros(self.total + 4, device=dev, dtype=torch.float32)
+        self.g = (self.g_alloc(self.total + 4) if self.g_alloc is not None
+                  else torch.zeros(self.total + 4, device=dev, dtype=torch.float32))
         self.m = torch.zeros(self.total, device=dev, dtype=torch.float32)
         self.v = torch.zeros(self.total, device=dev, dtype=torch.float32)
         # optimizer step at which each parameter first carried a gradient (-1: never);
@@ -981,7 +985,9 @@ class SVIEngine:
         self.lr = float(lr)
         self.enumerate_parallel = enumerate_parallel
         self.seed = int(seed)
-        self.flat = FlatParams(model, self.device)
+        self.peer = None          # parallel.PeerExchange of the current flat gradient buffer
+        self.flat = FlatParams(model, self.device, self._alloc_grad_buffer()
+                               if parallel.peer_exchange_enabled() else None)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.adam_ticket = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.updates_done = 0     # host mirror of step_counter
@@ -1002,6 +1008,29 @@ class SVIEngine:
     # ---- distributed -----------------------------------------------------
     def _attach_distributed(self):
         self.rank, self.world_size = parallel.rank_world()
+
+    def _alloc_grad_buffer(self):
+        """Allocator handed to FlatParams when the fused NVLink exchange is on: the flat
+        [gradients | loss] buffer comes from symmetric memory shared with the peer ranks
+        (collective: every rank builds its engine at the same point).  Falls back to NCCL's
+        all-reduce, with a warning, where symmetric memory is unavailable."""
+        def alloc(n):
+            try:
+                self.peer = parallel.PeerExchange(n, self.device)
+                return self.peer.g
+            except Exception as err:          # noqa: BLE001 -- any failure means "use NCCL"
+                warnings.warn("pyroved_b200: symmetric-memory exchange unavailable ({}); using "
+                              "the NCCL all-reduce".format(err))
+                self.peer = None
+                return torch.zeros(n, device=self.device, dtype=torch.float32)
+        return alloc
+
+    def _update_exchange(self):
+        """gradient all-reduce + Adam in one kernel over NVLink peer memory"""
+        flat, pe = self.flat, self.peer
+        ops.peer_allreduce_adam(flat.p, flat.m, flat.v, flat.g, flat.total, pe.peer_g, pe.peer_flags,
+                                pe.state, pe.rank, pe.world, self.lr, self.step_counter,
+                                flat.first_step)
 
     def eps_first_index(self, n_local):
         """Global index of this rank's first noise element: the noise of a
@@ -1104,7 +1133,13 @@ class SVIEngine:
             self.updates_done += 1
         bkey = tuple(beta) if isinstance(beta, (list, tuple)) else float(beta)
         key = (B, y is not None, mode, bkey, train, gen_eps, update)
-        if self.world_size > 1 and train:
+        if self.world_size > 1 and train and update and self.peer is not None:
+            # gradients -> fused NVLink all-reduce + Adam: ONE captured graph, no NCCL call
+            def whole():
+                self._run(prog, beta, True, gen_eps, False)
+                self._update_exchange()
+            self._execute(key + ("peer",), whole)
+        elif self.world_size > 1 and train:
             self._execute(key + ("grads",), lambda: self._run(prog, beta, True, gen_eps, False))
             self._allreduce()
             if update:

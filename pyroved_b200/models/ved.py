@@ -22,7 +22,8 @@ class VED(baseVAE):
         hidden_dim_e: conv filters per encoder block, default [(32,), (64, 64), (128, 128)]
         hidden_dim_d: conv filters per decoder block, default [(128, 128), (64, 64), (32,)]
         activation: 'lrelu' (default), 'relu', 'tanh', 'softplus', 'gelu'
-        batchnorm: not implemented here (must be False)
+        batchnorm: BatchNorm after every conv + activation (batch statistics, as the reference
+            never switches the nets to eval mode)
         sampler_d: 'bernoulli' (default) or 'gaussian'
         sigmoid_d: sigmoid on the decoder output (default True)
         seed: torch seed used for weight init

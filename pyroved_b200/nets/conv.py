@@ -5,7 +5,7 @@ nets/conv.py:24-277 (`encoder_z.feature_extractor.layers.{0,3,5,8,10}.*`,
 `decoder.upsampler.layers.{4,9,12}.conv.*`, ...), so `.pt` checkpoints interchange and the same
 seed gives the same initial weights.  The modules only OWN parameters and describe the layer
 sequence; `forward` (inference) and training (conv_engine.VEDProgram) run the hand-written CUDA
-kernels of csrc/pvb_conv.cu through the C ABI.  Not supported here: batchnorm=True and 3-D data.
+kernels of csrc/pvb_conv.cu / pvb_norm.cu through the C ABI.  Not supported here: 3-D data.
 """
 import os
 from typing import List, Tuple
@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..utils.nn import get_activation, get_conv, get_maxpool
+from ..utils.nn import get_activation, get_bnorm, get_conv, get_maxpool
 
 DEFAULT_ENC = [(32,), (64, 64), (128, 128)]
 DEFAULT_DEC = [(128, 128), (64, 64), (32,)]
@@ -33,11 +33,6 @@ def _check_ndim(ndim):
         raise AssertionError("ndim must be equal to 1, 2 or 3")
     if ndim == 3:
         raise NotImplementedError("pyroved_b200: 3-D convolutional nets are not implemented")
-
-
-def _no_bnorm(flag):
-    if flag:
-        raise NotImplementedError("pyroved_b200: batchnorm=True is not implemented")
 
 
 class UpsampleBlock(nn.Module):
@@ -65,9 +60,10 @@ class UpsampleBlock(nn.Module):
         return run_layers([self], x, None)
 
 
-def _conv_blocks(ndim, input_channels, conv_filters, activation, closer):
-    """conv(+activation) per filter count, `closer(block_index, convs_so_far, channels)` appended
-    after every block (pool / upsample); conv modules land at the reference's indices."""
+def _conv_blocks(ndim, input_channels, conv_filters, activation, batchnorm, closer):
+    """conv (+activation) (+batch norm, reference nets/conv.py:186-187) per filter count,
+    `closer(block_index, convs_so_far, channels)` appended after every block (pool / upsample);
+    the modules land at the reference's indices."""
     mods = []
     ch_in = input_channels
     n_convs = 0
@@ -76,6 +72,8 @@ def _conv_blocks(ndim, input_channels, conv_filters, activation, closer):
             mods.append(get_conv(ndim)(ch_in, ch, 3, 1, 1))
             if activation is not None:
                 mods.append(get_activation(activation)())
+            if batchnorm:
+                mods.append(get_bnorm(ndim)(ch))
             ch_in = ch
             n_convs += 1
         mods.extend(closer(i, n_convs, ch_in))
@@ -91,7 +89,6 @@ class FeatureExtractor(nn.Sequential):
                  activation: str = "lrelu", pool_last: bool = True) -> None:
         super().__init__()
         _check_ndim(ndim)
-        _no_bnorm(batchnorm)
         if (kernel_size, stride, padding) != (3, 1, 1):
             raise NotImplementedError("pyroved_b200: kernel_size=3, stride=1, padding=1 only")
         if conv_filters is None:
@@ -103,7 +100,7 @@ class FeatureExtractor(nn.Sequential):
                 return [get_maxpool(ndim)(2, 2)]
             return []
 
-        mods, _ = _conv_blocks(ndim, input_channels, conv_filters, activation, closer)
+        mods, _ = _conv_blocks(ndim, input_channels, conv_filters, activation, batchnorm, closer)
         self.activation = activation
         self.layers = nn.Sequential(*mods)
 
@@ -121,7 +118,6 @@ class Upsampler(nn.Sequential):
                  upsampling_mode: str = "bilinear") -> None:
         super().__init__()
         _check_ndim(ndim)
-        _no_bnorm(batchnorm)
         if (kernel_size, stride, padding) != (3, 1, 1):
             raise NotImplementedError("pyroved_b200: kernel_size=3, stride=1, padding=1 only")
         if conv_filters is None:
@@ -130,7 +126,7 @@ class Upsampler(nn.Sequential):
         def closer(i, n_convs, ch):
             return [UpsampleBlock(ndim, ch, ch, mode=upsampling_mode)]
 
-        mods, ch = _conv_blocks(ndim, input_channels, conv_filters, activation, closer)
+        mods, ch = _conv_blocks(ndim, input_channels, conv_filters, activation, batchnorm, closer)
         mods.append(get_conv(ndim)(ch, output_channels, 1, 1, 0))
         self.activation = activation
         self.layers = nn.Sequential(*mods)
@@ -218,8 +214,8 @@ class convDecoderNet(nn.Module):
 
 # ---- layer-sequence description shared by inference (here) and training (conv_engine) --------
 def layer_plan(layers, activation):
-    """[(kind, module, fused_activation)] with kind in 'conv' | 'pool' | 'up'.  An activation
-    module directly after a convolution is fused into that convolution's epilogue."""
+    """[(kind, module, fused_activation)] with kind in 'conv' | 'bn' | 'pool' | 'up'.  An
+    activation module directly after a convolution is fused into that convolution's epilogue."""
     mods = list(layers)
     plan, i = [], 0
     while i < len(mods):
@@ -231,10 +227,13 @@ def layer_plan(layers, activation):
                 raise NotImplementedError("pyroved_b200: conv layers must be k=1|3, stride 1, same padding")
             act = None
             if i + 1 < len(mods) and not isinstance(
-                    mods[i + 1], (nn.Conv1d, nn.Conv2d, nn.MaxPool1d, nn.MaxPool2d, UpsampleBlock)):
+                    mods[i + 1], (nn.Conv1d, nn.Conv2d, nn.MaxPool1d, nn.MaxPool2d, UpsampleBlock,
+                                  nn.BatchNorm1d, nn.BatchNorm2d)):
                 act = activation
                 i += 1
             plan.append(("conv", m, act))
+        elif isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            plan.append(("bn", m, None))
         elif isinstance(m, (nn.MaxPool1d, nn.MaxPool2d)):
             plan.append(("pool", m, None))
         elif isinstance(m, UpsampleBlock):
@@ -251,6 +250,8 @@ def out_shape(kind, mod, shape):
     c, sp = shape[0], list(shape[1:])
     if kind == "conv":
         return (mod.out_channels, *sp)
+    if kind == "bn":
+        return tuple(shape)
     if kind == "pool":
         return (c, *[s // 2 for s in sp])
     return (c, *[2 * s for s in sp])
@@ -268,6 +269,12 @@ def run_layers(layers, x, activation):
                 ops.conv_tc_fwd(x, mod.weight.data, bias, act, y, ops.conv_tc_workspace(mod.weight))
             else:
                 ops.conv_fwd(x, mod.weight.data, bias, act, y)
+        elif kind == "bn":
+            # like the reference, which never calls .eval(): batch statistics (and a running-
+            # statistics update) unless the caller put the module in eval mode
+            C = x.shape[1]
+            stats = torch.empty(2, C, device=x.device, dtype=torch.float32)
+            ops.bn_fwd(x, mod, y, stats[0], stats[1], ops.bn_workspace(C, x.device))
         elif kind == "pool":
             ops.maxpool2_fwd(x, y)
         else:

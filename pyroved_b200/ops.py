@@ -195,6 +195,21 @@ def adam_flat_step(p, g, m, v, n, lr, step_counter, ticket, first_step=None, bet
           "pvb_adam_flat_step")
 
 
+def peer_allreduce_adam(p, m, v, own_g, n, peer_g, peer_flags, state, rank, world, lr, step_counter,
+                        first_step=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    """All-reduce(SUM) of every rank's [n gradients | loss] buffer over NVLink peer memory fused
+    with the Adam update (csrc/pvb_peer.cu).  peer_g / peer_flags: int64 device tensors holding
+    the peer pointers."""
+    check(_lib.lib().pvb_peer_allreduce_adam(
+        _p(p), _p(m), _p(v), _p(own_g), n, peer_g.data_ptr(), peer_flags.data_ptr(), _p(state),
+        int(rank), int(world), float(lr), beta1, beta2, eps, _p(step_counter), _p(first_step),
+        _stream()), "pvb_peer_allreduce_adam")
+
+
+def peer_flag_words():
+    return int(_lib.lib().pvb_peer_flag_words())
+
+
 # ---- fused small-batch MLP kernels (argument blocks are built once per program) ---------
 def _ptrs(ctype_array, tensors):
     for i, t in enumerate(tensors):
@@ -320,6 +335,42 @@ def conv_bwd_weight(dpre, x, W, dW, db):
 def act_bwd(dy, y, pre, dpre, act):
     check(_lib.lib().pvb_act_bwd(_p(dy), _p(y), _p(pre), _p(dpre), y.numel(), ACT[act], _stream()),
           "pvb_act_bwd")
+
+
+def bn_workspace(C, device):
+    n = _lib.lib().pvb_bn_workspace_bytes(int(C))
+    return torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
+
+
+def _bn_dims(x):
+    B, C = x.shape[0], x.shape[1]
+    return B, C, (x.numel() // (B * C) if B * C else 1)
+
+
+def bn_fwd(x, bn, y, save_mean, save_invstd, ws, training=None):
+    """nn.BatchNorm{1,2}d module `bn` on x [B, C, *]; training=None -> bn.training.  Updates the
+    module's running statistics in training mode like torch does."""
+    if bn.momentum is None:
+        raise NotImplementedError("pyroved_b200: BatchNorm momentum=None (cumulative average)")
+    training = bn.training if training is None else training
+    track = bn.track_running_stats and bn.running_mean is not None
+    if not training and not track:
+        training = True          # torch: no running statistics -> batch statistics in eval too
+    upd = track and training
+    check(_lib.lib().pvb_bn_fwd(
+        _p(x), _p(bn.weight.data if bn.affine else None), _p(bn.bias.data if bn.affine else None),
+        _p(bn.running_mean if (upd or not training) else None),
+        _p(bn.running_var if (upd or not training) else None),
+        (bn.num_batches_tracked.data_ptr() if upd and bn.num_batches_tracked.is_cuda else None), _p(y), _p(save_mean), _p(save_invstd), _p(ws),
+        *_bn_dims(x), float(bn.eps), float(bn.momentum), int(bool(training)), _stream()), "pvb_bn_fwd")
+    return y
+
+
+def bn_bwd(dy, x, bn, save_mean, save_invstd, dx, dgamma, dbeta, ws):
+    check(_lib.lib().pvb_bn_bwd(_p(dy), _p(x), _p(bn.weight.data if bn.affine else None),
+                                _p(save_mean), _p(save_invstd), _p(dx), _p(dgamma), _p(dbeta), _p(ws),
+                                *_bn_dims(x), _stream()), "pvb_bn_bwd")
+    return dx
 
 
 def _plane(x):

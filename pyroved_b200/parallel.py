@@ -71,6 +71,41 @@ def allreduce_sum_(flat, group=None):
     return flat
 
 
+class PeerExchange:
+    """Symmetric-memory plumbing for the fused all-reduce + Adam kernel (csrc/pvb_peer.cu): every
+    rank's flat gradient buffer and a block of epoch flags are allocated from CUDA symmetric
+    memory (torch.distributed._symmetric_memory: VMM allocations whose handles the per-GPU
+    processes exchange) and mapped into all ranks; the kernel gets the peer pointers as two
+    small device arrays.  PyTorch only provides the allocation / handle exchange here -- the
+    data path is the kernel's own loads over NVLink."""
+
+    def __init__(self, n_floats, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.g = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(max(64, ops.peer_flag_words()), dtype=torch.int32, device=device)
+        self.g.zero_()
+        self.flags.zero_()
+        hg = symm_mem.rendezvous(self.g, group.group_name)
+        hf = symm_mem.rendezvous(self.flags, group.group_name)
+        self._handles = (hg, hf)
+        self.peer_g = torch.tensor([int(p) for p in hg.buffer_ptrs], dtype=torch.int64, device=device)
+        self.peer_flags = torch.tensor([int(p) for p in hf.buffer_ptrs], dtype=torch.int64,
+                                       device=device)
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)       # nobody signals before every rank's flags are zeroed
+
+
+def peer_exchange_enabled():
+    """The fused NVLink exchange is used for NCCL (CUDA) process groups unless PVB_PEER_REDUCE=0."""
+    return (os.environ.get("PVB_PEER_REDUCE", "1") != "0" and dist.is_available()
+            and dist.is_initialized() and dist.get_world_size() > 1
+            and dist.get_backend() == "nccl")
+
+
 class ShardedLoader:
     """Wraps a loader of GLOBAL batches; yields this rank's shard of each
     tensor (keeps the (x,) / (x, y) tuple protocol of the trainers)."""

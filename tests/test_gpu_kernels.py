@@ -171,3 +171,38 @@ def test_reductions_adam_and_regression_terms():
     dxc = torch.empty(37, 3, device="cuda")
     ops.linear_dx_cols(dpre, W, dxc, 100)
     assert torch.allclose(dxc, (dpre @ W)[:, 100:], atol=1e-4, rtol=1e-4)
+
+
+def test_peer_allreduce_adam_single_rank_equals_adam_flat_step():
+    """world = 1 degenerate case of the fused NVLink exchange (csrc/pvb_peer.cu): with only its own
+    buffer to read, the kernel must reproduce pvb_adam_flat_step bit for bit, publish the loss and
+    advance the step counter / epoch; run repeatedly (epoch flags re-arm)."""
+    torch.manual_seed(0)
+    n = 4 * 1000
+    dev = "cuda"
+    p0 = torch.randn(n, device=dev)
+    g = torch.zeros(n + 4, device=dev)
+    first = torch.zeros(n, dtype=torch.int32, device=dev)
+    first[100:200] = -1           # never carried a gradient
+    first[200:300] = 2            # joins at step 2
+    ref = dict(p=p0.clone(), m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev),
+               c=torch.zeros(1, dtype=torch.int32, device=dev),
+               t=torch.zeros(1, dtype=torch.int32, device=dev))
+    new = dict(p=p0.clone(), m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev),
+               c=torch.zeros(1, dtype=torch.int32, device=dev))
+    flags = torch.zeros(max(64, ops.peer_flag_words()), dtype=torch.int32, device=dev)
+    state = torch.zeros(4, dtype=torch.int32, device=dev)
+    peer_g = torch.tensor([g.data_ptr()], dtype=torch.int64, device=dev)
+    peer_f = torch.tensor([flags.data_ptr()], dtype=torch.int64, device=dev)
+    for it in range(4):
+        g[:n] = torch.randn(n, device=dev)
+        g[n] = 3.5 + it
+        ops.adam_flat_step(ref["p"], g, ref["m"], ref["v"], n, 1e-3, ref["c"], ref["t"], first)
+        ops.peer_allreduce_adam(new["p"], new["m"], new["v"], g, n, peer_g, peer_f, state, 0, 1, 1e-3,
+                                new["c"], first)
+        torch.cuda.synchronize()
+        for k in ("p", "m", "v"):
+            assert torch.equal(ref[k], new[k]), (it, k)
+        assert int(new["c"]) == it + 1 and int(state[0]) == it + 1 and int(state[1]) == 0
+        assert float(g[n]) == 3.5 + it
+    assert torch.equal(new["p"][100:200], p0[100:200])

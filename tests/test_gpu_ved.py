@@ -79,7 +79,7 @@ def test_ved_full_step_matches_reference_adam(name):
     kw = {k: float(v) for k, v in g.kw().items()}
     loss = tr.svi.step(x.cuda(), y.cuda(), _eps=g.eps().cuda(), **kw)
     assert abs(loss - g.loss_step) <= 1e-4 * abs(g.loss_step)
-    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    sd = {k: v.cpu().float() for k, v in m.state_dict().items()}   # incl. batch-norm buffers
     for k, v in g.group("w1").items():
         assert torch.allclose(sd[k], v, atol=5e-5), k
     for k, idx in g.group("w1idx", torch.int64).items():
@@ -131,8 +131,8 @@ def test_ved_inference_api():
     assert pm.shape == (5, 1, 64) and ps.shape == (5, 1, 64)
     man = m.manifold2d(3, plot=False)
     assert man.shape == (9, 1, 64)
-    with pytest.raises(NotImplementedError):
-        pv.models.VED((32, 32), (64,), batchnorm=True, device="cuda:0")
+    with pytest.raises(NotImplementedError):      # 3-D data is not implemented
+        pv.models.VED((8, 8, 8), (64,), device="cuda:0")
 
 
 # ---- kernel-level checks against plain PyTorch fp32 ops ---------------------------------
@@ -272,3 +272,77 @@ def test_tc_weight_gradient_with_few_input_channels(shape):
     ops.conv_tc_bwd_weight(dy, x, wt, dW, db)
     assert (dW - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
     assert (db - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("shape", [(6, 8, 16, 16), (5, 16, 7, 9), (3, 4, 33), (64, 32, 32, 32), (2, 3, 1, 1)])
+def test_batchnorm_kernels_vs_torch(shape):
+    """pvb_bn_fwd / pvb_bn_bwd against nn.BatchNorm{1,2}d (training and eval mode), including the
+    running-statistics update and a channel with a large mean (variance cancellation)."""
+    torch.manual_seed(sum(shape))
+    B, C = shape[:2]
+    x = torch.randn(*shape, device="cuda")
+    x[:, 0] += 300.0
+    dy = torch.randn(*shape, device="cuda")
+    cls = torch.nn.BatchNorm1d if len(shape) == 3 else torch.nn.BatchNorm2d
+    ref, bn = cls(C).cuda(), cls(C).cuda()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5)
+        ref.bias.normal_()
+        ref.running_mean.normal_()
+        ref.running_var.uniform_(0.5, 2.0)
+    bn.load_state_dict(ref.state_dict())
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(dy)
+    y = torch.empty_like(x)
+    stats = torch.empty(2, C, device="cuda")
+    ws = ops.bn_workspace(C, x.device)
+    ops.bn_fwd(x, bn, y, stats[0], stats[1], ws)
+    assert torch.allclose(y, yr, atol=2e-4, rtol=1e-4), (y - yr).abs().max().item()
+    assert torch.allclose(bn.running_mean, ref.running_mean, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(bn.running_var, ref.running_var, atol=1e-5, rtol=1e-4)
+    assert int(bn.num_batches_tracked) == 1
+    dx = torch.empty_like(x)
+    dg = torch.full((C,), 2.0, device="cuda")      # gradients accumulate
+    db = torch.full((C,), -1.0, device="cuda")
+    ops.bn_bwd(dy.clone(), x, bn, stats[0], stats[1], dx, dg, db, ws)
+    scale = xr.grad.abs().max().item() + 1e-6
+    assert (dx - xr.grad).abs().max().item() <= 2e-4 * scale + 1e-5
+    assert torch.allclose(dg - 2.0, ref.weight.grad, atol=1e-3 * ref.weight.grad.abs().max().item() + 1e-4)
+    assert torch.allclose(db + 1.0, ref.bias.grad, atol=1e-3 * ref.bias.grad.abs().max().item() + 1e-4)
+    # in place (dx aliases dy), as the engine calls it
+    dy2 = dy.clone()
+    ops.bn_bwd(dy2, x, bn, stats[0], stats[1], dy2, None, None, ws)
+    assert torch.equal(dy2, dx)
+    # eval mode: running statistics, nothing updated
+    ref.eval()
+    bn.eval()
+    ops.bn_fwd(x, bn, y, stats[0], stats[1], ws)
+    assert torch.allclose(y, ref(x), atol=2e-4, rtol=1e-4)
+    assert int(bn.num_batches_tracked) == 1
+
+
+def test_ved_batchnorm_training_and_inference():
+    """VED(batchnorm=True): state_dict keys as the reference lays them out, loss decreases over
+    steps replayed as a CUDA graph, encode / decode / predict run."""
+    os.environ["PVB_FORCE_GENERIC"] = "0"
+    m = pv.models.VED((16, 16), (32,), latent_dim=2, batchnorm=True, seed=2, device="cuda:0",
+                      hidden_dim_e=[(16,), (32, 32)], hidden_dim_d=[(32, 32), (16,)])
+    keys = set(m.state_dict().keys())
+    for k in ("encoder_z.feature_extractor.layers.2.running_mean",
+              "encoder_z.feature_extractor.layers.6.weight",
+              "decoder.upsampler.layers.2.num_batches_tracked",
+              "decoder.upsampler.layers.6.conv.weight"):
+        assert k in keys, k
+    tr = pv.trainers.SVItrainer(m, device="cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(16, 1, 16, 16, generator=gen).cuda()
+    y = torch.rand(16, 1, 32, generator=gen).cuda()
+    eps = torch.randn(16, 2, generator=gen).cuda()
+    ls = [tr.svi.step(x, y, _eps=eps) for _ in range(30)]
+    assert all(v == v for v in ls) and ls[-1] < ls[0], ls[::5]
+    assert int(m.encoder_z.feature_extractor.layers[2].num_batches_tracked) == 30
+    mu, sd = m.encode(x.cpu())
+    assert mu.shape == (16, 2) and torch.isfinite(mu).all() and (sd > 0).all()
+    rec = m.decode(mu)
+    assert rec.shape[0] == 16 and torch.isfinite(rec).all()

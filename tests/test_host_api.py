@@ -114,14 +114,20 @@ def test_dataloader_protocol():
 
 def test_ved_state_dict_keys_and_seeded_init_match_reference():
     """VED(seed) builds the reference's parameter names, shapes AND initial values."""
-    for name in ("ved_im2spec_32_64", "ved_spec2im_32_16"):
+    seeds = {"ved_spec2im_32_16": 2, "ved_bn_im2spec_16_32": 3, "ved_bn_spec2im_32_16": 4}
+    for name in ("ved_im2spec_32_64", "ved_spec2im_32_16", "ved_bn_im2spec_16_32",
+                 "ved_bn_spec2im_32_16"):
         g = Golden(name)
-        m = pv.models.VED(seed={"ved_spec2im_32_16": 2}.get(name, 1), device="cpu", **g.kwargs)
+        m = pv.models.VED(seed=seeds.get(name, 1), device="cpu", **g.kwargs)
         w0 = g.group("w0")
         sd = m.state_dict()
         assert list(sd.keys()) == list(w0.keys())
         for k in sd:
-            assert torch.equal(sd[k], w0[k]), k
+            assert torch.equal(sd[k].float(), w0[k]), k
+    # reference tests/test_conv.py:12-18: one BatchNorm per convolution when batchnorm=True
+    for hidden, bnorm, n in (([(8,)], True, 1), ([(8,)], False, 0), ([(8,), (16, 16)], True, 3)):
+        fe = pv.nets.conv.FeatureExtractor(2, conv_filters=hidden, batchnorm=bnorm)
+        assert len([k for k in fe.state_dict() if "running_mean" in k]) == n
     m = pv.models.VED((64, 64), (128,), device="cpu")
     keys = list(m.state_dict().keys())
     for i in (0, 3, 5, 8, 10):

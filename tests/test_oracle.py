@@ -78,8 +78,12 @@ def test_port_adam_step_matches_reference(name):
     g = Golden(name)
     fn, args, cfg = port_loss_fn(g)
     sd = g.group("w0")
-    out, grads = sp.loss_and_grads(fn, sd, *args)
+    stats = {}
+    kw = {"stats": stats} if getattr(cfg, "batchnorm", False) else {}
+    out, grads = sp.loss_and_grads(fn, sd, *args, **kw)
     new = sp.AdamState(lr=1e-3).step(dict(sd), grads)
+    new.update(stats)        # batch-norm running statistics after the step
+    assert not kw or len(stats) > 0
     for k, v in g.group("w1").items():
         assert torch.allclose(new[k], v, atol=2e-5), k
     for k, idx in g.group("w1idx", torch.int64).items():
