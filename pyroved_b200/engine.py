@@ -323,9 +323,12 @@ class DecoderOps:
         return dict(cfg=self.fold_cfg, cond=cond, Wc=cl.fc_coord.weight.data,
                     bc=cl.fc_coord.bias.data, Wz=cl.fc_latent.weight.data, Uv=self.Uv)
 
-    def forward(self, z, cond, x, w, want_grad, kl=None, beta=0.0, loss_out=None, uv_ready=False):
+    def forward(self, z, cond, x, w, want_grad, kl=None, beta=0.0, loss_out=None, uv_ready=False,
+                side_loss=False):
         """z [I,Zf], cond [I,Cd] or None, x [B,N], w [I] or None -> fills rowll/loc/ll.
-        With loss_out: also loss_out += -sum_i (ll_i + beta kl_i) in the same reduction."""
+        With loss_out: also loss_out += -sum_i (ll_i + beta kl_i) in the same reduction.
+        side_loss: nothing later in the step reads ll / writes loss_out, so that reduction runs
+        on the engine's side stream, off the critical path of the backward pass."""
         m = self.engine.model
         dec, samp = m.decoder, m.sampler_d
         if self.spatial:
@@ -356,7 +359,10 @@ class DecoderOps:
             ops.obs_loglik(self.logit, x, w, self.rowll, self.dlogit if want_grad else None,
                            self.loc, self.I, self.Bx, self.N, samp.name, dec.sigmoid_out,
                            samp.decoder_sig)
-        if loss_out is not None:
+        if loss_out is not None and side_loss and self.engine.overlap:
+            with self.engine.fork_side():
+                ops.elbo_reduce(self.rowll, kl, w, beta, self.ll, loss_out, True, self.I, self.N)
+        elif loss_out is not None:
             ops.elbo_reduce(self.rowll, kl, w, beta, self.ll, loss_out, True, self.I, self.N)
         else:
             ops.elbo_reduce(self.rowll, None, None, 0.0, self.ll, None, False, self.I, self.N)
@@ -396,8 +402,11 @@ class DecoderOps:
         L = linear_layers(dec.fc_layers)
         n_w = TC_WGRAD_FLOATS
         base = flat.offset(L[0].weight)
-        ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], self.tc_sizes.ctas,
-                            n_w, TC_WGRAD_STRIDE, True)
+        # the two partial-sum reductions only feed the optimizer: side stream, concurrent with the
+        # latent / encoder backward chain
+        with eng.fork_side():
+            ops.reduce_partials(self.wgrad_part, flat.g[base:base + n_w], self.tc_sizes.ctas,
+                                n_w, TC_WGRAD_STRIDE, True)
         if head is None:
             ops.latent_side_bwd(self.fold_cfg, z, cond, cl.fc_coord.weight.data,
                                 cl.fc_latent.weight.data, None, self.gUv_part, self.N, self.gz,
@@ -407,7 +416,8 @@ class DecoderOps:
                                 cl.fc_latent.weight.data, None, self.gUv_part, self.N, self.gz,
                                 self.gcond, self.fold_part, head.eps, head.sigma, head.s_pre, w,
                                 beta, head.gmu, head.gs_pre)
-        self._reduce_fold_partials(self.G_side)
+        with eng.fork_side():
+            self._reduce_fold_partials(self.G_side)
         return self.gz
 
     def backward(self, z, cond):
@@ -551,7 +561,8 @@ class SpatialVAEProgram(StepProgram):
         if self.fused:
             self.enc.forward(self.enc_in, gen_eps)
             self.dec.forward(self.head.z, self.y, self.x, None, want_grad, kl=self.head.kl,
-                             beta=float(beta), loss_out=flat.loss, uv_ready=self.dec.spatial)
+                             beta=float(beta), loss_out=flat.loss, uv_ready=self.dec.spatial,
+                             side_loss=True)
             return
         h = self.enc.forward(self.enc_in)
         self.head.forward(h, gen_eps)
@@ -985,6 +996,11 @@ class SVIEngine:
         self.lr = float(lr)
         self.enumerate_parallel = enumerate_parallel
         self.seed = int(seed)
+        # side stream for work that only feeds the optimizer / the loss read-back (forked and
+        # joined inside the step, so it becomes a parallel branch of the step's CUDA graph)
+        self.overlap = os.environ.get("PVB_SIDE_STREAM", "1") != "0"
+        self.side = torch.cuda.Stream(self.device)
+        self._side_used = False
         self.peer = None          # parallel.PeerExchange of the current flat gradient buffer
         self.flat = FlatParams(model, self.device, self._alloc_grad_buffer()
                                if parallel.peer_exchange_enabled() else None)
@@ -1067,8 +1083,24 @@ class SVIEngine:
         prog.forward(beta, train, gen_eps)
         if train:
             prog.backward(beta)
+        self.join_side()
         if update:
             self._update()
+
+    def fork_side(self):
+        """Context: launches go to the side stream, ordered after everything queued so far on
+        the current stream (PVB_SIDE_STREAM=0: they stay on the current stream)."""
+        cur = torch.cuda.current_stream(self.device)
+        if not self.overlap:
+            return torch.cuda.stream(cur)
+        self.side.wait_stream(cur)
+        self._side_used = True
+        return torch.cuda.stream(self.side)
+
+    def join_side(self):
+        if self._side_used:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+            self._side_used = False
 
     def _update(self):
         flat = self.flat
