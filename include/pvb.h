@@ -291,6 +291,26 @@ int pvb_upsample2_fwd(const float* x, float* y, int64_t BC, int H, int Wd,
 int pvb_upsample2_bwd(const float* dy, float* dx, int64_t BC, int H, int Wd,
                       int two_d, int bilinear, void* stream);
 
+/* ---- volumetric (3-D) variants of the conv-net layers (csrc/pvb_conv3d.cu; reference
+ * nets/conv.py with ndim = 3) ----  NCDHW fp32, cubic kernel k = 1 | 3, stride 1, padding
+ * k/2; same contracts as pvb_conv_* / pvb_maxpool2_* / pvb_upsample2_* (nearest only:
+ * the reference switches 'bilinear' to 'nearest' for 3-D data, conv.py:127-130). */
+int pvb_conv3d_fwd(const float* x, const float* W, const float* b, float* y, float* pre,
+                   int B, int Cin, int Cout, int D, int H, int Wd, int k, int act,
+                   void* stream);
+int pvb_conv3d_bwd_data(const float* dpre, const float* W, float* dx, int B, int Cin,
+                        int Cout, int D, int H, int Wd, int k, void* stream);
+int pvb_conv3d_bwd_weight(const float* dpre, const float* x, float* dW, float* db, int B,
+                          int Cin, int Cout, int D, int H, int Wd, int k, void* stream);
+int pvb_maxpool3d_fwd(const float* x, float* y, int64_t BC, int D, int H, int Wd,
+                      void* stream);
+int pvb_maxpool3d_bwd(const float* x, const float* dy, float* dx, int64_t BC, int D,
+                      int H, int Wd, void* stream);
+int pvb_upsample3d_fwd(const float* x, float* y, int64_t BC, int D, int H, int Wd,
+                       void* stream);
+int pvb_upsample3d_bwd(const float* dy, float* dx, int64_t BC, int D, int H, int Wd,
+                       void* stream);
+
 /* ---- data-parallel exchange over NVLink peer memory (csrc/pvb_peer.cu) ----
  * Fused SUM all-reduce of the flat [n gradients | loss] buffers of all ranks + the Adam
  * update of pvb_adam_flat_step, one kernel, deterministic (rank-order sums, identical on

@@ -247,6 +247,14 @@ def main_ved():
     m.to("cpu")
     run_case("ved_bn_spec2im_32_16", m, dev, (xs, yim),
              {"z": torch.randn(5, 2, generator=gen(30))}, {})
+    # volumetric data: Conv3d / MaxPool3d / nearest x2 up-sampling (nets/conv.py with ndim = 3)
+    g3 = gen(32)
+    xv = torch.rand(4, 1, 8, 8, 8, generator=g3)
+    yv = (torch.rand(4, 1, 8, 8, 8, generator=g3) < 0.4).float()
+    m = pv.models.VED((8, 8, 8), (8, 8, 8), latent_dim=2, seed=5,
+                      hidden_dim_e=[(4,), (8, 8)], hidden_dim_d=[(8, 8), (4,)])
+    m.to("cpu")
+    run_case("ved_vol_8", m, dev, (xv, yv), {"z": torch.randn(4, 2, generator=gen(33))}, {})
     # default architecture, two input channels, small spatial size (weights subsampled? no:
     # kept whole, the fixture is ~2 MB) -- skipped by default, enable with --ved-full
     if "--ved-full" in sys.argv:

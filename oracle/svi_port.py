@@ -407,7 +407,7 @@ class VedCfg:
 
 
 def _conv_nd(ndim):
-    return F.conv1d if ndim == 1 else F.conv2d
+    return {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[ndim]
 
 
 def _bnorm(sd, p, h, stats):
@@ -433,7 +433,7 @@ def ved_encoder(sd, cfg, x, stats=None):
     max-pool after a block while more convolutions remain, conv.py:173-195) -> flatten ->
     fc_latent -> split -> softplus on the second half."""
     nd = len(cfg.input_dim)
-    conv, pool = _conv_nd(nd), (F.max_pool1d if nd == 1 else F.max_pool2d)
+    conv, pool = _conv_nd(nd), {1: F.max_pool1d, 2: F.max_pool2d, 3: F.max_pool3d}[nd]
     act = activation_fn(cfg.activation)
     h = x.reshape(x.shape[0], cfg.input_channels, *cfg.input_dim)
     total = sum(len(b) for b in cfg.hidden_e)

@@ -97,6 +97,13 @@ SIGNATURES = {
     "pvb_conv_bwd_data": [_f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_bwd_weight": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_act_bwd": [_f, _f, _f, _f, _i64, _i32, _st],
+    "pvb_conv3d_fwd": [_f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_conv3d_bwd_data": [_f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_conv3d_bwd_weight": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_maxpool3d_fwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
+    "pvb_maxpool3d_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _st],
+    "pvb_upsample3d_fwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
+    "pvb_upsample3d_bwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_peer_flag_words": [],
     "pvb_peer_allreduce_adam": [_f, _f, _f, _f, _i64, _f, _f, _f, _i32, _i32, _fl, _fl, _fl, _fl,
                                 _f, _f, _st],

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall"
-SRCS="pvb_core.cu pvb_gemm.cu pvb_latent.cu pvb_sdec_simt.cu pvb_mlp.cu pvb_conv.cu pvb_conv_tc.cu pvb_norm.cu pvb_peer.cu"
+SRCS="pvb_core.cu pvb_gemm.cu pvb_latent.cu pvb_sdec_simt.cu pvb_mlp.cu pvb_conv.cu pvb_conv_tc.cu pvb_norm.cu pvb_peer.cu pvb_conv3d.cu"
 [ -f pvb_sdec_tc.cu ] && SRCS="$SRCS pvb_sdec_tc.cu"
 OBJS=""
 for s in $SRCS; do

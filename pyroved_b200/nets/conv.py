@@ -5,7 +5,7 @@ nets/conv.py:24-277 (`encoder_z.feature_extractor.layers.{0,3,5,8,10}.*`,
 `decoder.upsampler.layers.{4,9,12}.conv.*`, ...), so `.pt` checkpoints interchange and the same
 seed gives the same initial weights.  The modules only OWN parameters and describe the layer
 sequence; `forward` (inference) and training (conv_engine.VEDProgram) run the hand-written CUDA
-kernels of csrc/pvb_conv.cu / pvb_norm.cu through the C ABI.  Not supported here: 3-D data.
+kernels of csrc/pvb_conv.cu / pvb_conv3d.cu / pvb_norm.cu through the C ABI (1-D, 2-D and 3-D).
 """
 import os
 from typing import List, Tuple
@@ -31,8 +31,6 @@ def _prod(t):
 def _check_ndim(ndim):
     if not 0 < ndim < 4:
         raise AssertionError("ndim must be equal to 1, 2 or 3")
-    if ndim == 3:
-        raise NotImplementedError("pyroved_b200: 3-D convolutional nets are not implemented")
 
 
 class UpsampleBlock(nn.Module):
@@ -45,7 +43,7 @@ class UpsampleBlock(nn.Module):
         if mode not in ("bilinear", "nearest"):
             raise NotImplementedError("Use 'bilinear' or 'nearest' for upsampling mode")
         _check_ndim(ndim)
-        if mode == "bilinear" and ndim == 1:
+        if mode == "bilinear" and ndim in (3, 1):
             warn("'bilinear' mode is not supported for 1D and 3D; switching to 'nearest' mode",
                  category=UserWarning)
             mode = "nearest"
@@ -213,6 +211,11 @@ class convDecoderNet(nn.Module):
 
 
 # ---- layer-sequence description shared by inference (here) and training (conv_engine) --------
+_CONVS = (nn.Conv1d, nn.Conv2d, nn.Conv3d)
+_POOLS = (nn.MaxPool1d, nn.MaxPool2d, nn.MaxPool3d)
+_BNORMS = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)
+
+
 def layer_plan(layers, activation):
     """[(kind, module, fused_activation)] with kind in 'conv' | 'bn' | 'pool' | 'up'.  An
     activation module directly after a convolution is fused into that convolution's epilogue."""
@@ -220,21 +223,20 @@ def layer_plan(layers, activation):
     plan, i = [], 0
     while i < len(mods):
         m = mods[i]
-        if isinstance(m, (nn.Conv1d, nn.Conv2d)):
+        if isinstance(m, _CONVS):
             k = m.kernel_size[0]
             if (any(s != 1 for s in m.stride) or any(p != k // 2 for p in m.padding)
                     or k not in (1, 3) or any(kk != k for kk in m.kernel_size)):
                 raise NotImplementedError("pyroved_b200: conv layers must be k=1|3, stride 1, same padding")
             act = None
             if i + 1 < len(mods) and not isinstance(
-                    mods[i + 1], (nn.Conv1d, nn.Conv2d, nn.MaxPool1d, nn.MaxPool2d, UpsampleBlock,
-                                  nn.BatchNorm1d, nn.BatchNorm2d)):
+                    mods[i + 1], _CONVS + _POOLS + _BNORMS + (UpsampleBlock,)):
                 act = activation
                 i += 1
             plan.append(("conv", m, act))
-        elif isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+        elif isinstance(m, _BNORMS):
             plan.append(("bn", m, None))
-        elif isinstance(m, (nn.MaxPool1d, nn.MaxPool2d)):
+        elif isinstance(m, _POOLS):
             plan.append(("pool", m, None))
         elif isinstance(m, UpsampleBlock):
             plan.append(("up", m, None))

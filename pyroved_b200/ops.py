@@ -316,18 +316,42 @@ def _conv_dims(x, W):
     return B, Cin, W.shape[0], H, Wd, kh, kw
 
 
+def _conv3_dims(x, W):
+    """(B, Cin, Cout, D, H, Wd, k) of a volumetric layer: x [B,Cin,D,H,Wd], W [Cout,Cin,k,k,k]"""
+    if not (W.shape[2] == W.shape[3] == W.shape[4]):
+        raise NotImplementedError("pyroved_b200: 3-D convolutions need cubic kernels")
+    return x.shape[0], x.shape[1], W.shape[0], x.shape[2], x.shape[3], x.shape[4], W.shape[2]
+
+
+def _vol(x):
+    """(BC, D, H, Wd) of an NCDHW tensor"""
+    return x.shape[0] * x.shape[1], x.shape[2], x.shape[3], x.shape[4]
+
+
 def conv_fwd(x, W, b, act, out, pre=None):
+    if x.dim() == 5:
+        check(_lib.lib().pvb_conv3d_fwd(_p(x), _p(W), _p(b), _p(out), _p(pre), *_conv3_dims(x, W),
+                                        ACT[act], _stream()), "pvb_conv3d_fwd")
+        return out
     check(_lib.lib().pvb_conv_fwd(_p(x), _p(W), _p(b), _p(out), _p(pre), *_conv_dims(x, W),
                                   ACT[act], _stream()), "pvb_conv_fwd")
     return out
 
 
 def conv_bwd_data(dpre, W, dx):
+    if dx.dim() == 5:
+        check(_lib.lib().pvb_conv3d_bwd_data(_p(dpre), _p(W), _p(dx), *_conv3_dims(dx, W), _stream()),
+              "pvb_conv3d_bwd_data")
+        return
     check(_lib.lib().pvb_conv_bwd_data(_p(dpre), _p(W), _p(dx), *_conv_dims(dx, W), _stream()),
           "pvb_conv_bwd_data")
 
 
 def conv_bwd_weight(dpre, x, W, dW, db):
+    if x.dim() == 5:
+        check(_lib.lib().pvb_conv3d_bwd_weight(_p(dpre), _p(x), _p(dW), _p(db), *_conv3_dims(x, W),
+                                               _stream()), "pvb_conv3d_bwd_weight")
+        return
     check(_lib.lib().pvb_conv_bwd_weight(_p(dpre), _p(x), _p(dW), _p(db), *_conv_dims(x, W),
                                          _stream()), "pvb_conv_bwd_weight")
 
@@ -381,20 +405,35 @@ def _plane(x):
 
 
 def maxpool2_fwd(x, y):
+    if x.dim() == 5:
+        check(_lib.lib().pvb_maxpool3d_fwd(_p(x), _p(y), *_vol(x), _stream()), "pvb_maxpool3d_fwd")
+        return
     check(_lib.lib().pvb_maxpool2_fwd(_p(x), _p(y), *_plane(x), _stream()), "pvb_maxpool2_fwd")
 
 
 def maxpool2_bwd(x, dy, dx):
+    if x.dim() == 5:
+        check(_lib.lib().pvb_maxpool3d_bwd(_p(x), _p(dy), _p(dx), *_vol(x), _stream()),
+              "pvb_maxpool3d_bwd")
+        return
     check(_lib.lib().pvb_maxpool2_bwd(_p(x), _p(dy), _p(dx), *_plane(x), _stream()),
           "pvb_maxpool2_bwd")
 
 
 def upsample2_fwd(x, y, bilinear):
+    if x.dim() == 5:
+        if bilinear:
+            raise NotImplementedError("pyroved_b200: 3-D up-sampling is 'nearest' only")
+        check(_lib.lib().pvb_upsample3d_fwd(_p(x), _p(y), *_vol(x), _stream()), "pvb_upsample3d_fwd")
+        return
     check(_lib.lib().pvb_upsample2_fwd(_p(x), _p(y), *_plane(x), int(bool(bilinear)), _stream()),
           "pvb_upsample2_fwd")
 
 
 def upsample2_bwd(dy, dx, bilinear):
+    if dx.dim() == 5:
+        check(_lib.lib().pvb_upsample3d_bwd(_p(dy), _p(dx), *_vol(dx), _stream()), "pvb_upsample3d_bwd")
+        return
     check(_lib.lib().pvb_upsample2_bwd(_p(dy), _p(dx), *_plane(dx), int(bool(bilinear)), _stream()),
           "pvb_upsample2_bwd")
 
@@ -414,11 +453,15 @@ def linear_dx_cols(dpre, W, dx_cols, col0, accumulate=False):
 
 # ---- tensor-core convolutions (same tensors; operands converted on the fly) ----------------
 def conv_tc_supported(W):
+    if W.dim() == 5:
+        return False
     kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
     return bool(_lib.lib().pvb_conv_tc_supported(W.shape[1], W.shape[0], kh, kw))
 
 
 def conv_tc_wgrad_supported(W):
+    if W.dim() == 5:
+        return False
     kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
     return bool(_lib.lib().pvb_conv_tc_wgrad_supported(W.shape[1], W.shape[0], kh, kw))
 

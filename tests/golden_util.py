@@ -41,6 +41,10 @@ CASES = {
         input_dim=(32,), output_dim=(16, 16), latent_dim=3, activation="tanh",
         sampler_d="gaussian", sigmoid_d=False, decoder_sig=0.3,
         hidden_dim_e=[(8,), (16, 16)], hidden_dim_d=[(16, 16), (8,)])),
+    # volumetric input and output (Conv3d nets)
+    "ved_vol_8": ("ved", dict(
+        input_dim=(8, 8, 8), output_dim=(8, 8, 8), latent_dim=2,
+        hidden_dim_e=[(4,), (8, 8)], hidden_dim_d=[(8, 8), (4,)])),
     # batchnorm=True: BatchNorm2d encoder + BatchNorm1d decoder, and the other way round
     "ved_bn_im2spec_16_32": ("ved", dict(
         input_dim=(16, 16), output_dim=(32,), latent_dim=2, batchnorm=True,
