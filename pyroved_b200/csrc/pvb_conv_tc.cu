@@ -148,8 +148,11 @@ __device__ __forceinline__ void bias_act16(float* v, const float* __restrict__ b
 #ifdef PVB_TC_TRACE
 __device__ long long g_ctrace[2][64];
 #define CTRACE(role, ev) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4) && (ev) < 64) g_ctrace[role][ev] = clock64(); } while (0)
+__device__ long long g_wtrace[2][64];
+#define WTRACE(role, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == mma_warp) && (ev) < 64) g_wtrace[role][ev] = clock64(); } while (0)
 #else
 #define CTRACE(role, ev) do {} while (0)
+#define WTRACE(role, ev) do {} while (0)
 #endif
 
 template <bool BF16, bool SCALED>
@@ -282,142 +285,240 @@ conv_tc_pix_kernel(const float* __restrict__ src, const uint16_t* __restrict__ W
 // CTA (tap group, pixel split): accumulators [128 lanes = co][taps_in_group x Cin columns] in TMEM.
 // Per 128-pixel step: A = dpre tile [128 px][128 co (zero padded)] (MN-major), B_t = x tile shifted by
 // tap t [128 px][Cin] (MN-major), one N = Cin MMA chain (8 K-steps of 16 pixels) per tap.
-constexpr int WG_THREADS = 160;
-constexpr int WG_A = TP * 128 * 2;               // 32 KB: dpre tile, 16 chunk-columns
+constexpr int WG_MAX_GROUPS = 4;                // producer groups of 4 warps (thread = pixel row)
+#ifndef PVB_WG_PAD
+#define PVB_WG_PAD 0
+#endif
+// chunk-column stride of the MN-major operand tiles: 128 rows x 16 bytes (+ optional padding; measured:
+// a 16-byte pad, which spreads the 16-byte pieces of one K row over the banks, changes nothing)
+constexpr int WCS = TP * ROWB + PVB_WG_PAD;
+constexpr int WG_A = 16 * WCS;                   // dpre tile, 16 chunk-columns (128 output channels)
 constexpr int WG_MAX_TAPS = 9;                   // taps per CTA (<= (512 - 16) / Cin)
 constexpr int WG_STAGES = 2;
+struct WgItem { int src_off, shift, dst; short dh, dw; int is_x; };
+constexpr int WG_TBL_BYTES = (8 + 9 * 16) * (int)sizeof(WgItem);   // item table: <= 8 + 9 * 16 entries
 
+// The gathers are latency-bound (strided 4-byte loads, 16 in flight per thread), so the work of one
+// 128-pixel step is cut into 16-channel items -- 8 for the dpre tile, Cin/16 per tap for the shifted
+// x tiles -- dealt round-robin to up to four producer groups of 128 threads: up to 4x the loads in
+// flight per SM, same two-stage ring towards the MMA warp.
 template <bool BF16>
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(WG_MAX_GROUPS * 128 + 32, 1)
 conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dW,
                      float* __restrict__ db, int B, int Cin_real, int Cout, int H, int W, int kh, int kw,
                      int taps_per_cta, int64_t tiles_per_split) {
   // fewer than 16 input channels (the first layer): the x tile is zero-padded to 16 columns
   const int Cin = Cin_real < 16 ? 16 : Cin_real;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int b_tile = TP * Cin * 2;                       // one shifted x tile
-  const int stage_bytes = WG_A + taps_per_cta * b_tile + TP * ROWB * 2;   // + ones tile (16 columns)
+  const int b_tile = (Cin / 8) * WCS;                    // one shifted x tile
+  const int stage_bytes = WG_A + taps_per_cta * b_tile + 2 * WCS;   // + ones tile (16 columns)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + WG_STAGES;
   uint64_t* accb = bars + 2 * WG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_groups = (int)(blockDim.x >> 7);             // producer groups; the MMA warp comes last
+  const int mma_warp = n_groups * 4;
   const int taps = kh * kw, ph = kh / 2, pw = kw / 2;
   const int HW = H * W;
   const int64_t Mtot = (int64_t)B * HW;
   const int64_t n_tiles = (Mtot + TP - 1) / TP;
   const int tap0 = blockIdx.x * taps_per_cta;
   const int ntap = min(taps_per_cta, taps - tap0);
-  const int64_t t_begin = (int64_t)blockIdx.y * tiles_per_split;
-  const int64_t t_end = min(t_begin + tiles_per_split, n_tiles);
+  // pixel tiles are dealt round-robin to the gridDim.y CTAs of a tap group (tile = blockIdx.y +
+  // it * gridDim.y): at any moment the CTAs read one contiguous window of every channel plane, which
+  // keeps DRAM pages open across CTAs (a contiguous range per CTA made each CTA a separate stream of
+  // 512-byte pieces per plane)
+  const int64_t my_tiles = blockIdx.y < n_tiles ? (n_tiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
   const bool do_bias = db != nullptr && blockIdx.x == 0;
   const uint32_t col_bias = (uint32_t)(ntap * Cin);        // TMEM column block of the bias sums
-  if (warp == 4) umma::tmem_alloc<512>(tmem_slot);
+  if (warp == mma_warp) umma::tmem_alloc<512>(tmem_slot);
   if (tid == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
-      umma::mbar_init(full + s, 4);
+      umma::mbar_init(full + s, (uint32_t)mma_warp);       // one arrive per producer warp
       umma::mbar_init(empty + s, 1);
     }
     umma::mbar_init(accb, 1);
     umma::mbar_fence_init();
   }
+  // gather items of one 128-pixel step (16 channels each): Cout/16 blocks of the dpre tile, then
+  // Cin/16 blocks of each tap's shifted x tile; decoded once into shared memory
+  WgItem* tbl = reinterpret_cast<WgItem*>(smem + WG_STAGES * stage_bytes + 64);
+  const int a_items = Cout / 16, b_items = Cin / 16;
+  const int n_items = a_items + ntap * b_items;
+  for (int k = tid; k < n_items; k += blockDim.x) {
+    WgItem e;
+    if (k < a_items) {
+      e.src_off = k * 16 * HW;
+      e.shift = 0; e.dh = 0; e.dw = 0; e.is_x = 0;
+      e.dst = k * 2 * WCS;
+    } else {
+      const int kk = k - a_items, t = kk / b_items, cb = kk - t * b_items;
+      const int tap = tap0 + t;
+      e.dh = (short)(tap / kw - ph);
+      e.dw = (short)(tap % kw - pw);
+      e.shift = e.dh * W + e.dw;
+      e.src_off = cb * 16 * HW;
+      e.is_x = 1;
+      e.dst = WG_A + t * b_tile + cb * 2 * WCS;
+    }
+    tbl[k] = e;
+  }
+  if (warp < mma_warp) {
+    // output channels beyond Cout never change: zero those dpre chunk-columns once, in every stage
+    for (int s = 0; s < WG_STAGES; ++s)
+      for (int c8 = Cout / 8 + (warp >> 2); c8 < 16; c8 += n_groups)
+        *reinterpret_cast<uint4*>(smem + s * stage_bytes + c8 * WCS + (tid & 127) * ROWB) =
+            make_uint4(0u, 0u, 0u, 0u);
+    umma::fence_proxy_async();
+  }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tm = *tmem_slot;
-  const int64_t my_tiles = t_end > t_begin ? t_end - t_begin : 0;
 
-  if (warp == 4) {
-    const uint32_t id_w = idesc_16b(128, Cin, 1, 1, BF16);
-    const uint32_t id_b = idesc_16b(128, 16, 1, 1, BF16);
+  if (warp == mma_warp) {
+    // The tap tiles (and the ones tile behind them) are contiguous chunk-columns in shared memory
+    // and their accumulators contiguous TMEM columns, so one MMA spans several taps (N <= 256):
+    // the dpre operand (128 x 16, 4 KB) is read once per K-step instead of once per tap -- these
+    // small-N MN-major MMAs are bound by operand reads from shared memory, not by the math.
+    const int n_total = ntap * Cin + (do_bias ? 16 : 0);
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int s = (int)(it % WG_STAGES);
+      WTRACE(1, (int)(3 * it));
       umma::mbar_wait(full + s, (uint32_t)((it / WG_STAGES) & 1));
+      WTRACE(1, (int)(3 * it + 1));
       umma::fence_after_sync();
       if (lane == 0) {
         const uint32_t base = umma::smem_u32(smem + s * stage_bytes);
-        for (int t = 0; t < ntap; ++t) {
-          const uint32_t bt = base + WG_A + t * b_tile;
+        for (int n0 = 0; n0 < n_total; n0 += 256) {
+          const int nn = min(256, n_total - n0);
+          const uint32_t idesc = idesc_16b(128, nn, 1, 1, BF16);
+          const uint32_t bt = base + WG_A + (n0 / 8) * WCS;
           for (int k = 0; k < 8; ++k)   // 8 K-steps of 16 pixel rows
-            umma::mma_f16_ss(tm + t * Cin, umma::smem_desc(base + k * 256, 128, TP * ROWB),
-                             umma::smem_desc(bt + k * 256, 128, TP * ROWB), id_w,
-                             (it > 0 || k > 0) ? 1u : 0u);
-        }
-        if (do_bias) {
-          const uint32_t bo = base + WG_A + taps_per_cta * b_tile;
-          for (int k = 0; k < 8; ++k)
-            umma::mma_f16_ss(tm + col_bias, umma::smem_desc(base + k * 256, 128, TP * ROWB),
-                             umma::smem_desc(bo + k * 256, 128, TP * ROWB), id_b,
+            umma::mma_f16_ss(tm + n0, umma::smem_desc(base + k * 256, 128, WCS),
+                             umma::smem_desc(bt + k * 256, 128, WCS), idesc,
                              (it > 0 || k > 0) ? 1u : 0u);
         }
         umma::commit(empty + s);
         if (it == my_tiles - 1) umma::commit(accb);
       }
       __syncwarp();
+      WTRACE(1, (int)(3 * it + 2));
     }
   } else {
-    const int row = tid;
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int s = (int)(it % WG_STAGES);
-      if (it >= WG_STAGES) umma::mbar_wait(empty + s, (uint32_t)(((it / WG_STAGES) - 1) & 1));
-      uint8_t* st = smem + s * stage_bytes;
-      const int64_t gm = (t_begin + it) * TP + row;
-      const bool m_ok = gm < Mtot;
-      const int gb = m_ok ? (int)(gm / HW) : 0;
-      const int gr = m_ok ? (int)(gm - (int64_t)gb * HW) : 0;
-      const int gh = gr / W, gw = gr - gh * W;
-      // dpre tile: 128 co columns (zero beyond Cout)
-      const float* dp = dpre + (int64_t)gb * Cout * HW + gr;
-#pragma unroll
-      for (int h64 = 0; h64 < 2; ++h64) {
-        int cc = Cout - h64 * 64;
-        cc = cc < 0 ? 0 : (cc > 64 ? 64 : cc);
-        if (cc > 0)
-          gather_row<BF16, true>(dp + (int64_t)h64 * 64 * HW, HW, cc, m_ok, GRAD_SCALE,
-                                 st + h64 * 8 * (TP * ROWB) + row * ROWB);
-        if (cc < 64) {   // zero the padding columns (co >= Cout)
-          for (int c8 = (cc + 7) / 8; c8 < 8; ++c8)
-            *reinterpret_cast<uint4*>(st + (h64 * 8 + c8) * (TP * ROWB) + row * ROWB) =
-                make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-      // shifted x tiles, one per tap of this CTA
-      const float* xb = x + (int64_t)gb * Cin_real * HW + gr;
-      for (int t = 0; t < ntap; ++t) {
-        const int tap = tap0 + t;
-        const int dh = tap / kw - ph, dw = tap % kw - pw;
-        const int hh = gh + dh, ww = gw + dw;
-        const bool ok = m_ok && hh >= 0 && hh < H && ww >= 0 && ww < W;
-        const float* p = xb + (ok ? dh * W + dw : 0);
-        uint8_t* bt = st + WG_A + t * b_tile + row * ROWB;
-        if (Cin_real < 16) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = (ok && j < Cin_real) ? __ldg(p + (int64_t)j * HW) : 0.f;
-#pragma unroll
-          for (int c8 = 0; c8 < 2; ++c8)
-            *reinterpret_cast<uint4*>(bt + c8 * (TP * ROWB)) =
-                make_uint4(pack2<BF16>(v[c8 * 8], v[c8 * 8 + 1]), pack2<BF16>(v[c8 * 8 + 2], v[c8 * 8 + 3]),
-                           pack2<BF16>(v[c8 * 8 + 4], v[c8 * 8 + 5]), pack2<BF16>(v[c8 * 8 + 6], v[c8 * 8 + 7]));
-        } else {
-          for (int c0 = 0; c0 < Cin; c0 += 64)
-            gather_row<BF16, false>(p + (int64_t)c0 * HW, HW, min(64, Cin - c0), ok, 1.f,
-                                    bt + (c0 / 8) * (TP * ROWB));
-        }
-      }
-      if (do_bias) {
-        // ones tile [128 px][16]: column 0 = 1 for valid pixels -> bias sums in one N = 16 chain
-        uint8_t* bo = st + WG_A + taps_per_cta * b_tile;
-        uint32_t one = pack2<BF16>(m_ok ? 1.f : 0.f, 0.f);
-        *reinterpret_cast<uint4*>(bo + row * ROWB) = make_uint4(one, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(bo + TP * ROWB + row * ROWB) = make_uint4(0u, 0u, 0u, 0u);
-      }
-      umma::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(full + s);
+    const int row = tid & 127, grp = warp >> 2;
+    const int n_mine = (n_items - grp + n_groups - 1) / n_groups;    // >= 1 (host: groups <= items)
+    const int64_t total = my_tiles * n_mine;
+    const bool small_c = Cin_real < 16;
+    // ---- load cursor: tile geometry kept incrementally (no 64-bit divisions in the loop) ----
+    const int64_t adv = (int64_t)gridDim.y * TP;            // pixels between two tiles of this CTA
+    const int adv_b = (int)(adv / HW), adv_r = (int)(adv - (int64_t)adv_b * HW);
+    int l_gb, l_gr, l_gh, l_gw, l_i = 0;
+    bool l_ok;
+    const float *l_dp, *l_xp;
+    {
+      const int64_t gm = (int64_t)blockIdx.y * TP + row;
+      l_gb = (int)(gm / HW);
+      l_gr = (int)(gm - (int64_t)l_gb * HW);
     }
-    if (my_tiles > 0) {
+    auto tile_geometry = [&]() {
+      l_ok = l_gb < B;
+      const int gb = l_ok ? l_gb : 0;
+      l_gh = l_gr / W;
+      l_gw = l_gr - l_gh * W;
+      l_dp = dpre + (int64_t)gb * Cout * HW + l_gr;
+      l_xp = x + (int64_t)gb * Cin_real * HW + l_gr;
+    };
+    tile_geometry();
+    // One 16-channel item: 16 loads issued back to back; converted / stored one item later, so the
+    // loads of the next item (possibly of the next tile) are in flight meanwhile.
+    struct Pending { float v[16]; uint32_t dst; bool ok, is_x; };
+    auto issue = [&](Pending& pd) {
+      const WgItem e = tbl[grp + l_i * n_groups];
+      pd.is_x = e.is_x != 0;
+      pd.ok = l_ok && (!pd.is_x || ((unsigned)(l_gh + e.dh) < (unsigned)H &&
+                                    (unsigned)(l_gw + e.dw) < (unsigned)W));
+      pd.dst = (uint32_t)e.dst + (uint32_t)(row * ROWB);
+      // `p` always points at readable memory (the un-shifted pixel when the tap falls outside)
+      const float* p = (pd.is_x ? l_xp : l_dp) + e.src_off + (pd.ok ? e.shift : 0);
+      if (small_c && pd.is_x) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pd.v[j] = j < Cin_real ? __ldg(p + (int64_t)j * HW) : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pd.v[j] = __ldg(p + (int64_t)j * HW);
+      }
+      if (++l_i == n_mine) {       // next item belongs to the next tile of this CTA
+        l_i = 0;
+        l_gr += adv_r;
+        l_gb += adv_b;
+        if (l_gr >= HW) { l_gr -= HW; ++l_gb; }
+        tile_geometry();
+      }
+    };
+    // ---- store cursor ----
+    int64_t s_it = 0;
+    int s_i = 0;
+    int tr_ev = 0;      // trace event counter (debug builds only)
+    const __half2 hmax = __floats2half2_rn(F16_MAX, F16_MAX), hmin = __floats2half2_rn(-F16_MAX, -F16_MAX);
+    auto finish = [&](Pending& pd) {
+      const int s = (int)(s_it % WG_STAGES);
+      uint8_t* st = smem + s * stage_bytes;
+      WTRACE(0, tr_ev++);
+      if (s_i == 0 && s_it >= WG_STAGES)
+        umma::mbar_wait(empty + s, (uint32_t)(((s_it / WG_STAGES) - 1) & 1));   // stage free again
+      WTRACE(0, tr_ev++);
+      uint32_t pk[8];
+      if (pd.is_x) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack2<BF16>(pd.v[2 * j], pd.v[2 * j + 1]);
+      } else if (BF16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          pk[j] = pack2<true>(scl(pd.v[2 * j], GRAD_SCALE), scl(pd.v[2 * j + 1], GRAD_SCALE));
+      } else {
+        // scale (a power of two) in fp32, saturate after the conversion on packed pairs
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __half2 h = __floats2half2_rn(pd.v[2 * j] * GRAD_SCALE, pd.v[2 * j + 1] * GRAD_SCALE);
+          h = __hmin2(__hmax2(h, hmin), hmax);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      }
+      if (!pd.ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = 0u;
+      }
+      *reinterpret_cast<uint4*>(st + pd.dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(st + pd.dst + WCS) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      WTRACE(0, tr_ev++);
+      if (++s_i == n_mine) {
+        if (do_bias && grp == n_groups - 1) {
+          // ones tile [128 px][16]: column 0 = 1 for valid pixels -> bias sums in one N = 16 chain
+          const int64_t gm = ((int64_t)blockIdx.y + s_it * gridDim.y) * TP + row;
+          uint8_t* bo = st + WG_A + ntap * b_tile;
+          uint32_t one = pack2<BF16>(gm < Mtot ? 1.f : 0.f, 0.f);
+          *reinterpret_cast<uint4*>(bo + row * ROWB) = make_uint4(one, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(bo + WCS + row * ROWB) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        umma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(full + s);
+        s_i = 0;
+        ++s_it;
+      }
+    };
+    Pending pa, pb;
+    if (total > 0) issue(pa);
+    for (int64_t q = 0; q < total; q += 2) {
+      if (q + 1 < total) issue(pb);
+      finish(pa);
+      if (q + 2 < total) issue(pa);
+      if (q + 1 < total) finish(pb);
+    }
+    if (my_tiles > 0 && grp == 0) {
       umma::mbar_wait(accb, 0);
       umma::fence_after_sync();
       const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16);
@@ -446,7 +547,7 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
     }
   }
   __syncthreads();
-  if (warp == 4) umma::tmem_dealloc<512>(tm);
+  if (warp == mma_warp) umma::tmem_dealloc<512>(tm);
 }
 
 // operand type of the backward GEMMs.  bf16 has the range of fp32 but 8 mantissa bits: measured
@@ -525,17 +626,22 @@ extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, f
   if (tpc > taps) tpc = taps;
   {
     // two smem stages of (dpre tile + tpc shifted x tiles + ones tile) must fit
-    int by_smem = ((227 * 1024 - 64) / WG_STAGES - WG_A - TP * ROWB * 2) / (TP * Cin * 2);
+    int by_smem = ((227 * 1024 - 64 - WG_TBL_BYTES) / WG_STAGES - WG_A - 2 * WCS) / ((Cin / 8) * WCS);
     if (tpc > by_smem) tpc = by_smem;
   }
   PVB_CHECK_ARG(tpc >= 1, "pvb_conv_tc_wgrad: Cin too large");
   const int groups = (taps + tpc - 1) / tpc;
-  const int stage = WG_A + tpc * TP * Cin * 2 + TP * ROWB * 2;
-  const int smem = WG_STAGES * stage + 64;
+  const int stage = WG_A + tpc * (Cin / 8) * WCS + 2 * WCS;
+  const int smem = WG_STAGES * stage + 64 + WG_TBL_BYTES;
+  PVB_CHECK_ARG((int64_t)(Cin > Cout ? Cin : Cout) * H * Wd < (1ll << 31),
+                "pvb_conv_tc_wgrad: one image's activations must have fewer than 2^31 elements");
   PVB_CHECK_ARG(smem <= 227 * 1024, "pvb_conv_tc_wgrad: tile does not fit shared memory");
   const int64_t M = (int64_t)B * H * Wd;
   const int64_t n_tiles = (M + TP - 1) / TP;
-  int64_t splits = (148 + groups - 1) / groups;
+  // one CTA per SM (512 TMEM columns, ~200 KB smem): never more CTAs than SMs, or the extras
+  // run as a second wave and double the kernel time
+  int64_t splits = 148 / groups;
+  if (splits < 1) splits = 1;
   if (splits > n_tiles) splits = n_tiles;
   const int64_t per = (n_tiles + splits - 1) / splits;
   splits = (n_tiles + per - 1) / per;
@@ -545,13 +651,19 @@ extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, f
     attr_smem = 227 * 1024;
   }
   dim3 grid(groups, (unsigned)splits);
-  conv_tc_wgrad_kernel<BWD_BF16><<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(
+  // 16-channel gather items per 128-pixel step -> producer groups (no more groups than items)
+  const int items = Cout / 16 + tpc * (Cin / 16);
+  const int ng = items < WG_MAX_GROUPS ? (items < 1 ? 1 : items) : WG_MAX_GROUPS;
+  conv_tc_wgrad_kernel<BWD_BF16><<<grid, ng * 128 + 32, smem, (cudaStream_t)stream>>>(
       dpre, x, dW, db, B, Cin_real, Cout, H, Wd, kh, kw, tpc, per);
   pvb::count_launch();
   return pvb::launch_status();
 }
 
 #ifdef PVB_TC_TRACE
+extern "C" int pvb_wgrad_trace_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_wtrace, sizeof(long long) * 2 * 64);
+}
 extern "C" int pvb_conv_trace_read(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_ctrace, sizeof(long long) * 2 * 64);
 }
