@@ -283,8 +283,10 @@ int pvb_act_bwd(const float* dy, const float* y, const float* pre, float* dpre,
 /* nn.MaxPool{1,2}d(2, 2): x [BC, H, W] -> y [BC, H/2 (2-D) or H, W/2] */
 int pvb_maxpool2_fwd(const float* x, float* y, int64_t BC, int H, int Wd,
                      int two_d, void* stream);
+/* act != PVB_ACT_NONE: x is the OUTPUT of that activation; dx is then multiplied by the
+ * activation derivative at the routed element (= dpre of the layer below; not gelu) */
 int pvb_maxpool2_bwd(const float* x, const float* dy, float* dx, int64_t BC,
-                     int H, int Wd, int two_d, void* stream);
+                     int H, int Wd, int two_d, int act, void* stream);
 /* F.interpolate(scale_factor=2): nearest, or bilinear (2-D only, align_corners=False) */
 int pvb_upsample2_fwd(const float* x, float* y, int64_t BC, int H, int Wd,
                       int two_d, int bilinear, void* stream);

@@ -111,7 +111,7 @@ SIGNATURES = {
     "pvb_bn_fwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _fl, _fl, _i32, _st],
     "pvb_bn_bwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _st],
     "pvb_maxpool2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
-    "pvb_maxpool2_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _st],
+    "pvb_maxpool2_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_upsample2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_upsample2_bwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_normal_logprob": [_f, _f, _fl, _fl, _f, _f, _i64, _st],

@@ -78,9 +78,16 @@ class ConvStack:
             if want_dx:
                 buf = self.gbuf[0] if d.data_ptr() != self.gbuf[0].data_ptr() else self.gbuf[1]
                 dx = buf[:xin.numel()].view_as(xin)
+            # activation derivative of the layer BELOW folded into the kernel that produces dx
+            # (tensor-core backward-data epilogue, max-pool backward): saves a pass over dx
+            below = self.steps[k - 1] if k > 0 else None
+            fuse = (below is not None and below["kind"] == "conv"
+                    and below["act"] not in (None, "gelu") and not self.engine.force_generic
+                    and ((st["kind"] == "conv" and st["tc"]) or (st["kind"] == "pool" and xin.dim() < 5)))
             if st["kind"] == "conv":
-                if st["act"] is not None:
+                if st["act"] is not None and not st.get("dpre_ready", False):
                     ops.act_bwd(d, st["y"], st["pre"], d, st["act"])     # in place: d = dpre
+                st["dpre_ready"] = False
                 gb = flat.gv(m.bias) if m.bias is not None else None
                 if st["tc_wgrad"]:
                     ops.conv_tc_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
@@ -88,7 +95,11 @@ class ConvStack:
                     ops.conv_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
                 if want_dx:
                     if st["tc"]:
-                        ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"])
+                        if fuse:
+                            ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"], xin, below["act"])
+                            below["dpre_ready"] = True
+                        else:
+                            ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"])
                     else:
                         ops.conv_bwd_data(d, m.weight.data, dx)
             elif st["kind"] == "bn":
@@ -98,7 +109,9 @@ class ConvStack:
                 ops.bn_bwd(d, xin, m, st["stats"][0], st["stats"][1], dx, gg, gb, st["ws"])
             elif st["kind"] == "pool":
                 if want_dx:
-                    ops.maxpool2_bwd(xin, d, dx)
+                    ops.maxpool2_bwd(xin, d, dx, below["act"] if fuse else None)
+                    if fuse:
+                        below["dpre_ready"] = True
             else:
                 if want_dx:
                     ops.upsample2_bwd(d, dx, m.mode == "bilinear")

@@ -244,7 +244,7 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restri
 // whole window); elements outside any window (odd sizes) are zeroed by the trailing threads.
 __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                     float* __restrict__ dx, int64_t BC, int H, int W, int Ho, int Wo,
-                                    int two_d) {
+                                    int two_d, int act) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n_win = BC * Ho * Wo;
   if (i < n_win) {
@@ -257,7 +257,9 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __
 #pragma unroll
     for (int k = 1; k < 4; ++k)
       if (v[k] > v[best]) best = k;
-    const float g = dy[i];
+    // act != none: x is the activation output feeding the pool; the gradient that reaches the
+    // maximal element continues through that activation (dx = its dpre), saving a separate pass
+    const float g = dy[i] * (act ? pvb::act_grad(v[best], 0.f, act) : 1.f);
     float2 top = make_float2(best == 0 ? g : 0.f, best == 1 ? g : 0.f);
     if ((o & 1) == 0) {
       *reinterpret_cast<float2*>(dx + o) = top;
@@ -407,6 +409,76 @@ int check_dims(const ConvDims& d, const char* who) {
 
 }  // namespace
 
+// Weight gradient of a Cin == 1 layer (the first encoder layer): dW[co][t] = sum_px dpre[co][px]
+// x[px + d_t] has Cout * taps outputs and reads Cout planes of dpre once -- HBM-bound, so no GEMM
+// machinery: a thread keeps the <= 9 neighbours of its pixel in registers and accumulates the 8 output
+// channels of its CTA's channel group; one block reduction + atomics per CTA at the end.
+constexpr int C1_CO = 8;
+__global__ void __launch_bounds__(256)
+conv_c1_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dW,
+                     float* __restrict__ db, ConvDims d) {
+  __shared__ float red[8][C1_CO * 10];
+  const int taps = d.kh * d.kw, ph = d.kh / 2, pw = d.kw / 2;
+  const int HW = d.H * d.W;
+  const int64_t Mtot = (int64_t)d.B * HW;
+  const int co0 = blockIdx.y * C1_CO;
+  float acc[C1_CO][10];
+#pragma unroll
+  for (int c = 0; c < C1_CO; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[c][t] = 0.f;
+  // 32-bit pixel arithmetic (host checks B*H*W < 2^31); (b, r) advance incrementally
+  const unsigned stride = gridDim.x * 256u;
+  const unsigned sb = stride / (unsigned)HW, sr = stride - sb * (unsigned)HW;
+  unsigned m = blockIdx.x * 256u + threadIdx.x;
+  unsigned b = m / (unsigned)HW, r = m - b * (unsigned)HW;
+  for (; m < (unsigned)Mtot; m += stride) {
+    const int h = (int)(r / (unsigned)d.W), w = (int)r - h * d.W;
+    const float* xp = x + (int64_t)b * HW + r;
+    float in[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      in[t] = 0.f;
+      if (t < taps) {
+        const int dh = t / d.kw - ph, dw = t % d.kw - pw;
+        if ((unsigned)(h + dh) < (unsigned)d.H && (unsigned)(w + dw) < (unsigned)d.W)
+          in[t] = __ldg(xp + dh * d.W + dw);
+      }
+    }
+    const float* gp = dpre + ((int64_t)b * d.Cout + co0) * HW + r;
+    float g[C1_CO];
+#pragma unroll
+    for (int c = 0; c < C1_CO; ++c) g[c] = co0 + c < d.Cout ? __ldg(gp + (int64_t)c * HW) : 0.f;
+#pragma unroll
+    for (int c = 0; c < C1_CO; ++c) {
+      acc[c][9] += g[c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
+    }
+    r += sr;
+    b += sb;
+    if (r >= (unsigned)HW) { r -= (unsigned)HW; ++b; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < C1_CO; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+      const float v = pvb::warp_sum(acc[c][t]);
+      if (lane == 0) red[warp][c * 10 + t] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < C1_CO * 10) {
+    float s = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
+    const int c = threadIdx.x / 10, t = threadIdx.x - c * 10;
+    if (co0 + c < d.Cout) {
+      if (t < taps) atomicAdd(dW + (int64_t)(co0 + c) * taps + t, s);
+      else if (t == 9 && db) atomicAdd(db + co0 + c, s);
+    }
+  }
+}
+
 extern "C" int pvb_conv_fwd(const float* x, const float* W, const float* b, float* y, float* pre,
                             int B, int Cin, int Cout, int H, int Wd, int kh, int kw, int act,
                             void* stream) {
@@ -450,6 +522,15 @@ extern "C" int pvb_conv_bwd_weight(const float* dpre, const float* x, float* dW,
   PVB_CHECK_ARG(dpre && x && dW, "pvb_conv_bwd_weight: null pointer");
   if (B == 0) return 0;
   int64_t M = (int64_t)B * H * Wd;
+  if (Cin == 1 && M < (1ll << 31) - (1 << 20)) {
+    const int cgroups = (Cout + C1_CO - 1) / C1_CO;
+    int64_t px_blocks = (148 * 4 + cgroups - 1) / cgroups;
+    if (px_blocks > (M + 255) / 256) px_blocks = (M + 255) / 256;
+    dim3 grid1((unsigned)px_blocks, cgroups);
+    conv_c1_wgrad_kernel<<<grid1, 256, 0, (cudaStream_t)stream>>>(dpre, x, dW, db, d);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   int tiles = ((Cin * kh * kw + BN - 1) / BN) * ((Cout + BM - 1) / BM);
   int64_t splits = (148 * 4 + tiles - 1) / tiles;
   int64_t max_splits = (M + 255) / 256;
@@ -486,13 +567,15 @@ extern "C" int pvb_maxpool2_fwd(const float* x, float* y, int64_t BC, int H, int
 }
 
 extern "C" int pvb_maxpool2_bwd(const float* x, const float* dy, float* dx, int64_t BC, int H, int Wd,
-                                int two_d, void* stream) {
+                                int two_d, int act, void* stream) {
   PVB_CHECK_ARG(x && dy && dx && BC >= 0 && H > 0 && Wd > 1 && (!two_d || H > 1), "pvb_maxpool2_bwd: bad argument");
+  PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID && act != PVB_ACT_GELU,
+                "pvb_maxpool2_bwd: fused activation derivative must be computable from the output");
   int Ho = two_d ? H / 2 : H, Wo = Wd / 2;
   const int odd_w = Wd & 1, odd_h = two_d ? (H & 1) : 0;
   int64_t n = BC * Ho * Wo + BC * ((int64_t)odd_w * H + (int64_t)odd_h * (Wd - odd_w));
   if (n == 0) return 0;
-  maxpool2_bwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, BC, H, Wd, Ho, Wo, two_d);
+  maxpool2_bwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, BC, H, Wd, Ho, Wo, two_d, act);
   pvb::count_launch();
   return pvb::launch_status();
 }

@@ -268,7 +268,21 @@ conv_tc_pix_kernel(const float* __restrict__ src, const uint16_t* __restrict__ W
       umma::tmem_ld16(tm_lane + n0, v);
       umma::tmem_ld_wait();
       if (m_ok) {
-        bias_act16(v, bias, n0, d.out_scale, act, pbase, HW);
+        if (SCALED) {
+          // backward data: un-scale; with `pre` = the activations this gradient flows into (output of
+          // the previous layer) also apply that layer's activation derivative, so dst is its dpre
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= d.out_scale;
+          if (pbase) {
+            float yv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) yv[j] = __ldg(pbase + (int64_t)(n0 + j) * HW);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= pvb::act_grad(yv[j], 0.f, act);
+          }
+        } else {
+          bias_act16(v, bias, n0, d.out_scale, act, pbase, HW);
+        }
         float* o = obase + (int64_t)n0 * HW;
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j * HW] = v[j];
@@ -282,95 +296,76 @@ conv_tc_pix_kernel(const float* __restrict__ src, const uint16_t* __restrict__ W
 }
 
 // ---- backward weight ------------------------------------------------------------------------------
-// CTA (tap group, pixel split): accumulators [128 lanes = co][taps_in_group x Cin columns] in TMEM.
-// Per 128-pixel step: A = dpre tile [128 px][128 co (zero padded)] (MN-major), B_t = x tile shifted by
-// tap t [128 px][Cin] (MN-major), one N = Cin MMA chain (8 K-steps of 16 pixels) per tap.
-constexpr int WG_MAX_GROUPS = 4;                // producer groups of 4 warps (thread = pixel row)
-#ifndef PVB_WG_PAD
-#define PVB_WG_PAD 0
-#endif
-// chunk-column stride of the MN-major operand tiles: 128 rows x 16 bytes (+ optional padding; measured:
-// a 16-byte pad, which spreads the 16-byte pieces of one K row over the banks, changes nothing)
-constexpr int WCS = TP * ROWB + PVB_WG_PAD;
+// dW[co][ci][dh][dw] = sum over pixels of dpre[co][h][w] x[ci][h+dh][w+dw] as GEMMs with K = pixels:
+// accumulators [128 lanes = co][kw x Cin columns] in TMEM, both operands MN-major (K = tile rows,
+// exactly as the decoder kernel's dW GEMMs).
+//
+// Pixels are addressed through W-padded rows, q = (b*H + h)*Wp + wp with Wp = W + 1 for 3-wide kernels:
+// the extra column is the zero padding shared by the right border of one row and the left border of
+// the next, so "one pixel to the left / right" is q -/+ 1 everywhere.  CTA (g, y) owns kernel row
+// dh = g - kh/2 and the tiles y, y + gridDim.y, ...; per tile (ADV = 128 - 2*(kw/2) positions):
+//   A = dpre tile [128 rows: position q0 + r; rows >= ADV and padding positions are zero][128 co]
+//   X = x tile    [128 rows: position q0 - kw/2 + r of image row h + dh][Cin], staged ONCE;
+//   the B operand of tap (dh, dw) is X shifted by kw/2 + dw rows = +16 bytes per row in the smem
+//   descriptor (row-chunk layout), so the kw taps of a kernel row share one gather.
+// Gathers: 16-channel items (Cout/16 for A, Cin/16 for X) dealt round-robin to up to four producer
+// groups of 128 threads (thread = tile row), software-pipelined one item ahead across tiles.
+constexpr int WG_MAX_GROUPS = 4;
+constexpr int WCS = TP * ROWB;                   // chunk-column stride: 128 rows x 16 bytes
 constexpr int WG_A = 16 * WCS;                   // dpre tile, 16 chunk-columns (128 output channels)
-constexpr int WG_MAX_TAPS = 9;                   // taps per CTA (<= (512 - 16) / Cin)
-constexpr int WG_STAGES = 2;
-struct WgItem { int src_off, shift, dst; short dh, dw; int is_x; };
-constexpr int WG_TBL_BYTES = (8 + 9 * 16) * (int)sizeof(WgItem);   // item table: <= 8 + 9 * 16 entries
+constexpr int WG_ONES = 2 * WCS;                 // [128][16] tile, column 0 = 1: bias sums
+constexpr int WG_XPAD = 32;                      // two finite rows behind the last chunk-column of X
+constexpr int WG_MAX_STAGES = 3;
 
-// The gathers are latency-bound (strided 4-byte loads, 16 in flight per thread), so the work of one
-// 128-pixel step is cut into 16-channel items -- 8 for the dpre tile, Cin/16 per tap for the shifted
-// x tiles -- dealt round-robin to up to four producer groups of 128 threads: up to 4x the loads in
-// flight per SM, same two-stage ring towards the MMA warp.
 template <bool BF16>
 __global__ void __launch_bounds__(WG_MAX_GROUPS * 128 + 32, 1)
 conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dW,
                      float* __restrict__ db, int B, int Cin_real, int Cout, int H, int W, int kh, int kw,
-                     int taps_per_cta, int64_t tiles_per_split) {
+                     int n_stages, int n_tiles) {
   // fewer than 16 input channels (the first layer): the x tile is zero-padded to 16 columns
   const int Cin = Cin_real < 16 ? 16 : Cin_real;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int b_tile = (Cin / 8) * WCS;                    // one shifted x tile
-  const int stage_bytes = WG_A + taps_per_cta * b_tile + 2 * WCS;   // + ones tile (16 columns)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * stage_bytes);
+  const int x_tile = (Cin / 8) * WCS + WG_XPAD;
+  const int stage_bytes = WG_A + x_tile;
+  uint8_t* ones = smem + n_stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + WG_ONES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + WG_STAGES;
-  uint64_t* accb = bars + 2 * WG_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+  uint64_t* empty = bars + WG_MAX_STAGES;
+  uint64_t* accb = bars + 2 * WG_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_MAX_STAGES + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_groups = (int)(blockDim.x >> 7);             // producer groups; the MMA warp comes last
   const int mma_warp = n_groups * 4;
-  const int taps = kh * kw, ph = kh / 2, pw = kw / 2;
+  const int ph = kh / 2, pw = kw / 2;
+  const int dh = (int)blockIdx.x - ph;                     // kernel row of this CTA
+  const int Wp = W + pw, ADV = TP - 2 * pw;
   const int HW = H * W;
-  const int64_t Mtot = (int64_t)B * HW;
-  const int64_t n_tiles = (Mtot + TP - 1) / TP;
-  const int tap0 = blockIdx.x * taps_per_cta;
-  const int ntap = min(taps_per_cta, taps - tap0);
-  // pixel tiles are dealt round-robin to the gridDim.y CTAs of a tap group (tile = blockIdx.y +
-  // it * gridDim.y): at any moment the CTAs read one contiguous window of every channel plane, which
-  // keeps DRAM pages open across CTAs (a contiguous range per CTA made each CTA a separate stream of
-  // 512-byte pieces per plane)
-  const int64_t my_tiles = blockIdx.y < n_tiles ? (n_tiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
+  const int my_tiles = (int)blockIdx.y < n_tiles ? (n_tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
   const bool do_bias = db != nullptr && blockIdx.x == 0;
-  const uint32_t col_bias = (uint32_t)(ntap * Cin);        // TMEM column block of the bias sums
+  const uint32_t col_bias = (uint32_t)(kw * Cin);          // TMEM column block of the bias sums
   if (warp == mma_warp) umma::tmem_alloc<512>(tmem_slot);
   if (tid == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       umma::mbar_init(full + s, (uint32_t)mma_warp);       // one arrive per producer warp
       umma::mbar_init(empty + s, 1);
     }
     umma::mbar_init(accb, 1);
     umma::mbar_fence_init();
   }
-  // gather items of one 128-pixel step (16 channels each): Cout/16 blocks of the dpre tile, then
-  // Cin/16 blocks of each tap's shifted x tile; decoded once into shared memory
-  WgItem* tbl = reinterpret_cast<WgItem*>(smem + WG_STAGES * stage_bytes + 64);
-  const int a_items = Cout / 16, b_items = Cin / 16;
-  const int n_items = a_items + ntap * b_items;
-  for (int k = tid; k < n_items; k += blockDim.x) {
-    WgItem e;
-    if (k < a_items) {
-      e.src_off = k * 16 * HW;
-      e.shift = 0; e.dh = 0; e.dw = 0; e.is_x = 0;
-      e.dst = k * 2 * WCS;
-    } else {
-      const int kk = k - a_items, t = kk / b_items, cb = kk - t * b_items;
-      const int tap = tap0 + t;
-      e.dh = (short)(tap / kw - ph);
-      e.dw = (short)(tap % kw - pw);
-      e.shift = e.dh * W + e.dw;
-      e.src_off = cb * 16 * HW;
-      e.is_x = 1;
-      e.dst = WG_A + t * b_tile + cb * 2 * WCS;
-    }
-    tbl[k] = e;
-  }
   if (warp < mma_warp) {
-    // output channels beyond Cout never change: zero those dpre chunk-columns once, in every stage
-    for (int s = 0; s < WG_STAGES; ++s)
-      for (int c8 = Cout / 8 + (warp >> 2); c8 < 16; c8 += n_groups)
-        *reinterpret_cast<uint4*>(smem + s * stage_bytes + c8 * WCS + (tid & 127) * ROWB) =
+    const int r = tid & 127, g = warp >> 2;
+    for (int s = 0; s < n_stages; ++s) {
+      // output channels beyond Cout never change: zero those dpre chunk-columns once
+      for (int c8 = Cout / 8 + g; c8 < 16; c8 += n_groups)
+        *reinterpret_cast<uint4*>(smem + s * stage_bytes + c8 * WCS + r * ROWB) = make_uint4(0u, 0u, 0u, 0u);
+      if (tid < 2)
+        *reinterpret_cast<uint4*>(smem + s * stage_bytes + WG_A + (Cin / 8) * WCS + tid * ROWB) =
             make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (g == 0) {
+      *reinterpret_cast<uint4*>(ones + r * ROWB) = make_uint4(pack2<BF16>(1.f, 0.f), 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(ones + WCS + r * ROWB) = make_uint4(0u, 0u, 0u, 0u);
+    }
     umma::fence_proxy_async();
   }
   umma::fence_before_sync();
@@ -379,70 +374,66 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
   const uint32_t tm = *tmem_slot;
 
   if (warp == mma_warp) {
-    // The tap tiles (and the ones tile behind them) are contiguous chunk-columns in shared memory
-    // and their accumulators contiguous TMEM columns, so one MMA spans several taps (N <= 256):
-    // the dpre operand (128 x 16, 4 KB) is read once per K-step instead of once per tap -- these
-    // small-N MN-major MMAs are bound by operand reads from shared memory, not by the math.
-    const int n_total = ntap * Cin + (do_bias ? 16 : 0);
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int s = (int)(it % WG_STAGES);
-      WTRACE(1, (int)(3 * it));
-      umma::mbar_wait(full + s, (uint32_t)((it / WG_STAGES) & 1));
-      WTRACE(1, (int)(3 * it + 1));
+    const uint32_t id_w = idesc_16b(128, Cin, 1, 1, BF16);
+    const uint32_t id_b = idesc_16b(128, 16, 1, 1, BF16);
+    const uint32_t ones_a = umma::smem_u32(ones);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % n_stages;
+      WTRACE(1, 3 * it);
+      umma::mbar_wait(full + s, (uint32_t)((it / n_stages) & 1));
+      WTRACE(1, 3 * it + 1);
       umma::fence_after_sync();
       if (lane == 0) {
         const uint32_t base = umma::smem_u32(smem + s * stage_bytes);
-        for (int n0 = 0; n0 < n_total; n0 += 256) {
-          const int nn = min(256, n_total - n0);
-          const uint32_t idesc = idesc_16b(128, nn, 1, 1, BF16);
-          const uint32_t bt = base + WG_A + (n0 / 8) * WCS;
-          for (int k = 0; k < 8; ++k)   // 8 K-steps of 16 pixel rows
-            umma::mma_f16_ss(tm + n0, umma::smem_desc(base + k * 256, 128, WCS),
-                             umma::smem_desc(bt + k * 256, 128, WCS), idesc,
+        for (int j = 0; j < kw; ++j)       // tap (dh, j - pw): X shifted by j rows
+          for (int k = 0; k < 8; ++k)      // 8 K-steps of 16 tile rows
+            umma::mma_f16_ss(tm + j * Cin, umma::smem_desc(base + k * 256, 128, WCS),
+                             umma::smem_desc(base + WG_A + j * ROWB + k * 256, 128, WCS), id_w,
                              (it > 0 || k > 0) ? 1u : 0u);
-        }
+        if (do_bias)
+          for (int k = 0; k < 8; ++k)
+            umma::mma_f16_ss(tm + col_bias, umma::smem_desc(base + k * 256, 128, WCS),
+                             umma::smem_desc(ones_a + k * 256, 128, WCS), id_b,
+                             (it > 0 || k > 0) ? 1u : 0u);
         umma::commit(empty + s);
         if (it == my_tiles - 1) umma::commit(accb);
       }
       __syncwarp();
-      WTRACE(1, (int)(3 * it + 2));
+      WTRACE(1, 3 * it + 2);
     }
   } else {
     const int row = tid & 127, grp = warp >> 2;
+    const int a_items = Cout / 16, b_items = Cin / 16;
+    const int n_items = a_items + b_items;
     const int n_mine = (n_items - grp + n_groups - 1) / n_groups;    // >= 1 (host: groups <= items)
-    const int64_t total = my_tiles * n_mine;
+    const int total = my_tiles * n_mine;
     const bool small_c = Cin_real < 16;
-    // ---- load cursor: tile geometry kept incrementally (no 64-bit divisions in the loop) ----
-    const int64_t adv = (int64_t)gridDim.y * TP;            // pixels between two tiles of this CTA
-    const int adv_b = (int)(adv / HW), adv_r = (int)(adv - (int64_t)adv_b * HW);
-    int l_gb, l_gr, l_gh, l_gw, l_i = 0;
-    bool l_ok;
+    // ---- load cursor: position of this thread's tile row, decoded once per tile ----
+    int l_tile = (int)blockIdx.y, l_i = 0;
+    bool l_aok, l_xok;
     const float *l_dp, *l_xp;
-    {
-      const int64_t gm = (int64_t)blockIdx.y * TP + row;
-      l_gb = (int)(gm / HW);
-      l_gr = (int)(gm - (int64_t)l_gb * HW);
-    }
     auto tile_geometry = [&]() {
-      l_ok = l_gb < B;
-      const int gb = l_ok ? l_gb : 0;
-      l_gh = l_gr / W;
-      l_gw = l_gr - l_gh * W;
-      l_dp = dpre + (int64_t)gb * Cout * HW + l_gr;
-      l_xp = x + (int64_t)gb * Cin_real * HW + l_gr;
+      const unsigned qa = (unsigned)l_tile * (unsigned)ADV + (unsigned)row;   // A position of this row
+      const unsigned ri = qa / (unsigned)Wp;
+      const int wp = (int)(qa - ri * (unsigned)Wp);
+      const int b = (int)(ri / (unsigned)H), h = (int)(ri - (unsigned)b * (unsigned)H);
+      const bool in_b = b < B;
+      l_aok = in_b && row < ADV && wp < W;
+      const int wx = wp - pw, hx = h + dh;                 // X position: pw to the left, row h + dh
+      l_xok = in_b && wx >= 0 && wx < W && hx >= 0 && hx < H;
+      // the pointers always address readable memory (pixel 0 of image 0 when the position is void)
+      l_dp = dpre + (l_aok ? ((int64_t)b * Cout * H + h) * W + wp : 0);
+      l_xp = x + (l_xok ? ((int64_t)b * Cin_real * H + hx) * W + wx : 0);
     };
     tile_geometry();
-    // One 16-channel item: 16 loads issued back to back; converted / stored one item later, so the
-    // loads of the next item (possibly of the next tile) are in flight meanwhile.
     struct Pending { float v[16]; uint32_t dst; bool ok, is_x; };
     auto issue = [&](Pending& pd) {
-      const WgItem e = tbl[grp + l_i * n_groups];
-      pd.is_x = e.is_x != 0;
-      pd.ok = l_ok && (!pd.is_x || ((unsigned)(l_gh + e.dh) < (unsigned)H &&
-                                    (unsigned)(l_gw + e.dw) < (unsigned)W));
-      pd.dst = (uint32_t)e.dst + (uint32_t)(row * ROWB);
-      // `p` always points at readable memory (the un-shifted pixel when the tap falls outside)
-      const float* p = (pd.is_x ? l_xp : l_dp) + e.src_off + (pd.ok ? e.shift : 0);
+      const int k = grp + l_i * n_groups;
+      pd.is_x = k >= a_items;
+      const int cb = pd.is_x ? k - a_items : k;            // 16-channel block
+      pd.ok = pd.is_x ? l_xok : l_aok;
+      pd.dst = (uint32_t)((pd.is_x ? WG_A : 0) + cb * 2 * WCS + row * ROWB);
+      const float* p = (pd.is_x ? l_xp : l_dp) + (int64_t)cb * 16 * HW;
       if (small_c && pd.is_x) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) pd.v[j] = j < Cin_real ? __ldg(p + (int64_t)j * HW) : 0.f;
@@ -452,23 +443,21 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       }
       if (++l_i == n_mine) {       // next item belongs to the next tile of this CTA
         l_i = 0;
-        l_gr += adv_r;
-        l_gb += adv_b;
-        if (l_gr >= HW) { l_gr -= HW; ++l_gb; }
+        l_tile += (int)gridDim.y;
         tile_geometry();
       }
     };
     // ---- store cursor ----
-    int64_t s_it = 0;
-    int s_i = 0;
+    int s_it = 0, s_i = 0;
     int tr_ev = 0;      // trace event counter (debug builds only)
+    (void)tr_ev;
     const __half2 hmax = __floats2half2_rn(F16_MAX, F16_MAX), hmin = __floats2half2_rn(-F16_MAX, -F16_MAX);
     auto finish = [&](Pending& pd) {
-      const int s = (int)(s_it % WG_STAGES);
+      const int s = s_it % n_stages;
       uint8_t* st = smem + s * stage_bytes;
       WTRACE(0, tr_ev++);
-      if (s_i == 0 && s_it >= WG_STAGES)
-        umma::mbar_wait(empty + s, (uint32_t)(((s_it / WG_STAGES) - 1) & 1));   // stage free again
+      if (s_i == 0 && s_it >= n_stages)
+        umma::mbar_wait(empty + s, (uint32_t)(((s_it / n_stages) - 1) & 1));   // stage free again
       WTRACE(0, tr_ev++);
       uint32_t pk[8];
       if (pd.is_x) {
@@ -495,14 +484,6 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       *reinterpret_cast<uint4*>(st + pd.dst + WCS) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       WTRACE(0, tr_ev++);
       if (++s_i == n_mine) {
-        if (do_bias && grp == n_groups - 1) {
-          // ones tile [128 px][16]: column 0 = 1 for valid pixels -> bias sums in one N = 16 chain
-          const int64_t gm = ((int64_t)blockIdx.y + s_it * gridDim.y) * TP + row;
-          uint8_t* bo = st + WG_A + ntap * b_tile;
-          uint32_t one = pack2<BF16>(gm < Mtot ? 1.f : 0.f, 0.f);
-          *reinterpret_cast<uint4*>(bo + row * ROWB) = make_uint4(one, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(bo + WCS + row * ROWB) = make_uint4(0u, 0u, 0u, 0u);
-        }
         umma::fence_proxy_async();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(full + s);
@@ -512,7 +493,7 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
     };
     Pending pa, pb;
     if (total > 0) issue(pa);
-    for (int64_t q = 0; q < total; q += 2) {
+    for (int q = 0; q < total; q += 2) {
       if (q + 1 < total) issue(pb);
       finish(pa);
       if (q + 2 < total) issue(pa);
@@ -523,17 +504,18 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       umma::fence_after_sync();
       const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16);
       const int co = row;                                   // TMEM lane = output channel
-      for (int t = 0; t < ntap; ++t) {
-        const int tap = tap0 + t;
+      const int taps = kh * kw;
+      for (int j = 0; j < kw; ++j) {
+        const int tap = (int)blockIdx.x * kw + j;
         for (int n0 = 0; n0 < Cin; n0 += 16) {
           float v[16];
-          umma::tmem_ld16(tm_lane + t * Cin + n0, v);
+          umma::tmem_ld16(tm_lane + j * Cin + n0, v);
           umma::tmem_ld_wait();
           if (co < Cout) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + j < Cin_real)
-                atomicAdd(dW + ((int64_t)co * Cin_real + n0 + j) * taps + tap, v[j] * (1.f / GRAD_SCALE));
+            for (int jj = 0; jj < 16; ++jj)
+              if (n0 + jj < Cin_real)
+                atomicAdd(dW + ((int64_t)co * Cin_real + n0 + jj) * taps + tap, v[jj] * (1.f / GRAD_SCALE));
           }
         }
       }
@@ -568,6 +550,7 @@ extern "C" int pvb_conv_tc_supported(int Cin, int Cout, int kh, int kw) {
 }
 // the weight-gradient kernel alone also takes layers with fewer than 16 input channels
 extern "C" int pvb_conv_tc_wgrad_supported(int Cin, int Cout, int kh, int kw) {
+  if (Cin == 1) return 0;      // HBM-bound: the direct fp32 kernel of pvb_conv_bwd_weight is faster
   return tc_ok(Cin < 16 ? 16 : Cin, Cout, kh, kw) && Cout <= 128 ? 1 : 0;
 }
 
@@ -607,7 +590,10 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
   } else {
     conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
     pvb::count_launch();
-    conv_tc_pix_kernel<BWD_BF16, true><<<grid, PIX_THREADS, PIX_SMEM, st>>>(src, Wp, nullptr, dst, nullptr, d, 0);
+    // `pre` (optional) = output of the layer below, `act` its activation: dst = dx * act'(pre)
+    PVB_CHECK_ARG(!pre || (act != PVB_ACT_GELU), "pvb_conv_tc_pix: gelu's derivative needs the pre-activation");
+    conv_tc_pix_kernel<BWD_BF16, true><<<grid, PIX_THREADS, PIX_SMEM, st>>>(src, Wp, nullptr, dst, pre, d,
+                                                                           pre ? act : 0);
   }
   pvb::count_launch();
   return pvb::launch_status();
@@ -619,43 +605,32 @@ extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, f
   const int Cin_real = Cin;
   if (Cin < 16) Cin = 16;                        // zero-padded x tile
   PVB_CHECK_ARG(tc_ok(Cin, Cout, kh, kw) && Cout <= 128, "pvb_conv_tc_wgrad: unsupported shape");
+  PVB_CHECK_ARG(kw * Cin + 16 <= 512, "pvb_conv_tc_wgrad: Cin too large (kw * Cin + 16 TMEM columns)");
   if (B == 0) return 0;
-  const int taps = kh * kw;
-  int tpc = (512 - 16) / Cin;                    // taps per CTA: accumulators + 16 bias columns <= 512
-  if (tpc > WG_MAX_TAPS) tpc = WG_MAX_TAPS;
-  if (tpc > taps) tpc = taps;
-  {
-    // two smem stages of (dpre tile + tpc shifted x tiles + ones tile) must fit
-    int by_smem = ((227 * 1024 - 64 - WG_TBL_BYTES) / WG_STAGES - WG_A - 2 * WCS) / ((Cin / 8) * WCS);
-    if (tpc > by_smem) tpc = by_smem;
-  }
-  PVB_CHECK_ARG(tpc >= 1, "pvb_conv_tc_wgrad: Cin too large");
-  const int groups = (taps + tpc - 1) / tpc;
-  const int stage = WG_A + tpc * (Cin / 8) * WCS + 2 * WCS;
-  const int smem = WG_STAGES * stage + 64 + WG_TBL_BYTES;
-  PVB_CHECK_ARG((int64_t)(Cin > Cout ? Cin : Cout) * H * Wd < (1ll << 31),
-                "pvb_conv_tc_wgrad: one image's activations must have fewer than 2^31 elements");
-  PVB_CHECK_ARG(smem <= 227 * 1024, "pvb_conv_tc_wgrad: tile does not fit shared memory");
-  const int64_t M = (int64_t)B * H * Wd;
-  const int64_t n_tiles = (M + TP - 1) / TP;
-  // one CTA per SM (512 TMEM columns, ~200 KB smem): never more CTAs than SMs, or the extras
-  // run as a second wave and double the kernel time
-  int64_t splits = 148 / groups;
-  if (splits < 1) splits = 1;
+  const int pw = kw / 2, Wp = Wd + pw, adv = TP - 2 * pw;
+  const int64_t positions = (int64_t)B * H * Wp;          // W-padded pixel positions
+  PVB_CHECK_ARG(positions + TP < (1ll << 31) && (int64_t)(Cin > Cout ? Cin : Cout) * H * Wd < (1ll << 31),
+                "pvb_conv_tc_wgrad: tensor too large for 32-bit position arithmetic");
+  const int n_tiles = (int)((positions + adv - 1) / adv);
+  const int stage = WG_A + (Cin / 8) * WCS + WG_XPAD;
+  int n_stages = (227 * 1024 - 128 - WG_ONES) / stage;
+  if (n_stages > WG_MAX_STAGES) n_stages = WG_MAX_STAGES;
+  PVB_CHECK_ARG(n_stages >= 2, "pvb_conv_tc_wgrad: tile does not fit shared memory");
+  const int smem = n_stages * stage + WG_ONES + 128;
+  // one CTA per SM (512 TMEM columns): never more CTAs than SMs, or the extras run as a second wave
+  int splits = 148 / kh;
   if (splits > n_tiles) splits = n_tiles;
-  const int64_t per = (n_tiles + splits - 1) / splits;
-  splits = (n_tiles + per - 1) / per;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  static bool attr = false;
+  if (!attr) {
     cudaFuncSetAttribute(conv_tc_wgrad_kernel<BWD_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_smem = 227 * 1024;
+    attr = true;
   }
-  dim3 grid(groups, (unsigned)splits);
-  // 16-channel gather items per 128-pixel step -> producer groups (no more groups than items)
-  const int items = Cout / 16 + tpc * (Cin / 16);
-  const int ng = items < WG_MAX_GROUPS ? (items < 1 ? 1 : items) : WG_MAX_GROUPS;
+  dim3 grid(kh, (unsigned)splits);
+  // 16-channel gather items per tile -> producer groups (no more groups than items)
+  const int items = Cout / 16 + Cin / 16;
+  const int ng = items < WG_MAX_GROUPS ? items : WG_MAX_GROUPS;
   conv_tc_wgrad_kernel<BWD_BF16><<<grid, ng * 128 + 32, smem, (cudaStream_t)stream>>>(
-      dpre, x, dW, db, B, Cin_real, Cout, H, Wd, kh, kw, tpc, per);
+      dpre, x, dW, db, B, Cin_real, Cout, H, Wd, kh, kw, n_stages, n_tiles);
   pvb::count_launch();
   return pvb::launch_status();
 }

@@ -411,12 +411,15 @@ def maxpool2_fwd(x, y):
     check(_lib.lib().pvb_maxpool2_fwd(_p(x), _p(y), *_plane(x), _stream()), "pvb_maxpool2_fwd")
 
 
-def maxpool2_bwd(x, dy, dx):
+def maxpool2_bwd(x, dy, dx, act=None):
+    """act: activation whose OUTPUT is x -- its derivative is folded into dx (1-D / 2-D only)"""
     if x.dim() == 5:
         check(_lib.lib().pvb_maxpool3d_bwd(_p(x), _p(dy), _p(dx), *_vol(x), _stream()),
               "pvb_maxpool3d_bwd")
+        if act is not None:
+            act_bwd(dx, x, None, dx, act)
         return
-    check(_lib.lib().pvb_maxpool2_bwd(_p(x), _p(dy), _p(dx), *_plane(x), _stream()),
+    check(_lib.lib().pvb_maxpool2_bwd(_p(x), _p(dy), _p(dx), *_plane(x), ACT[act], _stream()),
           "pvb_maxpool2_bwd")
 
 
@@ -478,9 +481,12 @@ def conv_tc_fwd(x, W, b, act, out, ws, pre=None):
     return out
 
 
-def conv_tc_bwd_data(dpre, W, dx, ws):
-    check(_lib.lib().pvb_conv_tc_pix(_p(dpre), _p(W), None, _p(dx), None, _p(ws),
-                                     *_conv_dims(dx, W), 0, 1, _stream()), "pvb_conv_tc_pix")
+def conv_tc_bwd_data(dpre, W, dx, ws, y_below=None, act_below=None):
+    """dx = conv_transpose(dpre, W); with y_below (the output of the layer below, same shape as dx)
+    and its activation: dx *= act'(y_below), i.e. dx is that layer's dpre."""
+    check(_lib.lib().pvb_conv_tc_pix(_p(dpre), _p(W), None, _p(dx), _p(y_below), _p(ws),
+                                     *_conv_dims(dx, W), ACT[act_below if y_below is not None else None],
+                                     1, _stream()), "pvb_conv_tc_pix")
 
 
 def conv_tc_bwd_weight(dpre, x, W, dW, db):

@@ -80,8 +80,17 @@ def test_ved_full_step_matches_reference_adam(name):
     loss = tr.svi.step(x.cuda(), y.cuda(), _eps=g.eps().cuda(), **kw)
     assert abs(loss - g.loss_step) <= 1e-4 * abs(g.loss_step)
     sd = {k: v.cpu().float() for k, v in m.state_dict().items()}   # incl. batch-norm buffers
+    # Adam's first step is lr * sign(g) whatever |g|: an element whose gradient is rounding noise
+    # (a dead channel: |g| < 1e-4 of its tensor's largest entry) may legitimately step the other
+    # way, so those elements only have to stay within the two possible steps (2 lr).
+    grads = g.group("grad")
     for k, v in g.group("w1").items():
-        assert torch.allclose(sd[k], v, atol=5e-5), k
+        if k in grads:
+            solid = grads[k].abs() >= 1e-4 * grads[k].abs().max()
+            assert torch.allclose(sd[k][solid], v[solid], atol=5e-5), k
+            assert (sd[k] - v).abs().max().item() <= 2.1e-3, k
+        else:
+            assert torch.allclose(sd[k], v, atol=5e-5), k
     for k, idx in g.group("w1idx", torch.int64).items():
         assert torch.allclose(sd[k].reshape(-1)[idx], g.t("w1sub." + k), atol=5e-5), k
 
@@ -249,7 +258,8 @@ def test_tc_conv_kernels_vs_torch(shape):
     assert (db - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
 
 
-@pytest.mark.parametrize("shape", [(3, 1, 32, 16, 16, 3, 2), (2, 3, 64, 1, 40, 3, 1), (4, 5, 16, 7, 5, 1, 2)])
+@pytest.mark.parametrize("shape", [(3, 1, 32, 16, 16, 3, 2), (2, 3, 64, 1, 40, 3, 1), (4, 5, 16, 7, 5, 1, 2),
+                                   (5, 1, 48, 1, 33, 3, 1), (40, 1, 32, 64, 64, 3, 2)])
 def test_tc_weight_gradient_with_few_input_channels(shape):
     """first-layer case: Cin < 16 is zero-padded inside the tensor-core weight-gradient kernel"""
     B, Cin, Cout, H, W, k, nd = shape
@@ -262,7 +272,8 @@ def test_tc_weight_gradient_with_few_input_channels(shape):
         x = torch.randn(B, Cin, W, generator=g).cuda()
         wt = torch.randn(Cout, Cin, k, generator=g).cuda()
         conv = F.conv1d
-    assert ops.conv_tc_wgrad_supported(wt) and not ops.conv_tc_supported(wt)
+    # Cin == 1 is routed to the direct fp32 kernel (HBM-bound); the tensor-core kernel still takes it
+    assert ops.conv_tc_wgrad_supported(wt) == (Cin > 1) and not ops.conv_tc_supported(wt)
     b = torch.zeros(Cout).cuda()
     wr, br = wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
     yr = conv(x, wr, br, padding=k // 2)
@@ -272,6 +283,10 @@ def test_tc_weight_gradient_with_few_input_channels(shape):
     ops.conv_tc_bwd_weight(dy, x, wt, dW, db)
     assert (dW - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
     assert (db - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
+    dW, db = torch.ones_like(wt), torch.ones_like(b)             # fp32 kernels accumulate
+    ops.conv_bwd_weight(dy, x, wt, dW, db)
+    assert (dW - 1 - wr.grad).abs().max().item() <= 1e-4 * wr.grad.abs().max().item() + 1e-4
+    assert (db - 1 - br.grad).abs().max().item() <= 1e-4 * br.grad.abs().max().item() + 1e-4
 
 
 @pytest.mark.parametrize("shape", [(6, 8, 16, 16), (5, 16, 7, 9), (3, 4, 33), (64, 32, 32, 32), (2, 3, 1, 1)])
