@@ -16,6 +16,7 @@
 //               accumulators for a group of taps live in TMEM over the CTA's pixel range and are
 //               added to the fp32 gradient with atomics at the end.
 // Operands: fp16 (bf16 is a compile-time switch for the backward GEMMs); fp32 accumulate.
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "pvb_common.cuh"
 #include "umma.cuh"
@@ -293,6 +294,204 @@ conv_tc_pix_kernel(const float* __restrict__ src, const uint16_t* __restrict__ W
   }
   __syncthreads();
   if (warp == 4) umma::tmem_dealloc<128>(tm);
+}
+
+// ---- pixel GEMM with tap reuse ----------------------------------------------------------------------
+// Same GEMM as conv_tc_pix_kernel, but the input is gathered ONCE per 64-channel chunk instead of once
+// per tap.  Pixels are addressed in a padded position space, q = (b*Hs + h)*Wp + wp with Wp = W + kw/2
+// and Hs = H + kh/2: one zero column per row and one zero row per image, shared by the borders on
+// either side, so the neighbour (dh, dw) of ANY position is q + dh*Wp + dw.  A tile is 128 consecutive
+// positions (the padding positions compute garbage that is not stored: W/(W+1) * H/(H+1) of the MMA
+// rows are useful); the CTA stages rows q0 - halo .. q0 + 127 + halo (halo = kh/2 * Wp + kw/2) of a
+// channel chunk in the row-chunk layout, and the A operand of tap (dh, dw) is that buffer entered
+// halo + dh*Wp + dw rows further down: a 16-byte step per row in the shared-memory descriptor.
+// 8 producer / epilogue warps + 1 MMA warp; weights of (tap, chunk) stream through a 2-slot ring.
+constexpr int P2_PROD = 256;                     // producer threads
+constexpr int P2_THREADS = P2_PROD + 32;
+constexpr int P2_MAX_ROWS = 288;                 // staged rows per chunk (<= 128 + 2 * halo)
+
+struct P2Dims {
+  int B, Cg, Nout, H, W, kh, kw, sign;
+  float in_scale, out_scale;
+  int n_rows, x_stages;                          // staged rows per chunk; 1 or 2 chunk buffers
+};
+
+template <bool BF16, bool SCALED, int NCH>
+__device__ __forceinline__ void gather_cs(const float* __restrict__ p, int hw, bool ok, float scale,
+                                          uint8_t* dst, int cs) {
+  float v[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) v[j] = __ldg(p + j * hw);
+  const float f = ok ? scale : 0.f;
+#pragma unroll
+  for (int c8 = 0; c8 < NCH / 8; ++c8) {
+    float* w = v + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = SCALED ? scl(w[j], f) : w[j] * f;
+    *reinterpret_cast<uint4*>(dst + c8 * cs) =
+        make_uint4(pack2<BF16>(w[0], w[1]), pack2<BF16>(w[2], w[3]), pack2<BF16>(w[4], w[5]),
+                   pack2<BF16>(w[6], w[7]));
+  }
+}
+
+template <bool BF16, bool SCALED>
+__global__ void __launch_bounds__(P2_THREADS, 2)
+conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ Wp_,
+                    const float* __restrict__ bias, float* __restrict__ dst, float* __restrict__ pre,
+                    P2Dims d, int act) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int XCS = d.n_rows * ROWB;                 // chunk-column stride of the staged input
+  const int x_stage = 8 * XCS;
+  uint8_t* sX = smem;
+  uint8_t* sB = smem + d.x_stages * x_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * B_STAGE);
+  uint64_t* x_full = bars;          // [2] count 8 (producer warps)
+  uint64_t* x_empty = bars + 2;     // [2] tcgen05.commit
+  uint64_t* b_full = bars + 4;      // [2] count 8
+  uint64_t* b_empty = bars + 6;     // [2] tcgen05.commit
+  uint64_t* accb = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int taps = d.kh * d.kw, ph = d.kh / 2, pw = d.kw / 2;
+  const int Wp = d.W + pw, Hs = d.H + ph;
+  const int halo = ph * Wp + pw;
+  const int HW = d.H * d.W;
+  const int cchunks = (d.Cg + CC - 1) / CC;
+  const int Nout = d.Nout;
+  const int q0 = (int)blockIdx.x * TP;
+  if (warp == 8) umma::tmem_alloc<128>(tmem_slot);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(x_full + s, 8);
+      umma::mbar_init(x_empty + s, 1);
+      umma::mbar_init(b_full + s, 8);
+      umma::mbar_init(b_empty + s, 1);
+    }
+    umma::mbar_init(accb, 1);
+    umma::mbar_fence_init();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp == 8) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = idesc_16b(128, Nout, 0, 0, BF16);
+    const uint32_t x0 = umma::smem_u32(sX), b0 = umma::smem_u32(sB);
+    int i = 0;
+    for (int c = 0; c < cchunks; ++c) {
+      const int sx = c % d.x_stages;
+      umma::mbar_wait(x_full + sx, (uint32_t)((c / d.x_stages) & 1));
+      const int cc = min(CC, d.Cg - c * CC);
+      for (int t = 0; t < taps; ++t, ++i) {
+        const int sb = i & 1;
+        umma::mbar_wait(b_full + sb, (uint32_t)((i >> 1) & 1));
+        umma::fence_after_sync();
+        if (lane == 0) {
+          const int shift = halo + d.sign * ((t / d.kw - ph) * Wp + (t % d.kw - pw));
+          for (int k16 = 0; k16 < cc / 16; ++k16) {
+            uint64_t da = umma::smem_desc(x0 + sx * x_stage + shift * ROWB + k16 * 2 * XCS, XCS, 128);
+            uint64_t db = umma::smem_desc(b0 + sb * B_STAGE + k16 * 2 * (Nout * ROWB), Nout * ROWB, 128);
+            umma::mma_f16_ss(tm, da, db, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+          }
+          umma::commit(b_empty + sb);
+          if (t == taps - 1) umma::commit(x_empty + sx);
+          if (c == cchunks - 1 && t == taps - 1) umma::commit(accb);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= producers (then epilogue) =================
+    int i = 0;
+    for (int c = 0; c < cchunks; ++c) {
+      const int sx = c % d.x_stages;
+      if (c >= d.x_stages) umma::mbar_wait(x_empty + sx, (uint32_t)(((c / d.x_stages) - 1) & 1));
+      const int c0 = c * CC, cc = min(CC, d.Cg - c0);
+      // ---- stage the input rows of this chunk: row r <-> position q0 - halo + r ----
+      for (int r = tid; r < d.n_rows; r += P2_PROD) {
+        const int q = q0 - halo + r;
+        bool ok = q >= 0;
+        const unsigned ri = (unsigned)(ok ? q : 0) / (unsigned)Wp;
+        const int wp = (ok ? q : 0) - (int)ri * Wp;
+        const int b = (int)(ri / (unsigned)Hs), h = (int)ri - b * Hs;
+        ok = ok && wp < d.W && h < d.H && b < d.B;
+        const float* p = src + (ok ? ((int64_t)b * d.Cg + c0) * HW + h * d.W + wp : (int64_t)c0 * HW);
+        uint8_t* xd = sX + sx * x_stage + r * ROWB;
+        switch (cc) {   // uniform
+          case 64: gather_cs<BF16, SCALED, 64>(p, HW, ok, d.in_scale, xd, XCS); break;
+          case 48: gather_cs<BF16, SCALED, 48>(p, HW, ok, d.in_scale, xd, XCS); break;
+          case 32: gather_cs<BF16, SCALED, 32>(p, HW, ok, d.in_scale, xd, XCS); break;
+          case 16: gather_cs<BF16, SCALED, 16>(p, HW, ok, d.in_scale, xd, XCS); break;
+          default: break;
+        }
+      }
+      umma::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(x_full + sx);
+      // ---- weights of (tap, chunk): Wp[tap][n][c0 .. c0 + cc): thread -> row n, half of the chunk ----
+      const int n = tid & 127, half = tid >> 7;
+      for (int t = 0; t < taps; ++t, ++i) {
+        const int sb = i & 1;
+        if (i >= 2) umma::mbar_wait(b_empty + sb, (uint32_t)(((i >> 1) - 1) & 1));
+        if (n < Nout) {
+          const uint16_t* wrow = Wp_ + ((int64_t)t * Nout + n) * d.Cg + c0 + half * 32;
+          uint8_t* bd = sB + sb * B_STAGE + n * ROWB + half * 4 * (Nout * ROWB);
+          uint4 wq[4];
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8)
+            if (half * 32 + c8 * 8 < cc) wq[c8] = __ldg(reinterpret_cast<const uint4*>(wrow + c8 * 8));
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8)
+            if (half * 32 + c8 * 8 < cc) *reinterpret_cast<uint4*>(bd + c8 * (Nout * ROWB)) = wq[c8];
+        }
+        umma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(b_full + sb);
+      }
+    }
+    // ---- epilogue: TMEM -> bias + activation -> NCHW fp32; warps 0-3 / 4-7 split the columns ----
+    umma::mbar_wait(accb, 0);
+    umma::fence_after_sync();
+    const int q = q0 + (warp & 3) * 32 + lane;
+    const unsigned ri = (unsigned)q / (unsigned)Wp;
+    const int wp = q - (int)ri * Wp;
+    const int b = (int)(ri / (unsigned)Hs), h = (int)ri - b * Hs;
+    const bool m_ok = wp < d.W && h < d.H && b < d.B;
+    const int gr = h * d.W + wp;
+    const uint32_t tm_lane = tm + ((uint32_t)((warp & 3) * 32) << 16);
+    float* obase = dst + (int64_t)b * Nout * HW + gr;
+    float* pbase = pre ? pre + (int64_t)b * Nout * HW + gr : nullptr;
+    const int n_half = ((Nout / 16 + 1) / 2) * 16;          // columns of warps 0-3
+    const int n_lo = warp < 4 ? 0 : n_half, n_hi = warp < 4 ? n_half : Nout;
+    for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
+      float v[16];
+      umma::tmem_ld16(tm_lane + n0, v);
+      umma::tmem_ld_wait();
+      if (m_ok) {
+        if (SCALED) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= d.out_scale;
+          if (pbase) {
+            float yv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) yv[j] = __ldg(pbase + (int64_t)(n0 + j) * HW);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= pvb::act_grad(yv[j], 0.f, act);
+          }
+        } else {
+          bias_act16(v, bias, n0, d.out_scale, act, pbase, HW);
+        }
+        float* o = obase + (int64_t)n0 * HW;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j * HW] = v[j];
+      }
+    }
+    umma::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 8) umma::tmem_dealloc<128>(tm);
 }
 
 // ---- backward weight ------------------------------------------------------------------------------
@@ -578,6 +777,37 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
     cudaFuncSetAttribute(conv_tc_pix_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIX_SMEM);
     cudaFuncSetAttribute(conv_tc_pix_kernel<BWD_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIX_SMEM);
     attr = true;
+  }
+  // tap-reuse kernel whenever the staged rows (128 + 2 * halo) fit its buffers
+  const int ph2 = kh / 2, pw2 = kw / 2;
+  const int n_rows = TP + 2 * (ph2 * (Wd + pw2) + pw2);
+  const int64_t positions = (int64_t)B * (H + ph2) * (Wd + pw2);
+  static const bool use_pix2 = getenv("PVB_CONV_PIX1") == nullptr;
+  if (use_pix2 && n_rows <= P2_MAX_ROWS && positions + TP < (1ll << 31)) {
+    const int cch = (Cg + CC - 1) / CC;
+    P2Dims p2{B, Cg, Nout, H, Wd, kh, kw, mode == 0 ? 1 : -1,
+              mode == 0 ? 1.f : GRAD_SCALE, mode == 0 ? 1.f : 1.f / GRAD_SCALE, n_rows, cch > 1 ? 2 : 1};
+    const int smem2 = p2.x_stages * 8 * n_rows * ROWB + 2 * B_STAGE + 128;
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(conv_tc_pix2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+      cudaFuncSetAttribute(conv_tc_pix2_kernel<BWD_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+      attr2 = true;
+    }
+    const unsigned grid2 = (unsigned)((positions + TP - 1) / TP);
+    if (mode == 0) {
+      conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
+      pvb::count_launch();
+      conv_tc_pix2_kernel<false, false><<<grid2, P2_THREADS, smem2, st>>>(src, Wp, b, dst, pre, p2, act);
+    } else {
+      PVB_CHECK_ARG(!pre || (act != PVB_ACT_GELU), "pvb_conv_tc_pix: gelu's derivative needs the pre-activation");
+      conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
+      pvb::count_launch();
+      conv_tc_pix2_kernel<BWD_BF16, true><<<grid2, P2_THREADS, smem2, st>>>(src, Wp, nullptr, dst, pre, p2,
+                                                                           pre ? act : 0);
+    }
+    pvb::count_launch();
+    return pvb::launch_status();
   }
   TcDims d{B, Cg, Nout, H, Wd, kh, kw, mode == 0 ? 1 : -1,
            mode == 0 ? 1.f : GRAD_SCALE, mode == 0 ? 1.f : 1.f / GRAD_SCALE};
