@@ -151,9 +151,11 @@ __device__ long long g_ctrace[2][64];
 #define CTRACE(role, ev) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4) && (ev) < 64) g_ctrace[role][ev] = clock64(); } while (0)
 __device__ long long g_wtrace[2][64];
 #define WTRACE(role, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == mma_warp) && (ev) < 64) g_wtrace[role][ev] = clock64(); } while (0)
+#define PTRACE(role, ev) do { if (blockIdx.x == 300 && lane == 0 && (warp == 0 || warp == 8) && (ev) < 64) g_wtrace[role][ev] = clock64(); } while (0)
 #else
 #define CTRACE(role, ev) do {} while (0)
 #define WTRACE(role, ev) do {} while (0)
+#define PTRACE(role, ev) do {} while (0)
 #endif
 
 template <bool BF16, bool SCALED>
@@ -374,6 +376,7 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tm = *tmem_slot;
+  PTRACE(warp == 8 ? 1 : 0, 0);
 
   if (warp == 8) {
     // ================= MMA issuer =================
@@ -383,10 +386,12 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
     for (int c = 0; c < cchunks; ++c) {
       const int sx = c % d.x_stages;
       umma::mbar_wait(x_full + sx, (uint32_t)((c / d.x_stages) & 1));
+      PTRACE(1, 1);
       const int cc = min(CC, d.Cg - c * CC);
       for (int t = 0; t < taps; ++t, ++i) {
         const int sb = i & 1;
         umma::mbar_wait(b_full + sb, (uint32_t)((i >> 1) & 1));
+        PTRACE(1, 2 + 2 * i);
         umma::fence_after_sync();
         if (lane == 0) {
           const int shift = halo + d.sign * ((t / d.kw - ph) * Wp + (t % d.kw - pw));
@@ -400,6 +405,7 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
           if (c == cchunks - 1 && t == taps - 1) umma::commit(accb);
         }
         __syncwarp();
+        PTRACE(1, 3 + 2 * i);
       }
     }
   } else {
@@ -427,9 +433,11 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
           default: break;
         }
       }
+      PTRACE(0, 1);
       umma::fence_proxy_async();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(x_full + sx);
+      PTRACE(0, 2);
       // ---- weights of (tap, chunk): Wp[tap][n][c0 .. c0 + cc): thread -> row n, half of the chunk ----
       const int n = tid & 127, half = tid >> 7;
       for (int t = 0; t < taps; ++t, ++i) {
@@ -449,10 +457,12 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
         umma::fence_proxy_async();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(b_full + sb);
+        PTRACE(0, 3 + i);
       }
     }
     // ---- epilogue: TMEM -> bias + activation -> NCHW fp32; warps 0-3 / 4-7 split the columns ----
     umma::mbar_wait(accb, 0);
+    PTRACE(0, 40);
     umma::fence_after_sync();
     const int q = q0 + (warp & 3) * 32 + lane;
     const unsigned ri = (unsigned)q / (unsigned)Wp;
@@ -489,6 +499,7 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
       }
     }
     umma::fence_before_sync();
+    PTRACE(0, 41);
   }
   __syncthreads();
   if (warp == 8) umma::tmem_dealloc<128>(tm);

@@ -414,12 +414,117 @@ __global__ void colsum_kernel(const float* __restrict__ a, float* __restrict__ o
   }
 }
 
+// ---- skinny layers: N <= 8 outputs over a long K (VED's features2latent: 32768 -> 4) ----------------
+// HBM-bound (one pass over x / dx), so no tiling: dot products per row forward, a broadcast outer
+// product for dx, column-parallel sums over the rows for dW.
+constexpr int SK_MAXN = 8;
+
+__global__ void __launch_bounds__(256)
+skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                  float* __restrict__ y, float* __restrict__ pre, int N, int K, int act) {
+  __shared__ float red[8][SK_MAXN];
+  const int64_t row = blockIdx.x;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * K);
+  float acc[SK_MAXN];
+#pragma unroll
+  for (int n = 0; n < SK_MAXN; ++n) acc[n] = 0.f;
+  for (int k4 = threadIdx.x; k4 < K / 4; k4 += 256) {
+    const float4 xv = __ldg(xr + k4);
+#pragma unroll
+    for (int n = 0; n < SK_MAXN; ++n)
+      if (n < N) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * K) + k4);
+        acc[n] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[n]))));
+      }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int n = 0; n < SK_MAXN; ++n) {
+    const float v = pvb::warp_sum(acc[n]);
+    if (lane == 0) red[warp][n] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float s = b ? b[threadIdx.x] : 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    if (pre) pre[row * N + threadIdx.x] = s;
+    y[row * N + threadIdx.x] = pvb::act_fwd(s, act);
+  }
+}
+
+// dx[m][k] (+)= sum_n g[m][n] W[n][k]
+__global__ void __launch_bounds__(256)
+skinny_dx_kernel(const float* __restrict__ g, const float* __restrict__ W, float* __restrict__ dx,
+                 int64_t M, int N, int K, int accumulate) {
+  const int K4 = K / 4;
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= M * K4) return;
+  const int64_t m = idx / K4;
+  const int k4 = (int)(idx - m * K4);
+  float4 o = accumulate ? reinterpret_cast<const float4*>(dx)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int n = 0; n < SK_MAXN; ++n)
+    if (n < N) {
+      const float gv = __ldg(g + m * N + n);
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * K) + k4);
+      o.x = fmaf(gv, wv.x, o.x); o.y = fmaf(gv, wv.y, o.y);
+      o.z = fmaf(gv, wv.z, o.z); o.w = fmaf(gv, wv.w, o.w);
+    }
+  reinterpret_cast<float4*>(dx)[idx] = o;
+}
+
+// dW[n][k] += sum_m g[m][n] x[m][k]  (rows split over blockIdx.y, atomics);  db[n] += sum_m g[m][n]
+__global__ void __launch_bounds__(256)
+skinny_dw_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ dW,
+                 float* __restrict__ db, int64_t M, int N, int K, int rows_per_split) {
+  const int K4 = K / 4;
+  const int k4 = blockIdx.x * 256 + threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t m1 = m0 + rows_per_split < M ? m0 + rows_per_split : M;
+  if (db && blockIdx.x == 0 && threadIdx.x < N) {
+    float s = 0.f;
+    for (int64_t m = m0; m < m1; ++m) s += g[m * N + threadIdx.x];
+    atomicAdd(db + threadIdx.x, s);
+  }
+  if (k4 >= K4) return;
+  float4 acc[SK_MAXN];
+#pragma unroll
+  for (int n = 0; n < SK_MAXN; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t m = m0; m < m1; ++m) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + m * K) + k4);
+#pragma unroll
+    for (int n = 0; n < SK_MAXN; ++n)
+      if (n < N) {
+        const float gv = __ldg(g + m * N + n);     // warp-uniform address: one broadcast load
+        acc[n].x = fmaf(gv, xv.x, acc[n].x); acc[n].y = fmaf(gv, xv.y, acc[n].y);
+        acc[n].z = fmaf(gv, xv.z, acc[n].z); acc[n].w = fmaf(gv, xv.w, acc[n].w);
+      }
+  }
+#pragma unroll
+  for (int n = 0; n < SK_MAXN; ++n)
+    if (n < N) {
+      float* o = dW + (int64_t)n * K + (int64_t)k4 * 4;
+      atomicAdd(o, acc[n].x); atomicAdd(o + 1, acc[n].y);
+      atomicAdd(o + 2, acc[n].z); atomicAdd(o + 3, acc[n].w);
+    }
+}
+
+inline bool skinny_ok(int64_t M, int N, int K, const void* a, const void* b, const void* c) {
+  return N <= SK_MAXN && K >= 2048 && (K % 4) == 0 && M > 0 && M * (int64_t)(K / 4) < (1ll << 40) &&
+         (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+}
+
 }  // namespace
 
 extern "C" int pvb_linear_fwd(const float* x, const float* W, const float* b, float* y, float* pre,
                               int64_t M, int N, int K, int act, void* stream) {
   PVB_CHECK_ARG(x && W && y && M >= 0 && N > 0 && K > 0, "pvb_linear_fwd: bad argument");
   PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID, "pvb_linear_fwd: unknown activation %d", act);
+  if (skinny_ok(M, N, K, x, W, nullptr)) {
+    skinny_fwd_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(x, W, b, y, pre, N, K, act);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   // small batch, 16-byte aligned K-contiguous rows: pipelined single-launch kernel once a third
   // of the SMs get a tile
   if (M <= 8192 && (K % 4) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)W % 16) == 0) {
@@ -455,6 +560,27 @@ extern "C" int pvb_linear_bwd(const float* x, const float* W, const float* y, co
     int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
     act_bwd_kernel<<<blocks, 256, 0, st>>>(dy, y, pre, dpre_ws, n, act); pvb::count_launch();
     dpre = dpre_ws;
+  }
+  if (skinny_ok(M, N, K, x, W, dx) && ((uintptr_t)dW & 15) == 0) {
+    if (dx) {
+      const int64_t n4 = M * (K / 4);
+      skinny_dx_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dpre, W, dx, M, N, K, dx_accumulate);
+      pvb::count_launch();
+    }
+    if (dW) {
+      const int kblocks = (K / 4 + 255) / 256;
+      int splits = (148 * 4 + kblocks - 1) / kblocks;
+      if (splits > M) splits = (int)M;
+      const int rows = (int)((M + splits - 1) / splits);
+      dim3 grid(kblocks, (unsigned)((M + rows - 1) / rows));
+      skinny_dw_kernel<<<grid, 256, 0, st>>>(dpre, x, dW, db, M, N, K, rows);
+      pvb::count_launch();
+    } else if (db) {
+      dim3 blk(32, 32);
+      dim3 grid((N + 31) / 32, (unsigned)((M + CS_ROWS - 1) / CS_ROWS));
+      colsum_kernel<<<grid, blk, 0, st>>>(dpre, db, M, N); pvb::count_launch();
+    }
+    return pvb::launch_status();
   }
   int rc;
   if (dx) {

@@ -106,7 +106,9 @@ def test_mlp_tail_chain_wgrad_vs_torch(M, w_in, widths, hdims, act):
 
 
 @pytest.mark.parametrize("M,N,K,act", [(512, 128, 784, "tanh"), (100, 96, 260, "gelu"),
-                                       (1024, 128, 4100, None), (64, 48, 30, "relu")])
+                                       (1024, 128, 4100, None), (64, 48, 30, "relu"),
+                                       # skinny layers (N <= 8 over a long K: VED's features2latent)
+                                       (96, 4, 32768, None), (33, 7, 2052, "tanh"), (512, 2, 8192, None)])
 def test_linear_fwd_bwd_vs_torch(M, N, K, act):
     gen = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=gen).cuda()
@@ -129,6 +131,10 @@ def test_linear_fwd_bwd_vs_torch(M, N, K, act):
     assert torch.allclose(dx, xr.grad, atol=2e-4, rtol=1e-4)
     assert (dW - l.weight.grad).abs().max().item() <= 2e-4 * l.weight.grad.abs().max().item() + 1e-5
     assert torch.allclose(db, l.bias.grad, atol=5e-4, rtol=1e-4)
+    # accumulate into dx (second head sharing the input), gradients accumulate too
+    ops.linear_bwd(x, l.weight.data, y, pre, dy, ws, dx, True, dW, db, act)
+    assert torch.allclose(dx, 2 * xr.grad, atol=4e-4, rtol=1e-4)
+    assert (dW - 2 * l.weight.grad).abs().max().item() <= 4e-4 * l.weight.grad.abs().max().item() + 2e-5
 
 
 def test_reductions_adam_and_regression_terms():
