@@ -152,10 +152,13 @@ __device__ long long g_ctrace[2][64];
 __device__ long long g_wtrace[2][64];
 #define WTRACE(role, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == mma_warp) && (ev) < 64) g_wtrace[role][ev] = clock64(); } while (0)
 #define PTRACE(role, ev) do { if (blockIdx.x == 300 && lane == 0 && (warp == 0 || warp == 8) && (ev) < 64) g_wtrace[role][ev] = clock64(); } while (0)
+__device__ long long g_p3trace[3][64];
+#define P3TRACE(role, ev) do { if (blockIdx.x == 17 && lane == 0 && (ev) < 64) g_p3trace[role][ev] = clock64(); } while (0)
 #else
 #define CTRACE(role, ev) do {} while (0)
 #define WTRACE(role, ev) do {} while (0)
 #define PTRACE(role, ev) do {} while (0)
+#define P3TRACE(role, ev) do {} while (0)
 #endif
 
 template <bool BF16, bool SCALED>
@@ -505,6 +508,203 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
   if (warp == 8) umma::tmem_dealloc<128>(tm);
 }
 
+// ---- persistent pixel GEMM: weights resident, tiles pipelined -----------------------------------------
+// Same position space and tap addressing as conv_tc_pix2_kernel, for layers whose repacked weights
+// (taps x Cg x Nout fp16) fit in shared memory next to two staged input tiles.  One CTA per SM loops
+// over its tiles with three roles running concurrently on different tiles:
+//   warps 4-11  producers : gather the input rows of tile i + 1 (all channel chunks)
+//   warp  12    MMA       : taps x chunks x K-steps MMAs of tile i back to back (no per-tap hand-shake:
+//                           the weights never move), accumulator buffer i % 2 in TMEM
+//   warps 0-3   epilogue  : TMEM -> bias / activation (or activation derivative) -> NCHW of tile i - 1
+constexpr int P3_THREADS = 13 * 32;
+
+template <bool BF16, bool SCALED>
+__global__ void __launch_bounds__(P3_THREADS, 1)
+conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ Wp_,
+                    const float* __restrict__ bias, float* __restrict__ dst, float* __restrict__ pre,
+                    P2Dims d, int act, int n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int taps = d.kh * d.kw, ph = d.kh / 2, pw = d.kw / 2;
+  const int cchunks = (d.Cg + CC - 1) / CC;
+  const int Nout = d.Nout;
+  const int XCS = d.n_rows * ROWB;                 // chunk-column stride of a staged input chunk
+  const int x_chunk = 8 * XCS, x_stage = cchunks * x_chunk;
+  const int w_tile = Nout * CC * 2;                // weights of one (tap, chunk): [Nout][64] fp16
+  uint8_t* sW = smem;
+  uint8_t* sX = smem + taps * cchunks * w_tile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * x_stage);
+  uint64_t* x_full = bars;          // [2] count 8 (producer warps)
+  uint64_t* x_empty = bars + 2;     // [2] tcgen05.commit
+  uint64_t* a_full = bars + 4;      // [2] tcgen05.commit: accumulator of a tile complete
+  uint64_t* a_empty = bars + 6;     // [2] count 4 (epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Wp = d.W + pw, Hs = d.H + ph;
+  const int halo = ph * Wp + pw;
+  const int HW = d.H * d.W;
+  const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (warp == 12) umma::tmem_alloc<256>(tmem_slot);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(x_full + s, 8);
+      umma::mbar_init(x_empty + s, 1);
+      umma::mbar_init(a_full + s, 1);
+      umma::mbar_init(a_empty + s, 4);
+    }
+    umma::mbar_fence_init();
+  }
+  // resident weights: Wp_[tap][n][k] -> per (tap, chunk) a K-major row-chunk tile [Nout][64]
+  {
+    const int k8s = d.Cg / 8;                      // 16-byte pieces per weight row
+    const int total = taps * Nout * k8s;
+    for (int i = tid; i < total; i += P3_THREADS) {
+      const int k8 = i % k8s, n = (i / k8s) % Nout, t = i / (k8s * Nout);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(Wp_ + ((int64_t)t * Nout + n) * d.Cg) + k8);
+      const int c = k8 / 8, c8 = k8 % 8;
+      *reinterpret_cast<uint4*>(sW + (t * cchunks + c) * w_tile + c8 * (Nout * ROWB) + n * ROWB) = v;
+    }
+    umma::fence_proxy_async();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp == 12) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = idesc_16b(128, Nout, 0, 0, BF16);
+    const uint64_t da_base = umma::smem_desc(umma::smem_u32(sX), XCS, 128);
+    const uint64_t db_base = umma::smem_desc(umma::smem_u32(sW), Nout * ROWB, 128);
+    const uint64_t da_kstep = (uint64_t)((2 * XCS) >> 4), db_kstep = (uint64_t)((2 * Nout * ROWB) >> 4);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it & 1;
+      P3TRACE(1, 3 * it);
+      umma::mbar_wait(x_full + s, (uint32_t)((it >> 1) & 1));
+      if (it >= 2) umma::mbar_wait(a_empty + s, (uint32_t)(((it >> 1) - 1) & 1));
+      P3TRACE(1, 3 * it + 1);
+      umma::fence_after_sync();
+      if (lane == 0) {
+        // descriptors advance by plain additions on their start-address field (16-byte units): the
+        // issuing thread is a single dependent instruction stream, so divisions / descriptor
+        // re-encoding per MMA cost more than the MMA itself (measured 183 vs 49 cycles per MMA)
+        uint32_t first = 0u;
+        const uint64_t xa0 = da_base + (uint64_t)((s * x_stage) >> 4);
+        for (int c = 0; c < cchunks; ++c) {
+          const int ksteps = min(CC, d.Cg - c * CC) / 16;
+          int t = 0;
+          for (int th = 0; th < d.kh; ++th) {
+            const int row_shift = halo + d.sign * (th - ph) * Wp - d.sign * pw;
+            for (int tw = 0; tw < d.kw; ++tw, ++t) {
+              uint64_t da = xa0 + (uint64_t)((c * x_chunk + (row_shift + d.sign * tw) * ROWB) >> 4);
+              uint64_t db = db_base + (uint64_t)(((t * cchunks + c) * w_tile) >> 4);
+              // all descriptors of the tap first, then the MMAs back to back: the register ->
+              // uniform-register moves of the operands overlap instead of serialising per MMA
+              uint64_t das[4], dbs[4];
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16) {
+                das[k16] = da + (uint64_t)k16 * da_kstep;
+                dbs[k16] = db + (uint64_t)k16 * db_kstep;
+              }
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16)
+                if (k16 < ksteps) {
+                  umma::mma_f16_ss(tm + s * 128, das[k16], dbs[k16], idesc, first);
+                  first = 1u;
+                }
+            }
+          }
+        }
+        umma::commit(x_empty + s);
+        umma::commit(a_full + s);
+      }
+      __syncwarp();
+      P3TRACE(1, 3 * it + 2);
+    }
+  } else if (warp >= 4) {
+    // ================= producers =================
+    const int ptid = tid - 128;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it & 1;
+      if (warp == 4) P3TRACE(0, 3 * it);
+      if (it >= 2) umma::mbar_wait(x_empty + s, (uint32_t)(((it >> 1) - 1) & 1));
+      if (warp == 4) P3TRACE(0, 3 * it + 1);
+      const int q0 = ((int)blockIdx.x + it * (int)gridDim.x) * TP;
+      for (int r = ptid; r < d.n_rows; r += 256) {
+        const int q = q0 - halo + r;
+        bool ok = q >= 0;
+        const unsigned ri = (unsigned)(ok ? q : 0) / (unsigned)Wp;
+        const int wp = (ok ? q : 0) - (int)ri * Wp;
+        const int b = (int)(ri / (unsigned)Hs), h = (int)ri - b * Hs;
+        ok = ok && wp < d.W && h < d.H && b < d.B;
+        const float* p = src + (ok ? (int64_t)b * d.Cg * HW + h * d.W + wp : 0);
+        uint8_t* xd = sX + s * x_stage + r * ROWB;
+        for (int c = 0; c < cchunks; ++c) {
+          const int cc = min(CC, d.Cg - c * CC);
+          const float* pc = p + (int64_t)c * CC * HW;
+          switch (cc) {   // uniform
+            case 64: gather_cs<BF16, SCALED, 64>(pc, HW, ok, d.in_scale, xd + c * x_chunk, XCS); break;
+            case 48: gather_cs<BF16, SCALED, 48>(pc, HW, ok, d.in_scale, xd + c * x_chunk, XCS); break;
+            case 32: gather_cs<BF16, SCALED, 32>(pc, HW, ok, d.in_scale, xd + c * x_chunk, XCS); break;
+            case 16: gather_cs<BF16, SCALED, 16>(pc, HW, ok, d.in_scale, xd + c * x_chunk, XCS); break;
+            default: break;
+          }
+        }
+      }
+      umma::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(x_full + s);
+      if (warp == 4) P3TRACE(0, 3 * it + 2);
+    }
+  } else {
+    // ================= epilogue =================
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it & 1;
+      if (warp == 0) P3TRACE(2, 3 * it);
+      umma::mbar_wait(a_full + s, (uint32_t)((it >> 1) & 1));
+      if (warp == 0) P3TRACE(2, 3 * it + 1);
+      umma::fence_after_sync();
+      const int q = ((int)blockIdx.x + it * (int)gridDim.x) * TP + warp * 32 + lane;
+      const unsigned ri = (unsigned)q / (unsigned)Wp;
+      const int wp = q - (int)ri * Wp;
+      const int b = (int)(ri / (unsigned)Hs), h = (int)ri - b * Hs;
+      const bool m_ok = wp < d.W && h < d.H && b < d.B;
+      const int gr = h * d.W + wp;
+      const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * 128);
+      float* obase = dst + (int64_t)b * Nout * HW + gr;
+      float* pbase = pre ? pre + (int64_t)b * Nout * HW + gr : nullptr;
+      for (int n0 = 0; n0 < Nout; n0 += 16) {
+        float v[16];
+        umma::tmem_ld16(tm_lane + n0, v);
+        umma::tmem_ld_wait();
+        if (m_ok) {
+          if (SCALED) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= d.out_scale;
+            if (pbase) {
+              float yv[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) yv[j] = __ldg(pbase + (int64_t)(n0 + j) * HW);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= pvb::act_grad(yv[j], 0.f, act);
+            }
+          } else {
+            bias_act16(v, bias, n0, d.out_scale, act, pbase, HW);
+          }
+          float* o = obase + (int64_t)n0 * HW;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j * HW] = v[j];
+        }
+      }
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(a_empty + s);
+      if (warp == 0) P3TRACE(2, 3 * it + 2);
+    }
+  }
+  __syncthreads();
+  if (warp == 12) umma::tmem_dealloc<256>(tm);
+}
+
 // ---- backward weight ------------------------------------------------------------------------------
 // dW[co][ci][dh][dw] = sum over pixels of dpre[co][h][w] x[ci][h+dh][w+dw] as GEMMs with K = pixels:
 // accumulators [128 lanes = co][kw x Cin columns] in TMEM, both operands MN-major (K = tile rows,
@@ -806,6 +1006,31 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
       attr2 = true;
     }
     const unsigned grid2 = (unsigned)((positions + TP - 1) / TP);
+    // persistent variant when all repacked weights + two staged input tiles fit one CTA's shared memory
+    const int64_t smem3 = (int64_t)taps * cch * Nout * CC * 2 + 2ll * cch * 8 * n_rows * ROWB + 128;
+    static const bool use_pix3 = getenv("PVB_CONV_PIX2") == nullptr;
+    if (use_pix3 && smem3 <= 227 * 1024 && Cg % 8 == 0 && grid2 >= 148) {
+      static bool attr3 = false;
+      if (!attr3) {
+        cudaFuncSetAttribute(conv_tc_pix3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_pix3_kernel<BWD_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr3 = true;
+      }
+      if (mode == 0) {
+        conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
+        pvb::count_launch();
+        conv_tc_pix3_kernel<false, false><<<148, P3_THREADS, (size_t)smem3, st>>>(src, Wp, b, dst, pre, p2, act,
+                                                                              (int)grid2);
+      } else {
+        PVB_CHECK_ARG(!pre || (act != PVB_ACT_GELU), "pvb_conv_tc_pix: gelu's derivative needs the pre-activation");
+        conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
+        pvb::count_launch();
+        conv_tc_pix3_kernel<BWD_BF16, true><<<148, P3_THREADS, (size_t)smem3, st>>>(src, Wp, nullptr, dst, pre, p2,
+                                                                                pre ? act : 0, (int)grid2);
+      }
+      pvb::count_launch();
+      return pvb::launch_status();
+    }
     if (mode == 0) {
       conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
       pvb::count_launch();
@@ -877,6 +1102,9 @@ extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, f
 }
 
 #ifdef PVB_TC_TRACE
+extern "C" int pvb_pix3_trace_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_p3trace, sizeof(long long) * 3 * 64);
+}
 extern "C" int pvb_wgrad_trace_read(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_wtrace, sizeof(long long) * 2 * 64);
 }

@@ -225,8 +225,17 @@ def test_pool_and_upsample_kernels_vs_torch(shape):
     (4, 128, 64, 1, 32, 3, 1),     # 1-D
     (3, 64, 64, 1, 20, 1, 1),      # 1x1
     (2, 16, 48, 6, 6, 3, 2),       # small channel counts
+    # >= 148 tiles with weights that fit shared memory: the persistent kernel (conv_tc_pix3_kernel)
+    (20, 64, 64, 32, 32, 3, 2),    # one channel chunk, 171 tiles, ragged last tile
+    (24, 32, 64, 31, 33, 3, 2),    # 32-channel chunk forward, 64 -> 32 backward; odd sizes
+    (160, 128, 128, 1, 128, 3, 1),  # 1-D, two channel chunks
+    (72, 64, 128, 16, 16, 3, 2),   # 128 outputs forward / two chunks backward
+    (150, 48, 16, 1, 130, 1, 1),   # 1x1, 48-channel chunk
 ])
 def test_tc_conv_kernels_vs_torch(shape):
+    """the three pixel-GEMM kernels (per-tap gather for wide images, tap reuse per tile, persistent
+    with resident weights) share this test: the host picks by image width, tile count and weight size;
+    the fused activation derivative of the backward-data epilogue is checked against a separate pass"""
     B, Cin, Cout, H, W, k, nd = shape
     g = torch.Generator().manual_seed(sum(shape))
     if nd == 2:
@@ -252,6 +261,12 @@ def test_tc_conv_kernels_vs_torch(shape):
     dx = torch.empty_like(x)
     ops.conv_tc_bwd_data(dpre, wt, dx, ws)
     assert (dx - xr.grad).abs().max().item() <= 4e-3 * xr.grad.abs().max().item()
+    # fused: dx * tanh'(y_below) in the epilogue == separate activation-derivative pass
+    y_below = torch.tanh(torch.randn(x.shape, generator=g)).cuda()
+    dx_f = torch.empty_like(x)
+    ops.conv_tc_bwd_data(dpre, wt, dx_f, ws, y_below, "tanh")
+    ref_f = dx * (1 - y_below * y_below)
+    assert (dx_f - ref_f).abs().max().item() <= 1e-5 * ref_f.abs().max().item() + 1e-7
     dW, db = torch.zeros_like(wt), torch.zeros_like(b)
     ops.conv_tc_bwd_weight(dpre, x, wt, dW, db)
     assert (dW - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()

@@ -28,8 +28,18 @@ buf = (C.c_longlong * 128)()
 h.pvb_wgrad_trace_read(buf)
 v = list(buf)
 prod, mma = v[:64], v[64:]
-t0 = min(t for t in prod + mma if t > 0)
-print("producer warp 0: [0]=start [1]=gather done [2]=x arrived [3+i]=weights of tap i stored [40]=acc ready [41]=end")
-print({i: t - t0 for i, t in enumerate(prod) if t > 0})
-print("mma warp: [0]=start [1]=x ready [2+2i]=weights i ready [3+2i]=tap i issued")
-print({i: t - t0 for i, t in enumerate(mma) if t > 0})
+if any(t > 0 for t in prod + mma):      # the per-tile kernel (conv_tc_pix2_kernel) ran
+    t0 = min(t for t in prod + mma if t > 0)
+    print("producer warp 0: [0]=start [1]=gather done [2]=x arrived [3+i]=weights of tap i stored [40]=acc ready [41]=end")
+    print({i: t - t0 for i, t in enumerate(prod) if t > 0})
+    print("mma warp: [0]=start [1]=x ready [2+2i]=weights i ready [3+2i]=tap i issued")
+    print({i: t - t0 for i, t in enumerate(mma) if t > 0})
+
+if hasattr(h, "pvb_pix3_trace_read"):
+    buf3 = (C.c_longlong * 192)()
+    h.pvb_pix3_trace_read(buf3)
+    v3 = list(buf3)
+    if any(v3):
+        t0 = min(t for t in v3 if t > 0)
+        for name, arr in (("producer", v3[:64]), ("mma", v3[64:128]), ("epilogue", v3[128:])):
+            print("pix3", name, "(per tile: start / after wait / done):", [t - t0 for t in arr[:24] if t > 0])
