@@ -786,7 +786,12 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
   if (warp == mma_warp) {
     const uint32_t id_w = idesc_16b(128, Cin, 1, 1, BF16);
     const uint32_t id_b = idesc_16b(128, 16, 1, 1, BF16);
-    const uint32_t ones_a = umma::smem_u32(ones);
+    // descriptors are advanced by additions on their start-address field (16-byte units): the issuing
+    // thread is one dependent instruction stream, re-encoding a descriptor per MMA costs more than the MMA
+    const uint64_t da0 = umma::smem_desc(umma::smem_u32(smem), 128, WCS);              // dpre tile, stage 0
+    const uint64_t dx0 = umma::smem_desc(umma::smem_u32(smem) + WG_A, 128, WCS);       // x tile, stage 0
+    const uint64_t do0 = umma::smem_desc(umma::smem_u32(ones), 128, WCS);
+    const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % n_stages;
       WTRACE(1, 3 * it);
@@ -794,17 +799,20 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       WTRACE(1, 3 * it + 1);
       umma::fence_after_sync();
       if (lane == 0) {
-        const uint32_t base = umma::smem_u32(smem + s * stage_bytes);
-        for (int j = 0; j < kw; ++j)       // tap (dh, j - pw): X shifted by j rows
-          for (int k = 0; k < 8; ++k)      // 8 K-steps of 16 tile rows
-            umma::mma_f16_ss(tm + j * Cin, umma::smem_desc(base + k * 256, 128, WCS),
-                             umma::smem_desc(base + WG_A + j * ROWB + k * 256, 128, WCS), id_w,
-                             (it > 0 || k > 0) ? 1u : 0u);
-        if (do_bias)
+        const uint64_t da = da0 + (uint64_t)s * stage_step, dx = dx0 + (uint64_t)s * stage_step;
+        const uint32_t acc = it > 0 ? 1u : 0u;
+        for (int j = 0; j < kw; ++j) {     // tap (dh, j - pw): X shifted by j rows (16 bytes each)
+          const uint32_t tmj = tm + j * Cin;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // 8 K-steps of 16 tile rows (256 bytes)
+            umma::mma_f16_ss(tmj, da + (uint64_t)(k * 16), dx + (uint64_t)(j + k * 16), id_w, k > 0 ? 1u : acc);
+        }
+        if (do_bias) {
+#pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma::mma_f16_ss(tm + col_bias, umma::smem_desc(base + k * 256, 128, WCS),
-                             umma::smem_desc(ones_a + k * 256, 128, WCS), id_b,
-                             (it > 0 || k > 0) ? 1u : 0u);
+            umma::mma_f16_ss(tm + col_bias, da + (uint64_t)(k * 16), do0 + (uint64_t)(k * 16), id_b,
+                             k > 0 ? 1u : acc);
+        }
         umma::commit(empty + s);
         if (it == my_tiles - 1) umma::commit(accb);
       }
