@@ -328,6 +328,7 @@ int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* own_g, int64_t 
                             const void* peer_g, const void* peer_flags, int32_t* state,
                             int rank, int world, float lr, float beta1, float beta2,
                             float eps, int32_t* step_counter, const int32_t* first_step,
+                            float* loss_ring /* as pvb_adam_flat_step; may be NULL */,
                             void* stream);
 
 /* ---- nn.BatchNorm{1,2}d of the convolutional nets (csrc/pvb_norm.cu; reference
@@ -392,11 +393,15 @@ int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
                   void* stream);
 /* Same update with the step increment folded in: every element uses
  * t = *step_counter + 1 (- first_step[i]); the last CTA to finish stores
- * *step_counter += 1 (ticket must point to a zeroed int32 owned by the caller). */
+ * *step_counter += 1 (ticket must point to a zeroed int32 owned by the caller).
+ * loss_ring (optional): 4 floats of device-accessible memory, normally MAPPED PINNED HOST
+ * memory; slot (new step count & 3) receives *loss_src, i.e. the step's result reaches the
+ * host without a separate copy. */
 int pvb_adam_flat_step(float* p, const float* g, float* m, float* v, int64_t n,
                        float lr, float beta1, float beta2, float eps,
                        int32_t* step_counter, const int32_t* first_step,
-                       int32_t* ticket, void* stream);
+                       int32_t* ticket, const float* loss_src, float* loss_ring,
+                       void* stream);
 
 /* ---- spatial decoder, fused tcgen05 path (Hd = 128, two tanh layers) ----
  * One persistent kernel per step: grid -> h0 -> (128x128 tcgen05 GEMM + tanh)

@@ -86,7 +86,7 @@ SIGNATURES = {
     "pvb_reduce_partials": [_f, _f, _i32, _i64, _i64, _i32, _st],
     "pvb_counter_add": [_f, _i32, _st],
     "pvb_adam_flat": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _f, _st],
-    "pvb_adam_flat_step": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _f, _f, _st],
+    "pvb_adam_flat_step": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _f, _f, _f, _f, _st],
     "pvb_mlp_tail_fwd": [C.POINTER(MlpTailArgs), _st],
     "pvb_mlp_chain_bwd": [C.POINTER(MlpChainArgs), _st],
     "pvb_mlp_wgrad": [C.POINTER(WgradProblem), _i32, _i64, _st],
@@ -106,7 +106,7 @@ SIGNATURES = {
     "pvb_upsample3d_bwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_peer_flag_words": [],
     "pvb_peer_allreduce_adam": [_f, _f, _f, _f, _i64, _f, _f, _f, _i32, _i32, _fl, _fl, _fl, _fl,
-                                _f, _f, _st],
+                                _f, _f, _f, _st],
     "pvb_bn_workspace_bytes": [_i32],
     "pvb_bn_fwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _fl, _fl, _i32, _st],
     "pvb_bn_bwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _st],

@@ -106,7 +106,7 @@ __global__ void adam_flat_step_kernel(float* __restrict__ p, const float* __rest
                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
                                       float lr, float b1, float b2, float eps,
                                       int32_t* step_counter, const int32_t* __restrict__ first_step,
-                                      int32_t* ticket) {
+                                      int32_t* ticket, const float* loss_src, float* loss_ring) {
   const int step = *reinterpret_cast<volatile int32_t*>(step_counter) + 1;
   adam_update4(p, g, m, v, n, lr, b1, b2, eps, step, first_step);
   __syncthreads();
@@ -114,6 +114,8 @@ __global__ void adam_flat_step_kernel(float* __restrict__ p, const float* __rest
     __threadfence();
     int t = atomicAdd(ticket, 1);
     if (t == (int)gridDim.x - 1) {
+      // the step's loss goes straight to (mapped, pinned) host memory: slot = step & 3
+      if (loss_ring) loss_ring[step & 3] = *loss_src;
       *step_counter = step;
       *ticket = 0;
     }
@@ -136,14 +138,17 @@ extern "C" int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64
 
 extern "C" int pvb_adam_flat_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                                   float beta1, float beta2, float eps, int32_t* step_counter,
-                                  const int32_t* first_step, int32_t* ticket, void* stream) {
+                                  const int32_t* first_step, int32_t* ticket, const float* loss_src,
+                                  float* loss_ring, void* stream) {
   PVB_CHECK_ARG(p && g && m && v && step_counter && ticket && n >= 0, "pvb_adam_flat_step: bad argument");
+  PVB_CHECK_ARG(!loss_ring || loss_src, "pvb_adam_flat_step: loss_ring needs loss_src");
   PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                     ((uintptr_t)v % 16 == 0),
                 "pvb_adam_flat_step: buffers must be 16-byte aligned");
   if (n == 0) return 0;   // (the counter is not advanced for an empty parameter set)
   int64_t n4 = (n + 3) / 4;
   adam_flat_step_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, step_counter, first_step, ticket); pvb::count_launch();
+      p, g, m, v, n, lr, beta1, beta2, eps, step_counter, first_step, ticket, loss_src, loss_ring);
+  pvb::count_launch();
   return pvb::launch_status();
 }

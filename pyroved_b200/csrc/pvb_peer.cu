@@ -48,7 +48,7 @@ peer_allreduce_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* 
                            float* own_g, int64_t n, const float* const* __restrict__ peer_g,
                            uint32_t* const* __restrict__ peer_flags, int32_t* state, int rank, int world,
                            float lr, float b1, float b2, float eps, int32_t* step_counter,
-                           const int32_t* __restrict__ first_step) {
+                           const int32_t* __restrict__ first_step, float* loss_ring) {
   __shared__ const float* gp[MAX_WORLD];
   __shared__ int s_last;
   const uint32_t e = (uint32_t)(*reinterpret_cast<volatile int32_t*>(state)) + 1u;
@@ -113,7 +113,9 @@ peer_allreduce_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* 
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    own_g[n] = __int_as_float(*reinterpret_cast<volatile int32_t*>(state + 2));   // global loss
+    const float L = __int_as_float(*reinterpret_cast<volatile int32_t*>(state + 2));
+    own_g[n] = L;                                   // global loss
+    if (loss_ring) loss_ring[step & 3] = L;         // ... and straight to mapped host memory
     *step_counter = step;
     state[1] = 0;
     state[0] = (int32_t)e;
@@ -127,7 +129,8 @@ extern "C" int pvb_peer_flag_words(void) { return 2 * MAX_WORLD; }
 extern "C" int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* own_g, int64_t n,
                                        const void* peer_g, const void* peer_flags, int32_t* state,
                                        int rank, int world, float lr, float beta1, float beta2, float eps,
-                                       int32_t* step_counter, const int32_t* first_step, void* stream) {
+                                       int32_t* step_counter, const int32_t* first_step, float* loss_ring,
+                                       void* stream) {
   PVB_CHECK_ARG(p && m && v && own_g && peer_g && peer_flags && state && step_counter,
                 "pvb_peer_allreduce_adam: null pointer");
   PVB_CHECK_ARG(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world,
@@ -142,7 +145,7 @@ extern "C" int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* own_
   peer_allreduce_adam_kernel<<<(unsigned)blocks, NT, 0, (cudaStream_t)stream>>>(
       p, m, v, own_g, n, reinterpret_cast<const float* const*>(peer_g),
       reinterpret_cast<uint32_t* const*>(peer_flags), state, rank, world, lr, beta1, beta2, eps,
-      step_counter, first_step);
+      step_counter, first_step, loss_ring);
   pvb::count_launch();
   return pvb::launch_status();
 }

@@ -1006,6 +1006,9 @@ class SVIEngine:
                                if parallel.peer_exchange_enabled() else None)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.adam_ticket = torch.zeros(1, device=self.device, dtype=torch.int32)
+        # pinned host ring the optimizer kernel writes each step's loss into (slot = step count & 3):
+        # the step's result reaches the host without a copy call
+        self.loss_ring = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.updates_done = 0     # host mirror of step_counter
         self.programs = {}
         self.graphs = {}
@@ -1046,7 +1049,7 @@ class SVIEngine:
         flat, pe = self.flat, self.peer
         ops.peer_allreduce_adam(flat.p, flat.m, flat.v, flat.g, flat.total, pe.peer_g, pe.peer_flags,
                                 pe.state, pe.rank, pe.world, self.lr, self.step_counter,
-                                flat.first_step)
+                                flat.first_step, loss_ring=self.loss_ring)
 
     def eps_first_index(self, n_local):
         """Global index of this rank's first noise element: the noise of a
@@ -1105,7 +1108,8 @@ class SVIEngine:
     def _update(self):
         flat = self.flat
         ops.adam_flat_step(flat.p, flat.g, flat.m, flat.v, flat.total, self.lr, self.step_counter,
-                           self.adam_ticket, flat.first_step)
+                           self.adam_ticket, flat.first_step, loss_src=flat.loss,
+                           loss_ring=self.loss_ring)
 
     def _allreduce(self):
         parallel.allreduce_sum_(self.flat.g, self.process_group)
@@ -1152,10 +1156,14 @@ class SVIEngine:
         y = args[1] if len(args) > 1 else None
         eps = kwargs.pop("_eps", None)
         sync = kwargs.pop("_sync", True)
+        # _static: x / y live in buffers whose addresses recur (the trainer's staging slots), so the
+        # copy into the program's input buffers is captured in the step's graph (keyed by address)
+        static = kwargs.pop("_static", False) and self.use_graphs
         beta = self.model._beta(kwargs) if mode == "main" else self.model._aux_scale(kwargs)
         B = x.shape[0]
         prog = self._program(B, y is not None, mode)
-        prog.load(x, y)
+        if not static:
+            prog.load(x, y)
         if eps is not None and mode == "main":
             prog.set_eps(eps)
         gen_eps = eps is None
@@ -1165,19 +1173,29 @@ class SVIEngine:
             self.updates_done += 1
         bkey = tuple(beta) if isinstance(beta, (list, tuple)) else float(beta)
         key = (B, y is not None, mode, bkey, train, gen_eps, update)
+        if static:
+            key += (x.data_ptr(), y.data_ptr() if y is not None else 0)
         if self.world_size > 1 and train and update and self.peer is not None:
             # gradients -> fused NVLink all-reduce + Adam: ONE captured graph, no NCCL call
             def whole():
+                if static:
+                    prog.load(x, y)
                 self._run(prog, beta, True, gen_eps, False)
                 self._update_exchange()
             self._execute(key + ("peer",), whole)
         elif self.world_size > 1 and train:
+            if static:
+                prog.load(x, y)
             self._execute(key + ("grads",), lambda: self._run(prog, beta, True, gen_eps, False))
             self._allreduce()
             if update:
                 self._execute(("update",), self._update)
         else:
-            self._execute(key, lambda: self._run(prog, beta, train, gen_eps, update))
+            def single():
+                if static:
+                    prog.load(x, y)
+                self._run(prog, beta, train, gen_eps, update)
+            self._execute(key, single)
         self.last_loss_const = prog.loss_const * self.world_size
         if not sync:
             return self.flat.loss     # device scalar, no host synchronisation

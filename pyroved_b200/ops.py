@@ -187,23 +187,34 @@ def sdec_tc_gather_gUv(gUv_part, gUv, I, N):
           "pvb_sdec_tc_gather_gUv")
 
 
+def _host_ptr(t):
+    """device-visible address of a pinned host tensor (unified addressing), None -> NULL"""
+    if t is None:
+        return None
+    if not t.is_pinned():
+        raise _lib.PvbError("loss ring must be pinned host memory")
+    return t.data_ptr()
+
+
 def adam_flat_step(p, g, m, v, n, lr, step_counter, ticket, first_step=None, beta1=0.9, beta2=0.999,
-                   eps=1e-8):
-    """Adam update + step-counter increment in one launch."""
+                   eps=1e-8, loss_src=None, loss_ring=None):
+    """Adam update + step-counter increment in one launch; with loss_ring (4 pinned host floats) the
+    loss in loss_src is also written to ring slot (new step count & 3)."""
     check(_lib.lib().pvb_adam_flat_step(_p(p), _p(g), _p(m), _p(v), n, float(lr), beta1, beta2, eps,
-                                        _p(step_counter), _p(first_step), _p(ticket), _stream()),
+                                        _p(step_counter), _p(first_step), _p(ticket), _p(loss_src),
+                                        _host_ptr(loss_ring), _stream()),
           "pvb_adam_flat_step")
 
 
 def peer_allreduce_adam(p, m, v, own_g, n, peer_g, peer_flags, state, rank, world, lr, step_counter,
-                        first_step=None, beta1=0.9, beta2=0.999, eps=1e-8):
+                        first_step=None, beta1=0.9, beta2=0.999, eps=1e-8, loss_ring=None):
     """All-reduce(SUM) of every rank's [n gradients | loss] buffer over NVLink peer memory fused
     with the Adam update (csrc/pvb_peer.cu).  peer_g / peer_flags: int64 device tensors holding
     the peer pointers."""
     check(_lib.lib().pvb_peer_allreduce_adam(
         _p(p), _p(m), _p(v), _p(own_g), n, peer_g.data_ptr(), peer_flags.data_ptr(), _p(state),
         int(rank), int(world), float(lr), beta1, beta2, eps, _p(step_counter), _p(first_step),
-        _stream()), "pvb_peer_allreduce_adam")
+        _host_ptr(loss_ring), _stream()), "pvb_peer_allreduce_adam")
 
 
 def peer_flag_words():

@@ -53,7 +53,6 @@ class SVItrainer:
             self._copy_stream = torch.cuda.Stream(dev)
             self._stage = {}
             self._stage_free = [None, None]
-            self._loss_ring = torch.zeros(4, dtype=torch.float32).pin_memory()
         cs = self._copy_stream
 
         def upload(data, slot):
@@ -83,24 +82,23 @@ class SVItrainer:
             nxt = next(it, None)
             staged = upload(nxt, (i + 1) % 2) if nxt is not None else None
             main.wait_event(ev)
-            eng.step(*bufs, _sync=False, **kwargs)
+            # the staging slot's address recurs: its copy into the program input is part of the
+            # step's CUDA graph; the optimizer kernel writes the loss into eng.loss_ring (pinned
+            # host memory, slot = optimizer step count & 3) -- no copy call on either side
+            eng.step(*bufs, _sync=False, _static=True, **kwargs)
             free = torch.cuda.Event()
             free.record(main)
             self._stage_free[i % 2] = free
             if len(pending) >= 3:                       # ring slot about to be reused
                 k, e, c = pending.popleft()
                 e.synchronize()
-                epoch_loss += float(self._loss_ring[k]) + c
-            k = i % 4
-            self._loss_ring[k:k + 1].copy_(eng.flat.loss, non_blocking=True)
-            e = torch.cuda.Event()
-            e.record(main)
-            pending.append((k, e, eng.last_loss_const))
+                epoch_loss += float(eng.loss_ring[k]) + c
+            pending.append((eng.updates_done & 3, free, eng.last_loss_const))
             i += 1
         while pending:
             k, e, c = pending.popleft()
             e.synchronize()
-            epoch_loss += float(self._loss_ring[k]) + c
+            epoch_loss += float(eng.loss_ring[k]) + c
         return epoch_loss / len(train_loader.dataset)
 
     def evaluate(self, test_loader, **kwargs) -> float:
