@@ -199,3 +199,26 @@ def test_fused_decoder_small_images_many_slots_per_tile(dim, inv, B):
     assert abs(loss - float(ref["loss"])) <= LOSS_RTOL * abs(float(ref["loss"]))
     assert (prog.loc.cpu().reshape(B, -1) - ref["loc"]).abs().max().item() <= LOC_ATOL
     grad_check(m, grads, 2e-2)
+
+
+def test_epoch_loop_equals_step_by_step():
+    """SVItrainer.train (pipelined: staging-slot copies inside the step graphs, losses delivered through
+    the pinned host ring) == the same batches fed one by one through svi.step: same epoch loss, same
+    weights (to 1e-6).  5 batches of 512 + a ragged batch of 256: the 4-slot ring wraps and a second
+    program / graph pair serves the last batch; two epochs so every graph is replayed.  (Batches this
+    size run the fixed-order kernels throughout; tiny batches take the split-K GEMM whose atomics make
+    the last bit of the encoder output run-dependent, which Adam's g / sqrt(v) turns into lr-sized
+    differences on weights whose gradient is rounding noise.)"""
+    gen = torch.Generator().manual_seed(9)
+    x = (torch.rand(5 * 512 + 256, 28, 28, generator=gen) < 0.25).float()
+    loader = pv.utils.init_dataloader(x, batch_size=512, shuffle=False)
+    ma = pv.models.iVAE((28, 28), 2, ['r', 't'], seed=1, device="cuda:0")
+    ta = pv.trainers.SVItrainer(ma, seed=1, device="cuda:0")
+    mb = pv.models.iVAE((28, 28), 2, ['r', 't'], seed=1, device="cuda:0")
+    tb = pv.trainers.SVItrainer(mb, seed=1, device="cuda:0")
+    for epoch in range(2):
+        got = ta.train(loader) * len(loader.dataset)
+        ref = sum(tb.svi.step(xb.cuda()) for (xb,) in loader)
+        assert abs(got - ref) <= 1e-6 * abs(ref), (epoch, got, ref)
+    for (k, a), (_, b) in zip(ma.state_dict().items(), mb.state_dict().items()):
+        assert torch.allclose(a, b, atol=1e-6, rtol=0), (k, (a - b).abs().max().item())
