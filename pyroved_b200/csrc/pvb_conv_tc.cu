@@ -518,6 +518,33 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
 //   warps 0-3   epilogue  : TMEM -> bias / activation (or activation derivative) -> NCHW of tile i - 1
 constexpr int P3_THREADS = 13 * 32;
 
+// MMAs of one tile, issued by one thread: kernel shape compile-time so the tap / K-step loops unroll and
+// every descriptor is one 64-bit add away from a register-resident base (the issuing thread is a single
+// dependent instruction stream: its instruction count per MMA bounds the tile rate)
+template <int KH, int KW>
+__device__ __forceinline__ void issue_tile(uint32_t tacc, uint64_t xa0, uint64_t db_base, const uint32_t (&toff)[9],
+                                           int cchunks, int Cg, int x_chunk, int w_tile, uint64_t da_kstep,
+                                           uint64_t db_kstep, uint32_t idesc) {
+  uint32_t first = 0u;
+  for (int c = 0; c < cchunks; ++c) {
+    const int ksteps = min(CC, Cg - c * CC) / 16;
+    const uint64_t xc = xa0 + (uint64_t)((c * x_chunk) >> 4);
+    const uint64_t wc = db_base + (uint64_t)((c * w_tile) >> 4);
+    const uint64_t w_tap = (uint64_t)((cchunks * w_tile) >> 4);
+#pragma unroll
+    for (int t = 0; t < KH * KW; ++t) {
+      const uint64_t da = xc + (uint64_t)toff[t];
+      const uint64_t db = wc + (uint64_t)t * w_tap;
+#pragma unroll
+      for (int k16 = 0; k16 < 4; ++k16)
+        if (k16 < ksteps) {
+          umma::mma_f16_ss(tacc, da + (uint64_t)k16 * da_kstep, db + (uint64_t)k16 * db_kstep, idesc, first);
+          first = 1u;
+        }
+    }
+  }
+}
+
 template <bool BF16, bool SCALED>
 __global__ void __launch_bounds__(P3_THREADS, 1)
 conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ Wp_,
@@ -576,6 +603,13 @@ conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
     const uint64_t da_base = umma::smem_desc(umma::smem_u32(sX), XCS, 128);
     const uint64_t db_base = umma::smem_desc(umma::smem_u32(sW), Nout * ROWB, 128);
     const uint64_t da_kstep = (uint64_t)((2 * XCS) >> 4), db_kstep = (uint64_t)((2 * Nout * ROWB) >> 4);
+    // row offset of every tap inside the staged tile (16-byte units), kept in registers
+    uint32_t toff[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int th = t < taps ? t / d.kw : 0, tw = t < taps ? t % d.kw : 0;
+      toff[t] = (uint32_t)(halo + d.sign * ((th - ph) * Wp + (tw - pw)));
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
       P3TRACE(1, 3 * it);
@@ -584,36 +618,11 @@ conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
       P3TRACE(1, 3 * it + 1);
       umma::fence_after_sync();
       if (lane == 0) {
-        // descriptors advance by plain additions on their start-address field (16-byte units): the
-        // issuing thread is a single dependent instruction stream, so divisions / descriptor
-        // re-encoding per MMA cost more than the MMA itself (measured 183 vs 49 cycles per MMA)
-        uint32_t first = 0u;
         const uint64_t xa0 = da_base + (uint64_t)((s * x_stage) >> 4);
-        for (int c = 0; c < cchunks; ++c) {
-          const int ksteps = min(CC, d.Cg - c * CC) / 16;
-          int t = 0;
-          for (int th = 0; th < d.kh; ++th) {
-            const int row_shift = halo + d.sign * (th - ph) * Wp - d.sign * pw;
-            for (int tw = 0; tw < d.kw; ++tw, ++t) {
-              uint64_t da = xa0 + (uint64_t)((c * x_chunk + (row_shift + d.sign * tw) * ROWB) >> 4);
-              uint64_t db = db_base + (uint64_t)(((t * cchunks + c) * w_tile) >> 4);
-              // all descriptors of the tap first, then the MMAs back to back: the register ->
-              // uniform-register moves of the operands overlap instead of serialising per MMA
-              uint64_t das[4], dbs[4];
-#pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16) {
-                das[k16] = da + (uint64_t)k16 * da_kstep;
-                dbs[k16] = db + (uint64_t)k16 * db_kstep;
-              }
-#pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16)
-                if (k16 < ksteps) {
-                  umma::mma_f16_ss(tm + s * 128, das[k16], dbs[k16], idesc, first);
-                  first = 1u;
-                }
-            }
-          }
-        }
+        const uint32_t tacc = tm + s * 128;
+        if (d.kh == 3) issue_tile<3, 3>(tacc, xa0, db_base, toff, cchunks, d.Cg, x_chunk, w_tile, da_kstep, db_kstep, idesc);
+        else if (d.kw == 3) issue_tile<1, 3>(tacc, xa0, db_base, toff, cchunks, d.Cg, x_chunk, w_tile, da_kstep, db_kstep, idesc);
+        else issue_tile<1, 1>(tacc, xa0, db_base, toff, cchunks, d.Cg, x_chunk, w_tile, da_kstep, db_kstep, idesc);
         umma::commit(x_empty + s);
         umma::commit(a_full + s);
       }
