@@ -732,8 +732,10 @@ conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
 constexpr int WG_MAX_GROUPS = 4;
 constexpr int WCS = TP * ROWB;                   // chunk-column stride: 128 rows x 16 bytes
 constexpr int WG_A = 16 * WCS;                   // dpre tile, 16 chunk-columns (128 output channels)
-constexpr int WG_ONES = 2 * WCS;                 // [128][16] tile, column 0 = 1: bias sums
-constexpr int WG_XPAD = 32;                      // two finite rows behind the last chunk-column of X
+constexpr int WG_ONES = 2 * WCS;                 // [128][16] tile, column 0 = 1: bias sums; sits directly behind
+                                                 // the x tile of every stage, so the first tap's MMA spans
+                                                 // N = Cin + 16 and no separate bias MMAs are needed
+constexpr int WG_XPAD = 32;                      // two finite rows behind the last chunk-column
 constexpr int WG_MAX_STAGES = 3;
 
 template <bool BF16>
@@ -744,10 +746,9 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
   // fewer than 16 input channels (the first layer): the x tile is zero-padded to 16 columns
   const int Cin = Cin_real < 16 ? 16 : Cin_real;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int x_tile = (Cin / 8) * WCS + WG_XPAD;
+  const int x_tile = (Cin / 8) * WCS + WG_ONES + WG_XPAD;
   const int stage_bytes = WG_A + x_tile;
-  uint8_t* ones = smem + n_stages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + WG_ONES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + WG_MAX_STAGES;
   uint64_t* accb = bars + 2 * WG_MAX_STAGES;
@@ -761,7 +762,9 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
   const int HW = H * W;
   const int my_tiles = (int)blockIdx.y < n_tiles ? (n_tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
   const bool do_bias = db != nullptr && blockIdx.x == 0;
-  const uint32_t col_bias = (uint32_t)(kw * Cin);          // TMEM column block of the bias sums
+  // TMEM columns: tap 0 | bias sums (16, only where do_bias) | tap 1 | tap 2
+  const uint32_t col_bias = (uint32_t)Cin;
+  const uint32_t tap_gap = do_bias ? 16u : 0u;
   if (warp == mma_warp) umma::tmem_alloc<512>(tmem_slot);
   if (tid == 0) {
     for (int s = 0; s < n_stages; ++s) {
@@ -777,13 +780,12 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       // output channels beyond Cout never change: zero those dpre chunk-columns once
       for (int c8 = Cout / 8 + g; c8 < 16; c8 += n_groups)
         *reinterpret_cast<uint4*>(smem + s * stage_bytes + c8 * WCS + r * ROWB) = make_uint4(0u, 0u, 0u, 0u);
-      if (tid < 2)
-        *reinterpret_cast<uint4*>(smem + s * stage_bytes + WG_A + (Cin / 8) * WCS + tid * ROWB) =
-            make_uint4(0u, 0u, 0u, 0u);
-    }
-    if (g == 0) {
-      *reinterpret_cast<uint4*>(ones + r * ROWB) = make_uint4(pack2<BF16>(1.f, 0.f), 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(ones + WCS + r * ROWB) = make_uint4(0u, 0u, 0u, 0u);
+      uint8_t* ones = smem + s * stage_bytes + WG_A + (Cin / 8) * WCS;
+      if (g == 0) {
+        *reinterpret_cast<uint4*>(ones + r * ROWB) = make_uint4(pack2<BF16>(1.f, 0.f), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(ones + WCS + r * ROWB) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (tid < 2) *reinterpret_cast<uint4*>(ones + WG_ONES + tid * ROWB) = make_uint4(0u, 0u, 0u, 0u);
     }
     umma::fence_proxy_async();
   }
@@ -794,12 +796,11 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
 
   if (warp == mma_warp) {
     const uint32_t id_w = idesc_16b(128, Cin, 1, 1, BF16);
-    const uint32_t id_b = idesc_16b(128, 16, 1, 1, BF16);
+    const uint32_t id_wb = idesc_16b(128, Cin + 16, 1, 1, BF16);   // first tap + the ones columns
     // descriptors are advanced by additions on their start-address field (16-byte units): the issuing
     // thread is one dependent instruction stream, re-encoding a descriptor per MMA costs more than the MMA
     const uint64_t da0 = umma::smem_desc(umma::smem_u32(smem), 128, WCS);              // dpre tile, stage 0
     const uint64_t dx0 = umma::smem_desc(umma::smem_u32(smem) + WG_A, 128, WCS);       // x tile, stage 0
-    const uint64_t do0 = umma::smem_desc(umma::smem_u32(ones), 128, WCS);
     const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % n_stages;
@@ -811,16 +812,11 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
         const uint64_t da = da0 + (uint64_t)s * stage_step, dx = dx0 + (uint64_t)s * stage_step;
         const uint32_t acc = it > 0 ? 1u : 0u;
         for (int j = 0; j < kw; ++j) {     // tap (dh, j - pw): X shifted by j rows (16 bytes each)
-          const uint32_t tmj = tm + j * Cin;
+          const uint32_t tmj = tm + j * Cin + (j > 0 ? tap_gap : 0u);
+          const uint32_t idj = (j == 0 && do_bias) ? id_wb : id_w;
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // 8 K-steps of 16 tile rows (256 bytes)
-            umma::mma_f16_ss(tmj, da + (uint64_t)(k * 16), dx + (uint64_t)(j + k * 16), id_w, k > 0 ? 1u : acc);
-        }
-        if (do_bias) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma::mma_f16_ss(tm + col_bias, da + (uint64_t)(k * 16), do0 + (uint64_t)(k * 16), id_b,
-                             k > 0 ? 1u : acc);
+            umma::mma_f16_ss(tmj, da + (uint64_t)(k * 16), dx + (uint64_t)(j + k * 16), idj, k > 0 ? 1u : acc);
         }
         umma::commit(empty + s);
         if (it == my_tiles - 1) umma::commit(accb);
@@ -936,7 +932,7 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
         const int tap = (int)blockIdx.x * kw + j;
         for (int n0 = 0; n0 < Cin; n0 += 16) {
           float v[16];
-          umma::tmem_ld16(tm_lane + j * Cin + n0, v);
+          umma::tmem_ld16(tm_lane + j * Cin + (j > 0 ? tap_gap : 0u) + n0, v);
           umma::tmem_ld_wait();
           if (co < Cout) {
 #pragma unroll
@@ -978,7 +974,8 @@ extern "C" int pvb_conv_tc_supported(int Cin, int Cout, int kh, int kw) {
 // the weight-gradient kernel alone also takes layers with fewer than 16 input channels
 extern "C" int pvb_conv_tc_wgrad_supported(int Cin, int Cout, int kh, int kw) {
   if (Cin == 1) return 0;      // HBM-bound: the direct fp32 kernel of pvb_conv_bwd_weight is faster
-  return tc_ok(Cin < 16 ? 16 : Cin, Cout, kh, kw) && Cout <= 128 ? 1 : 0;
+  const int C = Cin < 16 ? 16 : Cin;
+  return tc_ok(C, Cout, kh, kw) && Cout <= 128 && kw * C + 16 <= 512 && C + 16 <= 256 ? 1 : 0;
 }
 
 extern "C" int64_t pvb_conv_tc_workspace_bytes(int Cin, int Cout, int kh, int kw) {
@@ -1088,18 +1085,19 @@ extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, f
   const int Cin_real = Cin;
   if (Cin < 16) Cin = 16;                        // zero-padded x tile
   PVB_CHECK_ARG(tc_ok(Cin, Cout, kh, kw) && Cout <= 128, "pvb_conv_tc_wgrad: unsupported shape");
-  PVB_CHECK_ARG(kw * Cin + 16 <= 512, "pvb_conv_tc_wgrad: Cin too large (kw * Cin + 16 TMEM columns)");
+  PVB_CHECK_ARG(kw * Cin + 16 <= 512 && Cin + 16 <= 256,
+                "pvb_conv_tc_wgrad: Cin too large (kw * Cin + 16 TMEM columns, Cin + 16 <= 256 per MMA)");
   if (B == 0) return 0;
   const int pw = kw / 2, Wp = Wd + pw, adv = TP - 2 * pw;
   const int64_t positions = (int64_t)B * H * Wp;          // W-padded pixel positions
   PVB_CHECK_ARG(positions + TP < (1ll << 31) && (int64_t)(Cin > Cout ? Cin : Cout) * H * Wd < (1ll << 31),
                 "pvb_conv_tc_wgrad: tensor too large for 32-bit position arithmetic");
   const int n_tiles = (int)((positions + adv - 1) / adv);
-  const int stage = WG_A + (Cin / 8) * WCS + WG_XPAD;
-  int n_stages = (227 * 1024 - 128 - WG_ONES) / stage;
+  const int stage = WG_A + (Cin / 8) * WCS + WG_ONES + WG_XPAD;
+  int n_stages = (227 * 1024 - 128) / stage;
   if (n_stages > WG_MAX_STAGES) n_stages = WG_MAX_STAGES;
   PVB_CHECK_ARG(n_stages >= 2, "pvb_conv_tc_wgrad: tile does not fit shared memory");
-  const int smem = n_stages * stage + WG_ONES + 128;
+  const int smem = n_stages * stage + 128;
   // one CTA per SM (512 TMEM columns): never more CTAs than SMs, or the extras run as a second wave
   int splits = 148 / kh;
   if (splits > n_tiles) splits = n_tiles;
