@@ -42,6 +42,16 @@ __device__ __forceinline__ float ld_peer1(const float* p) {
   return v;
 }
 
+// Wait until a peer's flag reaches this epoch.  Peers arrive within microseconds in steady state and
+// within seconds at start-up skew; a peer that never arrives (its process died) would hang this GPU,
+// so after ~2 minutes the kernel traps and the failure surfaces as a CUDA error instead.
+__device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t e) {
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_sys(flag) - e) < 0) {
+    if (clock64() - t0 > 240000000000ll) __trap();
+  }
+}
+
 // state: [0] epoch of the last finished invocation, [1] ticket, [2] loss (float bits)
 __global__ void __launch_bounds__(NT)
 peer_allreduce_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
@@ -60,7 +70,7 @@ peer_allreduce_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* 
       __threadfence_system();
       st_release_sys(peer_flags[threadIdx.x] + rank, e);            // ready[rank] on every peer
     }
-    while ((int32_t)(ld_acquire_sys(mine + threadIdx.x) - e) < 0) {}  // all peers ready
+    spin_until(mine + threadIdx.x, e);                              // all peers ready
   }
   __syncthreads();
   const int64_t n4 = (n + 3) / 4;
@@ -108,7 +118,7 @@ peer_allreduce_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* 
   // last CTA of this rank: every peer buffer has been read
   if (threadIdx.x < world) {
     st_release_sys(peer_flags[threadIdx.x] + MAX_WORLD + rank, e);   // done[rank] on every peer
-    while ((int32_t)(ld_acquire_sys(mine + MAX_WORLD + threadIdx.x) - e) < 0) {}
+    spin_until(mine + MAX_WORLD + threadIdx.x, e);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
