@@ -137,3 +137,35 @@ def test_ved_state_dict_keys_and_seeded_init_match_reference():
     assert m.state_dict()["encoder_z.features2latent.fc_latent.weight"].shape == (4, 32768)
     assert m.state_dict()["decoder.latent2features.fc.weight"].shape == (2048, 2)
     assert sum(p.numel() for p in m.parameters()) == 577893
+
+
+def test_conv_layer_plan_batchnorm_and_volumetric():
+    """Host-side description of the conv nets (no kernels): activation fused into the preceding
+    convolution, batch norm / pool / upsample as their own steps, shapes for 1-D / 2-D / 3-D data
+    (reference tests/test_conv.py: feature extractor / upsampler in every dimensionality)."""
+    from pyroved_b200.nets.conv import FeatureExtractor, Upsampler, layer_plan, out_shape
+    fe = FeatureExtractor(2, 1, [(8,), (16, 16)], batchnorm=True, activation="lrelu", pool_last=False)
+    plan = layer_plan(fe.layers, "lrelu")
+    assert [k for k, _, _ in plan] == ["conv", "bn", "pool", "conv", "bn", "conv", "bn"]
+    assert all(a == "lrelu" for k, _, a in plan if k == "conv")
+    shape = (1, 12, 10)
+    for kind, mod, _ in plan:
+        shape = out_shape(kind, mod, shape)
+    assert shape == (16, 6, 5)
+    for ndim, size in ((1, (8,)), (2, (8, 8)), (3, (8, 8, 8))):
+        fe = FeatureExtractor(ndim, 1, [(8, 8)], pool_last=True)
+        shape = (1, *size)
+        for kind, mod, _ in layer_plan(fe.layers, "lrelu"):
+            shape = out_shape(kind, mod, shape)
+        assert shape == (8, *[s // 2 for s in size])
+        up = Upsampler(ndim, 8, [(8,), (4,)], output_channels=2)
+        kinds = [k for k, _, _ in layer_plan(up.layers, "lrelu")]
+        assert kinds == ["conv", "up", "conv", "conv", "up", "conv", "conv"]
+        shape = (8, *size)
+        for kind, mod, _ in layer_plan(up.layers, "lrelu"):
+            shape = out_shape(kind, mod, shape)
+        assert shape == (2, *[4 * s for s in size])
+        blocks = [mod for kind, mod, _ in layer_plan(up.layers, "lrelu") if kind == "up"]
+        assert all(b.mode == ("bilinear" if ndim == 2 else "nearest") for b in blocks)
+    with pytest.raises(NotImplementedError):
+        FeatureExtractor(2, 1, [(8,)], kernel_size=5, padding=2)
