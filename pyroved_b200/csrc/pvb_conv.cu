@@ -399,6 +399,64 @@ conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
   }
 }
 
+// Same layer, four horizontally adjacent pixels per thread (W % 4 == 0, 16-byte aligned tensors): every
+// weight fetched from shared memory feeds four FMAs and every output channel is one 16-byte store --
+// the one-pixel kernel spends its time on 9 * Cout shared-memory loads and Cout 4-byte stores per pixel.
+__global__ void __launch_bounds__(256)
+conv_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
+                    const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ pre,
+                    ConvDims d, int act) {
+  extern __shared__ float wsm[];   // [Cout][12]: 9 taps (row-major kh x kw, zero padded) + bias
+  const int taps = d.kh * d.kw, ph = d.kh / 2, pw = d.kw / 2;
+  for (int k = threadIdx.x; k < d.Cout * 12; k += blockDim.x) {
+    const int co = k / 12, j = k - co * 12;
+    float v = 0.f;
+    if (j < 9) {                    // slot (r, c) of the 3 x 3 window <- tap (r - 1 + ph, c - 1 + pw)
+      const int r = j / 3 - 1 + ph, c = j % 3 - 1 + pw;
+      if (r >= 0 && r < d.kh && c >= 0 && c < d.kw) v = Wt[co * taps + r * d.kw + c];
+    } else if (j == 9) {
+      v = bias ? bias[co] : 0.f;
+    }
+    wsm[k] = v;
+  }
+  __syncthreads();
+  const int HW = d.H * d.W, W4 = d.W / 4;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // group of 4 pixels
+  if (q >= (int64_t)d.B * d.H * W4) return;
+  const int b = (int)(q / (d.H * W4)), rq = (int)(q - (int64_t)b * d.H * W4);
+  const int h = rq / W4, w0 = (rq - h * W4) * 4;
+  // 3 rows x 6 columns of inputs around the 4 pixels (zero outside the image)
+  float in[3][6];
+  const float* xb = x + (int64_t)b * HW;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int hh = h + r - 1;
+    const bool rok = hh >= 0 && hh < d.H;
+    const float4 mid = rok ? __ldg(reinterpret_cast<const float4*>(xb + hh * d.W + w0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    in[r][0] = (rok && w0 > 0) ? __ldg(xb + hh * d.W + w0 - 1) : 0.f;
+    in[r][1] = mid.x; in[r][2] = mid.y; in[r][3] = mid.z; in[r][4] = mid.w;
+    in[r][5] = (rok && w0 + 4 < d.W) ? __ldg(xb + hh * d.W + w0 + 4) : 0.f;
+  }
+  const int64_t obase = (int64_t)b * d.Cout * HW + h * d.W + w0;
+  for (int co = 0; co < d.Cout; ++co) {
+    const float4 wa = *reinterpret_cast<const float4*>(wsm + co * 12);
+    const float4 wb = *reinterpret_cast<const float4*>(wsm + co * 12 + 4);
+    const float4 wc = *reinterpret_cast<const float4*>(wsm + co * 12 + 8);
+    const float wk[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
+    float v[4] = {wc.y, wc.y, wc.y, wc.y};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) v[p] = fmaf(in[r][p + c], wk[r * 3 + c], v[p]);
+    if (pre) *reinterpret_cast<float4*>(pre + obase + (int64_t)co * HW) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(y + obase + (int64_t)co * HW) =
+        make_float4(pvb::act_fwd(v[0], act), pvb::act_fwd(v[1], act), pvb::act_fwd(v[2], act),
+                    pvb::act_fwd(v[3], act));
+  }
+}
+
 int check_dims(const ConvDims& d, const char* who) {
   PVB_CHECK_ARG(d.B >= 0 && d.Cin > 0 && d.Cout > 0 && d.H > 0 && d.W > 0, "%s: bad dims", who);
   PVB_CHECK_ARG((d.kh == 1 || d.kh == 3) && (d.kw == 1 || d.kw == 3), "%s: kernel size must be 1 or 3", who);
@@ -488,6 +546,14 @@ extern "C" int pvb_conv_fwd(const float* x, const float* W, const float* b, floa
   PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID, "pvb_conv_fwd: unknown activation %d", act);
   if (B == 0) return 0;
   int64_t M = (int64_t)B * H * Wd;
+  if (Cin == 1 && Wd % 4 == 0 && Cout * 12 * sizeof(float) <= 40 * 1024 &&
+      (((uintptr_t)x | (uintptr_t)y | (uintptr_t)pre) & 15) == 0) {
+    const int64_t groups = M / 4;
+    conv_c1_fwd4_kernel<<<pvb::cdiv(groups, 256), 256, (size_t)Cout * 12 * sizeof(float), (cudaStream_t)stream>>>(
+        x, W, b, y, pre, d, act);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   if (Cin == 1 && Cout * (kh * kw + 1) * sizeof(float) <= 40 * 1024) {
     size_t smem1 = (size_t)Cout * (kh * kw + 1) * sizeof(float);
     conv_c1_fwd_kernel<<<pvb::cdiv(M, 256), 256, smem1, (cudaStream_t)stream>>>(x, W, b, y, pre, d, act);

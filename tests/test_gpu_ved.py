@@ -151,6 +151,11 @@ def test_ved_inference_api():
     (4, 16, 24, 1, 37, 3, 1),    # 1-D
     (2, 33, 9, 6, 5, 1, 2),      # 1x1
     (3, 8, 8, 1, 16, 1, 1),
+    # single input channel (first encoder layer): direct kernels, 4 pixels per thread when W % 4 == 0
+    (5, 1, 32, 16, 12, 3, 2),
+    (3, 1, 12, 7, 9, 3, 2),      # W % 4 != 0: one pixel per thread
+    (4, 1, 8, 1, 32, 3, 1),      # 1-D
+    (2, 1, 16, 6, 8, 1, 2),      # 1x1
 ])
 @pytest.mark.parametrize("act", [None, "lrelu", "tanh"])
 def test_conv_kernels_vs_torch(shape, act):
