@@ -537,6 +537,78 @@ conv_c1_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
   }
 }
 
+// Same gradient, four horizontally adjacent pixels per iteration (W % 4 == 0, 16-byte aligned): the
+// Cout planes of dpre are read with 16-byte loads, the 3 x 6 input window once per group, and four output
+// channels per CTA keep the accumulators (4 x 10) + window + gradients under 100 registers.
+constexpr int C1_CO4 = 4;
+__global__ void __launch_bounds__(256)
+conv_c1_wgrad4_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dW,
+                      float* __restrict__ db, ConvDims d) {
+  __shared__ float red[8][C1_CO4 * 10];
+  const int taps = d.kh * d.kw, ph = d.kh / 2, pw = d.kw / 2;
+  const int HW = d.H * d.W, W4 = d.W / 4;
+  const unsigned G = (unsigned)d.B * (unsigned)d.H * (unsigned)W4;     // groups of 4 pixels
+  const int co0 = blockIdx.y * C1_CO4;
+  float acc[C1_CO4][10];
+#pragma unroll
+  for (int c = 0; c < C1_CO4; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[c][t] = 0.f;
+  for (unsigned q = blockIdx.x * 256u + threadIdx.x; q < G; q += gridDim.x * 256u) {
+    const unsigned b = q / (unsigned)(d.H * W4), rq = q - b * (unsigned)(d.H * W4);
+    const int h = (int)(rq / (unsigned)W4), w0 = (int)(rq - (unsigned)h * (unsigned)W4) * 4;
+    float in[3][6];
+    const float* xb = x + (int64_t)b * HW;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hh = h + r - 1;
+      const bool rok = hh >= 0 && hh < d.H;
+      const float4 mid = rok ? __ldg(reinterpret_cast<const float4*>(xb + hh * d.W + w0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      in[r][0] = (rok && w0 > 0) ? __ldg(xb + hh * d.W + w0 - 1) : 0.f;
+      in[r][1] = mid.x; in[r][2] = mid.y; in[r][3] = mid.z; in[r][4] = mid.w;
+      in[r][5] = (rok && w0 + 4 < d.W) ? __ldg(xb + hh * d.W + w0 + 4) : 0.f;
+    }
+    const float* gp = dpre + ((int64_t)b * d.Cout + co0) * HW + h * d.W + w0;
+    float4 g[C1_CO4];
+#pragma unroll
+    for (int c = 0; c < C1_CO4; ++c)
+      g[c] = co0 + c < d.Cout ? __ldg(reinterpret_cast<const float4*>(gp + (int64_t)c * HW)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < C1_CO4; ++c) {
+      const float gv[4] = {g[c].x, g[c].y, g[c].z, g[c].w};
+      acc[c][9] += (gv[0] + gv[1]) + (gv[2] + gv[3]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) acc[c][r * 3 + cc] = fmaf(gv[p], in[r][p + cc], acc[c][r * 3 + cc]);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < C1_CO4; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+      const float v = pvb::warp_sum(acc[c][t]);
+      if (lane == 0) red[warp][c * 10 + t] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < C1_CO4 * 10) {
+    float s = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
+    const int c = threadIdx.x / 10, j = threadIdx.x - c * 10;
+    if (co0 + c < d.Cout) {
+      if (j == 9) {
+        if (db) atomicAdd(db + co0 + c, s);
+      } else {                       // window slot (r, cc) -> tap (r - 1 + ph, cc - 1 + pw)
+        const int r = j / 3 - 1 + ph, cc = j % 3 - 1 + pw;
+        if (r >= 0 && r < d.kh && cc >= 0 && cc < d.kw) atomicAdd(dW + (int64_t)(co0 + c) * taps + r * d.kw + cc, s);
+      }
+    }
+  }
+}
+
 extern "C" int pvb_conv_fwd(const float* x, const float* W, const float* b, float* y, float* pre,
                             int B, int Cin, int Cout, int H, int Wd, int kh, int kw, int act,
                             void* stream) {
@@ -588,6 +660,16 @@ extern "C" int pvb_conv_bwd_weight(const float* dpre, const float* x, float* dW,
   PVB_CHECK_ARG(dpre && x && dW, "pvb_conv_bwd_weight: null pointer");
   if (B == 0) return 0;
   int64_t M = (int64_t)B * H * Wd;
+  if (Cin == 1 && M < (1ll << 31) - (1 << 20) && Wd % 4 == 0 &&
+      (((uintptr_t)x | (uintptr_t)dpre) & 15) == 0) {
+    const int cgroups4 = (Cout + C1_CO4 - 1) / C1_CO4;
+    int64_t px_blocks = (148 * 4 + cgroups4 - 1) / cgroups4;
+    if (px_blocks > (M / 4 + 255) / 256) px_blocks = (M / 4 + 255) / 256;
+    dim3 grid4((unsigned)px_blocks, cgroups4);
+    conv_c1_wgrad4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(dpre, x, dW, db, d);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   if (Cin == 1 && M < (1ll << 31) - (1 << 20)) {
     const int cgroups = (Cout + C1_CO - 1) / C1_CO;
     int64_t px_blocks = (148 * 4 + cgroups - 1) / cgroups;
