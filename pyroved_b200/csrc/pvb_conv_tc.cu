@@ -319,6 +319,9 @@ struct P2Dims {
   int B, Cg, Nout, H, W, kh, kw, sign;
   float in_scale, out_scale;
   int n_rows, x_stages;                          // staged rows per chunk; 1 or 2 chunk buffers
+  int n_total, n_off;                            // persistent kernel: this launch computes output channels
+                                                 // [n_off, n_off + Nout) of n_total (weights of a 128-wide
+                                                 // layer fit shared memory one half at a time)
 };
 
 template <bool BF16, bool SCALED, int NCH>
@@ -586,7 +589,7 @@ conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
     const int total = taps * Nout * k8s;
     for (int i = tid; i < total; i += P3_THREADS) {
       const int k8 = i % k8s, n = (i / k8s) % Nout, t = i / (k8s * Nout);
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(Wp_ + ((int64_t)t * Nout + n) * d.Cg) + k8);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(Wp_ + ((int64_t)t * d.n_total + d.n_off + n) * d.Cg) + k8);
       const int c = k8 / 8, c8 = k8 % 8;
       *reinterpret_cast<uint4*>(sW + (t * cchunks + c) * w_tile + c8 * (Nout * ROWB) + n * ROWB) = v;
     }
@@ -679,8 +682,9 @@ conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
       const bool m_ok = wp < d.W && h < d.H && b < d.B;
       const int gr = h * d.W + wp;
       const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * 128);
-      float* obase = dst + (int64_t)b * Nout * HW + gr;
-      float* pbase = pre ? pre + (int64_t)b * Nout * HW + gr : nullptr;
+      const int64_t ooff = ((int64_t)b * d.n_total + d.n_off) * HW + gr;
+      float* obase = dst + ooff;
+      float* pbase = pre ? pre + ooff : nullptr;
       for (int n0 = 0; n0 < Nout; n0 += 16) {
         float v[16];
         umma::tmem_ld16(tm_lane + n0, v);
@@ -1011,7 +1015,8 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
   if (use_pix2 && n_rows <= P2_MAX_ROWS && positions + TP < (1ll << 31)) {
     const int cch = (Cg + CC - 1) / CC;
     P2Dims p2{B, Cg, Nout, H, Wd, kh, kw, mode == 0 ? 1 : -1,
-              mode == 0 ? 1.f : GRAD_SCALE, mode == 0 ? 1.f : 1.f / GRAD_SCALE, n_rows, cch > 1 ? 2 : 1};
+              mode == 0 ? 1.f : GRAD_SCALE, mode == 0 ? 1.f : 1.f / GRAD_SCALE, n_rows, cch > 1 ? 2 : 1,
+              Nout, 0};
     const int smem2 = p2.x_stages * 8 * n_rows * ROWB + 2 * B_STAGE + 128;
     static bool attr2 = false;
     if (!attr2) {
@@ -1021,7 +1026,13 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
     }
     const unsigned grid2 = (unsigned)((positions + TP - 1) / TP);
     // persistent variant when all repacked weights + two staged input tiles fit one CTA's shared memory
-    const int64_t smem3 = (int64_t)taps * cch * Nout * CC * 2 + 2ll * cch * 8 * n_rows * ROWB + 128;
+    // (a 128-wide layer whose weights are too large runs as two launches of 64 output channels each)
+    int n_launch = Nout;
+    int64_t smem3 = (int64_t)taps * cch * n_launch * CC * 2 + 2ll * cch * 8 * n_rows * ROWB + 128;
+    if (smem3 > 227 * 1024 && Nout == 128) {
+      n_launch = 64;
+      smem3 = (int64_t)taps * cch * n_launch * CC * 2 + 2ll * cch * 8 * n_rows * ROWB + 128;
+    }
     static const bool use_pix3 = getenv("PVB_CONV_PIX2") == nullptr;
     if (use_pix3 && smem3 <= 227 * 1024 && Cg % 8 == 0 && grid2 >= 148) {
       static bool attr3 = false;
@@ -1032,17 +1043,24 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
       }
       if (mode == 0) {
         conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
-        pvb::count_launch();
-        conv_tc_pix3_kernel<false, false><<<148, P3_THREADS, (size_t)smem3, st>>>(src, Wp, b, dst, pre, p2, act,
-                                                                              (int)grid2);
       } else {
         PVB_CHECK_ARG(!pre || (act != PVB_ACT_GELU), "pvb_conv_tc_pix: gelu's derivative needs the pre-activation");
         conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
-        pvb::count_launch();
-        conv_tc_pix3_kernel<BWD_BF16, true><<<148, P3_THREADS, (size_t)smem3, st>>>(src, Wp, nullptr, dst, pre, p2,
-                                                                                pre ? act : 0, (int)grid2);
       }
       pvb::count_launch();
+      for (int n_off = 0; n_off < Nout; n_off += n_launch) {
+        P2Dims p3 = p2;
+        p3.Nout = n_launch;
+        p3.n_total = Nout;
+        p3.n_off = n_off;
+        if (mode == 0)
+          conv_tc_pix3_kernel<false, false><<<148, P3_THREADS, (size_t)smem3, st>>>(
+              src, Wp, b ? b + n_off : nullptr, dst, pre, p3, act, (int)grid2);
+        else
+          conv_tc_pix3_kernel<BWD_BF16, true><<<148, P3_THREADS, (size_t)smem3, st>>>(
+              src, Wp, nullptr, dst, pre, p3, pre ? act : 0, (int)grid2);
+        pvb::count_launch();
+      }
       return pvb::launch_status();
     }
     if (mode == 0) {

@@ -236,6 +236,7 @@ def test_pool_and_upsample_kernels_vs_torch(shape):
     (160, 128, 128, 1, 128, 3, 1),  # 1-D, two channel chunks
     (72, 64, 128, 16, 16, 3, 2),   # 128 outputs forward / two chunks backward
     (150, 48, 16, 1, 130, 1, 1),   # 1x1, 48-channel chunk
+    (72, 128, 128, 16, 16, 3, 2),  # weights exceed shared memory: two launches of 64 output channels
 ])
 def test_tc_conv_kernels_vs_torch(shape):
     """the three pixel-GEMM kernels (per-tap gather for wide images, tap reuse per tile, persistent
