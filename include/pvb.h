@@ -343,12 +343,14 @@ int pvb_bn_fwd(const float* x, const float* gamma, const float* beta,
                float* running_mean, float* running_var, int64_t* num_batches_tracked,
                float* y, float* save_mean, float* save_invstd, void* workspace, int B,
                int C, int64_t HW, float eps, float momentum, int training, void* stream);
-/* training-mode backward: dgamma[c] += sum dy xhat, dbeta[c] += sum dy (either may be
- * NULL), dx = gamma invstd (dy - mean(dy) - xhat mean(dy xhat)); dx may alias dy */
+/* backward: dgamma[c] += sum dy xhat, dbeta[c] += sum dy (either may be NULL);
+ * training != 0: dx = gamma invstd (dy - mean(dy) - xhat mean(dy xhat));
+ * training == 0 (the forward normalised with the running statistics, which are constants):
+ * dx = gamma invstd dy.  dx may alias dy */
 int pvb_bn_bwd(const float* dy, const float* x, const float* gamma,
                const float* save_mean, const float* save_invstd, float* dx,
                float* dgamma, float* dbeta, void* workspace, int B, int C, int64_t HW,
-               void* stream);
+               int training, void* stream);
 
 /* ---- regression variant (models/ss_reg_ivae.py:172-175,205-207,240-242) ----
  * loss_out[0] += scale * sum_i log N(y_i; loc_i, sigma)   (loc may be NULL = 0;
@@ -394,14 +396,22 @@ int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
 /* Same update with the step increment folded in: every element uses
  * t = *step_counter + 1 (- first_step[i]); the last CTA to finish stores
  * *step_counter += 1 (ticket must point to a zeroed int32 owned by the caller).
- * loss_ring (optional): 4 floats of device-accessible memory, normally MAPPED PINNED HOST
- * memory; slot (new step count & 3) receives *loss_src, i.e. the step's result reaches the
- * host without a separate copy. */
+ * loss_ring (optional): PVB_LOSS_RING floats of device-accessible memory, normally MAPPED
+ * PINNED HOST memory; slot (new step count & (PVB_LOSS_RING - 1)) receives *loss_src, i.e. the
+ * step's result reaches the host without a separate copy. */
+#define PVB_LOSS_RING 16
 int pvb_adam_flat_step(float* p, const float* g, float* m, float* v, int64_t n,
                        float lr, float beta1, float beta2, float eps,
                        int32_t* step_counter, const int32_t* first_step,
                        int32_t* ticket, const float* loss_src, float* loss_ring,
                        void* stream);
+
+/* dst[r][:] = src[idx[r]][:] for r < rows (row_floats fp32 each; 16-byte accesses when
+ * row_floats % 4 == 0 and both buffers are 16-byte aligned): the on-device shuffle of the
+ * GPU-resident batch loader (replaces the DataLoader's sampler + collate of the reference,
+ * utils/data.py:6-52), HBM-bound: 8 B per element. idx: int64, values in [0, n_src). */
+int pvb_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t rows,
+                    int64_t row_floats, int64_t n_src, void* stream);
 
 /* ---- spatial decoder, fused tcgen05 path (Hd = 128, two tanh layers) ----
  * One persistent kernel per step: grid -> h0 -> (128x128 tcgen05 GEMM + tanh)

@@ -293,7 +293,122 @@ def main_ssreg():
              {"aux_loss_multiplier": 30.0, "scale_factor": 2.0}, aux=True)
 
 
+def _trace_elbo_loss(model, guide, args, kw, eps_by_site):
+    """-ELBO of (model, guide) under the restated Trace_ELBO (the pinned estimator) with eps injected."""
+    runtime.EPS_HOOK[0] = lambda site, fn: eps_by_site.get(site)
+    try:
+        with torch.no_grad():
+            return float(pyro.infer.Trace_ELBO().differentiable_loss(model, guide, *args, **kw))
+    finally:
+        runtime.EPS_HOOK[0] = None
+
+
+def main_enum():
+    """Independent routes to the ENUMERATED ELBOs (jiVAE, unsupervised ssiVAE) that do not go through
+    the restated TraceEnum_ELBO (oracle/pyro_min/pyro/infer): only Trace_ELBO runs of the unmodified
+    reference (pinned estimator) and forward calls of the reference's own nets are used.
+
+      ssiVAE, unsupervised:  loss = -sum_b sum_k a_bk [ ELBO_sup(x_b, y = k; eps_kb) - log a_bk ],
+          ELBO_sup = supervised Trace_ELBO of the reference on the single sample (x_b, onehot_k)
+          (models/ssivae.py:153-215; it already contains log p(y) = log 1/K), a = encoder_y(x).
+      jiVAE:  loss = -sum_b [ b0 (log p(z_b) - log q(z_b)) + sum_k a_bk ( ll_kb + b1 (log 1/K - log a_bk) ) ]
+          with every term evaluated by calling the reference's encoder / decoder modules and
+          torch.distributions directly (models/jivae.py:152-220).  Dice weights are the UNSCALED
+          a_bk (Pyro builds them from score_parts.score_function, which poutine.scale does not
+          touch); with b1 = 1 that assumption is immaterial (golden jivae_28_r_beta1).
+    Writes tests/golden/jivae_28_r_beta1.npz and tests/golden/enum_indep.npz."""
+    import math
+    import torch.distributions as td
+    from pyroved.utils import transform_coordinates
+    dev = dict(device="cpu")
+    out = {}
+    # ---- jiVAE: the existing golden's inputs, and a beta1 = 1 variant ----------------------------
+    x = blobs(8, 28, 28, seed=10)
+    eps = torch.randn(8, 3, generator=gen(11))
+    for tag, sf in (("jivae_28_r", [3.0, 2.0]), ("jivae_28_r_beta1", [3.0, 1.0])):
+        m = pv.models.jiVAE((28, 28), latent_dim=2, discrete_dim=3, invariances=["r"], seed=1, **dev)
+        if tag.endswith("beta1"):
+            run_case(tag, m, dict(enumerate_parallel=True, **dev), (x,), {"latent_cont": eps},
+                     {"scale_factor": sf})
+            m = pv.models.jiVAE((28, 28), latent_dim=2, discrete_dim=3, invariances=["r"], seed=1,
+                                **dev)
+        K, B = 3, 8
+        with torch.no_grad():
+            mu, sig, alpha = m.encoder_z(x)
+            z = mu + sig * eps
+            kl = (td.Normal(0., 1.).log_prob(z) - td.Normal(mu, sig).log_prob(z)).sum(-1)   # [B]
+            tot = sf[0] * kl.sum()
+            for k in range(K):
+                onehot = torch.zeros(B, K)
+                onehot[:, k] = 1.
+                phi, dx, sc, zc = m.split_latent(z)
+                grid = m.grid.expand(B, *m.grid.shape)
+                xc = transform_coordinates(grid, phi, dx, sc)
+                loc = m.decoder(xc, [zc, onehot]).reshape(B, -1)
+                ll = td.Bernoulli(probs=loc, validate_args=False).log_prob(x.reshape(B, -1)).sum(-1)
+                a = alpha[:, k]
+                tot = tot + (a * (ll + sf[1] * (math.log(1.0 / K) - torch.log(a)))).sum()
+        out[tag] = np.float64(-float(tot))
+    # ---- ssiVAE unsupervised: K*B supervised single-sample Trace_ELBO runs of the reference -------
+    x = blobs(8, 16, 16, seed=12).flatten(1)
+    eps = torch.randn(4, 8, 3, generator=gen(13))
+    m = pv.models.ssiVAE((16, 16), latent_dim=2, num_classes=4, invariances=["r"], seed=1, **dev)
+    K, B = 4, 8
+    with torch.no_grad():
+        alpha = m.encoder_y(x)
+    tot = 0.0
+    for b in range(B):
+        for k in range(K):
+            y1 = torch.zeros(1, K)
+            y1[0, k] = 1.
+            elbo_sup = -_trace_elbo_loss(m.model, m.guide, (x[b:b + 1], y1), {},
+                                         {"z": eps[k, b:b + 1]})
+            a = float(alpha[b, k])
+            tot += a * (elbo_sup - math.log(a))
+    out["ssivae_16_r_unsup"] = np.float64(-tot)
+    np.savez_compressed(os.path.join(OUT, "enum_indep.npz"), **out)
+    for k, v in out.items():
+        ref = float(np.load(os.path.join(OUT, k + ".npz"))["loss"])
+        print("{:24s} independent route {:.6f}   TraceEnum golden {:.6f}   rel diff {:.2e}".format(
+            k, float(v), ref, abs(float(v) - ref) / abs(ref)))
+        assert abs(float(v) - ref) <= 2e-6 * abs(ref)
+
+
+def main_ved_eval():
+    """batchnorm=True VED in eval mode (reference models/ved.py:178,193,230: encode / decode /
+    manifold2d call self.eval(), so BatchNorm normalises with the RUNNING statistics): one training
+    step first so the running statistics are not the initial (0, 1), then the inference calls."""
+    dev = dict(device="cpu")
+    x = blobs(6, 16, 16, seed=25, binary=False)[:, None]
+    ysp = spectra(6, 32, seed=26)[:, None]
+    m = pv.models.VED((16, 16), (32,), latent_dim=2, seed=3, batchnorm=True,
+                      hidden_dim_e=[(8,), (16, 16)], hidden_dim_d=[(16, 16), (8,)])
+    m.to("cpu")
+    runtime.EPS_HOOK[0] = lambda site, fn: {"z": torch.randn(6, 2, generator=gen(27))}.get(site)
+    try:
+        tr = pv.trainers.SVItrainer(m, **dev)
+        for _ in range(3):
+            tr.svi.step(x, ysp, scale_factor=2.0)
+    finally:
+        runtime.EPS_HOOK[0] = None
+    out = {"w." + k: v.detach().clone().numpy() for k, v in m.state_dict().items()}
+    xn = blobs(3, 16, 16, seed=35, binary=False)[:, None]
+    zn = torch.randn(4, 2, generator=gen(36))
+    mu, sd = m.encode(xn)
+    out.update(x=xn.numpy(), z=zn.numpy(), mu=mu.numpy(), sigma=sd.numpy(),
+               dec=m.decode(zn).numpy(), man=m.manifold2d(3, plot=False).numpy())
+    assert not m.training
+    np.savez_compressed(os.path.join(OUT, "ved_bn_eval_16_32.npz"), **out)
+    print("ved_bn_eval_16_32: mu", mu[0].tolist(), "dec mean", float(out["dec"].mean()))
+
+
 def main():
+    if "--enum" in sys.argv:
+        main_enum()
+        return
+    if "--ved-eval" in sys.argv:
+        main_ved_eval()
+        return
     if "--ssreg" in sys.argv:
         main_ssreg()
         return

@@ -411,7 +411,8 @@ def _conv_nd(ndim):
 
 
 def _bnorm(sd, p, h, stats):
-    """nn.BatchNorm{1,2}d in training mode (the reference never calls .eval()): batch statistics,
+    """nn.BatchNorm{1,2}d in training mode (the SVI step runs the nets in their default mode; only
+    VED.encode / decode / manifold2d call .eval(), reference models/ved.py:178,193,230): batch statistics,
     biased variance, eps 1e-5.  `stats` (optional dict) receives the running statistics after
     torch's momentum-0.1 update (unbiased variance), keyed like the state_dict."""
     red = [0] + list(range(2, h.dim()))

@@ -87,6 +87,7 @@ SIGNATURES = {
     "pvb_counter_add": [_f, _i32, _st],
     "pvb_adam_flat": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _f, _st],
     "pvb_adam_flat_step": [_f, _f, _f, _f, _i64, _fl, _fl, _fl, _fl, _f, _f, _f, _f, _f, _st],
+    "pvb_gather_rows": [_f, C.c_void_p, _f, _i64, _i64, _i64, _st],
     "pvb_mlp_tail_fwd": [C.POINTER(MlpTailArgs), _st],
     "pvb_mlp_chain_bwd": [C.POINTER(MlpChainArgs), _st],
     "pvb_mlp_wgrad": [C.POINTER(WgradProblem), _i32, _i64, _st],
@@ -109,7 +110,7 @@ SIGNATURES = {
                                 _f, _f, _f, _st],
     "pvb_bn_workspace_bytes": [_i32],
     "pvb_bn_fwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _fl, _fl, _i32, _st],
-    "pvb_bn_bwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _st],
+    "pvb_bn_bwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _i32, _st],
     "pvb_maxpool2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_maxpool2_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_upsample2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],

@@ -54,9 +54,11 @@ class ConvStack:
                 else:
                     ops.conv_fwd(cur, m.weight.data, bias, st["act"], st["y"], st["pre"])
             elif st["kind"] == "bn":
-                # batch statistics + running-statistics update (the reference trains with the
-                # modules in their default training mode)
-                ops.bn_fwd(cur, m, st["y"], st["stats"][0], st["stats"][1], st["ws"], training=True)
+                # the module's own mode, like the reference: batch statistics + running-statistics
+                # update while training; the running statistics once the user has called
+                # encode / decode / manifold2d, which put the model in eval mode for good
+                # (reference models/ved.py:178,193,230) -- the step graph is keyed on the mode
+                ops.bn_fwd(cur, m, st["y"], st["stats"][0], st["stats"][1], st["ws"])
             elif st["kind"] == "pool":
                 ops.maxpool2_fwd(cur, st["y"])
             else:

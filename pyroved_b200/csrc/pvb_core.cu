@@ -114,8 +114,8 @@ __global__ void adam_flat_step_kernel(float* __restrict__ p, const float* __rest
     __threadfence();
     int t = atomicAdd(ticket, 1);
     if (t == (int)gridDim.x - 1) {
-      // the step's loss goes straight to (mapped, pinned) host memory: slot = step & 3
-      if (loss_ring) loss_ring[step & 3] = *loss_src;
+      // the step's loss goes straight to (mapped, pinned) host memory: slot = step & (PVB_LOSS_RING - 1)
+      if (loss_ring) loss_ring[step & (PVB_LOSS_RING - 1)] = *loss_src;
       *step_counter = step;
       *ticket = 0;
     }
@@ -152,3 +152,49 @@ extern "C" int pvb_adam_flat_step(float* p, const float* g, float* m, float* v, 
   pvb::count_launch();
   return pvb::launch_status();
 }
+
+// ---- row gather (on-device shuffle of the GPU-resident loader) -------------------------------------
+namespace {
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                   float* __restrict__ dst, int64_t rows, int64_t row_vecs, int64_t n_src) {
+  // one warp walks one row at a time: consecutive lanes read consecutive 4 / 16-byte words
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    int64_t s = idx[r];
+    if (s < 0 || s >= n_src) continue;          // out-of-range index: row left untouched
+    if (VEC == 4) {
+      const float4* a = reinterpret_cast<const float4*>(src) + s * row_vecs;
+      float4* b = reinterpret_cast<float4*>(dst) + r * row_vecs;
+      for (int64_t c = lane; c < row_vecs; c += 32) b[c] = __ldg(a + c);
+    } else {
+      const float* a = src + s * row_vecs;
+      float* b = dst + r * row_vecs;
+      for (int64_t c = lane; c < row_vecs; c += 32) b[c] = __ldg(a + c);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int pvb_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t rows,
+                               int64_t row_floats, int64_t n_src, void* stream) {
+  PVB_CHECK_ARG(src && idx && dst && rows >= 0 && row_floats > 0 && n_src > 0,
+                "pvb_gather_rows: bad argument");
+  if (rows == 0) return 0;
+  const bool vec = row_floats % 4 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+  // 8 warps per CTA, one row per warp per pass; never more CTAs than a few waves of 148 SMs
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (vec)
+    gather_rows_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, dst, rows,
+                                                                            row_floats / 4, n_src);
+  else
+    gather_rows_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, dst, rows,
+                                                                            row_floats, n_src);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+

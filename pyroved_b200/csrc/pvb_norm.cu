@@ -116,7 +116,7 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean,
 
 // dgamma / dbeta accumulate; (sum dy, sum dy xhat) / n kept for the element-wise pass
 __global__ void bn_bwd_finalize_kernel(float* __restrict__ part, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int C, int n) {
+                                       float* __restrict__ dbeta, int C, int n, int training) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
@@ -126,8 +126,9 @@ __global__ void bn_bwd_finalize_kernel(float* __restrict__ part, float* __restri
   }
   if (dbeta) dbeta[c] += (float)s1;
   if (dgamma) dgamma[c] += (float)s2;
-  part[(int64_t)c * NS * 2] = (float)(s1 / n);
-  part[(int64_t)c * NS * 2 + 1] = (float)(s2 / n);
+  // eval mode: the statistics are constants, dx = gamma invstd dy (no mean terms)
+  part[(int64_t)c * NS * 2] = training ? (float)(s1 / n) : 0.f;
+  part[(int64_t)c * NS * 2 + 1] = training ? (float)(s2 / n) : 0.f;
 }
 
 // MODE 0: y = (x - mean) invstd gamma + beta
@@ -222,7 +223,7 @@ extern "C" int pvb_bn_fwd(const float* x, const float* gamma, const float* beta,
 
 extern "C" int pvb_bn_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean,
                           const float* save_invstd, float* dx, float* dgamma, float* dbeta, void* workspace,
-                          int B, int C, int64_t HW, void* stream) {
+                          int B, int C, int64_t HW, int training, void* stream) {
   PVB_CHECK_ARG(dy && x && save_mean && save_invstd && dx && workspace, "pvb_bn_bwd: null pointer");
   PVB_CHECK_ARG(B >= 0 && C > 0 && HW > 0 && (int64_t)B * HW < (1ll << 31), "pvb_bn_bwd: bad shape");
   if (B == 0) return 0;
@@ -236,7 +237,7 @@ extern "C" int pvb_bn_bwd(const float* dy, const float* x, const float* gamma, c
   if (vec) bn_partial_kernel<1, 4><<<grid, NT, 0, st>>>(x, dy, save_mean, save_invstd, part, C, (int)HW, n, chunk);
   else bn_partial_kernel<1, 1><<<grid, NT, 0, st>>>(x, dy, save_mean, save_invstd, part, C, (int)HW, n, chunk);
   pvb::count_launch();
-  bn_bwd_finalize_kernel<<<pvb::cdiv(C, 128), 128, 0, st>>>(part, dgamma, dbeta, C, n);
+  bn_bwd_finalize_kernel<<<pvb::cdiv(C, 128), 128, 0, st>>>(part, dgamma, dbeta, C, n, training);
   pvb::count_launch();
   const int64_t total = (int64_t)B * C * HW;
   if (vec)

@@ -125,7 +125,7 @@ peer_allreduce_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* 
     __threadfence();
     const float L = __int_as_float(*reinterpret_cast<volatile int32_t*>(state + 2));
     own_g[n] = L;                                   // global loss
-    if (loss_ring) loss_ring[step & 3] = L;         // ... and straight to mapped host memory
+    if (loss_ring) loss_ring[step & (PVB_LOSS_RING - 1)] = L;         // ... and straight to mapped host memory
     *step_counter = step;
     state[1] = 0;
     state[0] = (int32_t)e;

@@ -515,6 +515,9 @@ class SpatialVAEProgram(StepProgram):
         if c_model > 0 and not has_y:
             raise ValueError("model was built with c_dim={} but no y was passed".format(c_model))
         self.loss_const = loss_const
+        # the ELBO reduction may run on the side stream only if nothing else in the step
+        # accumulates into the loss slot (SsRegProgram adds log-prob terms of y: it may not)
+        self.side_loss = True
         N, Z, C = self.N, self.Z, self.C
         f32 = dict(device=dev, dtype=torch.float32)
         self.enc_in = torch.zeros(B, N + C, **f32)
@@ -562,7 +565,7 @@ class SpatialVAEProgram(StepProgram):
             self.enc.forward(self.enc_in, gen_eps)
             self.dec.forward(self.head.z, self.y, self.x, None, want_grad, kl=self.head.kl,
                              beta=float(beta), loss_out=flat.loss, uv_ready=self.dec.spatial,
-                             side_loss=True)
+                             side_loss=self.side_loss)
             return
         h = self.enc.forward(self.enc_in)
         self.head.forward(h, gen_eps)
@@ -594,6 +597,7 @@ class SsRegProgram(SpatialVAEProgram):
     def __init__(self, engine, B, has_y):
         m = engine.model
         super().__init__(engine, B, True, cond_dim=m.reg_dim)
+        self.side_loss = False      # normal_logprob below adds to the loss slot on the main stream
         self.sup = has_y
         self.sig = float(m.reg_sig)
         self.has_y = has_y
@@ -983,7 +987,7 @@ class SVIEngine:
     step on a mini-batch and returns the (batch-sum) loss."""
 
     def __init__(self, model, lr=1e-3, enumerate_parallel=False, seed=1, device=None,
-                 use_graphs=None):
+                 use_graphs=None, force_generic=None):
         if device is None:
             device = getattr(model, "device", "cuda")
         self.device = torch.device(device if str(device) != "cuda" else "cuda:{}".format(
@@ -1006,16 +1010,20 @@ class SVIEngine:
                                if parallel.peer_exchange_enabled() else None)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.adam_ticket = torch.zeros(1, device=self.device, dtype=torch.int32)
-        # pinned host ring the optimizer kernel writes each step's loss into (slot = step count & 3):
-        # the step's result reaches the host without a copy call
-        self.loss_ring = torch.zeros(4, dtype=torch.float32).pin_memory()
+        # pinned host ring the optimizer kernel writes each step's loss into (slot = step count &
+        # (LOSS_RING - 1)): the step's result reaches the host without a copy call
+        self.loss_ring = torch.zeros(ops.LOSS_RING, dtype=torch.float32).pin_memory()
         self.updates_done = 0     # host mirror of step_counter
         self.programs = {}
         self.graphs = {}
         if use_graphs is None:
             use_graphs = os.environ.get("PVB_CUDA_GRAPHS", "1") != "0"
         self.use_graphs = use_graphs
-        self.force_generic = os.environ.get("PVB_FORCE_GENERIC", "0") == "1"
+        # force_generic=True: the exact fp32 kernels everywhere (no tcgen05 / fused small-batch
+        # stacks); None: taken from PVB_FORCE_GENERIC once, here
+        if force_generic is None:
+            force_generic = os.environ.get("PVB_FORCE_GENERIC", "0") == "1"
+        self.force_generic = bool(force_generic)
         self.launches_per_step = 0
         self.last_loss_const = 0.0
         # data-parallel state (pyroved_b200.parallel)
@@ -1119,19 +1127,28 @@ class SVIEngine:
         if not self.use_graphs:
             fn()
             return
-        entry = self.graphs.get(key)
+        entry = self.graphs.pop(key, None)
         if entry is None:
             fn()
             self.graphs[key] = "warm"
+            self._trim_graphs()
             return
         if entry == "warm":
             g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(self.device)
             with torch.cuda.graph(g):
                 fn()
-            self.graphs[key] = g
             entry = g
+        self.graphs[key] = entry          # most recently used last
         entry.replay()
+
+    MAX_GRAPHS = 48
+
+    def _trim_graphs(self):
+        """The graph key carries the scale factors: under KL annealing (a new scale_factor every
+        epoch) captured graphs of stale values would pile up; keep the most recently used ones."""
+        while len(self.graphs) > self.MAX_GRAPHS:
+            self.graphs.pop(next(iter(self.graphs)))
 
     def step(self, *args, **kwargs):
         return self._step(args, kwargs, train=True)
@@ -1150,6 +1167,11 @@ class SVIEngine:
         return self._step(args, kwargs, train=True, update=False)
 
     def _step(self, args, kwargs, train=True, update=True, mode="main"):
+        # every launch of the step goes to this engine's device, whatever the caller's current one
+        with torch.cuda.device(self.device):
+            return self._step_on_device(args, kwargs, train, update, mode)
+
+    def _step_on_device(self, args, kwargs, train, update, mode):
         self.flat.ensure() and self._invalidate()
         kwargs = dict(kwargs)
         x = args[0]
@@ -1172,7 +1194,8 @@ class SVIEngine:
         if update:
             self.updates_done += 1
         bkey = tuple(beta) if isinstance(beta, (list, tuple)) else float(beta)
-        key = (B, y is not None, mode, bkey, train, gen_eps, update)
+        # (model.training: BatchNorm layers follow the module's mode, conv_engine.ConvStack)
+        key = (B, y is not None, mode, bkey, train, gen_eps, update, bool(self.model.training))
         if static:
             key += (x.data_ptr(), y.data_ptr() if y is not None else 0)
         if self.world_size > 1 and train and update and self.peer is not None:

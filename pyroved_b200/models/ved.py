@@ -22,8 +22,11 @@ class VED(baseVAE):
         hidden_dim_e: conv filters per encoder block, default [(32,), (64, 64), (128, 128)]
         hidden_dim_d: conv filters per decoder block, default [(128, 128), (64, 64), (32,)]
         activation: 'lrelu' (default), 'relu', 'tanh', 'softplus', 'gelu'
-        batchnorm: BatchNorm after every conv + activation (batch statistics, as the reference
-            never switches the nets to eval mode)
+        batchnorm: BatchNorm after every conv + activation.  Training uses batch statistics;
+            `encode`, `decode` and `manifold2d` switch the model to eval mode like the reference
+            (models/ved.py:178,193,230), so they normalise with the running statistics -- and,
+            as in the reference, the model STAYS in eval mode afterwards (call `.train()` before
+            training further)
         sampler_d: 'bernoulli' (default) or 'gaussian'
         sigmoid_d: sigmoid on the decoder output (default True)
         seed: torch seed used for weight init
@@ -51,11 +54,14 @@ class VED(baseVAE):
         self.to(self.device)
 
     def encode(self, x_new: torch.Tensor, **kwargs: int):
-        """(z_mean, z_sd) of q(z|x), batch by batch."""
+        """(z_mean, z_sd) of q(z|x), batch by batch (eval mode, reference ved.py:178)."""
+        self.eval()
         z = self._encode(x_new, **kwargs)
         return z.split(self.z_dim, 1)
 
     def decode(self, z: torch.Tensor, **kwargs: int) -> torch.Tensor:
+        """Decoded latent codes (eval mode, reference ved.py:193)."""
+        self.eval()
         return self._decode(z.to(self.device), **kwargs)
 
     def predict(self, x_new: torch.Tensor, **kwargs: int):
@@ -73,6 +79,7 @@ class VED(baseVAE):
         return torch.cat(mus), torch.cat(sds)
 
     def manifold2d(self, d: int, plot: bool = True, **kwargs: Union[str, int]) -> torch.Tensor:
+        self.eval()                     # reference ved.py:230
         z, (grid_x, grid_y) = generate_latent_grid(d, **kwargs)
         loc = self.decoder(z.to(self.device)).cpu()
         if plot:

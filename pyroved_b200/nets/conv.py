@@ -272,8 +272,9 @@ def run_layers(layers, x, activation):
             else:
                 ops.conv_fwd(x, mod.weight.data, bias, act, y)
         elif kind == "bn":
-            # like the reference, which never calls .eval(): batch statistics (and a running-
-            # statistics update) unless the caller put the module in eval mode
+            # the module's own mode: running statistics in eval mode (VED.encode / decode /
+            # manifold2d switch to it like the reference), batch statistics + a running-statistics
+            # update otherwise (e.g. VED.predict before any eval() call, as in the reference)
             C = x.shape[1]
             stats = torch.empty(2, C, device=x.device, dtype=torch.float32)
             ops.bn_fwd(x, mod, y, stats[0], stats[1], ops.bn_workspace(C, x.device))

@@ -23,6 +23,10 @@ def _p(t):
     if not t.is_cuda:
         raise _lib.PvbError("pyroved_b200 kernels need CUDA tensors (no CPU fallback); got a "
                             "{} tensor".format(t.device))
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.PvbError("tensor lives on {} but the current CUDA device is {}: run the call "
+                            "under torch.cuda.device(...) (the trainers and models do this for "
+                            "their own device)".format(t.device, torch.cuda.current_device()))
     if t.dtype not in (torch.float32, torch.int32) or not t.is_contiguous():
         raise _lib.PvbError("expected a contiguous float32 tensor, got {} {}".format(
             t.dtype, "non-contiguous" if not t.is_contiguous() else ""))
@@ -187,6 +191,20 @@ def sdec_tc_gather_gUv(gUv_part, gUv, I, N):
           "pvb_sdec_tc_gather_gUv")
 
 
+LOSS_RING = 16     # PVB_LOSS_RING of include/pvb.h
+
+
+def gather_rows(src, idx, dst):
+    """dst[r] = src[idx[r]] over the leading dim (idx: int64 device tensor): on-device shuffle."""
+    rows = idx.numel()
+    row = src[0].numel()
+    assert dst.shape[0] >= rows and dst[0].numel() == row and idx.dtype == torch.int64
+    assert idx.is_cuda and idx.is_contiguous()
+    check(_lib.lib().pvb_gather_rows(_p(src), idx.data_ptr(), _p(dst), rows, row, src.shape[0],
+                                     _stream()), "pvb_gather_rows")
+    return dst
+
+
 def _host_ptr(t):
     """device-visible address of a pinned host tensor (unified addressing), None -> NULL"""
     if t is None:
@@ -198,8 +216,8 @@ def _host_ptr(t):
 
 def adam_flat_step(p, g, m, v, n, lr, step_counter, ticket, first_step=None, beta1=0.9, beta2=0.999,
                    eps=1e-8, loss_src=None, loss_ring=None):
-    """Adam update + step-counter increment in one launch; with loss_ring (4 pinned host floats) the
-    loss in loss_src is also written to ring slot (new step count & 3)."""
+    """Adam update + step-counter increment in one launch; with loss_ring (LOSS_RING pinned host
+    floats) the loss in loss_src is also written to ring slot (new step count & (LOSS_RING - 1))."""
     check(_lib.lib().pvb_adam_flat_step(_p(p), _p(g), _p(m), _p(v), n, float(lr), beta1, beta2, eps,
                                         _p(step_counter), _p(first_step), _p(ticket), _p(loss_src),
                                         _host_ptr(loss_ring), _stream()),
@@ -401,10 +419,20 @@ def bn_fwd(x, bn, y, save_mean, save_invstd, ws, training=None):
     return y
 
 
-def bn_bwd(dy, x, bn, save_mean, save_invstd, dx, dgamma, dbeta, ws):
+def bn_uses_batch_stats(bn, training=None):
+    """torch's rule: batch statistics in training mode, and in eval mode when the module tracks
+    no running statistics."""
+    training = bn.training if training is None else training
+    track = bn.track_running_stats and bn.running_mean is not None
+    return bool(training or not track)
+
+
+def bn_bwd(dy, x, bn, save_mean, save_invstd, dx, dgamma, dbeta, ws, training=None):
+    """Backward of bn_fwd under the same mode (training=None -> bn.training)."""
     check(_lib.lib().pvb_bn_bwd(_p(dy), _p(x), _p(bn.weight.data if bn.affine else None),
                                 _p(save_mean), _p(save_invstd), _p(dx), _p(dgamma), _p(dbeta), _p(ws),
-                                *_bn_dims(x), _stream()), "pvb_bn_bwd")
+                                *_bn_dims(x), int(bn_uses_batch_stats(bn, training)), _stream()),
+          "pvb_bn_bwd")
     return dx
 
 

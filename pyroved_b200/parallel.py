@@ -119,6 +119,14 @@ class ShardedLoader:
 
     def __iter__(self):
         for batch in self.loader:
+            n = batch[0].shape[0]
+            if n % self.world != 0:
+                # a ragged last batch: trim it evenly (every rank must run the same static
+                # shapes); the few dropped samples are seen in other epochs when shuffling
+                n = n // self.world * self.world
+                if n == 0:
+                    continue
+                batch = [t[:n] for t in batch]
             yield [shard(t, self.rank, self.world) for t in batch]
 
     def __len__(self):

@@ -11,6 +11,7 @@ from typing import Optional
 import torch
 
 from ..engine import SVIEngine
+from ._pipeline import StepPipeline, run_epoch
 from ..utils import average_weights, set_deterministic_mode
 
 
@@ -37,7 +38,7 @@ class auxSVItrainer:
         elif optimizer is not None:
             raise TypeError("pass optimizer=None or {'lr': ...}: Adam is fused into the CUDA step")
         self.svi = SVIEngine(model, lr=lr, enumerate_parallel=(task == "classification"), seed=seed,
-                             device=self.device)
+                             device=self.device, force_generic=kwargs.get("force_generic"))
         self.model = model
         self.history = {"training_loss": [], "test": []}
         self.current_epoch = 0
@@ -54,20 +55,30 @@ class auxSVItrainer:
         return loss + loss_aux
 
     def train(self, loader_unsup, loader_sup, **kwargs) -> float:
-        """One epoch; a labeled batch every p-th iteration (auxsvi.py:102-128)."""
+        """One epoch; a labeled batch every p-th iteration (auxsvi.py:102-128).  Same schedule and
+        the same two optimisation steps per batch as `compute_loss`, software-pipelined like
+        SVItrainer.train (trainers/_pipeline.py): no host synchronisation per step."""
         sup_batches = len(loader_sup)
         unsup_batches = len(loader_unsup)
         p = (sup_batches + unsup_batches) // sup_batches
-        loader_sup = iter(loader_sup)
-        epoch_loss = 0.
-        unsup_count = 0
-        for i, (xs,) in enumerate(loader_unsup):
-            epoch_loss += self.compute_loss(xs, **kwargs)
-            unsup_count += xs.shape[0]
-            if i % p == 1:
-                xs, ys = next(loader_sup)
-                _ = self.compute_loss(xs, ys, **kwargs)
-        return epoch_loss / unsup_count
+        eng = self.svi
+        steps = [eng.step, eng.step_aux]
+        counted = [0]
+
+        def schedule():
+            sup = iter(loader_sup)
+            for i, (xs,) in enumerate(loader_unsup):
+                counted[0] += xs.shape[0]
+                yield (xs,), steps, 1.0            # loss + auxiliary loss enter the epoch loss
+                if i % p == 1:
+                    xs_l, ys_l = next(sup)
+                    yield (xs_l, ys_l), steps, 0.0      # computed, not accumulated (auxsvi.py:126)
+
+        with torch.cuda.device(eng.device):
+            if not hasattr(self, "_pipe"):
+                self._pipe = StepPipeline(eng)
+            epoch_loss = run_epoch(self._pipe, schedule(), **kwargs)
+        return epoch_loss / counted[0]
 
     def evaluate(self, loader_val) -> float:
         if self.task == "regression":

@@ -1,11 +1,11 @@
 """SVItrainer: epoch loop around the fused CUDA SVI step
 (reference trainers/svi.py:11-175)."""
-from collections import deque
 from typing import Optional
 
 import torch
 
 from ..engine import SVIEngine
+from ._pipeline import StepPipeline, run_epoch
 from ..utils import set_deterministic_mode
 
 
@@ -35,7 +35,7 @@ class SVItrainer:
             raise TypeError("pyroved_b200 implements Trace_ELBO / TraceEnum_ELBO natively; "
                             "pass loss=None (use enumerate_parallel for discrete latents)")
         self.svi = SVIEngine(model, lr=lr, enumerate_parallel=enumerate_parallel, seed=seed,
-                             device=self.device)
+                             device=self.device, force_generic=kwargs.get("force_generic"))
         self.loss_history = {"training_loss": [], "test_loss": []}
         self.current_epoch = 0
 
@@ -43,62 +43,18 @@ class SVItrainer:
         """One epoch; returns loss / number of samples (reference svi.py:95-115).
 
         Same per-batch work as the reference loop (host batch -> device, one SVI step, the
-        step's loss back to the host), software-pipelined: the H2D copy of batch i+1 runs on a
-        copy stream under the kernels of batch i, and the 4-byte loss of step i is read from a
-        pinned ring two steps later, so neither transfer stalls the launch thread."""
+        step's loss back to the host), software-pipelined (trainers/_pipeline.py): the H2D copy
+        of batch i+1 runs on a copy stream under the kernels of batch i, and the 4-byte loss of
+        step i is read from a pinned ring a few steps later, so neither transfer stalls the
+        launch thread.  Batches of a GPU-resident loader (utils.DeviceBatchLoader) are used in
+        place."""
         eng = self.svi
-        dev = eng.device
-        main = torch.cuda.current_stream(dev)
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream(dev)
-            self._stage = {}
-            self._stage_free = [None, None]
-        cs = self._copy_stream
-
-        def upload(data, slot):
-            bufs = []
-            with torch.cuda.stream(cs):
-                if self._stage_free[slot] is not None:
-                    cs.wait_event(self._stage_free[slot])    # step that read this slot is done
-                for j, t in enumerate(data):
-                    key = (slot, j, tuple(t.shape), t.dtype)
-                    b = self._stage.get(key)
-                    if b is None:
-                        b = self._stage[key] = torch.empty(t.shape, dtype=t.dtype, device=dev)
-                    b.copy_(t, non_blocking=True)
-                    bufs.append(b)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-            return bufs, ev
-
-        epoch_loss = 0.
-        pending = deque()     # (ring index, event, host constant)
-        it = iter(train_loader)
-        nxt = next(it, None)
-        staged = upload(nxt, 0) if nxt is not None else None
-        i = 0
-        while staged is not None:
-            bufs, ev = staged
-            nxt = next(it, None)
-            staged = upload(nxt, (i + 1) % 2) if nxt is not None else None
-            main.wait_event(ev)
-            # the staging slot's address recurs: its copy into the program input is part of the
-            # step's CUDA graph; the optimizer kernel writes the loss into eng.loss_ring (pinned
-            # host memory, slot = optimizer step count & 3) -- no copy call on either side
-            eng.step(*bufs, _sync=False, _static=True, **kwargs)
-            free = torch.cuda.Event()
-            free.record(main)
-            self._stage_free[i % 2] = free
-            if len(pending) >= 3:                       # ring slot about to be reused
-                k, e, c = pending.popleft()
-                e.synchronize()
-                epoch_loss += float(eng.loss_ring[k]) + c
-            pending.append((eng.updates_done & 3, free, eng.last_loss_const))
-            i += 1
-        while pending:
-            k, e, c = pending.popleft()
-            e.synchronize()
-            epoch_loss += float(eng.loss_ring[k]) + c
+        with torch.cuda.device(eng.device):
+            if not hasattr(self, "_pipe"):
+                self._pipe = StepPipeline(eng)
+            steps = [eng.step]
+            epoch_loss = run_epoch(self._pipe, ((data, steps, 1.0) for data in train_loader),
+                                   **kwargs)
         return epoch_loss / len(train_loader.dataset)
 
     def evaluate(self, test_loader, **kwargs) -> float:

@@ -66,3 +66,68 @@ class TensorBatchLoader:
         for i in range(len(self)):
             lo = i * self.batch_size
             yield tuple(t[lo:lo + self.batch_size] for t in src)
+
+
+class DeviceBatchLoader:
+    """GPU-resident replacement for `init_dataloader` (reference utils/data.py:6-52): the whole
+    dataset lives in HBM (fp32; 180 GB per B200 holds ~57 M 28x28 images), every epoch draws a
+    permutation ON THE DEVICE, and each mini-batch is gathered by a hand-written row-gather kernel
+    (`pvb_gather_rows`, HBM-bound) into one of two device buffers whose addresses recur -- so the
+    trainers' step graphs take their input from it without any host -> device traffic.  Same
+    protocol as the DataLoader the reference builds, as far as the trainers use it: iteration
+    yields tuples `(x,)` / `(x, y)`, `len()` is the number of batches, `.dataset` has a length.
+
+    shuffle=False yields zero-copy views of the resident tensors.  `seed` makes the epoch
+    permutations reproducible (one generator, advanced every epoch)."""
+
+    def __init__(self, *tensors, batch_size=100, shuffle=True, device=None, seed=None,
+                 drop_last=False):
+        if device is None:
+            device = tensors[0].device if tensors[0].is_cuda else "cuda"
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceBatchLoader keeps the dataset in GPU memory; got device={!r}"
+                               .format(str(device)))
+        n = tensors[0].shape[0]
+        assert all(t.shape[0] == n for t in tensors)
+        self.tensors = [t.to(self.device, torch.float32).contiguous() for t in tensors]
+        self.batch_size, self.shuffle, self.drop_last = int(batch_size), bool(shuffle), drop_last
+        self.dataset = _Len(n)
+        self.gen = torch.Generator(device=self.device)
+        if seed is not None:
+            self.gen.manual_seed(int(seed))
+        self._bufs = None
+        self.last_perm = None
+
+    def __len__(self):
+        n = len(self.dataset)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        from .. import ops
+        n, bs = len(self.dataset), self.batch_size
+        if not self.shuffle:
+            for i in range(len(self)):
+                yield tuple(t[i * bs:(i + 1) * bs] for t in self.tensors)
+            return
+        with torch.cuda.device(self.device):
+            perm = torch.randperm(n, device=self.device, generator=self.gen)
+            self.last_perm = perm
+            if self._bufs is None:
+                self._bufs = [[torch.empty((bs, *t.shape[1:]), device=self.device) for t in self.tensors]
+                              for _ in range(2)]
+            for i in range(len(self)):
+                idx = perm[i * bs:(i + 1) * bs]
+                out = []
+                for t, b in zip(self.tensors, self._bufs[i % 2]):
+                    ops.gather_rows(t, idx, b)
+                    out.append(b[:idx.numel()])
+                yield tuple(out)
+
+
+class _Len:
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __len__(self):
+        return self.n

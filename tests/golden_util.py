@@ -25,6 +25,10 @@ CASES = {
                                      sampler_d="continuous_bernoulli")),
     "jivae_28_r": ("jivae", dict(data_dim=(28, 28), latent_dim=2, discrete_dim=3,
                                  invariances=["r"])),
+    # beta[1] = 1: the enumerated-site weighting does not depend on how poutine.scale interacts
+    # with the Dice weights
+    "jivae_28_r_beta1": ("jivae", dict(data_dim=(28, 28), latent_dim=2, discrete_dim=3,
+                                       invariances=["r"])),
     "ssivae_16_r_unsup": ("ssivae", dict(data_dim=(16, 16), latent_dim=2, num_classes=4,
                                          invariances=["r"])),
     "ssivae_16_r_sup": ("ssivae", dict(data_dim=(16, 16), latent_dim=2, num_classes=4,

@@ -4,14 +4,13 @@ through the C ABI via the drop-in Python classes, against
   (b) the CPU oracle port (oracle/svi_port.py) on fresh seeded inputs.
 Tolerances: ELBO (loss) <= 1e-3 relative and reconstruction max-abs <= 1e-3,
 as BASELINE.json's north_star states (fp32 reference)."""
-import os
-
 import pytest
 import torch
 
 import pyroved_b200 as pv
 from golden_util import CASES, Golden
 from oracle import svi_port as sp
+from parity_util import FP32_GRAD_TOL, TC_GRAD_TOL, check_w1, grad_check
 
 pytestmark = pytest.mark.gpu
 
@@ -23,22 +22,10 @@ IVAE_CASES = [n for n in sorted(CASES) if CASES[n][0] == "ivae"]
 
 
 def build_ivae(name, g, generic):
-    os.environ["PVB_FORCE_GENERIC"] = "1" if generic else "0"
     m = pv.models.iVAE(seed=SEEDS.get(name, 1), device="cuda:0", **g.kwargs)
     m.load_state_dict(g.group("w0"))
-    tr = pv.trainers.SVItrainer(m, seed=1, device="cuda:0")
+    tr = pv.trainers.SVItrainer(m, seed=1, device="cuda:0", force_generic=generic)
     return m, tr
-
-
-def grad_check(m, gref, rtol):
-    worst = 0.0
-    for k, p in m.named_parameters():
-        ref = gref[k].cuda()
-        scale = ref.abs().max().item() + 1e-6
-        err = (p.grad - ref).abs().max().item() / scale
-        worst = max(worst, err)
-        assert err <= rtol, (k, err)
-    return worst
 
 
 @pytest.mark.parametrize("generic", [True, False], ids=["fp32-generic", "default"])
@@ -57,30 +44,31 @@ def test_ivae_loss_recon_grads_vs_reference_golden(name, generic):
     assert torch.allclose(prog.mu.cpu(), g.t("mu"), atol=1e-4)
     assert torch.allclose(prog.sigma.cpu(), g.t("sigma"), atol=1e-4)
     tc = getattr(prog, "use_tc", False)
-    grad_check(m, g.group("grad"), 2e-2 if tc else 2e-3)
+    grad_check(m, g.group("grad"), TC_GRAD_TOL if tc else FP32_GRAD_TOL,
+               "golden {} {}".format(name, "tc" if tc else "fp32"))
 
 
+@pytest.mark.parametrize("generic", [True, False], ids=["fp32-generic", "default"])
 @pytest.mark.parametrize("name", ["ivae_28_rt", "ivae_1d_t"])
-def test_ivae_full_step_matches_reference_adam(name):
-    """loss_and_grads + Adam == reference SVI.step (weights after one step)."""
+def test_ivae_full_step_matches_reference_adam(name, generic):
+    """loss_and_grads + Adam == reference SVI.step (weights after one step), on both paths."""
     g = Golden(name)
-    m, tr = build_ivae(name, g, generic=True)
+    m, tr = build_ivae(name, g, generic=generic)
     x, y = g.args()
     loss = tr.svi.step(x.cuda(), _eps=g.eps().cuda())
     assert abs(loss - g.loss_step) <= LOSS_RTOL * abs(g.loss_step)
-    sd = {k: v.cpu() for k, v in m.state_dict().items()}
-    for k, v in g.group("w1").items():
-        assert torch.allclose(sd[k], v, atol=5e-5), k
-    for k, idx in g.group("w1idx", torch.int64).items():
-        assert torch.allclose(sd[k].reshape(-1)[idx], g.t("w1sub." + k), atol=5e-5), k
+    prog = next(iter(tr.svi.programs.values()))
+    assert bool(getattr(prog, "use_tc", False)) == (not generic)
+    check_w1(m, g, noise_floor=None if generic else TC_GRAD_TOL)
 
 
+@pytest.mark.parametrize("generic", [True, False], ids=["fp32-generic", "default"])
 @pytest.mark.parametrize("B", [1, 7, 64])
-def test_ivae_vs_oracle_fresh_inputs(B):
-    """Ragged / tiny batches against the oracle port on seeded inputs."""
+def test_ivae_vs_oracle_fresh_inputs(B, generic):
+    """Ragged / tiny batches against the oracle port on seeded inputs, on both paths."""
     torch.manual_seed(B)
     m = pv.models.iVAE((28, 28), 2, ['r', 't', 's'], seed=5, device="cuda:0")
-    tr = pv.trainers.SVItrainer(m, device="cuda:0")
+    tr = pv.trainers.SVItrainer(m, device="cuda:0", force_generic=generic)
     gen = torch.Generator().manual_seed(100 + B)
     x = (torch.rand(B, 28, 28, generator=gen) < 0.4).float()
     eps = torch.randn(B, m.z_dim, generator=gen)
@@ -90,8 +78,11 @@ def test_ivae_vs_oracle_fresh_inputs(B):
     ref, grads = sp.loss_and_grads(sp.ivae_loss, sd, cfg, x, eps, None, 2.0)
     assert abs(loss - float(ref["loss"])) <= LOSS_RTOL * abs(float(ref["loss"]))
     prog = next(iter(tr.svi.programs.values()))
+    assert bool(prog.use_tc) == (not generic)
     assert (prog.loc.cpu().reshape(B, -1) - ref["loc"]).abs().max().item() <= LOC_ATOL
     assert torch.allclose(prog.ll.cpu(), ref["ll"], rtol=1e-3, atol=1e-2)
+    grad_check(m, grads, FP32_GRAD_TOL if generic else TC_GRAD_TOL,
+               "fresh rts B={} {}".format(B, "fp32" if generic else "tc"))
 
 
 def test_graph_replay_equals_eager_and_training_reduces_loss():
@@ -184,9 +175,8 @@ def test_rng_is_counter_based_and_reproducible():
 def test_fused_decoder_small_images_many_slots_per_tile(dim, inv, B):
     """N = 36 / 33 / 45 pixels: a 128-row tile of the fused kernel touches up to 5 instances, tiles
     straddle instance boundaries and the last tile is partial (ragged R)."""
-    os.environ["PVB_FORCE_GENERIC"] = "0"
     m = pv.models.iVAE(dim, 2, inv, seed=7, device="cuda:0")
-    tr = pv.trainers.SVItrainer(m, device="cuda:0")
+    tr = pv.trainers.SVItrainer(m, device="cuda:0", force_generic=False)
     gen = torch.Generator().manual_seed(B)
     x = (torch.rand(B, *dim, generator=gen) < 0.4).float()
     eps = torch.randn(B, m.z_dim, generator=gen)
@@ -198,7 +188,7 @@ def test_fused_decoder_small_images_many_slots_per_tile(dim, inv, B):
     ref, grads = sp.loss_and_grads(sp.ivae_loss, sd, cfg, x, eps)
     assert abs(loss - float(ref["loss"])) <= LOSS_RTOL * abs(float(ref["loss"]))
     assert (prog.loc.cpu().reshape(B, -1) - ref["loc"]).abs().max().item() <= LOC_ATOL
-    grad_check(m, grads, 2e-2)
+    grad_check(m, grads, TC_GRAD_TOL, "small images {} B={}".format(dim, B))
 
 
 def test_epoch_loop_equals_step_by_step():

@@ -167,3 +167,37 @@ def test_ss_reg_aux_and_two_optimizer_steps():
     assert abs(float(out["loss"]) + float(out2["loss"]) - g.loss_step) <= 1e-5 * abs(g.loss_step)
     for k, v in g.group("w1").items():
         assert torch.allclose(sd2[k], v, atol=2e-5), k
+
+
+@pytest.mark.parametrize("name", ["jivae_28_r", "jivae_28_r_beta1", "ssivae_16_r_unsup"])
+def test_enumerated_elbo_independent_route(name):
+    """The enumerated goldens come from the restated TraceEnum_ELBO (oracle/pyro_min).  An
+    independent route that never touches it -- K*B single-sample supervised Trace_ELBO runs of the
+    unmodified reference for ssiVAE, direct calls of the reference's nets + torch.distributions for
+    jiVAE (oracle/make_golden.py::main_enum) -- gives the same losses; so does the port."""
+    import os
+    from golden_util import GOLDEN_DIR
+    indep = float(np.load(os.path.join(GOLDEN_DIR, "enum_indep.npz"))[name])
+    g = Golden(name)
+    assert abs(indep - g.loss) <= 2e-6 * abs(g.loss), (indep, g.loss)
+    fn, args, cfg = port_loss_fn(g)
+    out, _ = sp.loss_and_grads(fn, g.group("w0"), *args)
+    assert abs(float(out["loss"]) - indep) <= 2e-6 * abs(indep)
+
+
+def test_port_is_separable_over_the_batch():
+    """The SVI loss is a SUM over samples (plate "data"): evaluating the port on chunks of the
+    batch and adding losses / gradients equals one evaluation -- the GPU parity tests at the
+    benchmark shapes (tests/test_gpu_bench_shapes.py) rely on this to bound the oracle's memory."""
+    from benchlib import chunked_oracle
+    g = Golden("jivae_28_r")
+    fn, args, cfg = port_loss_fn(g)
+    sd = g.group("w0")
+    out, grads = sp.loss_and_grads(fn, sd, *args)
+    x, _ = g.args()
+    out_c, grads_c = chunked_oracle("jivae", sd, cfg, (x,), g.eps(), tuple(g.kw()["scale_factor"]),
+                                    chunk=3)
+    assert abs(float(out["loss"]) - out_c["loss"]) <= 1e-6 * abs(out_c["loss"])
+    assert torch.allclose(out["loc"].reshape(3, 8, -1), out_c["loc"], atol=1e-6)
+    for k, v in grads.items():
+        assert torch.allclose(v, grads_c[k], atol=1e-4 * v.abs().max().item() + 1e-7), k
