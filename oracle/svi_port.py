@@ -236,13 +236,18 @@ def _decode_spatial(sd, cfg, z, extra, grid):
 # --------------------------------------------------------------------------
 # iVAE  (models/ivae.py:165-221 under Trace_ELBO)
 # --------------------------------------------------------------------------
-def ivae_loss(sd, cfg, x, eps, y=None, beta=1.0):
+def ivae_loss(sd, cfg, x, eps, y=None, beta=1.0, conv_encoder=None):
     """Returns dict(loss, ll[B], kl_term[B], loc[B,N], z, mu, sigma).
-    loss = -( sum_b ll_b + beta * sum_b (log p(z_b) - log q(z_b)) )."""
+    loss = -( sum_b ll_b + beta * sum_b (log p(z_b) - log q(z_b)) ).
+    conv_encoder: a VedCfg describing a convEncoderNet installed with iVAE.set_encoder
+    (models/base.py:173-176; its latent_dim is the model's full latent width)."""
     b = x.shape[0]
     grid = generate_grid(cfg.data_dim, x.dtype) if cfg.coord > 0 else None
     enc_in = [x, y] if y is not None else x
-    mu, sig, _ = fc_encoder(sd, enc_in, cfg.activation, cfg.n_pix + cfg.c_dim)
+    if conv_encoder is not None:
+        mu, sig = ved_encoder(sd, conv_encoder, x)
+    else:
+        mu, sig, _ = fc_encoder(sd, enc_in, cfg.activation, cfg.n_pix + cfg.c_dim)
     z = mu + sig * eps
     log_q = normal_logprob(z, mu, sig)
     log_p = normal_logprob(z, torch.zeros_like(z), torch.ones_like(z))

@@ -128,30 +128,30 @@ def _numel(shape):
     return n
 
 
-class VEDProgram(StepProgram):
-    """One Trace_ELBO step of VED on a batch (x, y):
-    loss = -sum_b [ log p(y_b | decoder(z_b)) + beta (log p(z_b) - log q(z_b | x_b)) ]."""
+class ConvGaussEncoder:
+    """`convEncoderNet` as the guide q(z|x) of a Trace_ELBO step (reference nets/conv.py:24-64):
+    FeatureExtractor (ConvStack) -> flatten -> fc_latent, whose rows [0, L) give mu and [L, 2L) the
+    pre-softplus sigma (two heads on weight views) -> reparameterised sample + KL terms; and the
+    backward of all of it.  Buffer names follow engine.GaussHead (eps, mu, s_pre, sigma, z, kl)."""
 
-    def __init__(self, engine, B):
-        super().__init__(engine, B, True)
-        m = engine.model
-        dev, flat = engine.device, engine.flat
+    def __init__(self, engine, enc, B, L):
+        dev = engine.device
         f32 = dict(device=dev, dtype=torch.float32)
-        enc, dec = m.encoder_z, m.decoder
-        L = m.z_dim
-        self.L = L
-        self.in_shape = (m.input_channels, *m.input_dim)
-        self.N_out = m.output_channels * _numel(m.output_dim)
-        self.x = torch.zeros((B, *self.in_shape), **f32)
-        self.y = torch.zeros(B, self.N_out, **f32)
-        self.enc = ConvStack(engine, enc.feature_extractor.layers, m.activation, B, self.in_shape)
-        self.feat_dim = _numel(self.enc.out_shape)
+        self.engine, self.enc, self.B, self.L = engine, enc, B, L
+        self.in_shape = (enc.input_channels, *enc.input_dim)
+        fe = enc.feature_extractor
+        self.stack = ConvStack(engine, fe.layers, fe.activation, B, self.in_shape)
+        self.feat_dim = _numel(self.stack.out_shape)
         fcl = enc.features2latent.fc_latent
         if fcl.in_features != self.feat_dim:
             raise ValueError("encoder feature map has {} elements but features2latent expects {} "
                              "(reference nets/conv.py:44-45 assumes len(hidden_dim)-1 poolings)"
                              .format(self.feat_dim, fcl.in_features))
-        # fc_latent rows [0, L) -> mu, [L, 2L) -> pre-softplus sigma: two heads on weight views
+        if fcl.out_features != 2 * L:
+            raise ValueError("convEncoderNet(latent_dim={}) does not match the model's latent width {}"
+                             .format(fcl.out_features // 2, L))
+        if not getattr(enc, "softplus_out", True):
+            raise NotImplementedError("pyroved_b200: convEncoderNet(softplus_out=False) as a guide")
         self.W_mu, self.W_s = fcl.weight.data[:L], fcl.weight.data[L:]
         self.b_mu, self.b_s = fcl.bias.data[:L], fcl.bias.data[L:]
         self.eps = torch.zeros(B, L, **f32)
@@ -160,13 +160,63 @@ class VEDProgram(StepProgram):
         self.sigma = torch.empty(B, L, **f32)
         self.z = torch.empty(B, L, **f32)
         self.kl = torch.empty(B, **f32)
-        self.gz = torch.empty(B, L, **f32)
         self.gmu = torch.empty(B, L, **f32)
         self.gs_pre = torch.empty(B, L, **f32)
+        self.dfeat = torch.empty(B, self.feat_dim, **f32)
+
+    @property
+    def uses_tc(self):
+        return any(st["tc"] for st in self.stack.steps)
+
+    def forward(self, x, gen_eps):
+        eng = self.engine
+        feat = self.stack.forward(x.view(self.B, *self.in_shape)).view(self.B, self.feat_dim)
+        if gen_eps:
+            ops.randn(self.eps, eng.seed, eng.step_counter, eng.eps_first_index(self.eps.numel()))
+        ops.linear_fwd(feat, self.W_mu, self.b_mu, None, out=self.mu)
+        ops.linear_fwd(feat, self.W_s, self.b_s, None, out=self.s_pre)
+        ops.latent_fwd(self.mu, self.s_pre, self.eps, self.sigma, self.z, self.kl)
+
+    def backward(self, gz, w, beta):
+        """gz = dloss/dz [B, L] from the decoder side; adds the KL terms (times beta) and
+        propagates through the heads and the convolutional stack."""
+        flat = self.engine.flat
+        ops.latent_bwd(gz, self.eps, self.sigma, self.s_pre, self.z, w, beta, self.gmu, self.gs_pre)
+        fcl = self.enc.features2latent.fc_latent
+        gW, gb = flat.gv(fcl.weight), flat.gv(fcl.bias)
+        L = self.L
+        feat = self.stack.steps[-1]["y"].view(self.B, self.feat_dim)
+        ops.linear_bwd(feat, self.W_mu, None, None, self.gmu, self.gmu, self.dfeat, False,
+                       gW[:L], gb[:L], None)
+        ops.linear_bwd(feat, self.W_s, None, None, self.gs_pre, self.gs_pre, self.dfeat, True,
+                       gW[L:], gb[L:], None)
+        self.stack.backward(self.dfeat.view(self.B, *self.stack.out_shape), False)
+
+
+class VEDProgram(StepProgram):
+    """One Trace_ELBO step of VED on a batch (x, y):
+    loss = -sum_b [ log p(y_b | decoder(z_b)) + beta (log p(z_b) - log q(z_b | x_b)) ]."""
+
+    def __init__(self, engine, B):
+        super().__init__(engine, B, True)
+        m = engine.model
+        dev = engine.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        enc, dec = m.encoder_z, m.decoder
+        L = m.z_dim
+        self.L = L
+        self.N_out = m.output_channels * _numel(m.output_dim)
+        self.genc = ConvGaussEncoder(engine, enc, B, L)
+        self.in_shape = self.genc.in_shape
+        self.enc = self.genc.stack
+        self.x = torch.zeros((B, *self.in_shape), **f32)
+        self.y = torch.zeros(B, self.N_out, **f32)
+        self.gz = torch.empty(B, L, **f32)
         l2f = dec.latent2features
         self.dec_in_shape = tuple(l2f.reshape_)
         self.feat0 = torch.empty(B, _numel(self.dec_in_shape), **f32)
-        self.dec = ConvStack(engine, dec.upsampler.layers, m.activation, B, self.dec_in_shape)
+        self.dec = ConvStack(engine, dec.upsampler.layers, dec.upsampler.activation, B,
+                             self.dec_in_shape)
         if _numel(self.dec.out_shape) != self.N_out:
             raise ValueError("decoder output {} does not match output_dim {}".format(
                 self.dec.out_shape, m.output_dim))
@@ -174,9 +224,13 @@ class VEDProgram(StepProgram):
         self.dlogit = torch.empty(B * self.N_out, **f32)
         self._loc = torch.empty(B * self.N_out, **f32)
         self.ll = torch.empty(B, **f32)
-        self.dfeat = torch.empty(B, self.feat_dim, **f32)
 
     loc = property(lambda s: s._loc)
+    eps = property(lambda s: s.genc.eps)
+    mu = property(lambda s: s.genc.mu)
+    sigma = property(lambda s: s.genc.sigma)
+    z = property(lambda s: s.genc.z)
+    kl = property(lambda s: s.genc.kl)
     use_tc = property(lambda s: any(st["tc"] for st in s.enc.steps + s.dec.steps))
 
     def load(self, x, y):
@@ -188,12 +242,7 @@ class VEDProgram(StepProgram):
         eng = self.engine
         m = eng.model
         samp = m.sampler_d
-        feat = self.enc.forward(self.x).view(self.B, self.feat_dim)
-        if gen_eps:
-            ops.randn(self.eps, eng.seed, eng.step_counter, eng.eps_first_index(self.eps.numel()))
-        ops.linear_fwd(feat, self.W_mu, self.b_mu, None, out=self.mu)
-        ops.linear_fwd(feat, self.W_s, self.b_s, None, out=self.s_pre)
-        ops.latent_fwd(self.mu, self.s_pre, self.eps, self.sigma, self.z, self.kl)
+        self.genc.forward(self.x, gen_eps)
         fc = m.decoder.latent2features.fc
         ops.linear_fwd(self.z, fc.weight.data, fc.bias.data, None, out=self.feat0)
         logit = self.dec.forward(self.feat0.view(self.B, *self.dec_in_shape))
@@ -211,14 +260,4 @@ class VEDProgram(StepProgram):
         ops.linear_bwd(self.z, fc.weight.data, None, None, dfeat0.reshape(self.B, -1),
                        dfeat0.reshape(self.B, -1), self.gz, False, flat.gv(fc.weight),
                        flat.gv(fc.bias), None)
-        ops.latent_bwd(self.gz, self.eps, self.sigma, self.s_pre, self.z, None, beta, self.gmu,
-                       self.gs_pre)
-        fcl = m.encoder_z.features2latent.fc_latent
-        gW, gb = flat.gv(fcl.weight), flat.gv(fcl.bias)
-        L = self.L
-        feat = self.enc.steps[-1]["y"].view(self.B, self.feat_dim)
-        ops.linear_bwd(feat, self.W_mu, None, None, self.gmu, self.gmu, self.dfeat, False,
-                       gW[:L], gb[:L], None)
-        ops.linear_bwd(feat, self.W_s, None, None, self.gs_pre, self.gs_pre, self.dfeat, True,
-                       gW[L:], gb[L:], None)
-        self.enc.backward(self.dfeat.view(self.B, *self.enc.out_shape), False)
+        self.genc.backward(self.gz, None, beta)

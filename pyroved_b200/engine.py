@@ -32,6 +32,13 @@ def _align4(n):
     return (n + 3) // 4 * 4
 
 
+def _numel_shape(shape):
+    n = 1
+    for v in shape:
+        n *= int(v)
+    return n
+
+
 class FlatParams:
     """Flat parameter / gradient / Adam-state buffers with per-parameter views."""
 
@@ -524,8 +531,23 @@ class SpatialVAEProgram(StepProgram):
         self.x = torch.zeros(B, N, **f32) if C > 0 else self.enc_in
         self.y = torch.zeros(B, C, **f32) if C > 0 else None
         enc = m.encoder_z
-        self.head = GaussHead(engine, enc, B, Z)
         self.dec = DecoderOps(engine, B, B, C)
+        # a convolutional encoder installed with set_encoder (reference models/base.py:173-176;
+        # BASELINE configs[1] words the iVAE as "conv encoder / fc decoder")
+        self.conv_enc = hasattr(enc, "feature_extractor")
+        if self.conv_enc:
+            from .conv_engine import ConvGaussEncoder
+            if C > 0:
+                raise NotImplementedError("pyroved_b200: a convolutional encoder_z cannot take the "
+                                          "conditioning vector y (the reference's convEncoderNet "
+                                          "has no such input either)")
+            self.head = ConvGaussEncoder(engine, enc, B, Z)
+            if _numel_shape(self.head.in_shape) != N:
+                raise ValueError("encoder input {} does not match data_dim {}".format(
+                    self.head.in_shape, m._data_dim))
+            self.fused = False
+            return
+        self.head = GaussHead(engine, enc, B, Z)
         enc_layers = linear_layers(enc.fc_layers)
         self.fused = (not engine.force_generic and
                       FusedStack.eligible(enc_layers, [enc.fc11, enc.fc12], B))
@@ -567,12 +589,19 @@ class SpatialVAEProgram(StepProgram):
                              beta=float(beta), loss_out=flat.loss, uv_ready=self.dec.spatial,
                              side_loss=self.side_loss)
             return
-        h = self.enc.forward(self.enc_in)
-        self.head.forward(h, gen_eps)
+        if self.conv_enc:
+            self.head.forward(self.enc_in, gen_eps)
+        else:
+            h = self.enc.forward(self.enc_in)
+            self.head.forward(h, gen_eps)
         self.dec.forward(self.head.z, self.y, self.x, None, want_grad, kl=self.head.kl,
                          beta=float(beta), loss_out=flat.loss)
 
     def backward(self, beta):
+        if self.conv_enc:
+            gz = self.dec.backward(self.head.z, self.y)
+            self.head.backward(gz, None, beta)
+            return
         if self.fused and self.dec.spatial and self.dec.use_tc:
             self.dec.backward_fused(self.head, self.y, None, beta)
             self.enc.backward([self.head.gmu, self.head.gs_pre])
@@ -987,7 +1016,7 @@ class SVIEngine:
     step on a mini-batch and returns the (batch-sum) loss."""
 
     def __init__(self, model, lr=1e-3, enumerate_parallel=False, seed=1, device=None,
-                 use_graphs=None, force_generic=None):
+                 use_graphs=None, force_generic=None, data_parallel=None):
         if device is None:
             device = getattr(model, "device", "cuda")
         self.device = torch.device(device if str(device) != "cuda" else "cuda:{}".format(
@@ -1006,8 +1035,11 @@ class SVIEngine:
         self.side = torch.cuda.Stream(self.device)
         self._side_used = False
         self.peer = None          # parallel.PeerExchange of the current flat gradient buffer
+        # data_parallel=False: a purely local engine even inside an initialised process group
+        # (e.g. a single-GPU cross-check next to a data-parallel run); None: follow the group
+        self.data_parallel = data_parallel is not False
         self.flat = FlatParams(model, self.device, self._alloc_grad_buffer()
-                               if parallel.peer_exchange_enabled() else None)
+                               if self.data_parallel and parallel.peer_exchange_enabled() else None)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.adam_ticket = torch.zeros(1, device=self.device, dtype=torch.int32)
         # pinned host ring the optimizer kernel writes each step's loss into (slot = step count &
@@ -1034,7 +1066,8 @@ class SVIEngine:
 
     # ---- distributed -----------------------------------------------------
     def _attach_distributed(self):
-        self.rank, self.world_size = parallel.rank_world()
+        if self.data_parallel:
+            self.rank, self.world_size = parallel.rank_world()
 
     def _alloc_grad_buffer(self):
         """Allocator handed to FlatParams when the fused NVLink exchange is on: the flat

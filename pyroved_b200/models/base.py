@@ -177,10 +177,56 @@ class baseVAE(nn.Module):
 
     # ---- hooks ----------------------------------------------------------------
     def set_encoder(self, encoder_net: nn.Module) -> None:
+        """Replace the encoder (reference models/base.py:173-176).  The SVI step is a sequence of
+        hand-written kernels chosen from the structure of the nets, so the replacement must be one
+        of this package's net classes of a kind the model's step knows how to run: an
+        `fcEncoderNet`-family net of the model's own kind, or -- for iVAE -- a `convEncoderNet`
+        whose latent_dim equals the model's full latent width (transform + content latents).
+        Anything else raises TypeError (there is no eager / autograd fallback)."""
+        self._check_replacement("encoder_z", encoder_net)
         self.encoder_z = encoder_net.to(self.device)
 
     def set_decoder(self, decoder_net: nn.Module) -> None:
+        """Replace the decoder (reference models/base.py:178-181); see set_encoder."""
+        self._check_replacement("decoder", decoder_net)
         self.decoder = decoder_net.to(self.device)
+
+    def _check_replacement(self, slot, net):
+        from ..nets import conv as convnets
+        from ..nets import fc as fcnets
+        cur = getattr(self, slot)
+        own = tuple(c for c in list(vars(fcnets).values()) + list(vars(convnets).values())
+                    if isinstance(c, type) and issubclass(c, nn.Module))
+        if not isinstance(net, own):
+            raise TypeError(
+                "pyroved_b200 runs the SVI step as fused CUDA kernels selected from the structure "
+                "of the nets: set_{} accepts this package's net classes (pyroved_b200.nets), not {}"
+                .format("encoder" if slot == "encoder_z" else "decoder", type(net).__name__))
+        same_kind = cur is not None and type(net) is type(cur)
+        conv_for_ivae = (slot == "encoder_z" and isinstance(net, convnets.convEncoderNet)
+                         and type(self).__name__ == "iVAE")
+        if not (same_kind or conv_for_ivae):
+            raise TypeError("{} cannot replace the {} of a {} (supported: a net of the same class{})"
+                            .format(type(net).__name__, slot, type(self).__name__,
+                                    ", or convEncoderNet for iVAE" if slot == "encoder_z" else ""))
+        if conv_for_ivae:
+            if getattr(self, "c_dim", 0) > 0:
+                raise TypeError("a convolutional encoder cannot take the conditioning vector y")
+            if net.latent_dim != self.z_dim:
+                raise ValueError("convEncoderNet(latent_dim={}) must produce the model's full latent "
+                                 "vector: {} (= {} transform + {} content latents)".format(
+                                     net.latent_dim, self.z_dim, self.coord, self.z_dim - self.coord))
+            if tuple(net.input_dim) != tuple(self._data_dim):
+                raise ValueError("encoder input_dim {} does not match data_dim {}".format(
+                    net.input_dim, self._data_dim))
+        elif same_kind:
+            a = [(k, tuple(v.shape)) for k, v in cur.state_dict().items()]
+            b = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+            # hidden sizes may differ; input / output widths must fit the model
+            if a[0][1][-1] != b[0][1][-1] or a[-1][1][0] != b[-1][1][0]:
+                raise ValueError("replacement {} has input / output widths {} / {}, the model needs "
+                                 "{} / {}".format(type(net).__name__, b[0][1][-1], b[-1][1][0],
+                                                  a[0][1][-1], a[-1][1][0]))
 
     def save_weights(self, filepath: str) -> None:
         torch.save(self.state_dict(), filepath + '.pt')

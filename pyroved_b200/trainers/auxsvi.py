@@ -38,7 +38,8 @@ class auxSVItrainer:
         elif optimizer is not None:
             raise TypeError("pass optimizer=None or {'lr': ...}: Adam is fused into the CUDA step")
         self.svi = SVIEngine(model, lr=lr, enumerate_parallel=(task == "classification"), seed=seed,
-                             device=self.device, force_generic=kwargs.get("force_generic"))
+                             device=self.device, force_generic=kwargs.get("force_generic"),
+                             data_parallel=kwargs.get("data_parallel"))
         self.model = model
         self.history = {"training_loss": [], "test": []}
         self.current_epoch = 0

@@ -35,7 +35,8 @@ class SVItrainer:
             raise TypeError("pyroved_b200 implements Trace_ELBO / TraceEnum_ELBO natively; "
                             "pass loss=None (use enumerate_parallel for discrete latents)")
         self.svi = SVIEngine(model, lr=lr, enumerate_parallel=enumerate_parallel, seed=seed,
-                             device=self.device, force_generic=kwargs.get("force_generic"))
+                             device=self.device, force_generic=kwargs.get("force_generic"),
+                             data_parallel=kwargs.get("data_parallel"))
         self.loss_history = {"training_loss": [], "test_loss": []}
         self.current_epoch = 0
 

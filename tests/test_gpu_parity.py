@@ -212,3 +212,45 @@ def test_epoch_loop_equals_step_by_step():
         assert abs(got - ref) <= 1e-6 * abs(ref), (epoch, got, ref)
     for (k, a), (_, b) in zip(ma.state_dict().items(), mb.state_dict().items()):
         assert torch.allclose(a, b, atol=1e-6, rtol=0), (k, (a - b).abs().max().item())
+
+
+@pytest.mark.parametrize("generic", [True, False], ids=["fp32-generic", "default"])
+def test_ivae_with_conv_encoder_via_set_encoder(generic):
+    """iVAE.set_encoder(convEncoderNet(...)) (reference models/base.py:173-176; BASELINE configs[1]
+    words the model as "conv encoder / fc decoder"): convolutional guide on the conv kernels, fused
+    spatial decoder behind it; loss / reconstruction / gradients against the port, then training."""
+    from pyroved_b200.nets import convEncoderNet
+    B = 48
+    m = pv.models.iVAE((28, 28), 2, ['r', 't'], seed=1, device="cuda:0")
+    torch.manual_seed(11)
+    m.set_encoder(convEncoderNet((28, 28), latent_dim=m.z_dim, hidden_dim=[(16,), (32, 32)]))
+    tr = pv.trainers.SVItrainer(m, device="cuda:0", force_generic=generic)
+    gen = torch.Generator().manual_seed(12)
+    x = (torch.rand(B, 28, 28, generator=gen) < 0.3).float()
+    eps = torch.randn(B, m.z_dim, generator=gen)
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    loss = tr.svi.loss_and_grads(x.cuda(), _eps=eps.cuda(), scale_factor=2.0)
+    prog = next(iter(tr.svi.programs.values()))
+    assert prog.conv_enc and bool(prog.use_tc) == (not generic)
+    cfg = sp.Cfg((28, 28), 2, ['r', 't'])
+    vcfg = sp.VedCfg((28, 28), (1,), latent_dim=m.z_dim, hidden_dim_e=[(16,), (32, 32)])
+    ref, grads = sp.loss_and_grads(sp.ivae_loss, sd, cfg, x, eps, None, 2.0, conv_encoder=vcfg)
+    assert abs(loss - float(ref["loss"])) <= LOSS_RTOL * abs(float(ref["loss"]))
+    assert (prog.loc.cpu().reshape(B, -1) - ref["loc"]).abs().max().item() <= LOC_ATOL
+    assert torch.allclose(prog.mu.cpu(), ref["mu"], atol=1e-3 if not generic else 1e-4)
+    # decoder gradients at the decoder's tolerance; encoder (leaky-ReLU convolutions on fp16
+    # tensor-core operands on the default path) at the VED bound
+    dec_grads = {k: v for k, v in grads.items() if k.startswith("decoder.")}
+    sub = torch.nn.Module()
+    sub.decoder = m.decoder
+    grad_check(sub, dec_grads, FP32_GRAD_TOL if generic else TC_GRAD_TOL,
+               "conv-encoder iVAE decoder {}".format("fp32" if generic else "tc"))
+    for k, p in m.encoder_z.named_parameters():
+        r = grads["encoder_z." + k].cuda()
+        err = (p.grad - r).norm().item() / (r.norm().item() + 1e-9)
+        assert err <= (2e-3 if generic else 6e-2), (k, err)
+    xc, ec = x.cuda(), eps.cuda()
+    ls = [tr.svi.step(xc, _eps=ec) for _ in range(20)]
+    assert all(v == v for v in ls) and ls[-1] < ls[0], ls[::5]
+    mu, sig = m.encode(x)
+    assert mu.shape == (B, m.z_dim) and (sig > 0).all()

@@ -169,3 +169,27 @@ def test_conv_layer_plan_batchnorm_and_volumetric():
         assert all(b.mode == ("bilinear" if ndim == 2 else "nearest") for b in blocks)
     with pytest.raises(NotImplementedError):
         FeatureExtractor(2, 1, [(8,)], kernel_size=5, padding=2)
+
+
+def test_set_encoder_set_decoder_accept_package_nets_and_reject_foreign_modules():
+    """reference models/base.py:173-181: the plug-in hooks.  The step is built from the nets'
+    structure, so package nets are accepted (conv encoder for iVAE included), foreign modules and
+    nets of the wrong width are refused with a clear error (no silent eager fallback)."""
+    from pyroved_b200.nets import convEncoderNet, fcDecoderNet, fcEncoderNet, sDecoderNet
+    m = pv.models.iVAE((28, 28), 2, ['r', 't'], device="cpu")
+    m.set_encoder(convEncoderNet((28, 28), latent_dim=m.z_dim))
+    assert any(k.startswith("encoder_z.feature_extractor.layers.0") for k in m.state_dict())
+    m.set_decoder(sDecoderNet((28, 28), 2, 0, [128, 128], "tanh"))
+    with pytest.raises(TypeError):
+        m.set_encoder(torch.nn.Linear(784, 10))
+    with pytest.raises(ValueError):
+        m.set_encoder(convEncoderNet((28, 28), latent_dim=2))      # must cover the transform latents
+    with pytest.raises(TypeError):
+        m.set_decoder(fcDecoderNet((28, 28), 2))                   # spatial model, non-spatial decoder
+    m2 = pv.models.iVAE((28, 28), 2, ['r', 't'], device="cpu")
+    m2.set_encoder(fcEncoderNet((28, 28), 5, 0, [64, 64, 64], "relu"))
+    with pytest.raises(ValueError):
+        m2.set_encoder(fcEncoderNet((28, 28), 4, 0))
+    with pytest.raises(TypeError):
+        pv.models.jiVAE((28, 28), 2, 3, ['r'], device="cpu").set_encoder(
+            convEncoderNet((28, 28), latent_dim=3))
