@@ -5,11 +5,11 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall"
 SRCS="pvb_core.cu pvb_gemm.cu pvb_latent.cu pvb_sdec_simt.cu pvb_mlp.cu pvb_conv.cu pvb_conv_tc.cu pvb_norm.cu pvb_peer.cu pvb_conv3d.cu"
-[ -f pvb_sdec_tc.cu ] && SRCS="$SRCS pvb_sdec_tc.cu"
+[ -f pvb_sdec_tc.cu ] && SRCS="$SRCS pvb_sdec_tc.cu pvb_sdec_tc2.cu"
 OBJS=""
 for s in $SRCS; do
   o="${s%.cu}.o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ pvb_common.cuh -nt "$o" ] || [ pvb_fold.cuh -nt "$o" ] || [ umma.cuh -nt "$o" ] || [ ../../include/pvb.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ pvb_common.cuh -nt "$o" ] || [ pvb_fold.cuh -nt "$o" ] || [ umma.cuh -nt "$o" ] || [ pvb_sdec_tc.cuh -nt "$o" ] || [ ../../include/pvb.h -nt "$o" ]; then
     $NVCC $FLAGS ${PVB_EXTRA_FLAGS} -c "$s" -o "$o" &
   fi
   OBJS="$OBJS $o"

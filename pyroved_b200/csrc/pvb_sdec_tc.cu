@@ -35,9 +35,13 @@
 // the Bernoulli/Normal log_prob (utils/prob.py:25-29) and their autograd
 // backward on the reference path.
 #include "pvb_common.cuh"
+#include "pvb_sdec_tc.cuh"
 #include "umma.cuh"
 
+#include <cstdlib>
+
 namespace {
+using pvb_sdec::Params;
 
 constexpr int HD = 128;            // hidden width (fixed for this kernel)
 constexpr int TILE = 128;          // rows per tile
@@ -118,15 +122,6 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return y;
 }
 
-struct Params {
-  const float* Uv; const float* x; const float* w;
-  const float* W1; const float* b1; const float* W2; const float* b2;
-  const float* wo; const float* bo;
-  float* rowll; float* loc; float* gUv_part; float* wgrad_part;
-  int64_t R; int64_t B; int N; int H; int W; int ndim;
-  int sampler; int sigmoid_d; float sig; int backward; int64_t tiles;
-  int64_t step_q; int step_r; int step_qb;   // (TILE*grid) / N, % N, and step_q % B
-};
 
 // fp32 [128][128] row-major global weights -> fp16 row-chunk tile in smem
 __device__ __forceinline__ void stage_weight(const float* __restrict__ Wg, uint8_t* dst, int tid) {
@@ -860,6 +855,17 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
   P.step_q = step / N;
   P.step_r = (int)(step % N);
   P.step_qb = (int)(P.step_q % B);
+  // training step: the interleaved kernel (forward of tile i overlapped with the backward of tile
+  // i-1, csrc/pvb_sdec_tc2.cu) unless PVB_SDEC_V1=1 asks for the one-tile-in-flight kernel
+  // (A/B measurements); forward-only calls (inference) always run the kernel in this file
+  const char* v1_env = std::getenv("PVB_SDEC_V1");
+  const bool v1_only = v1_env && v1_env[0] == '1';
+  if (backward && !v1_only) {
+    int e = pvb_sdec::launch_v2(P, s.ctas, (cudaStream_t)stream);
+    if (e != 0) return e;
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   sdec_tc_kernel<<<s.ctas, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
   pvb::count_launch();
   return pvb::launch_status();

@@ -212,3 +212,69 @@ def test_peer_allreduce_adam_single_rank_equals_adam_flat_step():
         assert int(new["c"]) == it + 1 and int(state[0]) == it + 1 and int(state[1]) == 0
         assert float(g[n]) == 3.5 + it
     assert torch.equal(new["p"][100:200], p0[100:200])
+
+
+# ---- fused tcgen05 spatial decoder, kernel level ------------------------------------------------------
+def _sdec_torch_reference(Uv, x, w, W1, b1, W2, b2, wo, bo, H, W, B):
+    """Plain PyTorch fp32 (autograd) of what pvb_sdec_tc_step computes: h0 = tanh(U g + v) from the
+    folded first-layer coefficients, two tanh layers, output layer, Bernoulli(sigmoid) log-lik,
+    loss = -sum_i w_i sum_p ll_ip; gradients wrt Uv and the decoder weights."""
+    I = Uv.shape[0]
+    gx = torch.linspace(-1, 1, H, device=Uv.device)
+    gy = torch.linspace(1, -1, W, device=Uv.device)
+    g = torch.stack(torch.meshgrid(gx, gy, indexing="ij"), -1).reshape(-1, 2)      # [N,2]
+    leaves = [t.clone().requires_grad_(True) for t in (Uv, W1, b1, W2, b2, wo, bo)]
+    Uv_, W1_, b1_, W2_, b2_, wo_, bo_ = leaves
+    h0 = torch.tanh(g[None, :, 0, None] * Uv_[:, None, 0] + g[None, :, 1, None] * Uv_[:, None, 1]
+                    + Uv_[:, None, 2])                                           # [I,N,128]
+    h1 = torch.tanh(h0 @ W1_.t() + b1_)
+    h2 = torch.tanh(h1 @ W2_.t() + b2_)
+    logit = (h2 @ wo_.t() + bo_).squeeze(-1)                                        # [I,N]
+    xi = x[torch.arange(I, device=Uv.device) % B]
+    ll = xi * logit - torch.nn.functional.softplus(logit)
+    wt = w if w is not None else torch.ones(I, device=Uv.device)
+    (-(wt[:, None] * ll).sum()).backward()
+    return ll.detach(), torch.sigmoid(logit).detach(), [t.grad for t in leaves]
+
+
+@pytest.mark.parametrize("variant", ["interleaved", "one-tile"])
+@pytest.mark.parametrize("shape", [(64, 64, 28, 28, False), (12, 4, 28, 28, True), (37, 37, 6, 6, False),
+                                   (300, 300, 28, 28, False)])
+def test_sdec_tc_kernel_vs_torch(shape, variant, monkeypatch):
+    """pvb_sdec_tc_step (training: forward + backward in one launch) against PyTorch fp32 autograd,
+    both kernel variants: the interleaved two-tiles-in-flight kernel (csrc/pvb_sdec_tc2.cu, default)
+    and the one-tile-in-flight kernel (csrc/pvb_sdec_tc.cu, PVB_SDEC_V1=1).  Shapes: a CTA with one
+    tile only (64 x 784 rows = 392 tiles over 148 CTAs: 2-3 tiles each), enumerated instances with
+    weights (I = 3 B), tiny images (5 instances per tile, ragged last tile), and enough tiles that
+    every CTA pipelines many (300 x 784 / 128 = 1838 tiles)."""
+    from pyroved_b200._lib import TC_WGRAD_FLOATS, TC_WGRAD_STRIDE
+    monkeypatch.setenv("PVB_SDEC_V1", "1" if variant == "one-tile" else "0")
+    I, B, H, W, weighted = shape
+    N = H * W
+    gen = torch.Generator().manual_seed(I * 7 + H)
+    r = lambda *s_, sc=1.0: (torch.randn(*s_, generator=gen) * sc).cuda()   # noqa: E731
+    Uv = r(I, 3, 128, sc=0.8)
+    W1, b1, W2, b2 = r(128, 128, sc=0.09), r(128, sc=0.05), r(128, 128, sc=0.09), r(128, sc=0.05)
+    wo, bo = r(1, 128, sc=0.09), r(1, sc=0.05)
+    x = (torch.rand(B, N, generator=gen) < 0.3).float().cuda()
+    w = torch.rand(I, generator=gen).cuda() if weighted else None
+    sz = ops.sdec_tc_sizes(I, N)
+    rowll, loc = torch.empty(I * N, device="cuda"), torch.empty(I * N, device="cuda")
+    gpart = torch.zeros(max(sz.gUv_part_floats, 4), device="cuda")
+    wpart = torch.zeros(max(sz.wgrad_part_floats, 4), device="cuda")
+    for _ in range(2):       # twice: no state may leak from one launch into the next
+        ops.sdec_tc_step(Uv, x, w, W1, b1, W2, b2, wo, bo, rowll, loc, gpart, wpart, I, B, H, W, 2,
+                         "bernoulli", True, 0.5, True)
+    gUv = torch.empty(I, 3, 128, device="cuda")
+    ops.sdec_tc_gather_gUv(gpart, gUv, I, N)
+    wsum = wpart.view(sz.ctas, TC_WGRAD_STRIDE)[:, :TC_WGRAD_FLOATS].sum(0)
+    ll_ref, loc_ref, (gUv_r, gW1, gb1, gW2, gb2, gwo, gbo) = _sdec_torch_reference(
+        Uv, x, w, W1, b1, W2, b2, wo, bo, H, W, B)
+    assert (rowll.view(I, N) - ll_ref).abs().max().item() <= 2e-3
+    assert (loc.view(I, N) - loc_ref).abs().max().item() <= 1e-3
+    got = torch.split(wsum, [128 * 128, 128, 128 * 128, 128, 128, 1])
+    for name, a, b_ in (("dUv", gUv, gUv_r), ("dW1", got[0], gW1), ("db1", got[1], gb1),
+                        ("dW2", got[2], gW2), ("db2", got[3], gb2), ("dwo", got[4], gwo),
+                        ("dbo", got[5], gbo)):
+        err = (a.reshape(-1) - b_.reshape(-1)).abs().max().item() / (b_.abs().max().item() + 1e-6)
+        assert err <= 3e-3, (name, err)
