@@ -548,7 +548,7 @@ def run_ours(args):
         blocks = timed_blocks(D, lambda k: svi.step(pool[(W_ + k) % POOL], _sync=False),
                               args.steps, n_blocks)
     t_dev = median(blocks)
-    loss_last = float(svi.flat.loss.item()) / BATCH / world
+    loss_last = float(svi.flat.last_loss.item()) / BATCH / world
     # ---- end to end through the public API ------------------------------------------
     # `trainer.train(loader)` (= one epoch of SVItrainer.step): host batches in pinned memory,
     # every step copies its batch H2D and its loss D2H inside the timed region.

@@ -315,19 +315,26 @@ int pvb_upsample3d_bwd(const float* dy, float* dx, int64_t BC, int D, int H, int
 
 /* ---- data-parallel exchange over NVLink peer memory (csrc/pvb_peer.cu) ----
  * Fused SUM all-reduce of the flat [n gradients | loss] buffers of all ranks + the Adam
- * update of pvb_adam_flat_step, one kernel, deterministic (rank-order sums, identical on
- * every rank).  peer_g: DEVICE array of `world` pointers, entry r = rank r's gradient
- * buffer (n + 4 floats, symmetric memory mapped into this process; entry `rank` = own_g);
- * peer_flags: DEVICE array of `world` pointers to each rank's flag block of
- * pvb_peer_flag_words() zero-initialised uint32 (symmetric memory); state: 4 zero-initialised
- * int32 of this rank.  On return (stream order) p/m/v are updated, own_g[n] holds the global
- * loss, *step_counter is advanced, and every peer has finished reading own_g.
+ * update of pvb_adam_flat_step, one kernel, deterministic (fixed-order sums, identical on
+ * every rank).  g: this rank's LOCAL gradient buffer (n + 4 floats: n gradients, the loss
+ * accumulator g[n], the last step's global loss g[n+1], 2 pad).  stage_ptrs: DEVICE array of
+ * 2 * world pointers, entry parity * world + r = rank r's staging buffer of that parity (n + 4
+ * floats each, symmetric memory mapped into this process); peer_flags: DEVICE array of `world`
+ * pointers to each rank's flag block of pvb_peer_flag_words() zero-initialised uint32
+ * (symmetric memory); state: pvb_peer_state_words() zero-initialised int32 of this rank.
+ * two_shot != 0: reduce-scatter + all-gather over peer memory (inbound 2 (world-1)/world x n
+ * instead of (world-1) x n floats; pays off for world >= 4); every rank must pass the same value.
+ * On return (stream order) p/m/v are updated, g[0..n] is ZERO (ready for the next step's
+ * accumulation), g[n+1] holds the global loss, *step_counter is advanced.  There is no
+ * end-of-kernel handshake: staging buffers alternate by epoch parity.
  * Every rank must launch it the same number of times (SPMD); n % 4 == 0. */
 int pvb_peer_flag_words(void);
-int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* own_g, int64_t n,
-                            const void* peer_g, const void* peer_flags, int32_t* state,
-                            int rank, int world, float lr, float beta1, float beta2,
-                            float eps, int32_t* step_counter, const int32_t* first_step,
+int pvb_peer_state_words(void);
+int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* g, int64_t n,
+                            const void* stage_ptrs, const void* peer_flags, int32_t* state,
+                            int rank, int world, int two_shot, float lr, float beta1,
+                            float beta2, float eps, int32_t* step_counter,
+                            const int32_t* first_step,
                             float* loss_ring /* as pvb_adam_flat_step; may be NULL */,
                             void* stream);
 
@@ -396,14 +403,18 @@ int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
 /* Same update with the step increment folded in: every element uses
  * t = *step_counter + 1 (- first_step[i]); the last CTA to finish stores
  * *step_counter += 1 (ticket must point to a zeroed int32 owned by the caller).
- * loss_ring (optional): PVB_LOSS_RING floats of device-accessible memory, normally MAPPED
- * PINNED HOST memory; slot (new step count & (PVB_LOSS_RING - 1)) receives *loss_src, i.e. the
- * step's result reaches the host without a separate copy. */
+ * g[0..n) is ZEROED as it is consumed (Pyro zeroes the gradients after every optimizer step,
+ * svi.step; here it also saves the next step's memset).
+ * loss_src (optional): two floats {loss accumulator of this step, last loss}: the accumulator
+ * is copied to loss_src[1] and cleared.  loss_ring (optional, needs loss_src): PVB_LOSS_RING
+ * floats of device-accessible memory, normally MAPPED PINNED HOST memory; slot (new step count &
+ * (PVB_LOSS_RING - 1)) receives the step's loss, i.e. the result reaches the host without a
+ * separate copy. */
 #define PVB_LOSS_RING 16
-int pvb_adam_flat_step(float* p, const float* g, float* m, float* v, int64_t n,
+int pvb_adam_flat_step(float* p, float* g, float* m, float* v, int64_t n,
                        float lr, float beta1, float beta2, float eps,
                        int32_t* step_counter, const int32_t* first_step,
-                       int32_t* ticket, const float* loss_src, float* loss_ring,
+                       int32_t* ticket, float* loss_src, float* loss_ring,
                        void* stream);
 
 /* dst[r][:] = src[idx[r]][:] for r < rows (row_floats fp32 each; 16-byte accesses when

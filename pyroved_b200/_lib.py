@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpvb.so")
+# PVB_LIB: an alternative build of the library (kernel experiments, tools/build_variants.sh)
+LIB_PATH = os.environ.get("PVB_LIB") or os.path.join(_HERE, "csrc", "libpvb.so")
 
 _f = C.c_void_p      # device pointer (float*)
 _i64 = C.c_int64
@@ -106,7 +107,8 @@ SIGNATURES = {
     "pvb_upsample3d_fwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_upsample3d_bwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_peer_flag_words": [],
-    "pvb_peer_allreduce_adam": [_f, _f, _f, _f, _i64, _f, _f, _f, _i32, _i32, _fl, _fl, _fl, _fl,
+    "pvb_peer_state_words": [],
+    "pvb_peer_allreduce_adam": [_f, _f, _f, _f, _i64, _f, _f, _f, _i32, _i32, _i32, _fl, _fl, _fl, _fl,
                                 _f, _f, _f, _st],
     "pvb_bn_workspace_bytes": [_i32],
     "pvb_bn_fwd": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i64, _fl, _fl, _i32, _st],

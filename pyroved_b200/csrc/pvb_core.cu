@@ -67,7 +67,8 @@ extern "C" int pvb_counter_add(int32_t* counter, int32_t v, void* stream) {
 // torch.optim.Adam (defaults; no amsgrad / weight decay):
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2
 //   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
-__device__ __forceinline__ void adam_update4(float* __restrict__ p, const float* __restrict__ g,
+template <bool ZERO_G>
+__device__ __forceinline__ void adam_update4(float* __restrict__ p, float* __restrict__ g,
                                              float* __restrict__ m, float* __restrict__ v, int64_t n,
                                              float lr, float b1, float b2, float eps, int step,
                                              const int32_t* __restrict__ first_step) {
@@ -79,13 +80,17 @@ __device__ __forceinline__ void adam_update4(float* __restrict__ p, const float*
     int64_t j = i0 + k;
     if (j >= n) break;
     int t = first_step ? (first_step[j] < 0 ? 0 : step - first_step[j]) : step;
-    if (t <= 0) continue;   // parameter has never carried a gradient
+    if (t <= 0) {           // parameter has never carried a gradient
+      if (ZERO_G) g[j] = 0.f;
+      continue;
+    }
     if (t != last_t) {
       step_size = lr / (1.f - powf(b1, (float)t));
       bc2s = sqrtf(1.f - powf(b2, (float)t));
       last_t = t;
     }
     float gj = g[j];
+    if (ZERO_G) g[j] = 0.f;   // consumed: the buffer is clean for the next step's accumulation
     float mj = b1 * m[j] + (1.f - b1) * gj;
     float vj = b2 * v[j] + (1.f - b2) * gj * gj;
     m[j] = mj;
@@ -98,24 +103,29 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
                                  float b1, float b2, float eps,
                                  const int32_t* __restrict__ step_counter,
                                  const int32_t* __restrict__ first_step) {
-  adam_update4(p, g, m, v, n, lr, b1, b2, eps, *step_counter, first_step);
+  adam_update4<false>(p, const_cast<float*>(g), m, v, n, lr, b1, b2, eps, *step_counter, first_step);
 }
 // same, with the step increment folded in: all CTAs read the counter before taking a ticket,
 // the last ticket holder stores counter + 1 (and re-arms the ticket)
-__global__ void adam_flat_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+__global__ void adam_flat_step_kernel(float* __restrict__ p, float* __restrict__ g,
                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
                                       float lr, float b1, float b2, float eps,
                                       int32_t* step_counter, const int32_t* __restrict__ first_step,
-                                      int32_t* ticket, const float* loss_src, float* loss_ring) {
+                                      int32_t* ticket, float* loss_src, float* loss_ring) {
   const int step = *reinterpret_cast<volatile int32_t*>(step_counter) + 1;
-  adam_update4(p, g, m, v, n, lr, b1, b2, eps, step, first_step);
+  adam_update4<true>(p, g, m, v, n, lr, b1, b2, eps, step, first_step);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     int t = atomicAdd(ticket, 1);
     if (t == (int)gridDim.x - 1) {
       // the step's loss goes straight to (mapped, pinned) host memory: slot = step & (PVB_LOSS_RING - 1)
-      if (loss_ring) loss_ring[step & (PVB_LOSS_RING - 1)] = *loss_src;
+      if (loss_src) {
+        const float L = loss_src[0];
+        if (loss_ring) loss_ring[step & (PVB_LOSS_RING - 1)] = L;
+        loss_src[1] = L;       // "last loss" slot, read by the host side after the step
+        loss_src[0] = 0.f;     // loss accumulator of the next step
+      }
       *step_counter = step;
       *ticket = 0;
     }
@@ -136,9 +146,9 @@ extern "C" int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64
   return pvb::launch_status();
 }
 
-extern "C" int pvb_adam_flat_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+extern "C" int pvb_adam_flat_step(float* p, float* g, float* m, float* v, int64_t n, float lr,
                                   float beta1, float beta2, float eps, int32_t* step_counter,
-                                  const int32_t* first_step, int32_t* ticket, const float* loss_src,
+                                  const int32_t* first_step, int32_t* ticket, float* loss_src,
                                   float* loss_ring, void* stream) {
   PVB_CHECK_ARG(p && g && m && v && step_counter && ticket && n >= 0, "pvb_adam_flat_step: bad argument");
   PVB_CHECK_ARG(!loss_ring || loss_src, "pvb_adam_flat_step: loss_ring needs loss_src");

@@ -1,20 +1,29 @@
 // Data-parallel exchange step of the SVI update: the SUM all-reduce of the flat
 // [gradients | loss] buffer fused with the Adam update, in ONE kernel over NVLink / NVSwitch peer
-// memory.  Every rank's gradient buffer lives in symmetric memory mapped into all ranks (one
-// process per GPU); each rank loads every peer's buffer directly (one-shot: (world-1) x 0.6 MB
-// inbound per GPU for cfg2), adds the values in rank order 0..world-1 -- the same order on every
-// rank, so the replicas stay bit-identical -- and applies Adam to its own replica of the
-// parameters.  Replaces ncclAllReduce + the Adam kernel + the two graph boundaries between them;
-// being a plain kernel it is captured in the step's CUDA graph.
+// memory (one process per GPU).  Replaces ncclAllReduce + the Adam kernel + the two graph
+// boundaries between them; being a plain kernel it is captured in the step's CUDA graph.
 //
-// Cross-GPU synchronisation: two sets of epoch flags per rank in symmetric memory.
-//   ready[r] (written by rank r): rank r's gradients of this epoch are complete
-//   done[r]  (written by rank r): rank r has finished reading every peer's gradients
-// A kernel starts reading when all ready flags carry its epoch and retires when all done flags do
-// (its own gradient buffer may be zeroed by the next step only after every peer has read it).
-// No CTA waits on another CTA of the same grid except through the final ticket, and remote ranks
-// only wait on flags written by CTA 0 at its start / the last CTA at its end, so there is no
-// circular wait as long as every rank launches the kernel (the step is SPMD).
+// Every rank owns two STAGING buffers in symmetric memory (mapped into all ranks), used by epoch
+// parity.  One invocation (epoch e, parity e & 1):
+//   1. copy the local gradients into the own staging buffer of this parity; the last CTA to finish
+//      publishes ready[rank] = e to every peer (st.release.sys);
+//   2. wait until every peer's ready flag carries e;
+//   3. one-shot (small worlds): every rank loads every peer's staging buffer ((world-1) x size
+//      inbound), adds in rank order 0..world-1 -- the same order on every rank, so the replicas stay
+//      bit-identical -- and applies Adam to its replica;
+//      two-shot (world >= 4): rank r first reduces only slice r of every peer's buffer, in rank
+//      order, IN PLACE into its own staging buffer, publishes reduced[rank] = e, waits for the
+//      peers' flags and then gathers every reduced slice from its owner (inbound 2 (world-1)/world
+//      x size instead of (world-1) x size); every rank reads the same reduced values, so the
+//      replicas stay bit-identical here too;
+//   4. the gradient buffer is zeroed for the next step as it is consumed (no separate memset), the
+//      loss slots are summed, the step counter advances.
+// There is NO "done reading" round trip: a staging buffer of parity p is rewritten at epoch e + 2,
+// which this rank reaches only after it has seen ready[e + 1] from every peer -- and a peer
+// publishes ready[e + 1] from the kernel that follows, in stream order, the one in which it read
+// epoch e.  No CTA waits on another CTA of the same grid except through tickets whose last
+// arriver publishes the flag everybody then spins on, so there is no circular wait as long as
+// every rank launches the kernel (the step is SPMD) and the grid is co-resident (<= 4 CTAs / SM).
 #include "pvb_common.cuh"
 
 namespace {
@@ -52,82 +61,126 @@ __device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t e) {
   }
 }
 
-// state: [0] epoch of the last finished invocation, [1] ticket, [2] loss (float bits)
+// state (int32): [0] epoch of the last finished invocation, [1] [2] [3] tickets, [4] loss bits
+__device__ __forceinline__ bool grid_arrive_last(int32_t* ticket, int* s_last) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();          // this CTA's writes (staging / reduced slice) before the ticket
+    *s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    if (*s_last) __threadfence_system();
+  }
+  __syncthreads();
+  return *s_last != 0;
+}
+
+__device__ __forceinline__ void adam4(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                      const float* g4, int64_t j0, int64_t n, float lr, float b1,
+                                      float b2, float eps, int step,
+                                      const int32_t* __restrict__ first_step) {
+  int last_t = -1;
+  float step_size = 0.f, bc2s = 1.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t j = j0 + k;
+    if (j >= n) break;
+    const int t = first_step ? (first_step[j] < 0 ? 0 : step - first_step[j]) : step;
+    if (t <= 0) continue;                      // parameter has never carried a gradient
+    if (t != last_t) {
+      step_size = lr / (1.f - powf(b1, (float)t));
+      bc2s = sqrtf(1.f - powf(b2, (float)t));
+      last_t = t;
+    }
+    const float gj = g4[k];
+    const float mj = b1 * m[j] + (1.f - b1) * gj;
+    const float vj = b2 * v[j] + (1.f - b2) * gj * gj;
+    m[j] = mj;
+    v[j] = vj;
+    p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
+  }
+}
+
 __global__ void __launch_bounds__(NT)
-peer_allreduce_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                           float* own_g, int64_t n, const float* const* __restrict__ peer_g,
-                           uint32_t* const* __restrict__ peer_flags, int32_t* state, int rank, int world,
-                           float lr, float b1, float b2, float eps, int32_t* step_counter,
-                           const int32_t* __restrict__ first_step, float* loss_ring) {
-  __shared__ const float* gp[MAX_WORLD];
+peer_exchange_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                          float* g, int64_t n, float* const* __restrict__ stage_ptrs,
+                          uint32_t* const* __restrict__ peer_flags, int32_t* state, int rank, int world,
+                          int two_shot, float lr, float b1, float b2, float eps, int32_t* step_counter,
+                          const int32_t* __restrict__ first_step, float* loss_ring) {
+  __shared__ float* sp[MAX_WORLD];      // staging buffers of this epoch's parity, by rank
   __shared__ int s_last;
   const uint32_t e = (uint32_t)(*reinterpret_cast<volatile int32_t*>(state)) + 1u;
   const int step = *reinterpret_cast<volatile int32_t*>(step_counter) + 1;
   uint32_t* mine = peer_flags[rank];
-  if (threadIdx.x < world) {
-    gp[threadIdx.x] = peer_g[threadIdx.x];
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      st_release_sys(peer_flags[threadIdx.x] + rank, e);            // ready[rank] on every peer
-    }
-    spin_until(mine + threadIdx.x, e);                              // all peers ready
-  }
+  if (threadIdx.x < world) sp[threadIdx.x] = stage_ptrs[(e & 1u) * world + threadIdx.x];
   __syncthreads();
-  const int64_t n4 = (n + 3) / 4;
-  for (int64_t i4 = (int64_t)blockIdx.x * NT + threadIdx.x; i4 < n4; i4 += (int64_t)gridDim.x * NT) {
-    const int64_t j0 = i4 * 4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {            // fixed order: identical sums on every rank
-      const float4 a = ld_peer4(gp[r] + j0);
-      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-    }
-    const float g4[4] = {s.x, s.y, s.z, s.w};
-    int last_t = -1;
-    float step_size = 0.f, bc2s = 1.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int64_t j = j0 + k;
-      if (j >= n) break;
-      const int t = first_step ? (first_step[j] < 0 ? 0 : step - first_step[j]) : step;
-      if (t <= 0) continue;                      // parameter has never carried a gradient
-      if (t != last_t) {
-        step_size = lr / (1.f - powf(b1, (float)t));
-        bc2s = sqrtf(1.f - powf(b2, (float)t));
-        last_t = t;
-      }
-      const float gj = g4[k];
-      const float mj = b1 * m[j] + (1.f - b1) * gj;
-      const float vj = b2 * v[j] + (1.f - b2) * gj * gj;
-      m[j] = mj;
-      v[j] = vj;
-      p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {     // the loss slot follows the n gradients
+  float4* my_stage = reinterpret_cast<float4*>(sp[rank]);
+  float4* g4p = reinterpret_cast<float4*>(g);
+  const int64_t n4 = n / 4;                   // n % 4 == 0; quad n4 holds [loss, last loss, pad, pad]
+  const int64_t tid0 = (int64_t)blockIdx.x * NT + threadIdx.x, stride = (int64_t)gridDim.x * NT;
+
+  // ---- 1. local gradients (+ loss quad) -> own staging buffer; the last CTA publishes `ready` ----
+  for (int64_t i4 = tid0; i4 <= n4; i4 += stride) my_stage[i4] = g4p[i4];
+  if (grid_arrive_last(state + 1, &s_last) && threadIdx.x < world)
+    st_release_sys(peer_flags[threadIdx.x] + rank, e);
+  // ---- 2. all peers ready ----
+  if (threadIdx.x < world) spin_until(mine + threadIdx.x, e);
+  __syncthreads();
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {     // global loss: slot n of every buffer
     float L = 0.f;
-    for (int r = 0; r < world; ++r) L += ld_peer1(gp[r] + n);
-    state[2] = __float_as_int(L);
+    for (int r = 0; r < world; ++r) L += (r == rank) ? g[n] : ld_peer1(sp[r] + n);
+    state[4] = __float_as_int(L);
   }
-  __syncthreads();
+
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!two_shot) {
+    // ---- 3. one-shot: every rank sums every buffer, fixed order ----
+    for (int64_t i4 = tid0; i4 < n4; i4 += stride) {
+      float4 s = zero4;
+      for (int r = 0; r < world; ++r) {
+        const float4 a = (r == rank) ? g4p[i4] : ld_peer4(sp[r] + 4 * i4);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+      const float gs[4] = {s.x, s.y, s.z, s.w};
+      adam4(p, m, v, gs, 4 * i4, n, lr, b1, b2, eps, step, first_step);
+      g4p[i4] = zero4;                           // consumed: clean for the next step
+    }
+  } else {
+    // ---- 3a. reduce-scatter: this rank sums slice `rank` of every buffer, in place ----
+    const int64_t per = (n4 + world - 1) / world;
+    const int64_t lo = (int64_t)rank * per, hi = (lo + per < n4) ? lo + per : n4;
+    for (int64_t i4 = lo + tid0; i4 < hi; i4 += stride) {
+      float4 s = zero4;
+      for (int r = 0; r < world; ++r) {
+        const float4 a = (r == rank) ? g4p[i4] : ld_peer4(sp[r] + 4 * i4);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+      my_stage[i4] = s;
+    }
+    if (grid_arrive_last(state + 2, &s_last) && threadIdx.x < world)
+      st_release_sys(peer_flags[threadIdx.x] + MAX_WORLD + rank, e);
+    if (threadIdx.x < world) spin_until(mine + MAX_WORLD + threadIdx.x, e);
+    __syncthreads();
+    // ---- 3b. all-gather: every reduced slice from its owner ----
+    for (int64_t i4 = tid0; i4 < n4; i4 += stride) {
+      const int q = (int)(i4 / per);
+      const float4 s = ld_peer4(sp[q] + 4 * i4);      // own slice too: written by other CTAs of this grid
+      const float gs[4] = {s.x, s.y, s.z, s.w};
+      adam4(p, m, v, gs, 4 * i4, n, lr, b1, b2, eps, step, first_step);
+      g4p[i4] = zero4;
+    }
+  }
+  // ---- 4. last CTA of this rank: loss, counters, tickets ----
+  if (!grid_arrive_last(state + 3, &s_last)) return;
   if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = atomicAdd(state + 1, 1) == (int)gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  // last CTA of this rank: every peer buffer has been read
-  if (threadIdx.x < world) {
-    st_release_sys(peer_flags[threadIdx.x] + MAX_WORLD + rank, e);   // done[rank] on every peer
-    spin_until(mine + MAX_WORLD + threadIdx.x, e);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const float L = __int_as_float(*reinterpret_cast<volatile int32_t*>(state + 2));
-    own_g[n] = L;                                   // global loss
-    if (loss_ring) loss_ring[step & (PVB_LOSS_RING - 1)] = L;         // ... and straight to mapped host memory
+    const float L = __int_as_float(*reinterpret_cast<volatile int32_t*>(state + 4));
+    g[n] = 0.f;                                     // loss accumulator of the next step
+    g[n + 1] = L;                                   // global loss of this step (read by the host side)
+    if (loss_ring) loss_ring[step & (PVB_LOSS_RING - 1)] = L;   // ... and straight to mapped host memory
     *step_counter = step;
     state[1] = 0;
+    state[2] = 0;
+    state[3] = 0;
+    __threadfence();
     state[0] = (int32_t)e;
   }
 }
@@ -135,27 +188,28 @@ peer_allreduce_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* 
 }  // namespace
 
 extern "C" int pvb_peer_flag_words(void) { return 2 * MAX_WORLD; }
+extern "C" int pvb_peer_state_words(void) { return 8; }
 
-extern "C" int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* own_g, int64_t n,
-                                       const void* peer_g, const void* peer_flags, int32_t* state,
-                                       int rank, int world, float lr, float beta1, float beta2, float eps,
-                                       int32_t* step_counter, const int32_t* first_step, float* loss_ring,
-                                       void* stream) {
-  PVB_CHECK_ARG(p && m && v && own_g && peer_g && peer_flags && state && step_counter,
+extern "C" int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* g, int64_t n,
+                                       const void* stage_ptrs, const void* peer_flags, int32_t* state,
+                                       int rank, int world, int two_shot, float lr, float beta1,
+                                       float beta2, float eps, int32_t* step_counter,
+                                       const int32_t* first_step, float* loss_ring, void* stream) {
+  PVB_CHECK_ARG(p && m && v && g && stage_ptrs && peer_flags && state && step_counter,
                 "pvb_peer_allreduce_adam: null pointer");
   PVB_CHECK_ARG(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world,
                 "pvb_peer_allreduce_adam: bad rank / world (<= 16 ranks)");
   PVB_CHECK_ARG(n > 0 && n % 4 == 0, "pvb_peer_allreduce_adam: n must be a positive multiple of 4");
-  PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)own_g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+  PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                     ((uintptr_t)v % 16 == 0),
                 "pvb_peer_allreduce_adam: buffers must be 16-byte aligned");
   const int64_t n4 = n / 4;
   int64_t blocks = (n4 + NT - 1) / NT;
-  if (blocks > 148 * 4) blocks = 148 * 4;       // all CTAs co-resident
-  peer_allreduce_adam_kernel<<<(unsigned)blocks, NT, 0, (cudaStream_t)stream>>>(
-      p, m, v, own_g, n, reinterpret_cast<const float* const*>(peer_g),
-      reinterpret_cast<uint32_t* const*>(peer_flags), state, rank, world, lr, beta1, beta2, eps,
-      step_counter, first_step, loss_ring);
+  if (blocks > 148 * 4) blocks = 148 * 4;       // all CTAs co-resident (the kernel syncs grid-wide)
+  peer_exchange_adam_kernel<<<(unsigned)blocks, NT, 0, (cudaStream_t)stream>>>(
+      p, m, v, g, n, reinterpret_cast<float* const*>(stage_ptrs),
+      reinterpret_cast<uint32_t* const*>(peer_flags), state, rank, world, two_shot ? 1 : 0, lr, beta1,
+      beta2, eps, step_counter, first_step, loss_ring);
   pvb::count_launch();
   return pvb::launch_status();
 }

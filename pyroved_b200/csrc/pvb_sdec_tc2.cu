@@ -52,8 +52,8 @@ constexpr int SM_G = SM_DA + TILE_BYTES;         // [128][16] grid coords per sa
 constexpr int SM_ODL = SM_G + 2 * CHUNK;         // [128][16] column 0 = 1, column 1 = dl of the tile
 constexpr int SM_F32 = SM_ODL + 2 * CHUNK;
 constexpr int F_B1 = 0, F_B2 = 128, F_WO = 256;
-constexpr int F_PART = 384;                      // [4][128] partial dots per column group
-constexpr int F_RED = F_PART + 4 * TILE;         // [32] block reduction
+constexpr int F_PART = 384;                      // [2][4][128] partial dots per column group, by tile parity
+constexpr int F_RED = F_PART + 2 * 4 * TILE;     // [32] block reduction
 constexpr int F_STG = F_RED + 32;                // two staging buffers
 constexpr int UV_FLOATS = MAX_SLOTS * 3 * HD;
 constexpr int G_UV = 0, G_X = UV_FLOATS, G_WI = G_X + TILE, G_GX = G_WI + TILE, G_GY = G_GX + TILE,
@@ -83,6 +83,18 @@ constexpr uint32_t TM_DB2 = 400;
 constexpr uint32_t TM_DUV = 416;
 constexpr uint32_t TM_DWO = 432;   // column 1 = dwo
 constexpr int TM_COLS = 512;
+
+#ifdef PVB_TC2_TRACE
+// debug build only: per-stage timestamps of CTA 0 (epilogue warp 0 / MMA warp), tools/tc2_trace.py
+__device__ long long g_trace2[2][64][16];
+#define TRACE(role, ev)                                                                \
+  do {                                                                                 \
+    if (blockIdx.x == 0 && lane == 0 && (role == 1 || warp == 0) && i < 64)            \
+      g_trace2[role][i][ev] = clock64();                                               \
+  } while (0)
+#else
+#define TRACE(role, ev) do {} while (0)
+#endif
 
 // mbarrier wait with a watchdog: a protocol error traps (the launch fails with an error) after
 // ~2 s instead of hanging the GPU.  The clock is read once per 4096 polls: no cost on the fast path.
@@ -338,7 +350,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
       if (F) {
         // ---- G1(i): ACC = h0 W1^T ----
         mbar_wait(bars + BAR_OP + OP_S0, ph_op[OP_S0]); ph_op[OP_S0] ^= 1;
+        TRACE(1, 0);
         if (Bk) { mbar_wait(bars + BAR_ACCFREE, ph_free); ph_free ^= 1; }   // S6(i-1) holds G3's result
+        TRACE(1, 1);
         umma::fence_after_sync();
         if (lane == 0) {
 #pragma unroll
@@ -351,7 +365,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
       if (Bk) {
         // ---- G4(i-1): ACC = D1 W1 ; dW1' += D1^T h0 ; db1 += D1^T 1 ----
         mbar_wait(bars + BAR_OP + OP_S6, ph_op[OP_S6]); ph_op[OP_S6] ^= 1;
+        TRACE(1, 2);
         mbar_wait(bars + BAR_ACCFREE, ph_free); ph_free ^= 1;     // S2(i) (drain: S6(i-1))
+        TRACE(1, 3);
         umma::fence_after_sync();
         if (lane == 0) {
           const uint32_t accw = (i - 1) > 0 ? 1u : 0u;
@@ -359,14 +375,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_ACC, desc_kmajor(sDA, k), desc_mnmajor(sW1, k), ID_DH, k > 0);
           umma::commit(bars + BAR_ACCDONE);
+#ifndef PVB_TC2_NO_DW_MMA
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_DW1, desc_mnmajor(sDA, k), desc_mnmajor(sH0b, k), ID_DW,
                              (k > 0) ? 1u : accw);
+#endif
+#ifndef PVB_TC2_NO_BIAS_MMA     // (timing experiments only)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_DB1, desc_mnmajor(sDA, k), desc_mnmajor(sODL, k), ID_N16,
                              (k > 0) ? 1u : accw);
+#endif
           umma::commit(bars + BAR_DW1);
         }
         __syncwarp();
@@ -374,7 +394,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
       if (F) {
         // ---- G2(i): ACC = h1 W2^T ----
         mbar_wait(bars + BAR_OP + OP_S2, ph_op[OP_S2]); ph_op[OP_S2] ^= 1;
+        TRACE(1, 4);
         mbar_wait(bars + BAR_ACCFREE, ph_free); ph_free ^= 1;     // S8(i-1) (i == 0: S2(0))
+        TRACE(1, 5);
         umma::fence_after_sync();
         if (lane == 0) {
 #pragma unroll
@@ -387,6 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
       if (Bk) {
         // ---- dUv(i-1) = D0^T G ----
         mbar_wait(bars + BAR_OP + OP_S8, ph_op[OP_S8]); ph_op[OP_S8] ^= 1;
+        TRACE(1, 6);
         umma::fence_after_sync();
         if (lane == 0) {
 #pragma unroll
@@ -400,27 +423,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         // ---- dwo += h2^T dl ; G3(i): ACC = D2 W2 ; dW2' += D2^T h1 ; db2 += D2^T 1 ----
         // (S4 pulled the accumulator into registers before it published D2: no ACCFREE wait)
         mbar_wait(bars + BAR_OP + OP_S4, ph_op[OP_S4]); ph_op[OP_S4] ^= 1;
+        TRACE(1, 7);
         umma::fence_after_sync();
         if (lane == 0) {
           const uint32_t accw = i > 0 ? 1u : 0u;
           // h2 sits in the H0 buffer of the other parity, which S0(i+1) rewrites: first in line
+#ifndef PVB_TC2_NO_DWO_MMA
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_DWO, desc_mnmajor(sH0b, k), desc_mnmajor(sODL, k), ID_N16,
                              (k > 0) ? 1u : accw);
+#endif
           umma::commit(bars + BAR_DWO);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_ACC, desc_kmajor(sDA, k), desc_mnmajor(sW2, k), ID_DH, k > 0);
           umma::commit(bars + BAR_ACCDONE);
+#ifndef PVB_TC2_NO_DW_MMA
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_DW2, desc_mnmajor(sDA, k), desc_mnmajor(sH1, k), ID_DW,
                              (k > 0) ? 1u : accw);
+#endif
+#ifndef PVB_TC2_NO_BIAS_MMA
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_DB2, desc_mnmajor(sDA, k), desc_mnmajor(sODL, k), ID_N16,
                              (k > 0) ? 1u : accw);
+#endif
           umma::commit(bars + BAR_DW2);
         }
         __syncwarp();
@@ -455,6 +485,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
           write_duv(P, tm_lane, row, (int64_t)blockIdx.x + (int64_t)(i - 2) * gridDim.x,
                     (int)((slots_hist >> 4) & 0xf));
       }
+      TRACE(0, 0);
       // staging of tile i+1 (its buffer was last read in S0(i-1), before the S4(i-1) barrier)
       if (F) {
         TileCursor nxt_c = cur_c;
@@ -475,6 +506,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
           mbar_wait(bars + BAR_DWO, ph_dwo);
           ph_dwo ^= 1;
         }
+        TRACE(0, 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c0 = 8 * (4 * j + cg);
@@ -492,17 +524,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
           store_chunk(H0f, row, cg, j, *reinterpret_cast<uint4*>(hh));
         }
         publish_smem(bars + BAR_OP + OP_S0);
+        TRACE(0, 2);
       }
       // ---- S6(i-1): D1 = dh1 (1 - h1^2) -> DA ---------------------------------------------------------
       if (Bk) {
         mbar_wait(bars + BAR_ACCDONE, ph_acc);       // G3(i-1)
         ph_acc ^= 1;
+        TRACE(0, 3);
         umma::fence_after_sync();
         load_acc(tm_lane, cg, v);
         release_acc(bars);
         // dW2'(i-1) (issued right behind G3) has read D2 (DA) and h1 (H1): it ran under S0(i)
         mbar_wait(bars + BAR_DW2, ph_dw2);
         ph_dw2 ^= 1;
+        TRACE(0, 4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t off = umma::tile_off(TILE, row, 8 * (4 * j + cg));
@@ -510,11 +545,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
               dact8(v + 8 * j, *reinterpret_cast<const uint4*>(smem + SM_H1 + off));
         }
         publish_smem(bars + BAR_OP + OP_S6);
+        TRACE(0, 5);
       }
       // ---- S2(i): h1 = tanh(ACC + b1) -> H1 --------------------------------------------------------------
       if (F) {
         mbar_wait(bars + BAR_ACCDONE, ph_acc);       // G1(i)
         ph_acc ^= 1;
+        TRACE(0, 6);
         umma::fence_after_sync();
         load_acc(tm_lane, cg, v);
         release_acc(bars);
@@ -522,17 +559,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         for (int j = 0; j < 4; ++j)
           store_chunk(smem + SM_H1, row, cg, j, tanh8(v + 8 * j, f32 + F_B1 + 8 * (4 * j + cg)));
         publish_smem(bars + BAR_OP + OP_S2);
+        TRACE(0, 7);
       }
       // ---- S8(i-1): D0 = dh0 (1 - h0^2) -> H0b (in place), G tile of tile i-1 ---------------------------------
       if (Bk) {
         mbar_wait(bars + BAR_ACCDONE, ph_acc);       // G4(i-1)
         ph_acc ^= 1;
+        TRACE(0, 8);
         umma::fence_after_sync();
         load_acc(tm_lane, cg, v);
         release_acc(bars);
         // dW1'(i-1) (issued right behind G4) has read D1 (DA) and h0 (H0b): it ran under S2(i)
         mbar_wait(bars + BAR_DW1, ph_dw1);
         ph_dw1 ^= 1;
+        TRACE(0, 9);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t off = umma::tile_off(TILE, row, 8 * (4 * j + cg));
@@ -556,6 +596,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
               *reinterpret_cast<uint4*>(g8);
         }
         publish_smem(bars + BAR_OP + OP_S8);
+        TRACE(0, 10);
       }
       // ---- S4(i): h2, logit, dl, dwo, D2 -> DA; log-lik / reconstruction out -----------------------------------
       if (F) {
@@ -568,6 +609,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         const bool valid = (gi >> 8) & 1;
         mbar_wait(bars + BAR_ACCDONE, ph_acc);       // G2(i)
         ph_acc ^= 1;
+        TRACE(0, 11);
         umma::fence_after_sync();
         float pdot = 0.f;
 #pragma unroll
@@ -594,11 +636,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
           if (Bk && j == 0) mbar_wait(bars + BAR_DUV, ph_duv);
           store_chunk(H0b, row, cg, j, h2);      // h2: operand of dwo, re-read below for D2
         }
-        f32[F_PART + cg * TILE + row] = pdot;
+        float* part = f32 + F_PART + (i & 1) * 4 * TILE;   // by parity: a fast warp's next tile
+        part[cg * TILE + row] = pdot;                       // never overwrites a slow warp's reads
         cp_async_wait_all();   // this thread's share of the next tile's staging has landed
+        TRACE(0, 12);
         epi_bar();             // partial dots exchanged; staging of tile i+1 published
-        const float logit = ((f32[F_PART + row] + f32[F_PART + TILE + row]) +
-                             (f32[F_PART + 2 * TILE + row] + f32[F_PART + 3 * TILE + row])) + bo;
+        TRACE(0, 13);
+        const float logit = ((part[row] + part[TILE + row]) +
+                             (part[2 * TILE + row] + part[3 * TILE + row])) + bo;
         const float dnll = pvb::obs_dnll_fast(logit, xv, P.sampler, P.sigmoid_d, P.sig);
         const float dl = valid ? wi * dnll : 0.f;
 #pragma unroll
@@ -632,6 +677,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         if (cg == 0) dl_sum += dl;
         umma::fence_before_sync();   // accumulator reads ordered before G3 (issued behind OP_S4)
         publish_smem(bars + BAR_OP + OP_S4);
+        TRACE(0, 14);
         if (cg == 0 && valid) {
           // per-pixel log-likelihood and reconstruction (fast intrinsics, ~1e-6 relative)
           float ll, dn_unused, locv;
@@ -718,3 +764,9 @@ int launch_v2(const Params& P, int ctas, cudaStream_t stream) {
 }
 
 }  // namespace pvb_sdec
+
+#ifdef PVB_TC2_TRACE
+extern "C" int pvb_tc2_trace_read(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_trace2, sizeof(long long) * 2 * 64 * 16);
+}
+#endif

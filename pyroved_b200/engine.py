@@ -42,11 +42,9 @@ def _numel_shape(shape):
 class FlatParams:
     """Flat parameter / gradient / Adam-state buffers with per-parameter views."""
 
-    def __init__(self, module: nn.Module, device, g_alloc=None):
+    def __init__(self, module: nn.Module, device):
         self.module = module
         self.device = torch.device(device)
-        # g_alloc(n_floats) -> zeroed fp32 buffer (symmetric memory for the NVLink exchange)
-        self.g_alloc = g_alloc
         self._build()
 
     def _build(self):
@@ -64,9 +62,8 @@ class FlatParams:
             o, k, shp = self.offsets[n]
             new_p[o:o + k].copy_(p.data.reshape(-1).to(dev, torch.float32))
         self.p = new_p
-        # gradient buffer: [grads | loss, pad3]
-        self.g = (self.g_alloc(self.total + 4) if self.g_alloc is not None
-                  else torch.zeros(self.total + 4, device=dev, dtype=torch.float32))
+        # gradient buffer: [grads | loss accumulator, last step's loss, pad2]
+        self.g = torch.zeros(self.total + 4, device=dev, dtype=torch.float32)
         self.m = torch.zeros(self.total, device=dev, dtype=torch.float32)
         self.v = torch.zeros(self.total, device=dev, dtype=torch.float32)
         # optimizer step at which each parameter first carried a gradient (-1: never);
@@ -79,7 +76,9 @@ class FlatParams:
             p.data = self.p[o:o + k].view(shp)
             p.grad = self.g[o:o + k].view(shp)
             self._views[id(p)] = n
-        self.loss = self.g[self.total:self.total + 1]
+        self.loss = self.g[self.total:self.total + 1]            # accumulator of the running step
+        self.last_loss = self.g[self.total + 1:self.total + 2]   # written by the optimizer kernels
+        self.loss_pair = self.g[self.total:self.total + 2]
         self._ptrs = [(p, p.data_ptr()) for _, p in named]
 
     def intact(self):
@@ -1034,12 +1033,15 @@ class SVIEngine:
         self.overlap = os.environ.get("PVB_SIDE_STREAM", "1") != "0"
         self.side = torch.cuda.Stream(self.device)
         self._side_used = False
-        self.peer = None          # parallel.PeerExchange of the current flat gradient buffer
+        self.peer = None          # parallel.PeerExchange (staging buffers of the NVLink exchange)
         # data_parallel=False: a purely local engine even inside an initialised process group
         # (e.g. a single-GPU cross-check next to a data-parallel run); None: follow the group
         self.data_parallel = data_parallel is not False
-        self.flat = FlatParams(model, self.device, self._alloc_grad_buffer()
-                               if self.data_parallel and parallel.peer_exchange_enabled() else None)
+        self.flat = FlatParams(model, self.device)
+        # the optimizer kernels leave the gradient buffer zeroed; anything else (loss_and_grads,
+        # evaluate_loss) leaves it dirty and the next step clears it first
+        self._g_dirty = False
+        self._make_peer()
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.adam_ticket = torch.zeros(1, device=self.device, dtype=torch.int32)
         # pinned host ring the optimizer kernel writes each step's loss into (slot = step count &
@@ -1069,28 +1071,27 @@ class SVIEngine:
         if self.data_parallel:
             self.rank, self.world_size = parallel.rank_world()
 
-    def _alloc_grad_buffer(self):
-        """Allocator handed to FlatParams when the fused NVLink exchange is on: the flat
-        [gradients | loss] buffer comes from symmetric memory shared with the peer ranks
-        (collective: every rank builds its engine at the same point).  Falls back to NCCL's
-        all-reduce, with a warning, where symmetric memory is unavailable."""
-        def alloc(n):
-            try:
-                self.peer = parallel.PeerExchange(n, self.device)
-                return self.peer.g
-            except Exception as err:          # noqa: BLE001 -- any failure means "use NCCL"
-                warnings.warn("pyroved_b200: symmetric-memory exchange unavailable ({}); using "
-                              "the NCCL all-reduce".format(err))
-                self.peer = None
-                return torch.zeros(n, device=self.device, dtype=torch.float32)
-        return alloc
+    def _make_peer(self):
+        """Staging buffers of the fused NVLink exchange, sized to the flat gradient buffer
+        (collective: every rank builds / rebuilds its engine at the same point).  Falls back to
+        NCCL's all-reduce, with a warning, where symmetric memory is unavailable."""
+        self.peer = None
+        if not (self.data_parallel and parallel.peer_exchange_enabled()):
+            return
+        try:
+            self.peer = parallel.PeerExchange(self.flat.total + 4, self.device)
+        except Exception as err:          # noqa: BLE001 -- any failure means "use NCCL"
+            warnings.warn("pyroved_b200: symmetric-memory exchange unavailable ({}); using the "
+                          "NCCL all-reduce".format(err))
+            self.peer = None
 
     def _update_exchange(self):
         """gradient all-reduce + Adam in one kernel over NVLink peer memory"""
         flat, pe = self.flat, self.peer
-        ops.peer_allreduce_adam(flat.p, flat.m, flat.v, flat.g, flat.total, pe.peer_g, pe.peer_flags,
-                                pe.state, pe.rank, pe.world, self.lr, self.step_counter,
-                                flat.first_step, loss_ring=self.loss_ring)
+        ops.peer_allreduce_adam(flat.p, flat.m, flat.v, flat.g, flat.total, pe.stage_ptrs,
+                                pe.peer_flags, pe.state, pe.rank, pe.world, self.lr,
+                                self.step_counter, flat.first_step, loss_ring=self.loss_ring,
+                                two_shot=pe.two_shot)
 
     def eps_first_index(self, n_local):
         """Global index of this rank's first noise element: the noise of a
@@ -1119,11 +1120,8 @@ class SVIEngine:
 
     # ---- one step -------------------------------------------------------------
     def _run(self, prog, beta, train, gen_eps, update):
-        flat = self.flat
-        if train or update:
-            flat.g.zero_()
-        else:
-            flat.loss.zero_()
+        # (the gradient buffer is clean here: the optimizer kernels zero it as they consume it,
+        # _step_on_device clears it after a call that left gradients behind)
         prog.forward(beta, train, gen_eps)
         if train:
             prog.backward(beta)
@@ -1149,7 +1147,7 @@ class SVIEngine:
     def _update(self):
         flat = self.flat
         ops.adam_flat_step(flat.p, flat.g, flat.m, flat.v, flat.total, self.lr, self.step_counter,
-                           self.adam_ticket, flat.first_step, loss_src=flat.loss,
+                           self.adam_ticket, flat.first_step, loss_src=flat.loss_pair,
                            loss_ring=self.loss_ring)
 
     def _allreduce(self):
@@ -1206,6 +1204,9 @@ class SVIEngine:
 
     def _step_on_device(self, args, kwargs, train, update, mode):
         self.flat.ensure() and self._invalidate()
+        if self._g_dirty:
+            self.flat.g[:self.flat.total + 1].zero_()
+            self._g_dirty = False
         kwargs = dict(kwargs)
         x = args[0]
         y = args[1] if len(args) > 1 else None
@@ -1253,11 +1254,16 @@ class SVIEngine:
                 self._run(prog, beta, train, gen_eps, update)
             self._execute(key, single)
         self.last_loss_const = prog.loss_const * self.world_size
+        # the optimizer kernels move the step's loss to the "last loss" slot and clear the buffer
+        self._g_dirty = not update
+        out = self.flat.last_loss if update else self.flat.loss
         if not sync:
-            return self.flat.loss     # device scalar, no host synchronisation
-        return float(self.flat.loss.item()) + prog.loss_const * self.world_size
+            return out                # device scalar, no host synchronisation
+        return float(out.item()) + prog.loss_const * self.world_size
 
     def _invalidate(self):
         self.programs.clear()
         self.graphs.clear()
+        self._g_dirty = False        # a rebuilt FlatParams starts from zeroed buffers
+        self._make_peer()
         return True

@@ -216,23 +216,32 @@ def _host_ptr(t):
 
 def adam_flat_step(p, g, m, v, n, lr, step_counter, ticket, first_step=None, beta1=0.9, beta2=0.999,
                    eps=1e-8, loss_src=None, loss_ring=None):
-    """Adam update + step-counter increment in one launch; with loss_ring (LOSS_RING pinned host
-    floats) the loss in loss_src is also written to ring slot (new step count & (LOSS_RING - 1))."""
+    """Adam update + step-counter increment in one launch.  g[:n] is zeroed as it is consumed.
+    loss_src: two floats {this step's loss accumulator, last loss}: the accumulator moves to the
+    second slot and is cleared; with loss_ring (LOSS_RING pinned host floats) the loss is also
+    written to ring slot (new step count & (LOSS_RING - 1))."""
     check(_lib.lib().pvb_adam_flat_step(_p(p), _p(g), _p(m), _p(v), n, float(lr), beta1, beta2, eps,
                                         _p(step_counter), _p(first_step), _p(ticket), _p(loss_src),
                                         _host_ptr(loss_ring), _stream()),
           "pvb_adam_flat_step")
 
 
-def peer_allreduce_adam(p, m, v, own_g, n, peer_g, peer_flags, state, rank, world, lr, step_counter,
-                        first_step=None, beta1=0.9, beta2=0.999, eps=1e-8, loss_ring=None):
+def peer_allreduce_adam(p, m, v, g, n, stage_ptrs, peer_flags, state, rank, world, lr, step_counter,
+                        first_step=None, beta1=0.9, beta2=0.999, eps=1e-8, loss_ring=None,
+                        two_shot=False):
     """All-reduce(SUM) of every rank's [n gradients | loss] buffer over NVLink peer memory fused
-    with the Adam update (csrc/pvb_peer.cu).  peer_g / peer_flags: int64 device tensors holding
-    the peer pointers."""
+    with the Adam update (csrc/pvb_peer.cu).  g: the local gradient buffer (n + 4 floats; zeroed
+    as it is consumed, g[n+1] receives the global loss); stage_ptrs: int64 device tensor of
+    2 * world pointers (staging buffers by parity and rank); peer_flags: int64 device tensor of
+    the ranks' flag blocks."""
     check(_lib.lib().pvb_peer_allreduce_adam(
-        _p(p), _p(m), _p(v), _p(own_g), n, peer_g.data_ptr(), peer_flags.data_ptr(), _p(state),
-        int(rank), int(world), float(lr), beta1, beta2, eps, _p(step_counter), _p(first_step),
-        _host_ptr(loss_ring), _stream()), "pvb_peer_allreduce_adam")
+        _p(p), _p(m), _p(v), _p(g), n, stage_ptrs.data_ptr(), peer_flags.data_ptr(), _p(state),
+        int(rank), int(world), int(bool(two_shot)), float(lr), beta1, beta2, eps, _p(step_counter),
+        _p(first_step), _host_ptr(loss_ring), _stream()), "pvb_peer_allreduce_adam")
+
+
+def peer_state_words():
+    return int(_lib.lib().pvb_peer_state_words())
 
 
 def peer_flag_words():

@@ -73,28 +73,35 @@ def allreduce_sum_(flat, group=None):
 
 class PeerExchange:
     """Symmetric-memory plumbing for the fused all-reduce + Adam kernel (csrc/pvb_peer.cu): every
-    rank's flat gradient buffer and a block of epoch flags are allocated from CUDA symmetric
-    memory (torch.distributed._symmetric_memory: VMM allocations whose handles the per-GPU
-    processes exchange) and mapped into all ranks; the kernel gets the peer pointers as two
-    small device arrays.  PyTorch only provides the allocation / handle exchange here -- the
-    data path is the kernel's own loads over NVLink."""
+    rank owns two staging buffers (used by epoch parity) and a block of epoch flags in CUDA
+    symmetric memory (torch.distributed._symmetric_memory: VMM allocations whose handles the
+    per-GPU processes exchange) mapped into all ranks; the kernel gets the peer pointers as two
+    small device arrays.  PyTorch only provides the allocation / handle exchange here -- the data
+    path is the kernel's own loads over NVLink.  The gradient buffer itself stays local."""
 
     def __init__(self, n_floats, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
         from . import ops
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.g = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+        self.n_floats = int(n_floats)
+        self.stage = [symm_mem.empty(n_floats, dtype=torch.float32, device=device) for _ in range(2)]
         self.flags = symm_mem.empty(max(64, ops.peer_flag_words()), dtype=torch.int32, device=device)
-        self.g.zero_()
+        for t in self.stage:
+            t.zero_()
         self.flags.zero_()
-        hg = symm_mem.rendezvous(self.g, group.group_name)
+        hs = [symm_mem.rendezvous(t, group.group_name) for t in self.stage]
         hf = symm_mem.rendezvous(self.flags, group.group_name)
-        self._handles = (hg, hf)
-        self.peer_g = torch.tensor([int(p) for p in hg.buffer_ptrs], dtype=torch.int64, device=device)
+        self._handles = (hs, hf)
+        ptrs = [int(p) for h in hs for p in h.buffer_ptrs]        # [parity][rank]
+        self.stage_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
         self.peer_flags = torch.tensor([int(p) for p in hf.buffer_ptrs], dtype=torch.int64,
                                        device=device)
-        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        self.state = torch.zeros(ops.peer_state_words(), dtype=torch.int32, device=device)
+        # reduce-scatter + all-gather pays off from 4 ranks on (inbound 2 (W-1)/W instead of W-1
+        # buffer sizes); PVB_PEER_TWO_SHOT=0/1 forces either form (every rank alike)
+        env = os.environ.get("PVB_PEER_TWO_SHOT")
+        self.two_shot = (self.world >= 4) if env is None else (env == "1")
         torch.cuda.synchronize(device)
         dist.barrier(group)       # nobody signals before every rank's flags are zeroed
 

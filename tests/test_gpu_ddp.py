@@ -25,9 +25,9 @@ def _data():
     return x, eps
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, two_shot):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
-                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank), PVB_PEER_TWO_SHOT=two_shot)
     import pyroved_b200 as pv
     from pyroved_b200 import parallel
     parallel.init_process_group("nccl")
@@ -41,6 +41,7 @@ def _worker(rank, world, port, q):
     # auto-generated noise is keyed by the global sample index
     tr.svi.step(parallel.shard(x).to(dev))
     prog = next(iter(tr.svi.programs.values()))
+    assert tr.svi.peer is not None and tr.svi.peer.two_shot == (two_shot == "1")
     if rank == 0:
         q.put((losses, {k: v.cpu() for k, v in m.state_dict().items()}, prog.eps.cpu()))
     else:
@@ -51,7 +52,11 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_step_equals_single_gpu_step():
+@pytest.mark.parametrize("two_shot", ["0", "1"], ids=["one-shot", "two-shot"])
+def test_two_rank_step_equals_single_gpu_step(two_shot):
+    """Fused NVLink exchange (csrc/pvb_peer.cu), both forms: the one-shot sum every rank does for
+    small worlds, and the reduce-scatter + all-gather form used from 4 ranks on (forced here at 2
+    ranks): three data-parallel steps on half batches == three single-GPU steps on the full batch."""
     import pyroved_b200 as pv
     x, eps = _data()
     m = pv.models.iVAE((28, 28), 2, ['r', 't'], seed=1, device="cuda:0")
@@ -64,7 +69,7 @@ def test_two_rank_step_equals_single_gpu_step():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, two_shot)) for r in range(2)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(2)]

@@ -197,20 +197,27 @@ def test_peer_allreduce_adam_single_rank_equals_adam_flat_step():
     new = dict(p=p0.clone(), m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev),
                c=torch.zeros(1, dtype=torch.int32, device=dev))
     flags = torch.zeros(max(64, ops.peer_flag_words()), dtype=torch.int32, device=dev)
-    state = torch.zeros(4, dtype=torch.int32, device=dev)
-    peer_g = torch.tensor([g.data_ptr()], dtype=torch.int64, device=dev)
+    state = torch.zeros(ops.peer_state_words(), dtype=torch.int32, device=dev)
+    stage = [torch.zeros(n + 4, device=dev) for _ in range(2)]
+    stage_ptrs = torch.tensor([t.data_ptr() for t in stage], dtype=torch.int64, device=dev)
     peer_f = torch.tensor([flags.data_ptr()], dtype=torch.int64, device=dev)
     for it in range(4):
         g[:n] = torch.randn(n, device=dev)
         g[n] = 3.5 + it
-        ops.adam_flat_step(ref["p"], g, ref["m"], ref["v"], n, 1e-3, ref["c"], ref["t"], first)
-        ops.peer_allreduce_adam(new["p"], new["m"], new["v"], g, n, peer_g, peer_f, state, 0, 1, 1e-3,
-                                new["c"], first)
+        g2 = g.clone()
+        ops.adam_flat_step(ref["p"], g, ref["m"], ref["v"], n, 1e-3, ref["c"], ref["t"], first,
+                           loss_src=g[n:n + 2])
+        ops.peer_allreduce_adam(new["p"], new["m"], new["v"], g2, n, stage_ptrs, peer_f, state, 0, 1,
+                                1e-3, new["c"], first, two_shot=bool(it & 1))
         torch.cuda.synchronize()
         for k in ("p", "m", "v"):
             assert torch.equal(ref[k], new[k]), (it, k)
-        assert int(new["c"]) == it + 1 and int(state[0]) == it + 1 and int(state[1]) == 0
-        assert float(g[n]) == 3.5 + it
+        assert int(new["c"]) == it + 1 and int(state[0]) == it + 1
+        assert all(int(state[j]) == 0 for j in (1, 2, 3))
+        # both optimizer kernels consume the gradients: buffer zeroed, loss moved to the next slot
+        for buf in (g, g2):
+            assert float(buf[:n + 1].abs().max()) == 0.0
+            assert float(buf[n + 1]) == 3.5 + it
     assert torch.equal(new["p"][100:200], p0[100:200])
 
 

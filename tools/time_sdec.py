@@ -1,0 +1,73 @@
+"""Time the fused decoder kernel alone (CUDA events) at the cfg2 and cfg3 shapes for the library in
+use (PVB_LIB selects an experimental build) and, in the same process, the one-tile kernel
+(PVB_SDEC_V1=1).  With a -DPVB_TC2_TRACE build also prints the stage timeline of CTA 0."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from pyroved_b200 import _lib, ops  # noqa: E402
+
+
+def run(I, B, H, W, iters=20):
+    N = H * W
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).cuda()   # noqa: E731
+    Uv = r(I, 3, 128, sc=0.8)
+    W1, b1, W2, b2 = r(128, 128, sc=0.09), r(128, sc=0.05), r(128, 128, sc=0.09), r(128, sc=0.05)
+    wo, bo = r(1, 128, sc=0.09), r(1, sc=0.05)
+    x = (torch.rand(B, N, generator=g) < 0.3).float().cuda()
+    w = torch.rand(I, generator=g).cuda() if I != B else None
+    sz = ops.sdec_tc_sizes(I, N)
+    rowll, loc = torch.empty(I * N, device="cuda"), torch.empty(I * N, device="cuda")
+    gp = torch.zeros(max(sz.gUv_part_floats, 4), device="cuda")
+    wp = torch.zeros(max(sz.wgrad_part_floats, 4), device="cuda")
+
+    def once():
+        ops.sdec_tc_step(Uv, x, w, W1, b1, W2, b2, wo, bo, rowll, loc, gp, wp, I, B, H, W, 2,
+                         "bernoulli", True, 0.5, True)
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    tiles = (I * N + 127) // 128
+    return us, tiles
+
+
+name = os.path.basename(_lib.LIB_PATH)
+out = [name]
+for tag, (I, B) in (("cfg2", (512, 512)), ("cfg3", (10240, 1024))):
+    for v1 in ("0", "1"):
+        os.environ["PVB_SDEC_V1"] = v1
+        us, tiles = run(I, B, 28, 28, iters=20 if tag == "cfg2" else 5)
+        per = us * 1.965e3 / (tiles / 148.0)
+        out.append("{} {}: {:.1f} us ({:.0f} cyc/tile @1965MHz, {:.0f} TFLOP/s)".format(
+            tag, "one-tile" if v1 == "1" else "interleaved", us, per,
+            198912.0 * I * 784 / us / 1e6))
+print(" | ".join(out))
+lib = C.CDLL(_lib.LIB_PATH)
+if hasattr(lib, "pvb_tc2_trace_read"):
+    os.environ["PVB_SDEC_V1"] = "0"
+    run(512, 512, 28, 28, iters=1)
+    buf = np.zeros((2, 64, 16), dtype=np.int64)
+    assert lib.pvb_tc2_trace_read(buf.ctypes.data_as(C.POINTER(C.c_longlong))) == 0
+    E, M = buf[0], buf[1]
+    np.set_printoptions(linewidth=250)
+    en = ["top", "S0go", "S0pub", "S6acc", "S6dw2", "S6pub", "S2acc", "S2pub", "S8acc", "S8dw1", "S8pub",
+          "S4acc", "S4bar<", "S4bar>", "S4pub"]
+    print("epilogue warp 0 of CTA 0, cycles from the iteration top:", en)
+    for it in range(3, 9):
+        print(it, (E[it, :15] - E[it, 0]).tolist(), "period", int(E[it + 1, 0] - E[it, 0]))
+    mn = ["OP_S0", "G1go", "OP_S6", "G4go", "OP_S2", "G2go", "OP_S8(dUv go)", "OP_S4(G3 go)"]
+    print("MMA warp, same origin:", mn)
+    for it in range(3, 9):
+        print(it, (M[it, :8] - E[it, 0]).tolist())
