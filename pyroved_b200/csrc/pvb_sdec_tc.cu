@@ -168,14 +168,20 @@ __device__ __forceinline__ void lds8(const float* p, float* o) {
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
+// two tanh -> one packed fp16 pair.  (tanh.approx.f16x2 was tried: ptxas lowers it to TWO
+// MUFU.TANH.F16 operations, one per half, so it saves nothing on the MUFU pipe that bounds the
+// tanh stages, and it rounds the pre-activation to fp16 first.)
+__device__ __forceinline__ __half2 tanh_h2(float a, float b) {
+  return __floats2half2_rn(fast_tanh(a), fast_tanh(b));
+}
+
 // 8 columns of tanh(v + bias) -> four fp16 pairs
 __device__ __forceinline__ uint4 tanh8(const float* v, const float* bias) {
   float b[8];
   lds8(bias, b);
   __half2 hh[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e)
-    hh[e] = __floats2half2_rn(fast_tanh(v[2 * e] + b[2 * e]), fast_tanh(v[2 * e + 1] + b[2 * e + 1]));
+  for (int e = 0; e < 4; ++e) hh[e] = tanh_h2(v[2 * e] + b[2 * e], v[2 * e + 1] + b[2 * e + 1]);
   return *reinterpret_cast<uint4*>(hh);
 }
 
@@ -501,9 +507,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           __half2 hh[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float a = fast_tanh(fmaf(ux[2 * e], gx, fmaf(uy[2 * e], gy, uc[2 * e])));
-            float b = fast_tanh(fmaf(ux[2 * e + 1], gx, fmaf(uy[2 * e + 1], gy, uc[2 * e + 1])));
-            hh[e] = valid ? __floats2half2_rn(a, b) : __floats2half2_rn(0.f, 0.f);
+            const float a = fmaf(ux[2 * e], gx, fmaf(uy[2 * e], gy, uc[2 * e]));
+            const float b = fmaf(ux[2 * e + 1], gx, fmaf(uy[2 * e + 1], gy, uc[2 * e + 1]));
+            hh[e] = valid ? tanh_h2(a, b) : __floats2half2_rn(0.f, 0.f);
           }
           out[j] = *reinterpret_cast<uint4*>(hh);
           publish_chunk(bars, tm_lane, cg, j, out[j]);
@@ -593,12 +599,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           pdot = fmaf(hf2.x, wv[2 * e], pdot);
           pdot = fmaf(hf2.y, wv[2 * e + 1], pdot);
         }
-        if (P.backward) store_chunk(smem + SM_DB, row, cg, j, out[j]);   // h2: dwo operand
+        if (P.backward) {
+          store_chunk(smem + SM_DB, row, cg, j, out[j]);   // h2: dwo operand
+          // everything of D2 = dl wo (1 - h2^2) that does not need dl is formed here, in the shadow
+          // of the tanh stage: after the exchange below only one packed multiply per pair is left
+          const __half2 one = __float2half2_rn(1.f);
+          __half2 g2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            g2[e] = __hmul2(__floats2half2_rn(wv[2 * e], wv[2 * e + 1]),
+                            __hfma2(__hneg2(hh[e]), hh[e], one));
+          out[j] = *reinterpret_cast<uint4*>(g2);
+        }
       }
       f32[F_PART + cg * TILE + row] = pdot;
       cp_async_wait_all();   // this thread's share of the next tile's staging has landed
       TRACE(0, 10);
-      epi_bar();
+      // exchange of the partial dots: with a backward pass only the four warps that share these
+      // 32 rows have to meet (the staging of the next tile is published at the tile end);
+      // forward-only, this barrier also publishes the staging: all epilogue warps
+      if (P.backward) asm volatile("bar.sync %0, 128;\n" ::"r"(2 + q) : "memory");
+      else epi_bar();
       TRACE(0, 11);
       const float logit = ((f32[F_PART + row] + f32[F_PART + TILE + row]) +
                            (f32[F_PART + 2 * TILE + row] + f32[F_PART + 3 * TILE + row])) + bo;
@@ -609,18 +630,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         const float dnll = P.x ? pvb::obs_dnll_fast(logit, xv, P.sampler, P.sigmoid_d, P.sig) : 0.f;
         const float dl = valid ? wi * dnll : 0.f;
         uint4 d2[4];
+        const __half2 dl2 = __float2half2_rn(dl);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float wv[8];
-          lds8(f32 + F_WO + 8 * (4 * j + cg), wv);
-          const __half2 one = __float2half2_rn(1.f);
-          const __half2* hh = reinterpret_cast<const __half2*>(&out[j]);
+          const __half2* g2 = reinterpret_cast<const __half2*>(&out[j]);
           __half2 dd[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __half2 g = __hfma2(__hneg2(hh[e]), hh[e], one);
-            dd[e] = __hmul2(__floats2half2_rn(dl * wv[2 * e], dl * wv[2 * e + 1]), g);
-          }
+          for (int e = 0; e < 4; ++e) dd[e] = __hmul2(dl2, g2[e]);
           d2[j] = *reinterpret_cast<uint4*>(dd);
           publish_chunk(bars, tm_lane, cg, j, d2[j]);
           store_chunk(smem + SM_DA, row, cg, j, d2[j]);
@@ -855,12 +871,10 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
   P.step_q = step / N;
   P.step_r = (int)(step % N);
   P.step_qb = (int)(P.step_q % B);
-  // training step: the interleaved kernel (forward of tile i overlapped with the backward of tile
-  // i-1, csrc/pvb_sdec_tc2.cu) unless PVB_SDEC_V1=1 asks for the one-tile-in-flight kernel
-  // (A/B measurements); forward-only calls (inference) always run the kernel in this file
-  const char* v1_env = std::getenv("PVB_SDEC_V1");
-  const bool v1_only = v1_env && v1_env[0] == '1';
-  if (backward && !v1_only) {
+  // PVB_SDEC_V2=1: the experimental interleaved kernel (two tiles in flight, csrc/pvb_sdec_tc2.cu;
+  // measured slower than this one on B200) for the training step; default: this file
+  const char* v2_env = std::getenv("PVB_SDEC_V2");
+  if (backward && v2_env && v2_env[0] == '1') {
     int e = pvb_sdec::launch_v2(P, s.ctas, (cudaStream_t)stream);
     if (e != 0) return e;
     pvb::count_launch();

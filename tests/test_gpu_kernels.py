@@ -244,18 +244,18 @@ def _sdec_torch_reference(Uv, x, w, W1, b1, W2, b2, wo, bo, H, W, B):
     return ll.detach(), torch.sigmoid(logit).detach(), [t.grad for t in leaves]
 
 
-@pytest.mark.parametrize("variant", ["interleaved", "one-tile"])
+@pytest.mark.parametrize("variant", ["one-tile", "interleaved"])
 @pytest.mark.parametrize("shape", [(64, 64, 28, 28, False), (12, 4, 28, 28, True), (37, 37, 6, 6, False),
                                    (300, 300, 28, 28, False)])
 def test_sdec_tc_kernel_vs_torch(shape, variant, monkeypatch):
     """pvb_sdec_tc_step (training: forward + backward in one launch) against PyTorch fp32 autograd,
-    both kernel variants: the interleaved two-tiles-in-flight kernel (csrc/pvb_sdec_tc2.cu, default)
-    and the one-tile-in-flight kernel (csrc/pvb_sdec_tc.cu, PVB_SDEC_V1=1).  Shapes: a CTA with one
+    both kernel variants: the one-tile-in-flight kernel (csrc/pvb_sdec_tc.cu, default) and the
+    experimental interleaved two-tiles-in-flight kernel (csrc/pvb_sdec_tc2.cu, PVB_SDEC_V2=1).  Shapes: a CTA with one
     tile only (64 x 784 rows = 392 tiles over 148 CTAs: 2-3 tiles each), enumerated instances with
     weights (I = 3 B), tiny images (5 instances per tile, ragged last tile), and enough tiles that
     every CTA pipelines many (300 x 784 / 128 = 1838 tiles)."""
     from pyroved_b200._lib import TC_WGRAD_FLOATS, TC_WGRAD_STRIDE
-    monkeypatch.setenv("PVB_SDEC_V1", "1" if variant == "one-tile" else "0")
+    monkeypatch.setenv("PVB_SDEC_V2", "1" if variant == "interleaved" else "0")
     I, B, H, W, weighted = shape
     N = H * W
     gen = torch.Generator().manual_seed(I * 7 + H)

@@ -9,10 +9,6 @@ PT="python -m pytest -q -p no:cacheprovider --timeout 300"
 # 1. the two variants of the fused decoder kernel against PyTorch (a protocol error traps, see
 #    mbar_wait in csrc/pvb_sdec_tc2.cu; the timeout is the second line of defence)
 timeout 600 $PT tests/test_gpu_kernels.py -k sdec_tc 2>&1 | tail -15 > $O/${TAG}_sdec.log
-if grep -q "failed\|error\|Timeout" $O/${TAG}_sdec.log; then
-  echo "interleaved kernel NOT ok -> rest of the visit on the one-tile kernel" >> $O/${TAG}_sdec.log
-  export PVB_SDEC_V1=1
-fi
 tail -3 $O/${TAG}_sdec.log
 # 2. whole GPU suite
 timeout 1200 $PT tests -m gpu 2>&1 | tail -40 > $O/${TAG}_tests.log

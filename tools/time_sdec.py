@@ -1,6 +1,6 @@
 """Time the fused decoder kernel alone (CUDA events) at the cfg2 and cfg3 shapes for the library in
 use (PVB_LIB selects an experimental build) and, in the same process, the one-tile kernel
-(PVB_SDEC_V1=1).  With a -DPVB_TC2_TRACE build also prints the stage timeline of CTA 0."""
+(default; PVB_SDEC_V2=1 selects the interleaved one).  With a -DPVB_TC2_TRACE build also prints the stage timeline of CTA 0."""
 import ctypes as C
 import os
 import sys
@@ -47,7 +47,7 @@ name = os.path.basename(_lib.LIB_PATH)
 out = [name]
 for tag, (I, B) in (("cfg2", (512, 512)), ("cfg3", (10240, 1024))):
     for v1 in ("0", "1"):
-        os.environ["PVB_SDEC_V1"] = v1
+        os.environ["PVB_SDEC_V2"] = "0" if v1 == "1" else "1"
         us, tiles = run(I, B, 28, 28, iters=20 if tag == "cfg2" else 5)
         per = us * 1.965e3 / (tiles / 148.0)
         out.append("{} {}: {:.1f} us ({:.0f} cyc/tile @1965MHz, {:.0f} TFLOP/s)".format(
@@ -55,8 +55,24 @@ for tag, (I, B) in (("cfg2", (512, 512)), ("cfg3", (10240, 1024))):
             198912.0 * I * 784 / us / 1e6))
 print(" | ".join(out))
 lib = C.CDLL(_lib.LIB_PATH)
+if hasattr(lib, "pvb_tc_trace_read"):
+    # one-tile kernel (csrc/pvb_sdec_tc.cu built with -DPVB_TC_TRACE)
+    os.environ["PVB_SDEC_V2"] = "0"
+    run(512, 512, 28, 28, iters=1)
+    buf = np.zeros((2, 64, 32), dtype=np.int64)
+    assert lib.pvb_tc_trace_read(buf.ctypes.data_as(C.POINTER(C.c_longlong))) == 0
+    E, M = buf[0], buf[1]
+    np.set_printoptions(linewidth=250)
+    names = ["top", "S0c0", "S0c1", "S0c2", "S0c3", "S0smem", "staged", "acc1", "S2end", "acc2", "S4A",
+             "bar", "S4B", "S4end", "acc3", "S6end", "acc4", "S8end"]
+    print("one-tile kernel, epilogue warp 0 of CTA 0 (cycles from tile start):", names)
+    for it in range(3, 9):
+        print(it, (E[it, :18] - E[it, 0]).tolist(), "tile period", int(E[it + 1, 0] - E[it, 0]))
+    print("MMA warp: top, ready x4 for GEMM1..4, dUv operands ready (same origin)")
+    for it in range(3, 9):
+        print(it, (M[it, :18] - E[it, 0]).tolist())
 if hasattr(lib, "pvb_tc2_trace_read"):
-    os.environ["PVB_SDEC_V1"] = "0"
+    os.environ["PVB_SDEC_V2"] = "1"
     run(512, 512, 28, 28, iters=1)
     buf = np.zeros((2, 64, 16), dtype=np.int64)
     assert lib.pvb_tc2_trace_read(buf.ctypes.data_as(C.POINTER(C.c_longlong))) == 0
