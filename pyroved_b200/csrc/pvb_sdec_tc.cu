@@ -75,7 +75,10 @@ constexpr int F_GY = F_GX + TILE;                 // [128] grid y
 constexpr int F_GI = F_GY + TILE;                 // [128] int: slot | valid << 8 | n_slots << 16
 constexpr int F_PART = F_GI + TILE;               // [4][128] partial dots per column group
 constexpr int F_RED = F_PART + 4 * TILE;          // [32] block reduction
-constexpr int F_END = F_RED + 32;
+constexpr int F_LG = F_RED + 32;                  // [128] logit, [128] target, [128] valid flag of the tile:
+constexpr int F_LX = F_LG + TILE;                 // handed to the MMA warp, which writes the per-pixel
+constexpr int F_LV = F_LX + TILE;                 // log-likelihood / reconstruction out (training step)
+constexpr int F_END = F_LV + TILE;
 constexpr int SM_BAR = SM_F32 + F_END * 4;        // mbarriers + tmem base
 constexpr int BAR_READY = 0;                      // ready[4]: TMEM A column group written (16 warps)
 constexpr int BAR_SM = 4;                         // sm[5]: smem operands of S0,S2,S4,S6,S8 published
@@ -403,9 +406,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         __syncwarp();
       }
       rph ^= 1;
-      // shared-memory operands of S0 (h0), S2 (h1), S4 (h2, D2, dl) are published by now or soon
-#pragma unroll
-      for (int s = 0; s < 3; ++s) umma::mbar_wait(bars + BAR_SM + s, sph);
+      // shared-memory operands of S0 (h0), S2 (h1), S4 (h2, D2, dl): one publication, in S4
+      umma::mbar_wait(bars + BAR_SM + 2, sph);
       umma::fence_after_sync();
       if (lane == 0) {
         // dwo += h2^T dl ; Db (h2) may be overwritten with D1 once this completes
@@ -422,6 +424,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
                            (k > 0) ? 1u : acc);
       }
       __syncwarp();
+      // per-pixel log-likelihood and reconstruction of the tile: this warp is idle until the first
+      // column group of S6 lands, the epilogue warps are not (fast intrinsics, ~1e-6 relative)
+#pragma unroll
+      for (int k = 0; k < TILE / 32; ++k) {
+        const int r = lane + 32 * k;
+        if (reinterpret_cast<const int*>(f32)[F_LV + r]) {
+          float ll, dn_unused, locv;
+          pvb::obs_terms_fast(f32[F_LG + r], f32[F_LX + r], P.sampler, P.sigmoid_d, P.sig, ll,
+                              dn_unused, locv);
+          if (P.rowll) P.rowll[tile * TILE + r] = ll;
+          if (P.loc) P.loc[tile * TILE + r] = locv;
+        }
+      }
       // ---- GEMM4: ACC = D1 W1 ----
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -541,7 +556,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           *reinterpret_cast<uint4*>(smem + SM_G + umma::tile_off(TILE, row, hf * 8)) =
               *reinterpret_cast<uint4*>(g8);
         }
-        signal_smem(bars, 0);   // h0 (and G) visible to the tensor core
+        // (h0 and G are published by the fence of a later stage of this thread: S4 for the
+        // weight-gradient operands, S8 for G -- a proxy fence orders ALL earlier writes)
         if (prev_tile >= 0 && cg == 1) {
           // per-tile dUv partials of the previous tile: lane == hidden unit (after the fence:
           // a MEMBAR would otherwise wait for these global stores)
@@ -571,7 +587,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         publish_chunk(bars, tm_lane, cg, j, out[j]);
         if (P.backward) store_chunk(smem + SM_A1, row, cg, j, out[j]);
       }
-      if (P.backward) signal_smem(bars, 1);
       // next tile's staging: any time after GEMM1 of this tile (every warp has then consumed the
       // current copy).  Forward-only: here, published by the S4 barrier.  With backward: in the
       // shadow of GEMM4 + dW2' (tensor-bound phase), published by a barrier at the tile end.
@@ -651,10 +666,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           *reinterpret_cast<uint4*>(smem + SM_DL + umma::tile_off(TILE, row, 0)) =
               *reinterpret_cast<uint4*>(d8);
         }
-        if (cg == 0) dl_sum += dl;
+        if (cg == 0) {
+          dl_sum += dl;
+          f32[F_LG + row] = logit;       // -> MMA warp (published by the signal below)
+          f32[F_LX + row] = xv;
+          reinterpret_cast<int*>(f32)[F_LV + row] = valid ? 1 : 0;
+        }
         signal_smem(bars, 2);
       }
-      if (cg == 0 && valid) {
+      if (!P.backward && cg == 0 && valid) {
         // per-pixel log-likelihood and reconstruction (fast intrinsics, ~1e-6 relative)
         float ll = 0.f, dn_unused, locv;
         if (P.x) {
