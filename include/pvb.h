@@ -451,7 +451,16 @@ int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
                      float* rowll, float* loc, float* gUv_part,
                      float* wgrad_part, int64_t I, int64_t B, int H, int W,
                      int ndim, int sampler, int sigmoid_d, float decoder_sig,
-                     int backward, void* stream);
+                     int backward,
+                     const void* packed_w /* optional: pvb_sdec_tc_pack_weights output; then the
+                                             weight tiles come in by two TMA bulk copies
+                                             (cp.async.bulk) instead of being converted by
+                                             every CTA; NULL: converted from W1 / W2 */,
+                     void* stream);
+/* W1, W2 (fp32 [128][128]) -> the kernel's fp16 operand tiles, pvb_sdec_tc_packed_weight_bytes()
+ * bytes (W1 tile, then W2 tile); run once per optimizer step, off the critical path. */
+int64_t pvb_sdec_tc_packed_weight_bytes(void);
+int pvb_sdec_tc_pack_weights(const float* W1, const float* W2, void* packed, void* stream);
 /* gUv_part -> gUv [I,3,128] (deterministic) */
 int pvb_sdec_tc_gather_gUv(const float* gUv_part, float* gUv, int64_t I, int N,
                            void* stream);

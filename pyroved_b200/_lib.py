@@ -126,7 +126,9 @@ SIGNATURES = {
     "pvb_conv_tc_wgrad": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
     "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
-                         _i32, _i32, _i32, _i32, _i32, _fl, _i32, _st],
+                         _i32, _i32, _i32, _i32, _i32, _fl, _i32, _f, _st],
+    "pvb_sdec_tc_packed_weight_bytes": [],
+    "pvb_sdec_tc_pack_weights": [_f, _f, _f, _st],
     "pvb_sdec_tc_gather_gUv": [_f, _f, _i64, _i32, _st],
 }
 
@@ -156,7 +158,8 @@ def lib():
             fn.restype = (C.c_char_p if name == "pvb_last_error_string" else
                           C.c_longlong if name in ("pvb_launch_count",
                                                    "pvb_conv_tc_workspace_bytes",
-                                                   "pvb_bn_workspace_bytes") else C.c_int)
+                                                   "pvb_bn_workspace_bytes",
+                                                   "pvb_sdec_tc_packed_weight_bytes") else C.c_int)
         _LIB = handle
     return _LIB
 

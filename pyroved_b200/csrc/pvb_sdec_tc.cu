@@ -75,10 +75,7 @@ constexpr int F_GY = F_GX + TILE;                 // [128] grid y
 constexpr int F_GI = F_GY + TILE;                 // [128] int: slot | valid << 8 | n_slots << 16
 constexpr int F_PART = F_GI + TILE;               // [4][128] partial dots per column group
 constexpr int F_RED = F_PART + 4 * TILE;          // [32] block reduction
-constexpr int F_LG = F_RED + 32;                  // [128] logit, [128] target, [128] valid flag of the tile:
-constexpr int F_LX = F_LG + TILE;                 // handed to the MMA warp, which writes the per-pixel
-constexpr int F_LV = F_LX + TILE;                 // log-likelihood / reconstruction out (training step)
-constexpr int F_END = F_LV + TILE;
+constexpr int F_END = F_RED + 32;
 constexpr int SM_BAR = SM_F32 + F_END * 4;        // mbarriers + tmem base
 constexpr int BAR_READY = 0;                      // ready[4]: TMEM A column group written (16 warps)
 constexpr int BAR_SM = 4;                         // sm[5]: smem operands of S0,S2,S4,S6,S8 published
@@ -86,7 +83,8 @@ constexpr int BAR_ACC = 9;                        // accumulator of the current 
 constexpr int BAR_DUV = 10;                       // all MMAs of the tile complete (dUv last)
 constexpr int BAR_DW = 11;                        // dW1' MMAs complete (A0, Db reusable)
 constexpr int BAR_DWO = 12;                       // dwo MMAs complete (Db: h2 -> D1)
-constexpr int N_BARS = 13;
+constexpr int BAR_W = 13;                         // pre-packed weights landed (bulk copy, 64 KB)
+constexpr int N_BARS = 14;
 constexpr int SMEM_BYTES = SM_BAR + (N_BARS + 1) * 8;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 
@@ -296,8 +294,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
   const int row = q * 32 + lane;        // tile row == TMEM lane owned by this thread
 
   // ---- one-time setup ----------------------------------------------------------
-  stage_weight(P.W1, smem + SM_W1, tid);
-  stage_weight(P.W2, smem + SM_W2, tid);
+  // weights: pre-packed fp16 operand tiles come in through the TMA engine (one thread, two bulk
+  // copies, issued below once the barrier is initialised); otherwise every thread converts its
+  // share of the fp32 weights
+  if (!P.Wp) {
+    stage_weight(P.W1, smem + SM_W1, tid);
+    stage_weight(P.W2, smem + SM_W2, tid);
+  }
   if (tid < HD) {
     f32[F_B1 + tid] = P.b1[tid];
     f32[F_B2 + tid] = P.b2[tid];
@@ -331,7 +334,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     umma::mbar_init(bars + BAR_DUV, 1);
     umma::mbar_init(bars + BAR_DW, 1);
     umma::mbar_init(bars + BAR_DWO, 1);
+    umma::mbar_init(bars + BAR_W, 1);
     umma::mbar_fence_init();
+    if (P.Wp) pvb_sdec::bulk_load_weights(P.Wp, smem + SM_W1, smem + SM_W2, bars + BAR_W);
   }
   umma::fence_proxy_async();
   umma::fence_before_sync();
@@ -358,6 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     constexpr uint32_t ID_N16 = umma::idesc_f16(128, 16, 1, 1);    // both MN-major, N = 16
     uint32_t rph = 0, sph = 0;
     uint32_t acc = 0;  // 0 on this CTA's first tile: weight-gradient accumulators start fresh
+    if (P.Wp) umma::mbar_wait(bars + BAR_W, 0);   // both weight tiles have landed
     for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
       // ---- GEMM1: ACC = h0 W1^T, K-steps issued as the h0 column groups land in TMEM ----
       TRACE(1, 0);
@@ -424,19 +430,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
                            (k > 0) ? 1u : acc);
       }
       __syncwarp();
-      // per-pixel log-likelihood and reconstruction of the tile: this warp is idle until the first
-      // column group of S6 lands, the epilogue warps are not (fast intrinsics, ~1e-6 relative)
-#pragma unroll
-      for (int k = 0; k < TILE / 32; ++k) {
-        const int r = lane + 32 * k;
-        if (reinterpret_cast<const int*>(f32)[F_LV + r]) {
-          float ll, dn_unused, locv;
-          pvb::obs_terms_fast(f32[F_LG + r], f32[F_LX + r], P.sampler, P.sigmoid_d, P.sig, ll,
-                              dn_unused, locv);
-          if (P.rowll) P.rowll[tile * TILE + r] = ll;
-          if (P.loc) P.loc[tile * TILE + r] = locv;
-        }
-      }
       // ---- GEMM4: ACC = D1 W1 ----
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -666,15 +659,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           *reinterpret_cast<uint4*>(smem + SM_DL + umma::tile_off(TILE, row, 0)) =
               *reinterpret_cast<uint4*>(d8);
         }
-        if (cg == 0) {
-          dl_sum += dl;
-          f32[F_LG + row] = logit;       // -> MMA warp (published by the signal below)
-          f32[F_LX + row] = xv;
-          reinterpret_cast<int*>(f32)[F_LV + row] = valid ? 1 : 0;
-        }
+        if (cg == 0) dl_sum += dl;
         signal_smem(bars, 2);
       }
-      if (!P.backward && cg == 0 && valid) {
+      // (handing this block to the MMA warp was tried: its serial MUFU chains delayed the issue of
+      // GEMM4 by ~1.5 k cycles per tile)
+      if (cg == 0 && valid) {
         // per-pixel log-likelihood and reconstruction (fast intrinsics, ~1e-6 relative)
         float ll = 0.f, dn_unused, locv;
         if (P.x) {
@@ -855,12 +845,41 @@ extern "C" int pvb_sdec_tc_sizes(int64_t I, int N, pvb_tc_sizes* out) {
   return 0;
 }
 
+namespace {
+// fp32 [128][128] x 2 -> fp16 operand tiles (row-chunk layout), W1 at +0, W2 at +32 KB
+__global__ void sdec_pack_weights_kernel(const float* __restrict__ W1, const float* __restrict__ W2,
+                                         uint8_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte piece each
+  if (idx >= 2 * HD * (HD / 8)) return;
+  const int which = idx / (HD * (HD / 8)), rem = idx % (HD * (HD / 8));
+  const int r = rem / (HD / 8), c8 = rem % (HD / 8);
+  const float4* src = reinterpret_cast<const float4*>((which ? W2 : W1) + r * HD + c8 * 8);
+  const float4 a = __ldg(src), b = __ldg(src + 1);
+  __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w),
+                  __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+  *reinterpret_cast<uint4*>(out + which * 16 * CHUNK + umma::tile_off(TILE, r, c8 * 8)) =
+      *reinterpret_cast<uint4*>(h);
+}
+}  // namespace
+
+extern "C" int64_t pvb_sdec_tc_packed_weight_bytes(void) { return 2 * 16 * CHUNK; }
+
+extern "C" int pvb_sdec_tc_pack_weights(const float* W1, const float* W2, void* packed, void* stream) {
+  PVB_CHECK_ARG(W1 && W2 && packed, "pvb_sdec_tc_pack_weights: null pointer");
+  PVB_CHECK_ARG(((uintptr_t)W1 % 16 == 0) && ((uintptr_t)W2 % 16 == 0) && ((uintptr_t)packed % 16 == 0),
+                "pvb_sdec_tc_pack_weights: buffers must be 16-byte aligned");
+  sdec_pack_weights_kernel<<<(2 * HD * (HD / 8) + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      W1, W2, reinterpret_cast<uint8_t*>(packed));
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
 extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w, const float* W1,
                                 const float* b1, const float* W2, const float* b2, const float* wo,
                                 const float* bo, float* rowll, float* loc, float* gUv_part,
                                 float* wgrad_part, int64_t I, int64_t B, int H, int W, int ndim,
                                 int sampler, int sigmoid_d, float decoder_sig, int backward,
-                                void* stream) {
+                                const void* packed_w, void* stream) {
   PVB_CHECK_ARG(Uv && W1 && b1 && W2 && b2 && wo && bo, "pvb_sdec_tc_step: null weights");
   PVB_CHECK_ARG(ndim == 1 || ndim == 2, "pvb_sdec_tc_step: ndim must be 1 or 2");
   PVB_CHECK_ARG(I >= 0 && B > 0 && H > 0 && W > 0, "pvb_sdec_tc_step: bad dims");
@@ -869,6 +888,7 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
   PVB_CHECK_ARG(!backward || (x && gUv_part && wgrad_part), "pvb_sdec_tc_step: backward needs x and workspaces");
   PVB_CHECK_ARG(((uintptr_t)W1 % 16 == 0) && ((uintptr_t)W2 % 16 == 0), "pvb_sdec_tc_step: weights must be 16-byte aligned");
   PVB_CHECK_ARG(!backward || ((uintptr_t)wgrad_part % 16 == 0), "pvb_sdec_tc_step: wgrad_part must be 16-byte aligned");
+  PVB_CHECK_ARG((uintptr_t)packed_w % 16 == 0, "pvb_sdec_tc_step: packed weights must be 16-byte aligned");
   const int N = (ndim == 1) ? H : H * W;
   PVB_CHECK_ARG(N >= MIN_PIX, "pvb_sdec_tc_step: need >= 32 pixels per instance");
   PVB_CHECK_ARG(B < (1LL << 30) && I < (1LL << 40), "pvb_sdec_tc_step: batch too large");
@@ -883,6 +903,7 @@ extern "C" int pvb_sdec_tc_step(const float* Uv, const float* x, const float* w,
   }
   Params P;
   P.Uv = Uv; P.x = x; P.w = w; P.W1 = W1; P.b1 = b1; P.W2 = W2; P.b2 = b2; P.wo = wo; P.bo = bo;
+  P.Wp = packed_w;
   P.rowll = rowll; P.loc = loc; P.gUv_part = gUv_part; P.wgrad_part = wgrad_part;
   P.R = I * N; P.B = B; P.N = N; P.H = H; P.W = (ndim == 1) ? 1 : W; P.ndim = ndim;
   P.sampler = sampler; P.sigmoid_d = sigmoid_d; P.sig = decoder_sig; P.backward = backward;

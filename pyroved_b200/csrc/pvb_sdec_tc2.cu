@@ -69,7 +69,8 @@ constexpr int BAR_DW2 = 7;       // G3 + dW2' + db2 of a tile complete: DA (D2) 
 constexpr int BAR_DW1 = 8;       // G4 + dW1' + db1 complete: DA (D1) and H0 (h0) reusable
 constexpr int BAR_DUV = 9;       // dUv complete: H0 (D0), G and the dUv accumulator reusable
 constexpr int BAR_DWO = 10;      // dwo complete: H0 (borrowed for h2) reusable
-constexpr int N_BARS = 11;
+constexpr int BAR_W = 11;        // pre-packed weights landed (bulk copy, 64 KB)
+constexpr int N_BARS = 12;
 constexpr int SMEM_BYTES = SM_BAR + (N_BARS + 1) * 8;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 static_assert(SM_F32 % 16 == 0 && SM_BAR % 8 == 0, "alignment");
@@ -288,8 +289,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
   const int n_local = (int)((P.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   // ---- one-time setup ----------------------------------------------------------
-  stage_weight(P.W1, smem + SM_W1, tid);
-  stage_weight(P.W2, smem + SM_W2, tid);
+  if (!P.Wp) {       // otherwise: two bulk copies through the TMA engine, issued below
+    stage_weight(P.W1, smem + SM_W1, tid);
+    stage_weight(P.W2, smem + SM_W2, tid);
+  }
   if (tid < HD) {
     f32[F_B1 + tid] = P.b1[tid];
     f32[F_B2 + tid] = P.b2[tid];
@@ -321,7 +324,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
     umma::mbar_init(bars + BAR_DW1, 1);
     umma::mbar_init(bars + BAR_DUV, 1);
     umma::mbar_init(bars + BAR_DWO, 1);
+    umma::mbar_init(bars + BAR_W, 1);
     umma::mbar_fence_init();
+    if (P.Wp) pvb_sdec::bulk_load_weights(P.Wp, smem + SM_W1, smem + SM_W2, bars + BAR_W);
   }
   umma::fence_proxy_async();
   umma::fence_before_sync();
@@ -343,6 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
     constexpr uint32_t ID_N16 = umma::idesc_f16(128, 16, 1, 1);    // both MN-major, N = 16
     uint32_t ph_op[5] = {0, 0, 0, 0, 0};
     uint32_t ph_free = 0;
+    if (P.Wp) mbar_wait(bars + BAR_W, 0);   // both weight tiles have landed
     for (int i = 0; i <= n_local; ++i) {
       const bool F = i < n_local, Bk = i >= 1;
       const uint32_t sH0f = sH0 + (uint32_t)(i & 1) * TILE_BYTES;         // h0 of tile i

@@ -306,6 +306,9 @@ class DecoderOps:
                 self.tc_sizes = s
                 self.gUv_part = torch.empty(max(s.gUv_part_floats, 4), **f32)
                 self.wgrad_part = torch.empty(max(s.wgrad_part_floats, 4), **f32)
+                # the two 128x128 layers as fp16 operand tiles: repacked once per step on the side
+                # stream (prepare()), fetched by every CTA with two TMA bulk copies
+                self.w_packed = ops.sdec_tc_packed_weights(dev)
             else:
                 self.h0 = torch.empty(R, Hd0, **f32)
                 self.dmlp = MLP(layers, dec.activation, R, dev, flat)
@@ -322,6 +325,19 @@ class DecoderOps:
             self.dlogit = torch.empty(I, N, **f32)
             wmax = max([Hl, self.Zf + cond_dim] + [l.in_features for l in layers])
             self.dec_scratch = [torch.empty(I * wmax, **f32) for _ in range(3)]
+
+    def prepare(self):
+        """Start-of-step work that does not depend on the batch: repack the fused kernel's weights
+        (they changed in the last optimizer step) on the side stream, under the encoder forward."""
+        if self.spatial and self.use_tc:
+            eng = self.engine
+            L = linear_layers(eng.model.decoder.fc_layers)
+            if eng.overlap:
+                with eng.fork_side():
+                    ops.sdec_tc_pack_weights(L[0].weight.data, L[1].weight.data, self.w_packed)
+                self._pack_pending = True
+            else:
+                ops.sdec_tc_pack_weights(L[0].weight.data, L[1].weight.data, self.w_packed)
 
     def fold_ctx(self, cond):
         """Arguments of the coordinate-transform fold, for kernels that fuse it."""
@@ -344,11 +360,15 @@ class DecoderOps:
                              cl.fc_coord.bias.data, cl.fc_latent.weight.data, self.Uv)
             if self.use_tc:
                 L = linear_layers(dec.fc_layers)
+                if getattr(self, "_pack_pending", False):
+                    self.engine.join_side()          # the repacked weights are ready
+                    self._pack_pending = False
                 ops.sdec_tc_step(self.Uv, x, w, L[0].weight.data, L[0].bias.data,
                                  L[1].weight.data, L[1].bias.data, dec.out.weight.data,
                                  dec.out.bias.data, self.rowll, self.loc, self.gUv_part,
                                  self.wgrad_part, self.I, self.Bx, m._H, m._W, m.ndim, samp.name,
-                                 dec.sigmoid_out, samp.decoder_sig, want_grad)
+                                 dec.sigmoid_out, samp.decoder_sig, want_grad,
+                                 packed_w=self.w_packed)
             else:
                 ops.sdec_h0_fwd(self.Uv, self.h0, m._H, m._W, m.ndim)
                 hl = self.dmlp.forward(self.h0)
@@ -582,6 +602,7 @@ class SpatialVAEProgram(StepProgram):
 
     def forward(self, beta, want_grad, gen_eps):
         flat = self.engine.flat
+        self.dec.prepare()
         if self.fused:
             self.enc.forward(self.enc_in, gen_eps)
             self.dec.forward(self.head.z, self.y, self.x, None, want_grad, kl=self.head.kl,
@@ -871,6 +892,7 @@ class EnumVAEProgram(StepProgram):
         m = self.engine.model
         flat = self.engine.flat
         K, B, Z = self.K, self.B, self.Z
+        self.dec.prepare()
         if self.kind == "jivae":
             b0, b1 = beta
             enc = m.encoder_z

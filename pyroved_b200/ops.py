@@ -178,12 +178,26 @@ def sdec_tc_sizes(I, N):
 
 
 def sdec_tc_step(Uv, x, w, W1, b1, W2, b2, wo, bo, rowll, loc, gUv_part, wgrad_part, I, B, H, W,
-                 ndim, sampler, sigmoid_d, decoder_sig, backward):
+                 ndim, sampler, sigmoid_d, decoder_sig, backward, packed_w=None):
+    """packed_w: output of sdec_tc_pack_weights for (W1, W2): the kernel then fetches its weight
+    tiles with two TMA bulk copies instead of converting the fp32 weights in every CTA."""
     check(_lib.lib().pvb_sdec_tc_step(_p(Uv), _p(x), _p(w), _p(W1), _p(b1), _p(W2), _p(b2), _p(wo),
                                       _p(bo), _p(rowll), _p(loc), _p(gUv_part), _p(wgrad_part),
                                       I, B, H, W, ndim, SAMPLER[sampler], int(bool(sigmoid_d)),
-                                      float(decoder_sig), int(backward), _stream()),
+                                      float(decoder_sig), int(backward), _p(packed_w), _stream()),
           "pvb_sdec_tc_step")
+
+
+def sdec_tc_packed_weights(device):
+    """buffer for sdec_tc_pack_weights (two fp16 operand tiles)"""
+    n = int(_lib.lib().pvb_sdec_tc_packed_weight_bytes())
+    return torch.empty(n // 4, device=device, dtype=torch.float32)
+
+
+def sdec_tc_pack_weights(W1, W2, packed):
+    check(_lib.lib().pvb_sdec_tc_pack_weights(_p(W1), _p(W2), _p(packed), _stream()),
+          "pvb_sdec_tc_pack_weights")
+    return packed
 
 
 def sdec_tc_gather_gUv(gUv_part, gUv, I, N):

@@ -269,9 +269,13 @@ def test_sdec_tc_kernel_vs_torch(shape, variant, monkeypatch):
     rowll, loc = torch.empty(I * N, device="cuda"), torch.empty(I * N, device="cuda")
     gpart = torch.zeros(max(sz.gUv_part_floats, 4), device="cuda")
     wpart = torch.zeros(max(sz.wgrad_part_floats, 4), device="cuda")
-    for _ in range(2):       # twice: no state may leak from one launch into the next
+    # first launch: weights converted inside the kernel; second: pre-packed tiles fetched by TMA bulk
+    # copies (and no state may leak from one launch into the next)
+    packed = ops.sdec_tc_pack_weights(W1, W2, ops.sdec_tc_packed_weights("cuda"))
+    for pk in (None, packed):
+        rowll.fill_(7.0)
         ops.sdec_tc_step(Uv, x, w, W1, b1, W2, b2, wo, bo, rowll, loc, gpart, wpart, I, B, H, W, 2,
-                         "bernoulli", True, 0.5, True)
+                         "bernoulli", True, 0.5, True, packed_w=pk)
     gUv = torch.empty(I, 3, 128, device="cuda")
     ops.sdec_tc_gather_gUv(gpart, gUv, I, N)
     wsum = wpart.view(sz.ctas, TC_WGRAD_STRIDE)[:, :TC_WGRAD_FLOATS].sum(0)

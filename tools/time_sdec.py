@@ -26,9 +26,13 @@ def run(I, B, H, W, iters=20):
     gp = torch.zeros(max(sz.gUv_part_floats, 4), device="cuda")
     wp = torch.zeros(max(sz.wgrad_part_floats, 4), device="cuda")
 
+    packed = None
+    if os.environ.get("PVB_TIME_PACKED", "1") == "1":
+        packed = ops.sdec_tc_pack_weights(W1, W2, ops.sdec_tc_packed_weights("cuda"))
+
     def once():
         ops.sdec_tc_step(Uv, x, w, W1, b1, W2, b2, wo, bo, rowll, loc, gp, wp, I, B, H, W, 2,
-                         "bernoulli", True, 0.5, True)
+                         "bernoulli", True, 0.5, True, packed_w=packed)
     for _ in range(3):
         once()
     torch.cuda.synchronize()
