@@ -72,7 +72,12 @@ class ClockSampler:
             import torch
             pynvml.nvmlInit()
             uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
-            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode()))
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)      # probe
+            self.nvml = (pynvml, h)
         except Exception:
             self.nvml = None
 
