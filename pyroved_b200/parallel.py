@@ -98,10 +98,13 @@ class PeerExchange:
         self.peer_flags = torch.tensor([int(p) for p in hf.buffer_ptrs], dtype=torch.int64,
                                        device=device)
         self.state = torch.zeros(ops.peer_state_words(), dtype=torch.int32, device=device)
-        # reduce-scatter + all-gather pays off from 4 ranks on (inbound 2 (W-1)/W instead of W-1
-        # buffer sizes); PVB_PEER_TWO_SHOT=0/1 forces either form (every rank alike)
+        # reduce-scatter + all-gather (inbound 2 (W-1)/W instead of W-1 buffer sizes, one more flag
+        # round) pays off for large buffers on >= 4 ranks: measured at 8 GPUs, 4.5 MB (ssiVAE 64x64):
+        # 1.613 vs 1.668 ms per batch; 0.6 MB (iVAE 28x28): 0.251 vs 0.242 ms per step, so small
+        # buffers keep the one-shot form.  PVB_PEER_TWO_SHOT=0/1 forces either (every rank alike)
         env = os.environ.get("PVB_PEER_TWO_SHOT")
-        self.two_shot = (self.world >= 4) if env is None else (env == "1")
+        self.two_shot = ((self.world >= 4 and self.n_floats >= (1 << 19)) if env is None
+                         else (env == "1"))
         torch.cuda.synchronize(device)
         dist.barrier(group)       # nobody signals before every rank's flags are zeroed
 
