@@ -72,30 +72,60 @@ __device__ __forceinline__ void adam_update4(float* __restrict__ p, float* __res
                                              float* __restrict__ m, float* __restrict__ v, int64_t n,
                                              float lr, float b1, float b2, float eps, int step,
                                              const int32_t* __restrict__ first_step) {
-  int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  // one 16-byte access per thread and buffer (the buffers are 16-byte aligned and padded to a
+  // multiple of four floats by their owners; the last quad of an odd-sized buffer goes scalar)
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  const bool full = i0 + 4 <= n;
+  float gq[4], mq[4], vq[4], pq[4];
+  int fq[4] = {0, 0, 0, 0};
+  if (full) {
+    const float4 g4 = *reinterpret_cast<const float4*>(g + i0);
+    const float4 m4 = *reinterpret_cast<const float4*>(m + i0);
+    const float4 v4 = *reinterpret_cast<const float4*>(v + i0);
+    const float4 p4 = *reinterpret_cast<const float4*>(p + i0);
+    gq[0] = g4.x; gq[1] = g4.y; gq[2] = g4.z; gq[3] = g4.w;
+    mq[0] = m4.x; mq[1] = m4.y; mq[2] = m4.z; mq[3] = m4.w;
+    vq[0] = v4.x; vq[1] = v4.y; vq[2] = v4.z; vq[3] = v4.w;
+    pq[0] = p4.x; pq[1] = p4.y; pq[2] = p4.z; pq[3] = p4.w;
+    if (first_step) {
+      const int4 f4 = *reinterpret_cast<const int4*>(first_step + i0);
+      fq[0] = f4.x; fq[1] = f4.y; fq[2] = f4.z; fq[3] = f4.w;
+    }
+  } else {
+    for (int k = 0; k < 4 && i0 + k < n; ++k) {
+      gq[k] = g[i0 + k]; mq[k] = m[i0 + k]; vq[k] = v[i0 + k]; pq[k] = p[i0 + k];
+      if (first_step) fq[k] = first_step[i0 + k];
+    }
+  }
   int last_t = -1;
   float step_size = 0.f, bc2s = 1.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    int64_t j = i0 + k;
-    if (j >= n) break;
-    int t = first_step ? (first_step[j] < 0 ? 0 : step - first_step[j]) : step;
-    if (t <= 0) {           // parameter has never carried a gradient
-      if (ZERO_G) g[j] = 0.f;
-      continue;
-    }
+    if (!full && i0 + k >= n) break;
+    const int t = first_step ? (fq[k] < 0 ? 0 : step - fq[k]) : step;
+    if (t <= 0) continue;   // parameter has never carried a gradient
     if (t != last_t) {
       step_size = lr / (1.f - powf(b1, (float)t));
       bc2s = sqrtf(1.f - powf(b2, (float)t));
       last_t = t;
     }
-    float gj = g[j];
-    if (ZERO_G) g[j] = 0.f;   // consumed: the buffer is clean for the next step's accumulation
-    float mj = b1 * m[j] + (1.f - b1) * gj;
-    float vj = b2 * v[j] + (1.f - b2) * gj * gj;
-    m[j] = mj;
-    v[j] = vj;
-    p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
+    const float gj = gq[k];
+    mq[k] = b1 * mq[k] + (1.f - b1) * gj;
+    vq[k] = b2 * vq[k] + (1.f - b2) * gj * gj;
+    pq[k] -= step_size * mq[k] / (sqrtf(vq[k]) / bc2s + eps);
+  }
+  if (full) {
+    *reinterpret_cast<float4*>(m + i0) = make_float4(mq[0], mq[1], mq[2], mq[3]);
+    *reinterpret_cast<float4*>(v + i0) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+    *reinterpret_cast<float4*>(p + i0) = make_float4(pq[0], pq[1], pq[2], pq[3]);
+    // consumed: the gradient buffer is clean for the next step's accumulation
+    if (ZERO_G) *reinterpret_cast<float4*>(g + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int k = 0; k < 4 && i0 + k < n; ++k) {
+      m[i0 + k] = mq[k]; v[i0 + k] = vq[k]; p[i0 + k] = pq[k];
+      if (ZERO_G) g[i0 + k] = 0.f;
+    }
   }
 }
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -138,6 +168,7 @@ extern "C" int pvb_adam_flat(float* p, const float* g, float* m, float* v, int64
   PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                     ((uintptr_t)v % 16 == 0),
                 "pvb_adam_flat: buffers must be 16-byte aligned");
+  PVB_CHECK_ARG((uintptr_t)first_step % 16 == 0, "pvb_adam_flat: first_step must be 16-byte aligned");
   if (n == 0) return 0;
   int64_t n4 = (n + 3) / 4;
   adam_flat_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1,
@@ -155,6 +186,7 @@ extern "C" int pvb_adam_flat_step(float* p, float* g, float* m, float* v, int64_
   PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                     ((uintptr_t)v % 16 == 0),
                 "pvb_adam_flat_step: buffers must be 16-byte aligned");
+  PVB_CHECK_ARG((uintptr_t)first_step % 16 == 0, "pvb_adam_flat_step: first_step must be 16-byte aligned");
   if (n == 0) return 0;   // (the counter is not advanced for an empty parameter set)
   int64_t n4 = (n + 3) / 4;
   adam_flat_step_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(

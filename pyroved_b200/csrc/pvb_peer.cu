@@ -73,17 +73,26 @@ __device__ __forceinline__ bool grid_arrive_last(int32_t* ticket, int* s_last) {
   return *s_last != 0;
 }
 
+// Adam on one quad (n % 4 == 0, 16-byte aligned buffers: one 16-byte access per buffer)
 __device__ __forceinline__ void adam4(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                       const float* g4, int64_t j0, int64_t n, float lr, float b1,
                                       float b2, float eps, int step,
                                       const int32_t* __restrict__ first_step) {
+  const float4 m4 = *reinterpret_cast<const float4*>(m + j0);
+  const float4 v4 = *reinterpret_cast<const float4*>(v + j0);
+  const float4 p4 = *reinterpret_cast<const float4*>(p + j0);
+  float mq[4] = {m4.x, m4.y, m4.z, m4.w}, vq[4] = {v4.x, v4.y, v4.z, v4.w};
+  float pq[4] = {p4.x, p4.y, p4.z, p4.w};
+  int fq[4] = {0, 0, 0, 0};
+  if (first_step) {
+    const int4 f4 = *reinterpret_cast<const int4*>(first_step + j0);
+    fq[0] = f4.x; fq[1] = f4.y; fq[2] = f4.z; fq[3] = f4.w;
+  }
   int last_t = -1;
   float step_size = 0.f, bc2s = 1.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int64_t j = j0 + k;
-    if (j >= n) break;
-    const int t = first_step ? (first_step[j] < 0 ? 0 : step - first_step[j]) : step;
+    const int t = first_step ? (fq[k] < 0 ? 0 : step - fq[k]) : step;
     if (t <= 0) continue;                      // parameter has never carried a gradient
     if (t != last_t) {
       step_size = lr / (1.f - powf(b1, (float)t));
@@ -91,12 +100,13 @@ __device__ __forceinline__ void adam4(float* __restrict__ p, float* __restrict__
       last_t = t;
     }
     const float gj = g4[k];
-    const float mj = b1 * m[j] + (1.f - b1) * gj;
-    const float vj = b2 * v[j] + (1.f - b2) * gj * gj;
-    m[j] = mj;
-    v[j] = vj;
-    p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
+    mq[k] = b1 * mq[k] + (1.f - b1) * gj;
+    vq[k] = b2 * vq[k] + (1.f - b2) * gj * gj;
+    pq[k] -= step_size * mq[k] / (sqrtf(vq[k]) / bc2s + eps);
   }
+  *reinterpret_cast<float4*>(m + j0) = make_float4(mq[0], mq[1], mq[2], mq[3]);
+  *reinterpret_cast<float4*>(v + j0) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+  *reinterpret_cast<float4*>(p + j0) = make_float4(pq[0], pq[1], pq[2], pq[3]);
 }
 
 __global__ void __launch_bounds__(NT)
@@ -203,6 +213,7 @@ extern "C" int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* g, i
   PVB_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                     ((uintptr_t)v % 16 == 0),
                 "pvb_peer_allreduce_adam: buffers must be 16-byte aligned");
+  PVB_CHECK_ARG((uintptr_t)first_step % 16 == 0, "pvb_peer_allreduce_adam: first_step must be 16-byte aligned");
   const int64_t n4 = n / 4;
   int64_t blocks = (n4 + NT - 1) / NT;
   if (blocks > 148 * 4) blocks = 148 * 4;       // all CTAs co-resident (the kernel syncs grid-wide)
