@@ -84,7 +84,8 @@ constexpr int BAR_DUV = 10;                       // all MMAs of the tile comple
 constexpr int BAR_DW = 11;                        // dW1' MMAs complete (A0, Db reusable)
 constexpr int BAR_DWO = 12;                       // dwo MMAs complete (Db: h2 -> D1)
 constexpr int BAR_W = 13;                         // pre-packed weights landed (bulk copy, 64 KB)
-constexpr int N_BARS = 14;
+constexpr int BAR_DW2 = 14;                       // dW2' MMAs complete (Da: D2 -> D0)
+constexpr int N_BARS = 15;
 constexpr int SMEM_BYTES = SM_BAR + (N_BARS + 1) * 8;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     umma::mbar_init(bars + BAR_DW, 1);
     umma::mbar_init(bars + BAR_DWO, 1);
     umma::mbar_init(bars + BAR_W, 1);
+    umma::mbar_init(bars + BAR_DW2, 1);
     umma::mbar_fence_init();
     if (P.Wp) pvb_sdec::bulk_load_weights(P.Wp, smem + SM_W1, smem + SM_W2, bars + BAR_W);
   }
@@ -422,12 +424,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           umma::mma_f16_ss(tm + TM_DWO, desc_mnmajor(sDB, k), desc_mnmajor(sDL, k), ID_N16,
                            (k > 0) ? 1u : acc);
         umma::commit(bars + BAR_DWO);
-        // dW2' += D2^T [h1|1]: in the shadow of the S6 epilogue start (the tensor pipe is idle
-        // until its first column group lands)
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma::mma_f16_ss(tm + TM_DW2, desc_mnmajor(sDA, k), desc_mnmajor(sA1, k), ID_DW,
-                           (k > 0) ? 1u : acc);
       }
       __syncwarp();
       // ---- GEMM4: ACC = D1 W1 ----
@@ -439,11 +435,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         if (lane == 0) {
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_mnmajor(sW1, 2 * j), ID_DH, j > 0);
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_mnmajor(sW1, 2 * j + 1), ID_DH, 1);
-          if (j == 3) umma::commit(bars + BAR_ACC);   // also covers dW2': Da may be overwritten (D0)
+          if (j == 3) umma::commit(bars + BAR_ACC);
         }
         __syncwarp();
       }
       rph ^= 1;
+      // ---- dW2' += D2^T [h1|1]: BEHIND GEMM4 in the (in-order) tensor pipe -- in front of it, its
+      // 0.6 k cycles delayed GEMM4 and with it S8 (trace: 0.8 k of waiting per tile); S8 now waits
+      // for it only before it overwrites Da (D2 -> D0), after its arithmetic ----
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma::mma_f16_ss(tm + TM_DW2, desc_mnmajor(sDA, k), desc_mnmajor(sA1, k), ID_DW,
+                           (k > 0) ? 1u : acc);
+        umma::commit(bars + BAR_DW2);
+      }
+      __syncwarp();
       // ---- dW1' += D1^T [h0|1] (needs the shared-memory copy of D1) ----
       umma::mbar_wait(bars + BAR_SM + 3, sph);
       umma::fence_after_sync();
@@ -473,7 +480,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
   } else {
     // =========================== epilogue warps ====================================
     const float bo = P.bo[0];
-    uint32_t aph = 0, dph = 0, wph = 0, oph = 0;
+    uint32_t aph = 0, dph = 0, wph = 0, oph = 0, w2ph = 0;
     int64_t prev_tile = -1;
     int prev_slots = 0;
     TileCursor cur_c;
@@ -498,11 +505,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       const float wi = f32[F_WI + row];
       uint4 out[4];
       // ---- S0: first layer h0 = tanh(U g + v) -> TMEM A (+ A0) ------------------------------
-      if (P.backward && prev_tile >= 0) {
-        // dW1' of the previous tile has finished reading A0 / Db (long done: no stall)
-        umma::mbar_wait(bars + BAR_DW, wph);
-        wph ^= 1;
-      }
       {
         const float* u = f32 + F_UV + slot * 3 * HD;
 #pragma unroll
@@ -521,6 +523,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
           }
           out[j] = *reinterpret_cast<uint4*>(hh);
           publish_chunk(bars, tm_lane, cg, j, out[j]);
+          if (j == 0 && P.backward && prev_tile >= 0) {
+            // dW1' of the previous tile (last but one in the tensor queue) has finished reading
+            // A0 / Db: waited for here, behind the first chunk's arithmetic, not at the tile start
+            umma::mbar_wait(bars + BAR_DW, wph);
+            wph ^= 1;
+          }
           // smem copy right behind the signal: by the end of the stage only the last store
           // is still in flight when the proxy fence drains them
           if (P.backward) store_chunk(smem + SM_A0, row, cg, j, out[j]);
@@ -710,8 +718,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       for (int j = 0; j < 4; ++j) {
         const uint32_t off = umma::tile_off(TILE, row, 8 * (4 * j + cg));
         out[j] = dact8(v + 8 * j, *reinterpret_cast<const uint4*>(smem + SM_A0 + off));
-        *reinterpret_cast<uint4*>(smem + SM_DA + off) = out[j];
       }
+      umma::mbar_wait(bars + BAR_DW2, w2ph);   // dW2' has read D2 from Da
+      w2ph ^= 1;
+      store_tile4(smem + SM_DA, row, cg, out);
       umma::fence_before_sync();   // accumulator reads done before the next tile's signals
       signal_smem(bars, 4);
       cp_async_wait_all();
