@@ -239,6 +239,64 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restri
   if (two_d) m = fmaxf(m, fmaxf(p[W], p[W + 1]));
   y[i] = m;
 }
+// 2-D, W % 8 == 0, even H, 16-byte aligned planes: one thread per FOUR horizontally adjacent windows --
+// two 32-byte row segments in (four 16-byte loads), one 16-byte store; a warp reads 2 x 1 KB of
+// contiguous bytes.  HBM-bound: 5 B per input element.
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_vec_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n_quads, int W,
+                        int Wo4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_quads) return;
+  const int64_t rowo = i / Wo4;                  // output row index over all planes (b, c, ho)
+  const int q = (int)(i - rowo * Wo4);
+  const float4* p0 = reinterpret_cast<const float4*>(x + (2 * rowo) * W + 8 * q);
+  const float4* p1 = reinterpret_cast<const float4*>(x + (2 * rowo + 1) * W + 8 * q);
+  const float4 a0 = __ldg(p0), a1 = __ldg(p0 + 1), b0 = __ldg(p1), b1 = __ldg(p1 + 1);
+  float4 o;
+  o.x = fmaxf(fmaxf(a0.x, a0.y), fmaxf(b0.x, b0.y));
+  o.y = fmaxf(fmaxf(a0.z, a0.w), fmaxf(b0.z, b0.w));
+  o.z = fmaxf(fmaxf(a1.x, a1.y), fmaxf(b1.x, b1.y));
+  o.w = fmaxf(fmaxf(a1.z, a1.w), fmaxf(b1.z, b1.w));
+  reinterpret_cast<float4*>(y)[i] = o;
+}
+// backward of the same case: four windows per thread, 16-byte accesses throughout
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                        int64_t n_quads, int W, int Wo4, int act) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_quads) return;
+  const int64_t rowo = i / Wo4;
+  const int q = (int)(i - rowo * Wo4);
+  const int64_t o0 = (2 * rowo) * W + 8 * q, o1 = o0 + W;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + o0)),
+               a1 = __ldg(reinterpret_cast<const float4*>(x + o0) + 1),
+               b0 = __ldg(reinterpret_cast<const float4*>(x + o1)),
+               b1 = __ldg(reinterpret_cast<const float4*>(x + o1) + 1);
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy) + i);
+  const float top[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float bot[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+  float dt[8], db[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // first maximal element in row-major window order (torch's tie-breaking)
+    const float v[4] = {top[2 * k], top[2 * k + 1], bot[2 * k], bot[2 * k + 1]};
+    int best = 0;
+    float vb = v[0];
+#pragma unroll
+    for (int e = 1; e < 4; ++e)
+      if (v[e] > vb) { vb = v[e]; best = e; }
+    const float g = gg[k] * (act ? pvb::act_grad(vb, 0.f, act) : 1.f);
+    dt[2 * k] = best == 0 ? g : 0.f;
+    dt[2 * k + 1] = best == 1 ? g : 0.f;
+    db[2 * k] = best == 2 ? g : 0.f;
+    db[2 * k + 1] = best == 3 ? g : 0.f;
+  }
+  reinterpret_cast<float4*>(dx + o0)[0] = make_float4(dt[0], dt[1], dt[2], dt[3]);
+  reinterpret_cast<float4*>(dx + o0)[1] = make_float4(dt[4], dt[5], dt[6], dt[7]);
+  reinterpret_cast<float4*>(dx + o1)[0] = make_float4(db[0], db[1], db[2], db[3]);
+  reinterpret_cast<float4*>(dx + o1)[1] = make_float4(db[4], db[5], db[6], db[7]);
+}
 // dx = dy routed to the first maximal element of each window (torch tie-breaking: first in
 // row-major window order).  One thread per output window (reads its 2 / 4 inputs once, writes the
 // whole window); elements outside any window (odd sizes) are zeroed by the trailing threads.
@@ -709,6 +767,13 @@ extern "C" int pvb_maxpool2_fwd(const float* x, float* y, int64_t BC, int H, int
   int Ho = two_d ? H / 2 : H, Wo = Wd / 2;
   int64_t n = BC * Ho * Wo;
   if (n == 0) return 0;
+  if (two_d && (Wd % 8) == 0 && (H % 2) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    const int64_t nq = n / 4;
+    maxpool2_fwd_vec_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, nq, Wd,
+                                                                                             Wo / 4);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   maxpool2_fwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, BC, H, Wd, Ho, Wo, two_d);
   pvb::count_launch();
   return pvb::launch_status();
@@ -723,6 +788,14 @@ extern "C" int pvb_maxpool2_bwd(const float* x, const float* dy, float* dx, int6
   const int odd_w = Wd & 1, odd_h = two_d ? (H & 1) : 0;
   int64_t n = BC * Ho * Wo + BC * ((int64_t)odd_w * H + (int64_t)odd_h * (Wd - odd_w));
   if (n == 0) return 0;
+  if (two_d && (Wd % 8) == 0 && (H % 2) == 0 &&
+      (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0) {
+    const int64_t nq = BC * Ho * Wo / 4;
+    maxpool2_bwd_vec_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, dy, dx, nq, Wd, Wo / 4, act);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   maxpool2_bwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, BC, H, Wd, Ho, Wo, two_d, act);
   pvb::count_launch();
   return pvb::launch_status();

@@ -268,6 +268,21 @@ __device__ __forceinline__ void publish_chunk(uint64_t* bars, uint32_t tm_lane, 
   __syncwarp();
   if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bars + BAR_READY + j);
 }
+// chunks j0, j0 + 1 with ONE store-wait / fence / warp handshake (both column groups are signalled):
+// for the stages whose arithmetic per chunk is a handful of packed multiplies, the handshake
+// (~120 cycles) costs more than the earlier start of two K-steps gains
+__device__ __forceinline__ void publish_pair(uint64_t* bars, uint32_t tm_lane, int cg, int j0, uint4 a,
+                                             uint4 b) {
+  umma::tmem_st4(tm_lane + TM_AT + 4 * (4 * j0 + cg), a);
+  umma::tmem_st4(tm_lane + TM_AT + 4 * (4 * (j0 + 1) + cg), b);
+  umma::tmem_st_wait();
+  umma::fence_before_sync();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    umma::mbar_arrive(bars + BAR_READY + j0);
+    umma::mbar_arrive(bars + BAR_READY + j0 + 1);
+  }
+}
 // this thread's 4 chunks -> row-chunk tile in shared memory (operands of the weight-gradient
 // MMAs and of later element-wise passes), then one proxy fence + signal per warp
 __device__ __forceinline__ void store_tile4(uint8_t* tile, int row, int cg, const uint4* out) {
@@ -654,8 +669,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) dd[e] = __hmul2(dl2, g2[e]);
           d2[j] = *reinterpret_cast<uint4*>(dd);
-          publish_chunk(bars, tm_lane, cg, j, d2[j]);
-          store_chunk(smem + SM_DA, row, cg, j, d2[j]);
+          if (j & 1) {
+            publish_pair(bars, tm_lane, cg, j - 1, d2[j - 1], d2[j]);
+            store_chunk(smem + SM_DA, row, cg, j - 1, d2[j - 1]);
+            store_chunk(smem + SM_DA, row, cg, j, d2[j]);
+          }
         }
         TRACE(0, 12);
         // dl -> DL (dwo operand)
@@ -700,7 +718,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       for (int j = 0; j < 4; ++j) {
         const uint32_t off = umma::tile_off(TILE, row, 8 * (4 * j + cg));
         out[j] = dact8(v + 8 * j, *reinterpret_cast<const uint4*>(smem + SM_A1 + off));
-        publish_chunk(bars, tm_lane, cg, j, out[j]);
+        if (j & 1) publish_pair(bars, tm_lane, cg, j - 1, out[j - 1], out[j]);
       }
       if (nxt_c.tile < P.tiles) stage_tile(P, f32, nxt_c, tid, row, cg);
       umma::mbar_wait(bars + BAR_DWO, oph);   // dwo has finished reading h2 from Db

@@ -289,3 +289,16 @@ def test_sdec_tc_kernel_vs_torch(shape, variant, monkeypatch):
                         ("dbo", got[5], gbo)):
         err = (a.reshape(-1) - b_.reshape(-1)).abs().max().item() / (b_.abs().max().item() + 1e-6)
         assert err <= 3e-3, (name, err)
+
+
+@pytest.mark.parametrize("M", [5, 301, 512])
+def test_skinny_linear_forward_vs_torch(M):
+    """<= 8 outputs over a long K (VED's 32768 -> 4 features2latent layer, as two 2-output heads):
+    the one-row-per-block kernel (small M) and the four-rows-per-block kernel (M >= 296, ragged tail)."""
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, 4096, generator=g).cuda()
+    W = (torch.randn(2, 4096, generator=g) * 0.02).cuda()
+    b = torch.randn(2, generator=g).cuda()
+    y = ops.linear_fwd(x, W, b, None)
+    ref = x @ W.t() + b
+    assert torch.allclose(y, ref, atol=2e-4, rtol=1e-4), (y - ref).abs().max().item()

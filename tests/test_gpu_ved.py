@@ -200,7 +200,8 @@ def test_conv_kernels_vs_torch(shape, act):
     assert torch.allclose(db, br.grad, atol=1e-3, rtol=1e-4)
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 8, 10), (1, 5, 7, 9), (3, 4, 1, 13), (2, 2, 1, 16)])
+@pytest.mark.parametrize("shape", [(2, 3, 8, 10), (1, 5, 7, 9), (3, 4, 1, 13), (2, 2, 1, 16),
+                                   (3, 5, 16, 24), (2, 32, 64, 64)])     # W % 8 == 0: 16-byte kernels
 def test_pool_and_upsample_kernels_vs_torch(shape):
     B, C, H, W = shape
     g = torch.Generator().manual_seed(sum(shape))
@@ -217,6 +218,10 @@ def test_pool_and_upsample_kernels_vs_torch(shape):
     dx = torch.empty_like(x)
     ops.maxpool2_bwd(x, dy, dx)
     assert torch.allclose(dx, xr.grad)
+    # fused activation derivative of the layer below (x = leaky-relu output feeding the pool)
+    dxa = torch.empty_like(x)
+    ops.maxpool2_bwd(x, dy, dxa, "lrelu")
+    assert torch.allclose(dxa, xr.grad * torch.where(x > 0, 1.0, 0.01))
     for mode in (["nearest", "bilinear"] if nd == 2 else ["nearest"]):
         xr = x.clone().requires_grad_(True)
         yr = F.interpolate(xr, scale_factor=2, mode=mode)
