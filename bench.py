@@ -236,18 +236,25 @@ def run_reference(args):
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------------
-def time_kernel_alone(fn, iters=20, warm=3):
+def time_kernel_alone(fn, iters=20, warm=3, rounds=5):
+    """Average launch duration (CUDA events around `iters` back-to-back launches), median of
+    `rounds` such averages: one slow round (clock ramp, a neighbour's L2 traffic) does not decide
+    the roofline number."""
     import torch
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / iters
+    per = []
+    for _ in range(rounds):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        per.append(e0.elapsed_time(e1) * 1e-3 / iters)
+    per.sort()
+    return per[len(per) // 2]
 
 
 class Dist:

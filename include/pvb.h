@@ -377,10 +377,14 @@ int pvb_linear_dx_cols(const float* dpre, const float* W, float* dx_cols, int64_
 int pvb_conv_tc_supported(int Cin, int Cout, int kh, int kw);
 int pvb_conv_tc_wgrad_supported(int Cin, int Cout, int kh, int kw);  /* also Cin < 16 (padded) */
 int64_t pvb_conv_tc_workspace_bytes(int Cin, int Cout, int kh, int kw);
-/* mode 0: dst = act(conv(src = x, W) + b), pre optional; mode 1: dst = dx from src = dpre */
+/* mode 0: dst = act(conv(src = x, W) + b), pre optional; mode 1: dst = dx from src = dpre.
+ * mode | 2: the workspace already holds this mode's repacked weights (pvb_conv_tc_prep, e.g. once
+ * per optimizer step off the critical path); otherwise the call repacks them first. */
 int pvb_conv_tc_pix(const float* src, const float* W, const float* b, float* dst,
                     float* pre, void* workspace, int B, int Cin, int Cout, int H,
                     int Wd, int kh, int kw, int act, int mode, void* stream);
+int pvb_conv_tc_prep(const float* W, void* workspace, int Cin, int Cout, int kh, int kw,
+                     int mode, void* stream);
 /* dW += dpre (*) x ; db += sum dpre  (atomic accumulation) */
 int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, float* db, int B,
                       int Cin, int Cout, int H, int Wd, int kh, int kw, void* stream);

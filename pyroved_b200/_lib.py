@@ -122,6 +122,7 @@ SIGNATURES = {
     "pvb_conv_tc_supported": [_i32, _i32, _i32, _i32],
     "pvb_conv_tc_wgrad_supported": [_i32, _i32, _i32, _i32],
     "pvb_conv_tc_workspace_bytes": [_i32, _i32, _i32, _i32],
+    "pvb_conv_tc_prep": [_f, _f, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_tc_pix": [_f, _f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_tc_wgrad": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],

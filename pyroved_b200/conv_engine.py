@@ -29,7 +29,10 @@ class ConvStack:
             st["tc"] = (kind == "conv" and not engine.force_generic
                         and ops.conv_tc_supported(mod.weight))
             if st["tc"]:
+                # repacked weights, one workspace per direction: both are refreshed once per step
+                # on the side stream (prepare()), off the critical path
                 st["ws"] = ops.conv_tc_workspace(mod.weight)
+                st["ws_bwd"] = ops.conv_tc_workspace(mod.weight)
             st["tc_wgrad"] = (kind == "conv" and not engine.force_generic
                               and ops.conv_tc_wgrad_supported(mod.weight))
             if kind == "bn":
@@ -42,15 +45,29 @@ class ConvStack:
         self.gbuf = [torch.empty(biggest, **f32) for _ in range(2)]
         self.x = None
 
+    def prepare(self):
+        """Repack the tensor-core layers' weights for both directions (they changed in the last
+        optimizer step).  Called at the start of a step inside engine.fork_side(): the repacks run
+        concurrently with the first layers of the forward pass."""
+        for st in self.steps:
+            if st["kind"] == "conv" and st["tc"]:
+                ops.conv_tc_prep(st["mod"].weight.data, st["ws"], 0)
+                ops.conv_tc_prep(st["mod"].weight.data, st["ws_bwd"], 1)
+        self.prepped = True
+
     def forward(self, x):
         self.x = x
         cur = x
+        prepped = getattr(self, "prepped", False)
         for st in self.steps:
             m = st["mod"]
             if st["kind"] == "conv":
                 bias = m.bias.data if m.bias is not None else None
                 if st["tc"]:
-                    ops.conv_tc_fwd(cur, m.weight.data, bias, st["act"], st["y"], st["ws"], st["pre"])
+                    if prepped and self.engine._side_used:
+                        self.engine.join_side()        # the repacked weights are ready
+                    ops.conv_tc_fwd(cur, m.weight.data, bias, st["act"], st["y"], st["ws"], st["pre"],
+                                    prepped=prepped)
                 else:
                     ops.conv_fwd(cur, m.weight.data, bias, st["act"], st["y"], st["pre"])
             elif st["kind"] == "bn":
@@ -97,11 +114,13 @@ class ConvStack:
                     ops.conv_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
                 if want_dx:
                     if st["tc"]:
+                        pp = getattr(self, "prepped", False)
                         if fuse:
-                            ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"], xin, below["act"])
+                            ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws_bwd"], xin, below["act"],
+                                                 prepped=pp)
                             below["dpre_ready"] = True
                         else:
-                            ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws"])
+                            ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws_bwd"], prepped=pp)
                     else:
                         ops.conv_bwd_data(d, m.weight.data, dx)
             elif st["kind"] == "bn":
@@ -242,6 +261,11 @@ class VEDProgram(StepProgram):
         eng = self.engine
         m = eng.model
         samp = m.sampler_d
+        # weights of the tensor-core convolutions -> fp16 operand layout, both directions, once per
+        # step on the side stream (24 small launches that used to sit on the critical path)
+        with eng.fork_side():
+            self.enc.prepare()
+            self.dec.prepare()
         self.genc.forward(self.x, gen_eps)
         fc = m.decoder.latent2features.fc
         ops.linear_fwd(self.z, fc.weight.data, fc.bias.data, None, out=self.feat0)

@@ -988,10 +988,28 @@ extern "C" int64_t pvb_conv_tc_workspace_bytes(int Cin, int Cout, int kh, int kw
 
 // mode 0: y = act(conv(x, W) + b)   (fp16 operands)     src = x   [B, Cin, H, W]
 // mode 1: dx = conv_transpose(dpre, W)  (bf16 operands)  src = dpre [B, Cout, H, W]
+extern "C" int pvb_conv_tc_prep(const float* W, void* workspace, int Cin, int Cout, int kh, int kw, int mode,
+                                void* stream) {
+  PVB_CHECK_ARG(W && workspace && (mode == 0 || mode == 1), "pvb_conv_tc_prep: bad argument");
+  PVB_CHECK_ARG(((uintptr_t)workspace % 16) == 0, "pvb_conv_tc_prep: workspace must be 16-byte aligned");
+  const int taps = kh * kw;
+  const int64_t total = (int64_t)Cin * Cout * taps;
+  uint16_t* Wp = reinterpret_cast<uint16_t*>(workspace);
+  if (mode == 0)
+    conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(W, Wp, Cout, Cin, taps, 0);
+  else
+    conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(W, Wp, Cout, Cin, taps, 1);
+  pvb::count_launch();
+  return pvb::launch_status();
+}
+
 extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b, float* dst, float* pre,
                                void* workspace, int B, int Cin, int Cout, int H, int Wd, int kh, int kw,
-                               int act, int mode, void* stream) {
+                               int act, int mode_flags, void* stream) {
   PVB_CHECK_ARG(src && W && dst && workspace, "pvb_conv_tc_pix: null pointer");
+  // bit 1: the workspace already holds this mode's repacked weights (pvb_conv_tc_prep, once per step)
+  const bool prepped = (mode_flags & 2) != 0;
+  const int mode = mode_flags & ~2;
   PVB_CHECK_ARG(mode == 0 || mode == 1, "pvb_conv_tc_pix: mode must be 0 (forward) or 1 (backward data)");
   const int Cg = mode == 0 ? Cin : Cout, Nout = mode == 0 ? Cout : Cin;
   PVB_CHECK_ARG(tc_ok(Cg, Nout, kh, kw), "pvb_conv_tc_pix: unsupported shape (channels must be multiples of 16, N <= 128)");
@@ -1042,12 +1060,12 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
         attr3 = true;
       }
       if (mode == 0) {
-        conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
+        if (!prepped) conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
       } else {
         PVB_CHECK_ARG(!pre || (act != PVB_ACT_GELU), "pvb_conv_tc_pix: gelu's derivative needs the pre-activation");
-        conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
+        if (!prepped) conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
       }
-      pvb::count_launch();
+      if (!prepped) pvb::count_launch();
       for (int n_off = 0; n_off < Nout; n_off += n_launch) {
         P2Dims p3 = p2;
         p3.Nout = n_launch;
@@ -1064,13 +1082,13 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
       return pvb::launch_status();
     }
     if (mode == 0) {
-      conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
-      pvb::count_launch();
+      if (!prepped) conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
+      if (!prepped) pvb::count_launch();
       conv_tc_pix2_kernel<false, false><<<grid2, P2_THREADS, smem2, st>>>(src, Wp, b, dst, pre, p2, act);
     } else {
       PVB_CHECK_ARG(!pre || (act != PVB_ACT_GELU), "pvb_conv_tc_pix: gelu's derivative needs the pre-activation");
-      conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
-      pvb::count_launch();
+      if (!prepped) conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
+      if (!prepped) pvb::count_launch();
       conv_tc_pix2_kernel<BWD_BF16, true><<<grid2, P2_THREADS, smem2, st>>>(src, Wp, nullptr, dst, pre, p2,
                                                                            pre ? act : 0);
     }
@@ -1082,12 +1100,12 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
   const int64_t M = (int64_t)B * H * Wd;
   const unsigned grid = (unsigned)((M + TP - 1) / TP);
   if (mode == 0) {
-    conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
-    pvb::count_launch();
+    if (!prepped) conv_tc_prep_kernel<false><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 0);
+    if (!prepped) pvb::count_launch();
     conv_tc_pix_kernel<false, false><<<grid, PIX_THREADS, PIX_SMEM, st>>>(src, Wp, b, dst, pre, d, act);
   } else {
-    conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
-    pvb::count_launch();
+    if (!prepped) conv_tc_prep_kernel<BWD_BF16><<<pvb::cdiv(total, 256), 256, 0, st>>>(W, Wp, Cout, Cin, taps, 1);
+    if (!prepped) pvb::count_launch();
     // `pre` (optional) = output of the layer below, `act` its activation: dst = dx * act'(pre)
     PVB_CHECK_ARG(!pre || (act != PVB_ACT_GELU), "pvb_conv_tc_pix: gelu's derivative needs the pre-activation");
     conv_tc_pix_kernel<BWD_BF16, true><<<grid, PIX_THREADS, PIX_SMEM, st>>>(src, Wp, nullptr, dst, pre, d,

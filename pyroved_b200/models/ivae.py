@@ -79,6 +79,15 @@ class iVAE(baseVAE):
                 plot_spect_grid(loc, d, **kwargs)
         return loc
 
+    def predict_on_latent(self, *args, **kwargs):
+        """Reference models/ivae.py:312-349 fits a Pyro Gaussian process (`pyro.contrib.gp`,
+        utils/gp.py) on the encoded data: outside the SVI hot path this package implements
+        (DESIGN.md 8).  Use `encode()` / `decode()` / `manifold2d()` and any GP library on the
+        codes."""
+        raise NotImplementedError(
+            "pyroved_b200 implements the SVI training / inference path, not the Pyro GP regression "
+            "of predict_on_latent; encode() the data and fit a GP on the latent codes instead")
+
     def _make_program(self, engine, B, has_y, mode="main"):
         from ..engine import SpatialVAEProgram
         return SpatialVAEProgram(engine, B, has_y)

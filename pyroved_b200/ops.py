@@ -537,18 +537,27 @@ def conv_tc_workspace(W):
     return torch.empty((n + 3) // 4, device=W.device, dtype=torch.float32)
 
 
-def conv_tc_fwd(x, W, b, act, out, ws, pre=None):
+def conv_tc_prep(W, ws, mode):
+    """Repack W for mode 0 (forward) / 1 (backward data) into ws; the conv calls then take
+    prepped=True (weights are constant within an optimizer step)."""
+    kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
+    check(_lib.lib().pvb_conv_tc_prep(_p(W), _p(ws), W.shape[1], W.shape[0], kh, kw, int(mode),
+                                      _stream()), "pvb_conv_tc_prep")
+
+
+def conv_tc_fwd(x, W, b, act, out, ws, pre=None, prepped=False):
     check(_lib.lib().pvb_conv_tc_pix(_p(x), _p(W), _p(b), _p(out), _p(pre), _p(ws),
-                                     *_conv_dims(x, W), ACT[act], 0, _stream()), "pvb_conv_tc_pix")
+                                     *_conv_dims(x, W), ACT[act], 0 | (2 if prepped else 0),
+                                     _stream()), "pvb_conv_tc_pix")
     return out
 
 
-def conv_tc_bwd_data(dpre, W, dx, ws, y_below=None, act_below=None):
+def conv_tc_bwd_data(dpre, W, dx, ws, y_below=None, act_below=None, prepped=False):
     """dx = conv_transpose(dpre, W); with y_below (the output of the layer below, same shape as dx)
     and its activation: dx *= act'(y_below), i.e. dx is that layer's dpre."""
     check(_lib.lib().pvb_conv_tc_pix(_p(dpre), _p(W), None, _p(dx), _p(y_below), _p(ws),
                                      *_conv_dims(dx, W), ACT[act_below if y_below is not None else None],
-                                     1, _stream()), "pvb_conv_tc_pix")
+                                     1 | (2 if prepped else 0), _stream()), "pvb_conv_tc_pix")
 
 
 def conv_tc_bwd_weight(dpre, x, W, dW, db):
