@@ -103,10 +103,11 @@ class baseVAE(nn.Module):
         loader = init_dataloader(*input_args, shuffle=False,
                                  batch_size=kwargs.get("batch_size", 100))
         out = []
-        for batch in loader:
-            batch = [t.to(self.device) for t in batch]
-            enc = self.encoder_z(batch[0] if len(batch) == 1 else batch)
-            out.append(torch.cat(enc, -1).cpu())
+        with self._on_device():
+            for batch in loader:
+                batch = [t.to(self.device) for t in batch]
+                enc = self.encoder_z(batch[0] if len(batch) == 1 else batch)
+                out.append(torch.cat(enc, -1).cpu())
         return torch.cat(out)
 
     def _decode(self, z_new: torch.Tensor, **kwargs) -> torch.Tensor:
@@ -117,13 +118,23 @@ class baseVAE(nn.Module):
         dev = self.device
         out = []
         spatial = bool(self.invariances) and self.coord > 0
-        for s in range(0, z_new.shape[0], bs):
-            z = z_new[s:s + bs].to(dev).float().contiguous()
-            if spatial:
-                out.append(self._decode_spatial_batch(z, **kwargs).cpu())
-            else:
-                out.append(self.decoder(z).cpu())
+        with self._on_device():
+            for s in range(0, z_new.shape[0], bs):
+                z = z_new[s:s + bs].to(dev).float().contiguous()
+                if spatial:
+                    out.append(self._decode_spatial_batch(z, **kwargs).cpu())
+                else:
+                    out.append(self.decoder(z).cpu())
         return torch.cat(out)
+
+    def _on_device(self):
+        """Context in which the kernels of an inference call launch: the model's own CUDA device,
+        whatever the caller's current device is (the kernels take torch's current stream)."""
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            import contextlib
+            return contextlib.nullcontext()
+        return torch.cuda.device(dev)
 
     def _decode_spatial_batch(self, z, **kwargs):
         dec = self.decoder
