@@ -206,7 +206,7 @@ conv_tc_pix_kernel(const float* __restrict__ src, const uint16_t* __restrict__ W
       umma::mbar_wait(full + s, ph_full);
       CTRACE(1, 1 + 2 * c);
       umma::fence_after_sync();
-      if (lane == 0) {
+      if (umma::elect_one()) {
         const int cc = min(CC, d.Cg - (c % cchunks) * CC);   // channels in this chunk (multiple of 16)
         for (int k16 = 0; k16 < cc / 16; ++k16) {
           uint64_t da = umma::smem_desc(a0 + s * A_STAGE + k16 * 2 * (TP * ROWB), TP * ROWB, 128);
@@ -399,7 +399,7 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
         umma::mbar_wait(b_full + sb, (uint32_t)((i >> 1) & 1));
         PTRACE(1, 2 + 2 * i);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           const int shift = halo + d.sign * ((t / d.kw - ph) * Wp + (t % d.kw - pw));
           for (int k16 = 0; k16 < cc / 16; ++k16) {
             uint64_t da = umma::smem_desc(x0 + sx * x_stage + shift * ROWB + k16 * 2 * XCS, XCS, 128);
@@ -620,7 +620,7 @@ conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
       if (it >= 2) umma::mbar_wait(a_empty + s, (uint32_t)(((it >> 1) - 1) & 1));
       P3TRACE(1, 3 * it + 1);
       umma::fence_after_sync();
-      if (lane == 0) {
+      if (umma::elect_one()) {
         const uint64_t xa0 = da_base + (uint64_t)((s * x_stage) >> 4);
         const uint32_t tacc = tm + s * 128;
         if (d.kh == 3) issue_tile<3, 3>(tacc, xa0, db_base, toff, cchunks, d.Cg, x_chunk, w_tile, da_kstep, db_kstep, idesc);
@@ -812,7 +812,7 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       umma::mbar_wait(full + s, (uint32_t)((it / n_stages) & 1));
       WTRACE(1, 3 * it + 1);
       umma::fence_after_sync();
-      if (lane == 0) {
+      if (umma::elect_one()) {
         const uint64_t da = da0 + (uint64_t)s * stage_step, dx = dx0 + (uint64_t)s * stage_step;
         const uint32_t acc = it > 0 ? 1u : 0u;
         for (int j = 0; j < kw; ++j) {     // tap (dh, j - pw): X shifted by j rows (16 bytes each)

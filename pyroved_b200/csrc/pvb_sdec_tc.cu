@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         umma::mbar_wait(bars + BAR_READY + j, rph);
         TRACE(1, 1 + j);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_kmajor(sW1, 2 * j), ID_FWD, j > 0);
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_kmajor(sW1, 2 * j + 1), ID_FWD, 1);
           if (j == 3) umma::commit(bars + BAR_ACC);
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         umma::mbar_wait(bars + BAR_READY + j, rph);
         TRACE(1, 5 + j);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_kmajor(sW2, 2 * j), ID_FWD, j > 0);
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_kmajor(sW2, 2 * j + 1), ID_FWD, 1);
           if (j == 3) umma::commit(bars + BAR_ACC);
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         umma::mbar_wait(bars + BAR_READY + j, rph);
         TRACE(1, 9 + j);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_mnmajor(sW2, 2 * j), ID_DH, j > 0);
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_mnmajor(sW2, 2 * j + 1), ID_DH, 1);
           if (j == 3) umma::commit(bars + BAR_ACC);
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       // shared-memory operands of S0 (h0), S2 (h1), S4 (h2, D2, dl): one publication, in S4
       umma::mbar_wait(bars + BAR_SM + 2, sph);
       umma::fence_after_sync();
-      if (lane == 0) {
+      if (umma::elect_one()) {
         // dwo += h2^T dl ; Db (h2) may be overwritten with D1 once this completes
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         umma::mbar_wait(bars + BAR_READY + j, rph);
         TRACE(1, 13 + j);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j, desc_mnmajor(sW1, 2 * j), ID_DH, j > 0);
           umma::mma_f16_ts(tm + TM_ACC, tA + 16 * j + 8, desc_mnmajor(sW1, 2 * j + 1), ID_DH, 1);
           if (j == 3) umma::commit(bars + BAR_ACC);
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       // ---- dW2' += D2^T [h1|1]: BEHIND GEMM4 in the (in-order) tensor pipe -- in front of it, its
       // 0.6 k cycles delayed GEMM4 and with it S8 (trace: 0.8 k of waiting per tile); S8 now waits
       // for it only before it overwrites Da (D2 -> D0), after its arithmetic ----
-      if (lane == 0) {
+      if (umma::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma::mma_f16_ss(tm + TM_DW2, desc_mnmajor(sDA, k), desc_mnmajor(sA1, k), ID_DW,
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       // ---- dW1' += D1^T [h0|1] (needs the shared-memory copy of D1) ----
       umma::mbar_wait(bars + BAR_SM + 3, sph);
       umma::fence_after_sync();
-      if (lane == 0) {
+      if (umma::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma::mma_f16_ss(tm + TM_DW1, desc_mnmajor(sDB, k), desc_mnmajor(sA0, k), ID_DW,
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       sph ^= 1;
       TRACE(1, 17);
       umma::fence_after_sync();
-      if (lane == 0) {
+      if (umma::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma::mma_f16_ss(tm + TM_DUV, desc_mnmajor(sDA, k), desc_mnmajor(sG, k), ID_N16, k > 0);

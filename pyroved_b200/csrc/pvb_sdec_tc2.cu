@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         if (Bk) { mbar_wait(bars + BAR_ACCFREE, ph_free); ph_free ^= 1; }   // S6(i-1) holds G3's result
         TRACE(1, 1);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_ACC, desc_kmajor(sH0f, k), desc_kmajor(sW1, k), ID_FWD, k > 0);
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         mbar_wait(bars + BAR_ACCFREE, ph_free); ph_free ^= 1;     // S2(i) (drain: S6(i-1))
         TRACE(1, 3);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           const uint32_t accw = (i - 1) > 0 ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         mbar_wait(bars + BAR_ACCFREE, ph_free); ph_free ^= 1;     // S8(i-1) (i == 0: S2(0))
         TRACE(1, 5);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_ACC, desc_kmajor(sH1, k), desc_kmajor(sW2, k), ID_FWD, k > 0);
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         mbar_wait(bars + BAR_OP + OP_S8, ph_op[OP_S8]); ph_op[OP_S8] ^= 1;
         TRACE(1, 6);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma::mma_f16_ss(tm + TM_DUV, desc_mnmajor(sH0b, k), desc_mnmajor(sG, k), ID_N16, k > 0);
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc2_kernel(Params P) {
         mbar_wait(bars + BAR_OP + OP_S4, ph_op[OP_S4]); ph_op[OP_S4] ^= 1;
         TRACE(1, 7);
         umma::fence_after_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           const uint32_t accw = i > 0 ? 1u : 0u;
           // h2 sits in the H0 buffer of the other parity, which S0(i+1) rewrites: first in line
 #ifndef PVB_TC2_NO_DWO_MMA

@@ -37,6 +37,21 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, i
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// One lane of a CONVERGED warp (elect.sync).  Guarding the MMA issue with this instead of `lane == 0` tells
+// ptxas that a single thread is active, so descriptors move to uniform registers with plain R2UR instead of
+// an ELECT / R2UR.BROADCAST waterfall loop per instruction (26 -> ~8 SASS instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                            uint32_t idesc, uint32_t accumulate) {

@@ -39,6 +39,32 @@ def _check(tag, loss, ref, prog_loc, m, grads, gtol=TC_GRAD_TOL):
     grad_check(m, grads, gtol, tag, allow_missing=True)
 
 
+def test_cfg1_shift_ivae_1d_b64():
+    """BASELINE configs[0]: 1-D shift-invariant iVAE on 1x64 spectra, latent_dim=2, batch 64 (the
+    reference's own CPU-runnable case), data as examples/shiftVAE.ipynb: noisy shifted Gaussian peaks."""
+    import pyroved_b200 as pv
+    from oracle import svi_port as sp
+    B, L = 64, 64
+    g = torch.Generator().manual_seed(1)
+    xs = torch.linspace(-12, 12, L)
+    mu = (torch.rand(B, generator=g) - 0.5) * 14
+    sig = 1.0 + torch.rand(B, generator=g)
+    x = torch.exp(-0.5 * ((xs[None] - mu[:, None]) / sig[:, None]) ** 2) + 0.05 * torch.randn(B, L, generator=g)
+    x = (x - x.min()) / (x.max() - x.min())                        # [B, 64], scaled to [0, 1]
+    eps = torch.randn(B, 3, generator=g)
+    for generic in (True, False):
+        m = pv.models.iVAE((L,), latent_dim=2, invariances=['t'], seed=1, device="cuda:0")
+        tr = pv.trainers.SVItrainer(m, seed=1, device="cuda:0", force_generic=generic)
+        sd = _sd(m)
+        loss = tr.svi.loss_and_grads(x.cuda(), _eps=eps.cuda())
+        prog = next(iter(tr.svi.programs.values()))
+        assert bool(prog.use_tc) == (not generic)
+        ref, grads = sp.loss_and_grads(sp.ivae_loss, sd, sp.Cfg((L,), 2, ['t']), x, eps)
+        ref = dict(ref, loss=float(ref["loss"]))
+        _check("cfg1 1-D shift B=64 {}".format("fp32" if generic else "tc"), loss, ref, prog.loc, m, grads,
+               2e-3 if generic else TC_GRAD_TOL)
+
+
 def test_cfg2_ivae_b512():
     name = "cfg2"
     m, tr = bl.build(name, "cuda:0")
