@@ -416,7 +416,19 @@ __global__ void act_bwd_flat_kernel(const float* __restrict__ dy, const float* _
                                     int act) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dpre[i] = dy[i] * pvb::act_grad(y[i], pre ? pre[i] : 0.f, act);
+  // 16-byte accesses over the aligned body, scalar tail
+  const bool vec = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) |
+                     reinterpret_cast<uintptr_t>(dpre) | (pre ? reinterpret_cast<uintptr_t>(pre) : 0)) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  for (int64_t k = i; k < n4; k += stride) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + k);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y) + k);
+    const float4 p = pre ? __ldg(reinterpret_cast<const float4*>(pre) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(dpre)[k] =
+        make_float4(g.x * pvb::act_grad(v.x, p.x, act), g.y * pvb::act_grad(v.y, p.y, act),
+                    g.z * pvb::act_grad(v.z, p.z, act), g.w * pvb::act_grad(v.w, p.w, act));
+  }
+  for (int64_t k = 4 * n4 + i; k < n; k += stride) dpre[k] = dy[k] * pvb::act_grad(y[k], pre ? pre[k] : 0.f, act);
 }
 
 // Cin == 1 (the first encoder layer): HBM-write bound, so no GEMM machinery -- one thread per

@@ -146,6 +146,30 @@ __device__ __forceinline__ void bias_act16(float* v, const float* __restrict__ b
   }
 }
 
+// v[j] *= act'(y[j]) on 16 columns, the activation switch hoisted out of the loop (per element it costs ~20
+// instructions on the four epilogue warps: the backward-data kernel ran 51 M warp instructions against the
+// forward's 32 M and took 2.9x its time)
+__device__ __forceinline__ void act_grad16(float* v, const float* y, int act) {
+  switch (act) {
+    case PVB_ACT_NONE: break;
+    case PVB_ACT_LRELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = y[j] > 0.f ? v[j] : 0.01f * v[j];
+      break;
+    case PVB_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = y[j] > 0.f ? v[j] : 0.f;
+      break;
+    case PVB_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= 1.f - y[j] * y[j];
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= pvb::act_grad(y[j], 0.f, act);
+  }
+}
+
 #ifdef PVB_TC_TRACE
 __device__ long long g_ctrace[2][64];
 #define CTRACE(role, ev) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4) && (ev) < 64) g_ctrace[role][ev] = clock64(); } while (0)
@@ -283,8 +307,7 @@ conv_tc_pix_kernel(const float* __restrict__ src, const uint16_t* __restrict__ W
             float yv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) yv[j] = __ldg(pbase + (int64_t)(n0 + j) * HW);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] *= pvb::act_grad(yv[j], 0.f, act);
+            act_grad16(v, yv, act);
           }
         } else {
           bias_act16(v, bias, n0, d.out_scale, act, pbase, HW);
@@ -493,8 +516,7 @@ conv_tc_pix2_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
             float yv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) yv[j] = __ldg(pbase + (int64_t)(n0 + j) * HW);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] *= pvb::act_grad(yv[j], 0.f, act);
+            act_grad16(v, yv, act);
           }
         } else {
           bias_act16(v, bias, n0, d.out_scale, act, pbase, HW);
@@ -697,8 +719,7 @@ conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
               float yv[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) yv[j] = __ldg(pbase + (int64_t)(n0 + j) * HW);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] *= pvb::act_grad(yv[j], 0.f, act);
+              act_grad16(v, yv, act);
             }
           } else {
             bias_act16(v, bias, n0, d.out_scale, act, pbase, HW);
