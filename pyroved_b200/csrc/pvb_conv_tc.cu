@@ -56,6 +56,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// scaled pair -> 16-bit pair, saturated: fp16 in ONE instruction (F2FP.SATFINITE clamps to the largest finite
+// value; the fmin/fmax pair per element it replaces was a fifth of the gather instructions)
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2s(float a, float b, float s) {
+  if (BF16) return pack2<true>(scl(a, s), scl(b, s));
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b * s), "f"(a * s));   // {upper, lower}
+  return r;
+}
+
 __host__ __device__ constexpr uint32_t idesc_16b(int M, int N, int a_mn, int b_mn, bool bf16) {
   return umma::idesc_f16(M, N, a_mn, b_mn) | (bf16 ? ((1u << 7) | (1u << 10)) : 0u);
 }
@@ -99,13 +109,11 @@ __device__ __forceinline__ void gather_n(const float* __restrict__ p, int hw, bo
 #pragma unroll
   for (int c8 = 0; c8 < NCH / 8; ++c8) {
     float* w = v + c8 * 8;
-    if (SCALED) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) w[j] = scl(w[j], scale);
-    }
     *reinterpret_cast<uint4*>(dst + c8 * (TP * ROWB)) =
-        make_uint4(pack2<BF16>(w[0], w[1]), pack2<BF16>(w[2], w[3]), pack2<BF16>(w[4], w[5]),
-                   pack2<BF16>(w[6], w[7]));
+        SCALED ? make_uint4(pack2s<BF16>(w[0], w[1], scale), pack2s<BF16>(w[2], w[3], scale),
+                            pack2s<BF16>(w[4], w[5], scale), pack2s<BF16>(w[6], w[7], scale))
+               : make_uint4(pack2<BF16>(w[0], w[1]), pack2<BF16>(w[2], w[3]), pack2<BF16>(w[4], w[5]),
+                            pack2<BF16>(w[6], w[7]));
   }
 }
 template <bool BF16, bool SCALED>
@@ -357,11 +365,15 @@ __device__ __forceinline__ void gather_cs(const float* __restrict__ p, int hw, b
 #pragma unroll
   for (int c8 = 0; c8 < NCH / 8; ++c8) {
     float* w = v + c8 * 8;
+    if (!SCALED) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = SCALED ? scl(w[j], f) : w[j] * f;
+      for (int j = 0; j < 8; ++j) w[j] *= f;
+    }
     *reinterpret_cast<uint4*>(dst + c8 * cs) =
-        make_uint4(pack2<BF16>(w[0], w[1]), pack2<BF16>(w[2], w[3]), pack2<BF16>(w[4], w[5]),
-                   pack2<BF16>(w[6], w[7]));
+        SCALED ? make_uint4(pack2s<BF16>(w[0], w[1], f), pack2s<BF16>(w[2], w[3], f),
+                            pack2s<BF16>(w[4], w[5], f), pack2s<BF16>(w[6], w[7], f))
+               : make_uint4(pack2<BF16>(w[0], w[1]), pack2<BF16>(w[2], w[3]), pack2<BF16>(w[4], w[5]),
+                            pack2<BF16>(w[6], w[7]));
   }
 }
 
@@ -739,6 +751,19 @@ conv_tc_pix3_kernel(const float* __restrict__ src, const uint16_t* __restrict__ 
   if (warp == 12) umma::tmem_dealloc<256>(tm);
 }
 
+// floor(n / d) for n < 2^31 by one widening multiply and a shift: mul = floor(2^p / d) + 1, p = 31 + ceil(log2 d)
+// (the error term n * (mul * d - 2^p) <= n * 2^(p - 31) stays below 2^p).  Built once per thread; the hardware
+// has no integer divider and the two divisions of the per-tile geometry were ~50 instructions per thread.
+struct FastDiv {
+  uint32_t mul, p;
+  __device__ __forceinline__ explicit FastDiv(uint32_t d) {
+    const uint32_t sh = d > 1 ? 32u - (uint32_t)__clz(d - 1) : 0u;
+    p = 31u + sh;
+    mul = (uint32_t)((1ull << p) / d) + 1u;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return (uint32_t)(((uint64_t)n * mul) >> p); }
+};
+
 // ---- backward weight ------------------------------------------------------------------------------
 // dW[co][ci][dh][dw] = sum over pixels of dpre[co][h][w] x[ci][h+dh][w+dw] as GEMMs with K = pixels:
 // accumulators [128 lanes = co][kw x Cin columns] in TMEM, both operands MN-major (K = tile rows,
@@ -827,10 +852,11 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
     const uint64_t da0 = umma::smem_desc(umma::smem_u32(smem), 128, WCS);              // dpre tile, stage 0
     const uint64_t dx0 = umma::smem_desc(umma::smem_u32(smem) + WG_A, 128, WCS);       // x tile, stage 0
     const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
-    for (int it = 0; it < my_tiles; ++it) {
-      const int s = it % n_stages;
+    int s = 0;
+    uint32_t fpar = 0;
+    for (int it = 0; it < my_tiles; ++it, s = (s + 1 == n_stages ? 0 : s + 1), fpar ^= (s == 0 ? 1u : 0u)) {
       WTRACE(1, 3 * it);
-      umma::mbar_wait(full + s, (uint32_t)((it / n_stages) & 1));
+      umma::mbar_wait(full + s, fpar);
       WTRACE(1, 3 * it + 1);
       umma::fence_after_sync();
       if (umma::elect_one()) {
@@ -860,12 +886,14 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
     int l_tile = (int)blockIdx.y, l_i = 0;
     bool l_aok, l_xok;
     const float *l_dp, *l_xp;
+    const FastDiv div_wp((uint32_t)Wp), div_h((uint32_t)H);
     auto tile_geometry = [&]() {
-      const unsigned qa = (unsigned)l_tile * (unsigned)ADV + (unsigned)row;   // A position of this row
-      const unsigned ri = qa / (unsigned)Wp;
+      const bool live = l_tile < n_tiles;     // the cursor runs one tile past the end (nothing is loaded there)
+      const unsigned qa = (unsigned)(live ? l_tile : 0) * (unsigned)ADV + (unsigned)row;   // A position (< 2^31: host)
+      const unsigned ri = div_wp.div(qa);
       const int wp = (int)(qa - ri * (unsigned)Wp);
-      const int b = (int)(ri / (unsigned)H), h = (int)(ri - (unsigned)b * (unsigned)H);
-      const bool in_b = b < B;
+      const int b = (int)div_h.div(ri), h = (int)(ri - (unsigned)b * (unsigned)H);
+      const bool in_b = live && b < B;
       l_aok = in_b && row < ADV && wp < W;
       const int wx = wp - pw, hx = h + dh;                 // X position: pw to the left, row h + dh
       l_xok = in_b && wx >= 0 && wx < W && hx >= 0 && hx < H;
@@ -882,12 +910,15 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       pd.ok = pd.is_x ? l_xok : l_aok;
       pd.dst = (uint32_t)((pd.is_x ? WG_A : 0) + cb * 2 * WCS + row * ROWB);
       const float* p = (pd.is_x ? l_xp : l_dp) + (int64_t)cb * 16 * HW;
+      // plane offsets in 32-bit arithmetic (16 planes of one image: far below 2^31): one IMAD.WIDE per
+      // load; as 64-bit products the address arithmetic was 7 instructions per load and the kernel's
+      // largest cost (ncu: 107 M warp instructions for the 64 -> 64 layer at 32 x 32)
       if (small_c && pd.is_x) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pd.v[j] = j < Cin_real ? __ldg(p + (int64_t)j * HW) : 0.f;
+        for (int j = 0; j < 16; ++j) pd.v[j] = j < Cin_real ? __ldg(p + j * HW) : 0.f;
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pd.v[j] = __ldg(p + (int64_t)j * HW);
+        for (int j = 0; j < 16; ++j) pd.v[j] = __ldg(p + j * HW);
       }
       if (++l_i == n_mine) {       // next item belongs to the next tile of this CTA
         l_i = 0;
@@ -896,33 +927,23 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       }
     };
     // ---- store cursor ----
-    int s_it = 0, s_i = 0;
+    int s_it = 0, s_i = 0, s_stage = 0;          // tile, item within it, stage = s_it % n_stages
+    uint32_t s_par = 1;                           // parity of the `empty` phase that frees the stage: ((s_it / n_stages) - 1) & 1
     int tr_ev = 0;      // trace event counter (debug builds only)
     (void)tr_ev;
-    const __half2 hmax = __floats2half2_rn(F16_MAX, F16_MAX), hmin = __floats2half2_rn(-F16_MAX, -F16_MAX);
     auto finish = [&](Pending& pd) {
-      const int s = s_it % n_stages;
+      const int s = s_stage;
       uint8_t* st = smem + s * stage_bytes;
       WTRACE(0, tr_ev++);
-      if (s_i == 0 && s_it >= n_stages)
-        umma::mbar_wait(empty + s, (uint32_t)(((s_it / n_stages) - 1) & 1));   // stage free again
+      if (s_i == 0 && s_it >= n_stages) umma::mbar_wait(empty + s, s_par);   // stage free again
       WTRACE(0, tr_ev++);
       uint32_t pk[8];
       if (pd.is_x) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) pk[j] = pack2<BF16>(pd.v[2 * j], pd.v[2 * j + 1]);
-      } else if (BF16) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          pk[j] = pack2<true>(scl(pd.v[2 * j], GRAD_SCALE), scl(pd.v[2 * j + 1], GRAD_SCALE));
       } else {
-        // scale (a power of two) in fp32, saturate after the conversion on packed pairs
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __half2 h = __floats2half2_rn(pd.v[2 * j] * GRAD_SCALE, pd.v[2 * j + 1] * GRAD_SCALE);
-          h = __hmin2(__hmax2(h, hmin), hmax);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h);
-        }
+        for (int j = 0; j < 8; ++j) pk[j] = pack2s<BF16>(pd.v[2 * j], pd.v[2 * j + 1], GRAD_SCALE);
       }
       if (!pd.ok) {
 #pragma unroll
@@ -937,6 +958,10 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
         if (lane == 0) umma::mbar_arrive(full + s);
         s_i = 0;
         ++s_it;
+        if (++s_stage == n_stages) {
+          s_stage = 0;
+          s_par ^= 1u;
+        }
       }
     };
     Pending pa, pb;
