@@ -917,8 +917,14 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
 #pragma unroll
         for (int j = 0; j < 16; ++j) pd.v[j] = j < Cin_real ? __ldg(p + j * HW) : 0.f;
       } else {
+        // the item's base pointer is materialised (opaque to the optimiser) so that each load address
+        // is ONE IMAD.WIDE of a 32-bit plane offset; left to itself the compiler carried a 64-bit element
+        // index and rebuilt base + 4 * (index + j * HW) with five instructions per load
+        unsigned long long pb = reinterpret_cast<unsigned long long>(p);
+        asm volatile("" : "+l"(pb));
+        const float* pq = reinterpret_cast<const float*>(pb);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pd.v[j] = __ldg(p + j * HW);
+        for (int j = 0; j < 16; ++j) pd.v[j] = __ldg(pq + j * HW);
       }
       if (++l_i == n_mine) {       // next item belongs to the next tile of this CTA
         l_i = 0;
