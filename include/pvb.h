@@ -385,9 +385,15 @@ int pvb_conv_tc_pix(const float* src, const float* W, const float* b, float* dst
                     int Wd, int kh, int kw, int act, int mode, void* stream);
 int pvb_conv_tc_prep(const float* W, void* workspace, int Cin, int Cout, int kh, int kw,
                      int mode, void* stream);
-/* dW += dpre (*) x ; db += sum dpre  (atomic accumulation) */
+/* dW += dpre (*) x ; db += sum dpre  (atomic accumulation).
+ * scratch (optional): pvb_conv_tc_wgrad_scratch_bytes(...) bytes of ZEROED device memory, left
+ * zeroed on return (reusable by the next call on the same stream, for any layer that fits).  With
+ * it the per-CTA accumulators are added coalesced into a transposed copy and folded into dW by a
+ * second small kernel; without it they are added straight into dW (strided, slower). */
+int64_t pvb_conv_tc_wgrad_scratch_bytes(int Cin, int Cout, int kh, int kw);
 int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, float* db, int B,
-                      int Cin, int Cout, int H, int Wd, int kh, int kw, void* stream);
+                      int Cin, int Cout, int H, int Wd, int kh, int kw, void* scratch,
+                      void* stream);
 
 /* ---- optimizer / reductions -------------------------------------------- */
 /* out[j] (+)= sum_g part[g*part_stride + j], j < n, fixed order (deterministic) */

@@ -124,7 +124,8 @@ SIGNATURES = {
     "pvb_conv_tc_workspace_bytes": [_i32, _i32, _i32, _i32],
     "pvb_conv_tc_prep": [_f, _f, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_tc_pix": [_f, _f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
-    "pvb_conv_tc_wgrad": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_conv_tc_wgrad_scratch_bytes": [_i32, _i32, _i32, _i32],
+    "pvb_conv_tc_wgrad": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
     "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
                          _i32, _i32, _i32, _i32, _i32, _fl, _i32, _f, _st],
@@ -159,6 +160,7 @@ def lib():
             fn.restype = (C.c_char_p if name == "pvb_last_error_string" else
                           C.c_longlong if name in ("pvb_launch_count",
                                                    "pvb_conv_tc_workspace_bytes",
+                                                   "pvb_conv_tc_wgrad_scratch_bytes",
                                                    "pvb_bn_workspace_bytes",
                                                    "pvb_sdec_tc_packed_weight_bytes") else C.c_int)
         _LIB = handle

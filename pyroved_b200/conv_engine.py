@@ -42,6 +42,10 @@ class ConvStack:
             shape = oshape
             biggest = max(biggest, B * _numel(shape))
         self.out_shape = shape
+        # zeroed scratch of the tensor-core weight-gradient kernels (coalesced accumulator read-out; each
+        # call leaves it zeroed, the backward pass runs them one after another on one stream)
+        wg = [st["mod"].weight for st in self.steps if st["kind"] == "conv" and st["tc_wgrad"]]
+        self.wg_scratch = ops.conv_tc_wgrad_scratch(wg, dev) if wg else None
         self.gbuf = [torch.empty(biggest, **f32) for _ in range(2)]
         self.x = None
 
@@ -109,7 +113,7 @@ class ConvStack:
                 st["dpre_ready"] = False
                 gb = flat.gv(m.bias) if m.bias is not None else None
                 if st["tc_wgrad"]:
-                    ops.conv_tc_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
+                    ops.conv_tc_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb, self.wg_scratch)
                 else:
                     ops.conv_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
                 if want_dx:

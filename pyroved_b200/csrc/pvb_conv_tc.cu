@@ -791,8 +791,8 @@ constexpr int WG_MAX_STAGES = 3;
 template <bool BF16>
 __global__ void __launch_bounds__(WG_MAX_GROUPS * 128 + 32, 1)
 conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dW,
-                     float* __restrict__ db, int B, int Cin_real, int Cout, int H, int W, int kh, int kw,
-                     int n_stages, int n_tiles) {
+                     float* __restrict__ db, float* __restrict__ scratch, int B, int Cin_real, int Cout, int H,
+                     int W, int kh, int kw, int n_stages, int n_tiles) {
   // fewer than 16 input channels (the first layer): the x tile is zero-padded to 16 columns
   const int Cin = Cin_real < 16 ? 16 : Cin_real;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -978,7 +978,42 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
       if (q + 2 < total) issue(pa);
       if (q + 1 < total) finish(pb);
     }
-    if (my_tiles > 0 && grp == 0) {
+    if (my_tiles > 0 && scratch != nullptr) {
+      // Accumulator read-out, coalesced: a TMEM lane is an output channel, so the 32 lanes of a warp add 32
+      // CONSECUTIVE floats of the transposed scratch gradient S[tap][ci][co] (one 128-byte reduction per
+      // instruction); wgrad_finish_kernel folds S into dW[co][ci][tap].  Every producer warp takes part: warp w
+      // reads lane quarter w % 4, the column blocks are dealt to the n_groups warps of a quarter.  (Adding into
+      // dW directly put the lanes Cin * taps floats apart -- 32 sectors per instruction, issued by four warps:
+      // ~25 us per launch at 128 channels, most of the time of the small 1-D layers.)
+      umma::mbar_wait(accb, 0);
+      umma::fence_after_sync();
+      const int quarter = warp & 3;
+      const int co = quarter * 32 + lane;
+      if (quarter * 32 < Cout) {
+        const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);
+        const int cblk = Cin / 16, nblk = kw * cblk;
+        for (int blk = grp; blk < nblk; blk += n_groups) {
+          const int j = blk / cblk, n0 = (blk - j * cblk) * 16;
+          const int tap = (int)blockIdx.x * kw + j;
+          float v[16];
+          umma::tmem_ld16(tm_lane + j * Cin + (j > 0 ? tap_gap : 0u) + n0, v);
+          umma::tmem_ld_wait();
+          if (co < Cout) {
+            float* sp = scratch + ((int64_t)tap * Cin_real + n0) * Cout + co;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj)
+              if (n0 + jj < Cin_real) atomicAdd(sp + jj * Cout, v[jj]);
+          }
+        }
+        if (do_bias && grp == 0) {
+          float v[16];
+          umma::tmem_ld16(tm_lane + col_bias, v);
+          umma::tmem_ld_wait();
+          if (co < Cout) atomicAdd(scratch + (int64_t)kh * kw * Cin_real * Cout + co, v[0]);
+        }
+      }
+      umma::fence_before_sync();
+    } else if (my_tiles > 0 && grp == 0) {
       umma::mbar_wait(accb, 0);
       umma::fence_after_sync();
       const uint32_t tm_lane = tm + ((uint32_t)(warp * 32) << 16);
@@ -1009,6 +1044,23 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
   }
   __syncthreads();
   if (warp == mma_warp) umma::tmem_dealloc<512>(tm);
+}
+
+// dW[co][ci][tap] += S[tap][ci][co] / GRAD_SCALE, db[co] += S_b[co] / GRAD_SCALE, and S is left zero for the
+// next call (thread = scratch element: coalesced read + clear, one strided read-modify-write per weight)
+__global__ void wgrad_finish_kernel(float* __restrict__ scratch, float* __restrict__ dW, float* __restrict__ db,
+                                    int Cin, int Cout, int taps) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int nW = taps * Cin * Cout;
+  if (i >= nW + Cout) return;
+  const float v = scratch[i];
+  scratch[i] = 0.f;
+  if (i < nW) {
+    const int co = i % Cout, r = i / Cout, ci = r % Cin, t = r / Cin;
+    dW[((int64_t)co * Cin + ci) * taps + t] += v * (1.f / GRAD_SCALE);
+  } else if (db) {
+    db[i - nW] += v * (1.f / GRAD_SCALE);
+  }
 }
 
 // operand type of the backward GEMMs.  bf16 has the range of fp32 but 8 mantissa bits: measured
@@ -1167,9 +1219,14 @@ extern "C" int pvb_conv_tc_pix(const float* src, const float* W, const float* b,
   return pvb::launch_status();
 }
 
+extern "C" int64_t pvb_conv_tc_wgrad_scratch_bytes(int Cin, int Cout, int kh, int kw) {
+  return ((int64_t)kh * kw * Cin * Cout + Cout) * (int64_t)sizeof(float);
+}
+
 extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, float* db, int B, int Cin,
-                                 int Cout, int H, int Wd, int kh, int kw, void* stream) {
+                                 int Cout, int H, int Wd, int kh, int kw, void* scratch, void* stream) {
   PVB_CHECK_ARG(dpre && x && dW, "pvb_conv_tc_wgrad: null pointer");
+  PVB_CHECK_ARG(((uintptr_t)scratch % 4) == 0, "pvb_conv_tc_wgrad: scratch must be float-aligned");
   const int Cin_real = Cin;
   if (Cin < 16) Cin = 16;                        // zero-padded x tile
   PVB_CHECK_ARG(tc_ok(Cin, Cout, kh, kw) && Cout <= 128, "pvb_conv_tc_wgrad: unsupported shape");
@@ -1199,8 +1256,14 @@ extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, f
   const int items = Cout / 16 + Cin / 16;
   const int ng = items < WG_MAX_GROUPS ? items : WG_MAX_GROUPS;
   conv_tc_wgrad_kernel<BWD_BF16><<<grid, ng * 128 + 32, smem, (cudaStream_t)stream>>>(
-      dpre, x, dW, db, B, Cin_real, Cout, H, Wd, kh, kw, n_stages, n_tiles);
+      dpre, x, dW, db, reinterpret_cast<float*>(scratch), B, Cin_real, Cout, H, Wd, kh, kw, n_stages, n_tiles);
   pvb::count_launch();
+  if (scratch) {
+    const int n = kh * kw * Cin_real * Cout + Cout;
+    wgrad_finish_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(scratch), dW, db,
+                                                                          Cin_real, Cout, kh * kw);
+    pvb::count_launch();
+  }
   return pvb::launch_status();
 }
 

@@ -560,6 +560,16 @@ def conv_tc_bwd_data(dpre, W, dx, ws, y_below=None, act_below=None, prepped=Fals
                                      1 | (2 if prepped else 0), _stream()), "pvb_conv_tc_pix")
 
 
-def conv_tc_bwd_weight(dpre, x, W, dW, db):
+def conv_tc_wgrad_scratch(weights, device):
+    """Zeroed scratch for conv_tc_bwd_weight, large enough for every weight in `weights`; each call leaves
+    it zeroed again, so one buffer serves all layers that run on one stream."""
+    n = 4
+    for W in weights:
+        kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
+        n = max(n, _lib.lib().pvb_conv_tc_wgrad_scratch_bytes(W.shape[1], W.shape[0], kh, kw))
+    return torch.zeros((n + 3) // 4, device=device, dtype=torch.float32)
+
+
+def conv_tc_bwd_weight(dpre, x, W, dW, db, scratch=None):
     check(_lib.lib().pvb_conv_tc_wgrad(_p(dpre), _p(x), _p(dW), _p(db), *_conv_dims(x, W),
-                                       _stream()), "pvb_conv_tc_wgrad")
+                                       _p(scratch), _stream()), "pvb_conv_tc_wgrad")

@@ -290,6 +290,15 @@ def test_tc_conv_kernels_vs_torch(shape):
     ops.conv_tc_bwd_weight(dpre, x, wt, dW, db)
     assert (dW - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
     assert (db - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
+    # with the zeroed scratch (coalesced accumulator read-out + folding kernel): same sums, ACCUMULATED into
+    # dW / db, and the scratch -- sized here for a larger layer, as the engine shares one -- is zero again
+    sc = ops.conv_tc_wgrad_scratch([wt, torch.empty(2 * Cout, Cin, *wt.shape[2:])], "cuda")
+    dW2, db2 = torch.ones_like(wt), torch.ones_like(b)
+    ops.conv_tc_bwd_weight(dpre, x, wt, dW2, db2, sc)
+    assert (dW2 - 1 - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
+    assert (db2 - 1 - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
+    assert (dW2 - 1 - dW).abs().max().item() <= 1e-4 * wr.grad.abs().max().item() + 1e-6
+    assert not sc.any().item()
 
 
 @pytest.mark.parametrize("shape", [(3, 1, 32, 16, 16, 3, 2), (2, 3, 64, 1, 40, 3, 1), (4, 5, 16, 7, 5, 1, 2),
@@ -317,6 +326,13 @@ def test_tc_weight_gradient_with_few_input_channels(shape):
     ops.conv_tc_bwd_weight(dy, x, wt, dW, db)
     assert (dW - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
     assert (db - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
+    sc = ops.conv_tc_wgrad_scratch([wt], "cuda")                 # scratch path, twice: it cleans up after itself
+    dW2, db2 = torch.zeros_like(wt), torch.zeros_like(b)
+    for _ in range(2):
+        ops.conv_tc_bwd_weight(dy, x, wt, dW2, db2, sc)
+    assert (dW2 / 2 - wr.grad).abs().max().item() <= 4e-3 * wr.grad.abs().max().item()
+    assert (db2 / 2 - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
+    assert not sc.any().item()
     dW, db = torch.ones_like(wt), torch.ones_like(b)             # fp32 kernels accumulate
     ops.conv_bwd_weight(dy, x, wt, dW, db)
     assert (dW - 1 - wr.grad).abs().max().item() <= 1e-4 * wr.grad.abs().max().item() + 1e-4
