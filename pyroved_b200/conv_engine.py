@@ -153,8 +153,8 @@ def _numel(shape):
 
 class ConvGaussEncoder:
     """`convEncoderNet` as the guide q(z|x) of a Trace_ELBO step (reference nets/conv.py:24-64):
-    FeatureExtractor (ConvStack) -> flatten -> fc_latent, whose rows [0, L) give mu and [L, 2L) the
-    pre-softplus sigma (two heads on weight views) -> reparameterised sample + KL terms; and the
+    FeatureExtractor (ConvStack) -> flatten -> fc_latent, whose outputs [0, L) give mu and [L, 2L) the
+    pre-softplus sigma -> reparameterised sample + KL terms; and the
     backward of all of it.  Buffer names follow engine.GaussHead (eps, mu, s_pre, sigma, z, kl)."""
 
     def __init__(self, engine, enc, B, L):
@@ -175,8 +175,10 @@ class ConvGaussEncoder:
                              .format(fcl.out_features // 2, L))
         if not getattr(enc, "softplus_out", True):
             raise NotImplementedError("pyroved_b200: convEncoderNet(softplus_out=False) as a guide")
-        self.W_mu, self.W_s = fcl.weight.data[:L], fcl.weight.data[L:]
-        self.b_mu, self.b_s = fcl.bias.data[:L], fcl.bias.data[L:]
+        # both heads in ONE pass over the feature map (it is the large operand: 32768 features per sample in
+        # the default VED, three passes of 67 MB per head otherwise); split / joined by [B, L] copies
+        self.ms = torch.empty(B, 2 * L, **f32)
+        self.gms = torch.empty(B, 2 * L, **f32)
         self.eps = torch.zeros(B, L, **f32)
         self.mu = torch.empty(B, L, **f32)
         self.s_pre = torch.empty(B, L, **f32)
@@ -196,8 +198,10 @@ class ConvGaussEncoder:
         feat = self.stack.forward(x.view(self.B, *self.in_shape)).view(self.B, self.feat_dim)
         if gen_eps:
             ops.randn(self.eps, eng.seed, eng.step_counter, eng.eps_first_index(self.eps.numel()))
-        ops.linear_fwd(feat, self.W_mu, self.b_mu, None, out=self.mu)
-        ops.linear_fwd(feat, self.W_s, self.b_s, None, out=self.s_pre)
+        fcl = self.enc.features2latent.fc_latent
+        ops.linear_fwd(feat, fcl.weight.data, fcl.bias.data, None, out=self.ms)
+        self.mu.copy_(self.ms[:, :self.L])
+        self.s_pre.copy_(self.ms[:, self.L:])
         ops.latent_fwd(self.mu, self.s_pre, self.eps, self.sigma, self.z, self.kl)
 
     def backward(self, gz, w, beta):
@@ -209,10 +213,9 @@ class ConvGaussEncoder:
         gW, gb = flat.gv(fcl.weight), flat.gv(fcl.bias)
         L = self.L
         feat = self.stack.steps[-1]["y"].view(self.B, self.feat_dim)
-        ops.linear_bwd(feat, self.W_mu, None, None, self.gmu, self.gmu, self.dfeat, False,
-                       gW[:L], gb[:L], None)
-        ops.linear_bwd(feat, self.W_s, None, None, self.gs_pre, self.gs_pre, self.dfeat, True,
-                       gW[L:], gb[L:], None)
+        self.gms[:, :L].copy_(self.gmu)
+        self.gms[:, L:].copy_(self.gs_pre)
+        ops.linear_bwd(feat, fcl.weight.data, None, None, self.gms, self.gms, self.dfeat, False, gW, gb, None)
         self.stack.backward(self.dfeat.view(self.B, *self.stack.out_shape), False)
 
 
