@@ -234,15 +234,34 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
   }
 }
 
+// fp32 -> (hi, lo) TF32 pair by truncation: hi = the top 11 significant bits, lo = a - hi (exact; the tensor
+// core reads its top 11 bits), so a = hi + lo to 2^-22 and three MMAs (lo*hi, hi*lo, hi*hi) give an
+// fp32-grade product on the warp-level tensor-core path.  (cvt.rna.tf32 is emulated on sm_100 -- seven ALU
+// instructions per conversion, which made the loop issue-bound; the mask + subtract is two.)
+__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(a) & 0xffffe000u;
+  lo = __float_as_uint(a - __uint_as_float(hi));
+}
+// D(16x8) += A(16x8, row) B(8x8, col), TF32 operands, fp32 accumulators
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 // ---- forward layer for small batches: C = act(A[M,K] B[N,K]^T + bias) ------------------------
 // Both operands are K-contiguous: tiles are staged with 16-byte cp.async into K-major smem.
-// A 32 x 32 output tile per CTA leaves one warp per scheduler, which cannot hide FMA / LDS
-// latency, so the K loop is split over LKG = 4 thread groups of the same CTA (group g takes
-// chunks g, g+4, ... through its own cp.async ring and named barrier); the four partial tiles
+// A 32 x 32 output tile per CTA; the K loop is split over LKG = 4 thread groups of the same CTA (group g
+// takes chunks g, g+4, ... through its own cp.async ring and named barrier); the four partial tiles
 // are summed in a fixed order (deterministic), then bias + activation.
-// Thread (ty, tx) of a group: rows {2ty, 2ty+1}, columns {tx, tx+8, tx+16, tx+24}.
+// The products run on the warp-level tensor-core path (mma.sync m16n8k8, 3 x TF32 = fp32-grade): as FFMA
+// on a 2 x 4 register tile the loop issued 6 LDS.128 per 32 FMA and was bound by shared-memory bandwidth
+// (12.7 us warm for the 784 -> 128 layer at batch 512).
 constexpr int FLD = SBK + 4;
-constexpr int LKG = 4;       // K groups per CTA
+#ifndef PVB_LKG
+#define PVB_LKG 4
+#endif
+constexpr int LKG = PVB_LKG;  // K groups per CTA
 constexpr int LGS = 3;       // cp.async stages per group
 constexpr int LS_THREADS = LKG * SNT;
 constexpr int LS_SMEM = LKG * LGS * (SBM + SBN) * FLD * 4;
@@ -257,7 +276,9 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
   float (*As)[SBM][FLD] = reinterpret_cast<float (*)[SBM][FLD]>(ls_smem + g * LGS * (SBM + SBN) * FLD);
   float (*Bs)[SBN][FLD] = reinterpret_cast<float (*)[SBN][FLD]>(ls_smem + g * LGS * (SBM + SBN) * FLD +
                                                                  LGS * SBM * FLD);
-  const int tx = tid & 7, ty = tid >> 3;
+  // warp w of a group owns the 16 x 16 sub-tile (rows 16 (w & 1), columns 16 (w >> 1)) as two m16n8k8 MMAs
+  const int wq = tid >> 5, lane = tid & 31, fg = lane >> 2, ft = lane & 3;
+  const int wr = (wq & 1) * 16, wc = (wq >> 1) * 16;
   const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
   const int n_chunks = (K + SBK - 1) / SBK;
   const int my_n = (n_chunks - g + LKG - 1) / LKG;   // chunks g, g + LKG, ...
@@ -298,14 +319,21 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     const int buf = c % LGS;
 #pragma unroll
-    for (int k = 0; k < SBK; k += 4) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][2 * ty][k]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][2 * ty + 1][k]);
+    for (int k = 0; k < SBK; k += 8) {
+      // fragments straight from the K-major tiles: bank = (4 fg + ft) mod 32 with the 36-float row stride
+      uint32_t ah[4], al[4];
+      split_tf32(As[buf][wr + fg][k + ft], ah[0], al[0]);
+      split_tf32(As[buf][wr + fg + 8][k + ft], ah[1], al[1]);
+      split_tf32(As[buf][wr + fg][k + ft + 4], ah[2], al[2]);
+      split_tf32(As[buf][wr + fg + 8][k + ft + 4], ah[3], al[3]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 b = *reinterpret_cast<const float4*>(&Bs[buf][tx + 8 * j][k]);
-        acc[0][j] = fmaf(a0.x, b.x, fmaf(a0.y, b.y, fmaf(a0.z, b.z, fmaf(a0.w, b.w, acc[0][j]))));
-        acc[1][j] = fmaf(a1.x, b.x, fmaf(a1.y, b.y, fmaf(a1.z, b.z, fmaf(a1.w, b.w, acc[1][j]))));
+      for (int j = 0; j < 2; ++j) {
+        uint32_t bh[2], bl[2];
+        split_tf32(Bs[buf][wc + 8 * j + fg][k + ft], bh[0], bl[0]);
+        split_tf32(Bs[buf][wc + 8 * j + fg][k + ft + 4], bh[1], bl[1]);
+        mma_tf32(acc[j], al, bh);      // small terms first
+        mma_tf32(acc[j], ah, bl);
+        mma_tf32(acc[j], ah, bh);
       }
     }
   }
@@ -314,10 +342,13 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
   __syncthreads();
   float* red = ls_smem;   // [LKG][SBM][SBN + 1]
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      red[(g * SBM + 2 * ty + i) * (SBN + 1) + tx + 8 * j] = acc[i][j];
+  for (int j = 0; j < 2; ++j) {     // accumulator fragment: (fg, 2 ft), (fg, 2 ft + 1), (fg + 8, 2 ft), (fg + 8, 2 ft + 1)
+    float* r0 = red + (g * SBM + wr + fg) * (SBN + 1) + wc + 8 * j + 2 * ft;
+    r0[0] = acc[j][0];
+    r0[1] = acc[j][1];
+    r0[8 * (SBN + 1)] = acc[j][2];
+    r0[8 * (SBN + 1) + 1] = acc[j][3];
+  }
   __syncthreads();
   for (int idx = threadIdx.x; idx < SBM * SBN; idx += LS_THREADS) {
     int r = idx / SBN, c = idx - r * SBN;
