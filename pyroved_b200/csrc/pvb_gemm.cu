@@ -264,31 +264,38 @@ constexpr int FLD = SBK + 4;
 constexpr int LKG = PVB_LKG;  // K groups per CTA
 constexpr int LGS = 3;       // cp.async stages per group
 constexpr int LS_THREADS = LKG * SNT;
-constexpr int LS_SMEM = LKG * LGS * (SBM + SBN) * FLD * 4;
-static_assert(LKG * SBM * (SBN + 1) * 4 <= LS_SMEM, "reduction scratch aliases the stage buffers");
+// BN = 32, or 16 when 32-wide tiles would leave more than half of the SMs idle (the 784 -> 128 layer at
+// batch 512: 64 tiles of 32 x 32, 128 of 32 x 16 -- the kernel is bound by its own instruction stream, so
+// spreading it over twice the SMs is worth the repeated A fragments)
+template <int BN>
+constexpr int ls_smem_bytes() { return LKG * LGS * (SBM + BN) * FLD * 4; }
+static_assert(LKG * SBM * (32 + 1) * 4 <= ls_smem_bytes<16>(), "reduction scratch aliases the stage buffers");
 
+template <int BN>
 __global__ void __launch_bounds__(LS_THREADS)
 linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                     float* __restrict__ Cpre, const float* __restrict__ bias, int M, int N, int K,
                     int act) {
   extern __shared__ __align__(16) float ls_smem[];
   const int g = threadIdx.x >> 7, tid = threadIdx.x & 127;
-  float (*As)[SBM][FLD] = reinterpret_cast<float (*)[SBM][FLD]>(ls_smem + g * LGS * (SBM + SBN) * FLD);
-  float (*Bs)[SBN][FLD] = reinterpret_cast<float (*)[SBN][FLD]>(ls_smem + g * LGS * (SBM + SBN) * FLD +
-                                                                 LGS * SBM * FLD);
-  // warp w of a group owns the 16 x 16 sub-tile (rows 16 (w & 1), columns 16 (w >> 1)) as two m16n8k8 MMAs
+  float (*As)[SBM][FLD] = reinterpret_cast<float (*)[SBM][FLD]>(ls_smem + g * LGS * (SBM + BN) * FLD);
+  float (*Bs)[BN][FLD] = reinterpret_cast<float (*)[BN][FLD]>(ls_smem + g * LGS * (SBM + BN) * FLD +
+                                                               LGS * SBM * FLD);
+  // warp w of a group owns the 16 x (BN / 2) sub-tile (rows 16 (w & 1), columns (BN / 2) (w >> 1)) as
+  // NJ = BN / 16 m16n8k8 MMAs
+  constexpr int NJ = BN / 16;
   const int wq = tid >> 5, lane = tid & 31, fg = lane >> 2, ft = lane & 3;
-  const int wr = (wq & 1) * 16, wc = (wq >> 1) * 16;
-  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int wr = (wq & 1) * 16, wc = (wq >> 1) * (BN / 2);
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * BN;
   const int n_chunks = (K + SBK - 1) / SBK;
   const int my_n = (n_chunks - g + LKG - 1) / LKG;   // chunks g, g + LKG, ...
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float acc[NJ][4] = {};
   auto stage = [&](int ci) {
     const int buf = ci % LGS;
     const int k0 = (g + ci * LKG) * SBK;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      int idx = tid + it * SNT;          // 256 16-byte pieces per operand tile
+      int idx = tid + it * SNT;          // 256 16-byte pieces of the A tile, 8 * BN of the B tile
       int r = idx >> 3, q = idx & 7;
       int gk = k0 + 4 * q;
       {
@@ -298,7 +305,7 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
         int sz = ok ? 16 : 0;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
       }
-      {
+      if (idx < 8 * BN) {
         bool ok = (n0 + r < N) && (gk < K);
         unsigned d = (unsigned)__cvta_generic_to_shared(&Bs[buf][r][4 * q]);
         const float* src = ok ? B + (int64_t)(n0 + r) * K + gk : B;
@@ -327,7 +334,7 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
       split_tf32(As[buf][wr + fg][k + ft + 4], ah[2], al[2]);
       split_tf32(As[buf][wr + fg + 8][k + ft + 4], ah[3], al[3]);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         uint32_t bh[2], bl[2];
         split_tf32(Bs[buf][wc + 8 * j + fg][k + ft], bh[0], bl[0]);
         split_tf32(Bs[buf][wc + 8 * j + fg][k + ft + 4], bh[1], bl[1]);
@@ -340,23 +347,23 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
   // cross-group reduction through smem (aliases the stage buffers: everyone is done with them)
   asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
-  float* red = ls_smem;   // [LKG][SBM][SBN + 1]
+  float* red = ls_smem;   // [LKG][SBM][BN + 1]
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {     // accumulator fragment: (fg, 2 ft), (fg, 2 ft + 1), (fg + 8, 2 ft), (fg + 8, 2 ft + 1)
-    float* r0 = red + (g * SBM + wr + fg) * (SBN + 1) + wc + 8 * j + 2 * ft;
+  for (int j = 0; j < NJ; ++j) {     // accumulator fragment: (fg, 2 ft), (fg, 2 ft + 1), (fg + 8, 2 ft), (fg + 8, 2 ft + 1)
+    float* r0 = red + (g * SBM + wr + fg) * (BN + 1) + wc + 8 * j + 2 * ft;
     r0[0] = acc[j][0];
     r0[1] = acc[j][1];
-    r0[8 * (SBN + 1)] = acc[j][2];
-    r0[8 * (SBN + 1) + 1] = acc[j][3];
+    r0[8 * (BN + 1)] = acc[j][2];
+    r0[8 * (BN + 1) + 1] = acc[j][3];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < SBM * SBN; idx += LS_THREADS) {
-    int r = idx / SBN, c = idx - r * SBN;
+  for (int idx = threadIdx.x; idx < SBM * BN; idx += LS_THREADS) {
+    int r = idx / BN, c = idx - r * BN;
     int gm = m0 + r, gn = n0 + c;
     if (gm >= M || gn >= N) continue;
     float v = 0.f;
 #pragma unroll
-    for (int q = 0; q < LKG; ++q) v += red[(q * SBM + r) * (SBN + 1) + c];
+    for (int q = 0; q < LKG; ++q) v += red[(q * SBM + r) * (BN + 1) + c];
     if (bias) v += bias[gn];
     if (Cpre) Cpre[(int64_t)gm * N + gn] = v;
     C[(int64_t)gm * N + gn] = pvb::act_fwd(v, act);
@@ -615,13 +622,21 @@ extern "C" int pvb_linear_fwd(const float* x, const float* W, const float* b, fl
     int tiles = (int)(((M + SBM - 1) / SBM) * ((N + SBN - 1) / SBN));
     if (tiles >= 48 && tiles < 4 * 148) {
       if (M == 0) return 0;
-      dim3 grid((N + SBN - 1) / SBN, (unsigned)((M + SBM - 1) / SBM));
       static bool attr = false;
       if (!attr) {
-        cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM);
+        cudaFuncSetAttribute(linear_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ls_smem_bytes<32>());
+        cudaFuncSetAttribute(linear_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ls_smem_bytes<16>());
         attr = true;
       }
-      linear_small_kernel<<<grid, LS_THREADS, LS_SMEM, (cudaStream_t)stream>>>(x, W, y, pre, b, (int)M, N, K, act);
+      if (tiles <= 74 && N % 16 == 0) {     // half of the SMs or fewer: 16-wide tiles
+        dim3 grid((N + 15) / 16, (unsigned)((M + SBM - 1) / SBM));
+        linear_small_kernel<16><<<grid, LS_THREADS, ls_smem_bytes<16>(), (cudaStream_t)stream>>>(x, W, y, pre, b, (int)M,
+                                                                                                 N, K, act);
+      } else {
+        dim3 grid((N + SBN - 1) / SBN, (unsigned)((M + SBM - 1) / SBM));
+        linear_small_kernel<32><<<grid, LS_THREADS, ls_smem_bytes<32>(), (cudaStream_t)stream>>>(x, W, y, pre, b, (int)M,
+                                                                                                 N, K, act);
+      }
       pvb::count_launch();
       return pvb::launch_status();
     }
