@@ -63,6 +63,21 @@ __device__ __forceinline__ float act_grad(float y, float pre, int act) {
   }
 }
 
+// fp32 -> (hi, lo) TF32 pair by truncation: hi = the top 11 significant bits, lo = a - hi (exact; the tensor
+// core reads its top 11 bits), so a = hi + lo to 2^-22 and three MMAs (lo*hi, hi*lo, hi*hi) give an
+// fp32-grade product on the warp-level tensor-core path.  (cvt.rna.tf32 is emulated on sm_100 -- seven ALU
+// instructions per conversion, which made the loop issue-bound; the mask + subtract is two.)
+__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(a) & 0xffffe000u;
+  lo = __float_as_uint(a - __uint_as_float(hi));
+}
+// D(16x8) += A(16x8, row) B(8x8, col), TF32 operands, fp32 accumulators
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -234,21 +234,6 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
   }
 }
 
-// fp32 -> (hi, lo) TF32 pair by truncation: hi = the top 11 significant bits, lo = a - hi (exact; the tensor
-// core reads its top 11 bits), so a = hi + lo to 2^-22 and three MMAs (lo*hi, hi*lo, hi*hi) give an
-// fp32-grade product on the warp-level tensor-core path.  (cvt.rna.tf32 is emulated on sm_100 -- seven ALU
-// instructions per conversion, which made the loop issue-bound; the mask + subtract is two.)
-__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(a) & 0xffffe000u;
-  lo = __float_as_uint(a - __uint_as_float(hi));
-}
-// D(16x8) += A(16x8, row) B(8x8, col), TF32 operands, fp32 accumulators
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
 // ---- forward layer for small batches: C = act(A[M,K] B[N,K]^T + bias) ------------------------
 // Both operands are K-contiguous: tiles are staged with 16-byte cp.async into K-major smem.
 // A 32 x 32 output tile per CTA; the K loop is split over LKG = 4 thread groups of the same CTA (group g
@@ -329,18 +314,18 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
     for (int k = 0; k < SBK; k += 8) {
       // fragments straight from the K-major tiles: bank = (4 fg + ft) mod 32 with the 36-float row stride
       uint32_t ah[4], al[4];
-      split_tf32(As[buf][wr + fg][k + ft], ah[0], al[0]);
-      split_tf32(As[buf][wr + fg + 8][k + ft], ah[1], al[1]);
-      split_tf32(As[buf][wr + fg][k + ft + 4], ah[2], al[2]);
-      split_tf32(As[buf][wr + fg + 8][k + ft + 4], ah[3], al[3]);
+      pvb::split_tf32(As[buf][wr + fg][k + ft], ah[0], al[0]);
+      pvb::split_tf32(As[buf][wr + fg + 8][k + ft], ah[1], al[1]);
+      pvb::split_tf32(As[buf][wr + fg][k + ft + 4], ah[2], al[2]);
+      pvb::split_tf32(As[buf][wr + fg + 8][k + ft + 4], ah[3], al[3]);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         uint32_t bh[2], bl[2];
-        split_tf32(Bs[buf][wc + 8 * j + fg][k + ft], bh[0], bl[0]);
-        split_tf32(Bs[buf][wc + 8 * j + fg][k + ft + 4], bh[1], bl[1]);
-        mma_tf32(acc[j], al, bh);      // small terms first
-        mma_tf32(acc[j], ah, bl);
-        mma_tf32(acc[j], ah, bh);
+        pvb::split_tf32(Bs[buf][wc + 8 * j + fg][k + ft], bh[0], bl[0]);
+        pvb::split_tf32(Bs[buf][wc + 8 * j + fg][k + ft + 4], bh[1], bl[1]);
+        pvb::mma_tf32(acc[j], al, bh);      // small terms first
+        pvb::mma_tf32(acc[j], ah, bl);
+        pvb::mma_tf32(acc[j], ah, bh);
       }
     }
   }

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(MT) mlp_chain_bwd_kernel(pvb_mlp_chain_args a)
 // fixed order.
 constexpr int WG_T = 32, WG_NT = 128, WG_MAXP = 8, WG_ST = 3, WG_G = 4;
 constexpr int WG_THREADS = WG_G * WG_NT;
-constexpr int WG_LD = WG_T + 4;
+constexpr int WG_LD = WG_T + 8;     // row stride = 8 mod 32 banks: the MMA fragment loads (4 rows x 8 columns) are conflict-free
 constexpr int WG_SMEM = WG_G * WG_ST * 2 * WG_T * WG_LD * 4;
 struct WgradArgs {
   int64_t M;
@@ -293,7 +293,11 @@ __global__ void __launch_bounds__(WG_THREADS) mlp_wgrad_kernel(WgradArgs a) {
   const int t = blockIdx.x - a.tile0[pi];
   const int tk_n = (pr.K + WG_T - 1) / WG_T;
   const int n0 = (t / tk_n) * WG_T, kk0 = (t % tk_n) * WG_T;
-  const int tx = tid & 7, ty = tid >> 3;   // 8 k-quads x 16 n-pairs
+  // warp w of a group owns the 16 x 16 sub-tile (n rows 16 (w & 1), k columns 16 (w >> 1)) of the group's partial
+  // tile as two m16n8k8 MMAs per 8 batch rows, 3 x TF32 (fp32-grade, see split_tf32); as FFMA on a 2 x 4 register
+  // tile the loop issued 3 shared-memory loads per 8 FMA and the kernel was bound by its instruction stream
+  const int wq = tid >> 5, lane = tid & 31, fg = lane >> 2, ft = lane & 3;
+  const int wr = (wq & 1) * 16, wc = (wq >> 1) * 16;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   float bsum = 0.f;   // threads 0..31 of each group in the k-tile 0 CTA: column sum of d
   const bool do_bias = pr.db && kk0 == 0;
@@ -344,13 +348,22 @@ __global__ void __launch_bounds__(WG_THREADS) mlp_wgrad_kernel(WgradArgs a) {
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     const int buf = c % WG_ST;
 #pragma unroll
-    for (int m = 0; m < WG_T; ++m) {
-      float2 a2 = *reinterpret_cast<const float2*>(&As[buf][m][ty * 2]);
-      float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][m][tx * 4]);
-      acc[0][0] = fmaf(a2.x, b4.x, acc[0][0]); acc[0][1] = fmaf(a2.x, b4.y, acc[0][1]);
-      acc[0][2] = fmaf(a2.x, b4.z, acc[0][2]); acc[0][3] = fmaf(a2.x, b4.w, acc[0][3]);
-      acc[1][0] = fmaf(a2.y, b4.x, acc[1][0]); acc[1][1] = fmaf(a2.y, b4.y, acc[1][1]);
-      acc[1][2] = fmaf(a2.y, b4.z, acc[1][2]); acc[1][3] = fmaf(a2.y, b4.w, acc[1][3]);
+    for (int m = 0; m < WG_T; m += 8) {
+      // A = d^T: element (row n, col m) = As[m][n]; B: element (row m, col k) = Bs[m][k]
+      uint32_t ah[4], al[4];
+      pvb::split_tf32(As[buf][m + ft][wr + fg], ah[0], al[0]);
+      pvb::split_tf32(As[buf][m + ft][wr + fg + 8], ah[1], al[1]);
+      pvb::split_tf32(As[buf][m + ft + 4][wr + fg], ah[2], al[2]);
+      pvb::split_tf32(As[buf][m + ft + 4][wr + fg + 8], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t bh[2], bl[2];
+        pvb::split_tf32(Bs[buf][m + ft][wc + 8 * j + fg], bh[0], bl[0]);
+        pvb::split_tf32(Bs[buf][m + ft + 4][wc + 8 * j + fg], bh[1], bl[1]);
+        pvb::mma_tf32(acc[j], al, bh);      // small terms first
+        pvb::mma_tf32(acc[j], ah, bl);
+        pvb::mma_tf32(acc[j], ah, bh);
+      }
     }
     if (do_bias && tid < WG_T) {
 #pragma unroll
@@ -363,9 +376,13 @@ __global__ void __launch_bounds__(WG_THREADS) mlp_wgrad_kernel(WgradArgs a) {
   float* red = wg_smem;                       // [WG_G][32][33]
   float* bred = wg_smem + WG_G * WG_T * (WG_T + 1);   // [WG_G][32]
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) red[(g * WG_T + ty * 2 + i) * (WG_T + 1) + tx * 4 + j] = acc[i][j];
+  for (int j = 0; j < 2; ++j) {     // accumulator fragment: (fg, 2 ft), (fg, 2 ft + 1), (fg + 8, 2 ft), (fg + 8, 2 ft + 1)
+    float* r0 = red + (g * WG_T + wr + fg) * (WG_T + 1) + wc + 8 * j + 2 * ft;
+    r0[0] = acc[j][0];
+    r0[1] = acc[j][1];
+    r0[8 * (WG_T + 1)] = acc[j][2];
+    r0[8 * (WG_T + 1) + 1] = acc[j][3];
+  }
   if (do_bias && tid < WG_T) bred[g * WG_T + tid] = bsum;
   __syncthreads();
   for (int idx = threadIdx.x; idx < WG_T * WG_T; idx += WG_THREADS) {
