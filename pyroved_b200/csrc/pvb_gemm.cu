@@ -2,6 +2,8 @@
 // Used for the (small) encoder / classifier layers and by the generic
 // spatial-decoder path; the hot 128x128 decoder layers run on tcgen05
 // (pvb_sdec_tc.cu).
+#include <cooperative_groups.h>
+
 #include "pvb_common.cuh"
 
 namespace {
@@ -524,6 +526,74 @@ skinny_fwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ W,
   }
 }
 
+// same rows-per-block kernel with the K range split over the SK_SPLIT CTAs of a thread-block cluster
+// (blockIdx.y = cluster rank): 8x the CTAs, so the stream over x has ~250 KB in flight per SM instead of 32 KB
+// (the one-CTA-per-4-rows version ran 128 CTAs of 8 warps, latency-bound at 1 TB/s: 68 us for 67 MB).  The partial
+// [SK_ROWS][N] sums go to rank 0 through distributed shared memory and are added there in rank order
+// (deterministic), then bias + activation.
+constexpr int SK_SPLIT = 8;
+__global__ void __launch_bounds__(256)
+skinny_fwd_rows_cluster_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                               const float* __restrict__ b, float* __restrict__ y, float* __restrict__ pre,
+                               int64_t M, int N, int K, int act) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float red[8][SK_ROWS][4];
+  __shared__ float cpart[SK_SPLIT][SK_ROWS][4];     // rank 0's copy collects every rank's partial sums
+  const unsigned rank = cluster.block_rank();
+  const int64_t row0 = (int64_t)blockIdx.x * SK_ROWS;
+  const int K4 = K / 4, per = (K4 + SK_SPLIT - 1) / SK_SPLIT;
+  const int k_lo = (int)rank * per, k_hi = min(K4, k_lo + per);
+  float acc[SK_ROWS][4];
+#pragma unroll
+  for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[r][n] = 0.f;
+  for (int k4 = k_lo + (int)threadIdx.x; k4 < k_hi; k4 += 256) {
+    float4 xv[SK_ROWS];
+#pragma unroll
+    for (int r = 0; r < SK_ROWS; ++r)
+      xv[r] = (row0 + r < M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * K) + k4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      if (n < N) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * K) + k4);
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; ++r)
+          acc[r][n] = fmaf(xv[r].x, wv.x, fmaf(xv[r].y, wv.y, fmaf(xv[r].z, wv.z, fmaf(xv[r].w, wv.w, acc[r][n]))));
+      }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float v = pvb::warp_sum(acc[r][n]);
+      if (lane == 0) red[warp][r][n] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < SK_ROWS * 4) {
+    const int r = threadIdx.x >> 2, n = threadIdx.x & 3;
+    float s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s2 += red[w][r][n];
+    float* dst = cluster.map_shared_rank(&cpart[0][0][0], 0);
+    dst[(rank * SK_ROWS + r) * 4 + n] = s2;
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x < SK_ROWS * 4) {
+    const int r = threadIdx.x >> 2, n = threadIdx.x & 3;
+    if (n < N && row0 + r < M) {
+      float s2 = b ? b[n] : 0.f;
+#pragma unroll
+      for (int q = 0; q < SK_SPLIT; ++q) s2 += cpart[q][r][n];
+      if (pre) pre[(row0 + r) * N + n] = s2;
+      y[(row0 + r) * N + n] = pvb::act_fwd(s2, act);
+    }
+  }
+}
+
 // dx[m][k] (+)= sum_n g[m][n] W[n][k]
 __global__ void __launch_bounds__(256)
 skinny_dx_kernel(const float* __restrict__ g, const float* __restrict__ W, float* __restrict__ dx,
@@ -593,7 +663,21 @@ extern "C" int pvb_linear_fwd(const float* x, const float* W, const float* b, fl
   PVB_CHECK_ARG(x && W && y && M >= 0 && N > 0 && K > 0, "pvb_linear_fwd: bad argument");
   PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID, "pvb_linear_fwd: unknown activation %d", act);
   if (skinny_ok(M, N, K, x, W, nullptr)) {
-    if (M >= 4 * 148 / 2 && N <= 4)     // enough rows to fill the SMs with SK_ROWS rows per block
+    if (M >= 4 * 148 / 2 && N <= 4 && K >= 4 * 256 * SK_SPLIT) {
+      // SK_ROWS rows per cluster of SK_SPLIT CTAs along K
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)((M + SK_ROWS - 1) / SK_ROWS), SK_SPLIT, 1);
+      cfg.blockDim = dim3(256, 1, 1);
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 1;
+      at[0].val.clusterDim.y = SK_SPLIT;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, skinny_fwd_rows_cluster_kernel, x, W, b, y, pre, M, N, K, act);
+    } else if (M >= 4 * 148 / 2 && N <= 4)     // enough rows to fill the SMs with SK_ROWS rows per block
       skinny_fwd_rows_kernel<<<(unsigned)((M + SK_ROWS - 1) / SK_ROWS), 256, 0, (cudaStream_t)stream>>>(
           x, W, b, y, pre, M, N, K, act);
     else

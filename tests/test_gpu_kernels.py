@@ -291,14 +291,19 @@ def test_sdec_tc_kernel_vs_torch(shape, variant, monkeypatch):
         assert err <= 3e-3, (name, err)
 
 
-@pytest.mark.parametrize("M", [5, 301, 512])
-def test_skinny_linear_forward_vs_torch(M):
-    """<= 8 outputs over a long K (VED's 32768 -> 4 features2latent layer, as two 2-output heads):
-    the one-row-per-block kernel (small M) and the four-rows-per-block kernel (M >= 296, ragged tail)."""
-    g = torch.Generator().manual_seed(M)
-    x = torch.randn(M, 4096, generator=g).cuda()
-    W = (torch.randn(2, 4096, generator=g) * 0.02).cuda()
-    b = torch.randn(2, generator=g).cuda()
+@pytest.mark.parametrize("M,N,K", [(5, 2, 4096), (301, 2, 4096), (512, 2, 4096), (512, 4, 32768),
+                                   (301, 3, 8200), (298, 1, 8192)])
+def test_skinny_linear_forward_vs_torch(M, N, K):
+    """<= 8 outputs over a long K (VED's 32768 -> 4 features2latent layer): the one-row-per-block kernel
+    (small M), the four-rows-per-block kernel (M >= 296, ragged tail) and, for K >= 8192, its variant with the
+    K range split over a cluster of 8 CTAs (partial sums joined through distributed shared memory; a K that
+    does not divide evenly, fewer than 4 outputs)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.02).cuda()
+    b = torch.randn(N, generator=g).cuda()
     y = ops.linear_fwd(x, W, b, None)
     ref = x @ W.t() + b
+    if K >= 8192:      # deterministic: rank-ordered sums
+        assert torch.equal(y, ops.linear_fwd(x, W, b, None))
     assert torch.allclose(y, ref, atol=2e-4, rtol=1e-4), (y - ref).abs().max().item()
