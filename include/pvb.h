@@ -389,11 +389,22 @@ int pvb_conv_tc_prep(const float* W, void* workspace, int Cin, int Cout, int kh,
  * scratch (optional): pvb_conv_tc_wgrad_scratch_bytes(...) bytes of ZEROED device memory, left
  * zeroed on return (reusable by the next call on the same stream, for any layer that fits).  With
  * it the per-CTA accumulators are added coalesced into a transposed copy and folded into dW by a
- * second small kernel; without it they are added straight into dW (strided, slower). */
+ * small kernel (below); without it they are added straight into dW (strided, slower). */
 int64_t pvb_conv_tc_wgrad_scratch_bytes(int Cin, int Cout, int kh, int kw);
+/* fold != 0: the scratch copy is folded into dW / db (and cleared) before returning; fold == 0: the
+ * sums stay in this layer's OWN scratch until pvb_conv_tc_wgrad_fold, which folds up to any number
+ * of layers in one launch (a backward pass: one fold for all its layers). */
 int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, float* db, int B,
                       int Cin, int Cout, int H, int Wd, int kh, int kw, void* scratch,
-                      void* stream);
+                      int fold, void* stream);
+#define PVB_WGRAD_FOLD_MAX 16      /* layers per launch (more are folded by further launches) */
+typedef struct {
+  float* scratch;                  /* the layer's scratch (pvb_conv_tc_wgrad_scratch_bytes) */
+  float* dW;                       /* [Cout][Cin][taps], accumulated into */
+  float* db;                       /* [Cout] or NULL */
+  int Cin, Cout, taps;
+} pvb_wgrad_fold;
+int pvb_conv_tc_wgrad_fold(const pvb_wgrad_fold* layers, int n, void* stream);
 
 /* ---- optimizer / reductions -------------------------------------------- */
 /* out[j] (+)= sum_g part[g*part_stride + j], j < n, fixed order (deterministic) */

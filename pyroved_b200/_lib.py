@@ -32,6 +32,12 @@ class TcSizes(C.Structure):
                 ("gUv_part_floats", C.c_int64), ("wgrad_part_floats", C.c_int64)]
 
 
+class WgradFold(C.Structure):
+    """pvb_wgrad_fold"""
+    _fields_ = [("scratch", C.c_void_p), ("dW", C.c_void_p), ("db", C.c_void_p),
+                ("Cin", C.c_int32), ("Cout", C.c_int32), ("taps", C.c_int32)]
+
+
 class MlpTailArgs(C.Structure):
     """pvb_mlp_tail_args"""
     _fields_ = [("M", C.c_int64), ("n_layers", C.c_int32), ("w_in", C.c_int32), ("h_in", C.c_void_p),
@@ -125,7 +131,8 @@ SIGNATURES = {
     "pvb_conv_tc_prep": [_f, _f, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_tc_pix": [_f, _f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_tc_wgrad_scratch_bytes": [_i32, _i32, _i32, _i32],
-    "pvb_conv_tc_wgrad": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f, _st],
+    "pvb_conv_tc_wgrad": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f, _i32, _st],
+    "pvb_conv_tc_wgrad_fold": [C.POINTER(WgradFold), _i32, _st],
     "pvb_sdec_tc_sizes": [_i64, _i32, C.POINTER(TcSizes)],
     "pvb_sdec_tc_step": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _i64,
                          _i32, _i32, _i32, _i32, _i32, _fl, _i32, _f, _st],

@@ -42,10 +42,12 @@ class ConvStack:
             shape = oshape
             biggest = max(biggest, B * _numel(shape))
         self.out_shape = shape
-        # zeroed scratch of the tensor-core weight-gradient kernels (coalesced accumulator read-out; each
-        # call leaves it zeroed, the backward pass runs them one after another on one stream)
-        wg = [st["mod"].weight for st in self.steps if st["kind"] == "conv" and st["tc_wgrad"]]
-        self.wg_scratch = ops.conv_tc_wgrad_scratch(wg, dev) if wg else None
+        # zeroed scratch of the tensor-core weight-gradient kernels (coalesced accumulator read-out)
+        # (one slice per layer: the layers of a backward pass are folded into the gradients by ONE launch)
+        wg = [st for st in self.steps if st["kind"] == "conv" and st["tc_wgrad"]]
+        for st, sc in zip(wg, ops.conv_tc_wgrad_scratch([st["mod"].weight for st in wg], dev, shared=False)
+                          if wg else []):
+            st["wg_scratch"] = sc
         self.gbuf = [torch.empty(biggest, **f32) for _ in range(2)]
         self.x = None
 
@@ -92,6 +94,7 @@ class ConvStack:
         into the flat gradient buffer; returns the gradient wrt the stack input (or None)."""
         flat = self.engine.flat
         d = dy
+        folds = []          # tensor-core weight gradients still in their scratch copies
         for k in range(len(self.steps) - 1, -1, -1):
             st = self.steps[k]
             m = st["mod"]
@@ -113,7 +116,9 @@ class ConvStack:
                 st["dpre_ready"] = False
                 gb = flat.gv(m.bias) if m.bias is not None else None
                 if st["tc_wgrad"]:
-                    ops.conv_tc_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb, self.wg_scratch)
+                    ops.conv_tc_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb, st["wg_scratch"],
+                                           fold=False)
+                    folds.append((st["wg_scratch"], m.weight.data, flat.gv(m.weight), gb))
                 else:
                     ops.conv_bwd_weight(d, xin, m.weight.data, flat.gv(m.weight), gb)
                 if want_dx:
@@ -141,6 +146,7 @@ class ConvStack:
                 if want_dx:
                     ops.upsample2_bwd(d, dx, m.mode == "bilinear")
             d = dx
+        ops.conv_tc_wgrad_fold(folds)
         return d
 
 

@@ -1047,19 +1047,51 @@ conv_tc_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x
 }
 
 // dW[co][ci][tap] += S[tap][ci][co] / GRAD_SCALE, db[co] += S_b[co] / GRAD_SCALE, and S is left zero for the
-// next call (thread = scratch element: coalesced read + clear, one strided read-modify-write per weight)
-__global__ void wgrad_finish_kernel(float* __restrict__ scratch, float* __restrict__ dW, float* __restrict__ db,
-                                    int Cin, int Cout, int taps) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  const int nW = taps * Cin * Cout;
-  if (i >= nW + Cout) return;
-  const float v = scratch[i];
-  scratch[i] = 0.f;
-  if (i < nW) {
-    const int co = i % Cout, r = i / Cout, ci = r % Cin, t = r / Cin;
-    dW[((int64_t)co * Cin + ci) * taps + t] += v * (1.f / GRAD_SCALE);
-  } else if (db) {
-    db[i - nW] += v * (1.f / GRAD_SCALE);
+// next call.  A CTA transposes one (32 co x 32 ci x all taps) block through shared memory, so that both the
+// scratch rows (co contiguous) and the weight rows (ci, tap contiguous) move in full lines -- element-wise,
+// one side is always 4 bytes per 32-byte sector and the fold of a whole backward pass cost ~50 us.
+// blockIdx.y = layer: one launch folds every layer of a backward pass.
+struct FoldArgs {
+  pvb_wgrad_fold p[PVB_WGRAD_FOLD_MAX];
+};
+constexpr int FOLD_MAX_TAPS = 9;
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(FoldArgs a) {
+  __shared__ float tile[FOLD_MAX_TAPS][32][33];
+  const pvb_wgrad_fold pr = a.p[blockIdx.y];
+  const int cob = (pr.Cout + 31) / 32, cib = (pr.Cin + 31) / 32;
+  if ((int)blockIdx.x >= cob * cib) return;
+  const int co0 = ((int)blockIdx.x % cob) * 32, ci0 = ((int)blockIdx.x / cob) * 32;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  // scratch -> tile (and clear): row (t, ci) of 32 consecutive co per warp
+  for (int r = wy; r < pr.taps * 32; r += 8) {
+    const int t = r >> 5, ci = ci0 + (r & 31), co = co0 + lane;
+    float v = 0.f;
+    if (ci < pr.Cin && co < pr.Cout) {
+      float* sp = pr.scratch + ((int64_t)t * pr.Cin + ci) * pr.Cout + co;
+      v = *sp;
+      *sp = 0.f;
+    }
+    tile[t][r & 31][lane] = v;
+  }
+  __syncthreads();
+  // tile -> dW: for one co, the (ci, tap) block is nci * taps consecutive floats
+  const int nci = min(32, pr.Cin - ci0), run = nci * pr.taps;
+  for (int c = wy; c < 32; c += 8) {
+    const int co = co0 + c;
+    if (co >= pr.Cout) break;
+    float* wp = pr.dW + ((int64_t)co * pr.Cin + ci0) * pr.taps;
+    for (int e = lane; e < run; e += 32) {
+      const int ci = e / pr.taps, t = e - ci * pr.taps;
+      wp[e] += tile[t][ci][c] * (1.f / GRAD_SCALE);
+    }
+  }
+  if (blockIdx.x == 0) {
+    float* sb = pr.scratch + (int64_t)pr.taps * pr.Cin * pr.Cout;
+    for (int co = threadIdx.x; co < pr.Cout; co += 256) {
+      const float v = sb[co];
+      sb[co] = 0.f;
+      if (pr.db) pr.db[co] += v * (1.f / GRAD_SCALE);
+    }
   }
 }
 
@@ -1223,8 +1255,29 @@ extern "C" int64_t pvb_conv_tc_wgrad_scratch_bytes(int Cin, int Cout, int kh, in
   return ((int64_t)kh * kw * Cin * Cout + Cout) * (int64_t)sizeof(float);
 }
 
+extern "C" int pvb_conv_tc_wgrad_fold(const pvb_wgrad_fold* probs, int n, void* stream) {
+  PVB_CHECK_ARG(probs && n >= 0, "pvb_conv_tc_wgrad_fold: bad argument");
+  for (int i0 = 0; i0 < n; i0 += PVB_WGRAD_FOLD_MAX) {
+    FoldArgs a;
+    const int cnt = n - i0 < PVB_WGRAD_FOLD_MAX ? n - i0 : PVB_WGRAD_FOLD_MAX;
+    int bx = 1;
+    for (int i = 0; i < cnt; ++i) {
+      a.p[i] = probs[i0 + i];
+      PVB_CHECK_ARG(a.p[i].scratch && a.p[i].dW && a.p[i].Cin > 0 && a.p[i].Cout > 0 && a.p[i].taps > 0 &&
+                        a.p[i].taps <= FOLD_MAX_TAPS,
+                    "pvb_conv_tc_wgrad_fold: bad problem %d", i0 + i);
+      const int tiles = ((a.p[i].Cout + 31) / 32) * ((a.p[i].Cin + 31) / 32);
+      bx = tiles > bx ? tiles : bx;
+    }
+    wgrad_finish_kernel<<<dim3((unsigned)bx, (unsigned)cnt), 256, 0, (cudaStream_t)stream>>>(a);
+    pvb::count_launch();
+  }
+  return pvb::launch_status();
+}
+
 extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, float* db, int B, int Cin,
-                                 int Cout, int H, int Wd, int kh, int kw, void* scratch, void* stream) {
+                                 int Cout, int H, int Wd, int kh, int kw, void* scratch, int fold,
+                                 void* stream) {
   PVB_CHECK_ARG(dpre && x && dW, "pvb_conv_tc_wgrad: null pointer");
   PVB_CHECK_ARG(((uintptr_t)scratch % 4) == 0, "pvb_conv_tc_wgrad: scratch must be float-aligned");
   const int Cin_real = Cin;
@@ -1258,11 +1311,9 @@ extern "C" int pvb_conv_tc_wgrad(const float* dpre, const float* x, float* dW, f
   conv_tc_wgrad_kernel<BWD_BF16><<<grid, ng * 128 + 32, smem, (cudaStream_t)stream>>>(
       dpre, x, dW, db, reinterpret_cast<float*>(scratch), B, Cin_real, Cout, H, Wd, kh, kw, n_stages, n_tiles);
   pvb::count_launch();
-  if (scratch) {
-    const int n = kh * kw * Cin_real * Cout + Cout;
-    wgrad_finish_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(scratch), dW, db,
-                                                                          Cin_real, Cout, kh * kw);
-    pvb::count_launch();
+  if (scratch && fold) {
+    const pvb_wgrad_fold pr{reinterpret_cast<float*>(scratch), dW, db, Cin_real, Cout, kh * kw};
+    return pvb_conv_tc_wgrad_fold(&pr, 1, stream);
   }
   return pvb::launch_status();
 }

@@ -560,16 +560,40 @@ def conv_tc_bwd_data(dpre, W, dx, ws, y_below=None, act_below=None, prepped=Fals
                                      1 | (2 if prepped else 0), _stream()), "pvb_conv_tc_pix")
 
 
-def conv_tc_wgrad_scratch(weights, device):
-    """Zeroed scratch for conv_tc_bwd_weight, large enough for every weight in `weights`; each call leaves
-    it zeroed again, so one buffer serves all layers that run on one stream."""
-    n = 4
-    for W in weights:
-        kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
-        n = max(n, _lib.lib().pvb_conv_tc_wgrad_scratch_bytes(W.shape[1], W.shape[0], kh, kw))
-    return torch.zeros((n + 3) // 4, device=device, dtype=torch.float32)
+def _wgrad_scratch_floats(W):
+    kh, kw = (1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3])
+    return (_lib.lib().pvb_conv_tc_wgrad_scratch_bytes(W.shape[1], W.shape[0], kh, kw) + 3) // 4
 
 
-def conv_tc_bwd_weight(dpre, x, W, dW, db, scratch=None):
+def conv_tc_wgrad_scratch(weights, device, shared=True):
+    """Zeroed scratch for conv_tc_bwd_weight.  shared=True: ONE buffer large enough for every weight in
+    `weights` (each folding call leaves it zeroed, so it serves all layers that run on one stream);
+    shared=False: a list of per-layer slices of one buffer, for calls with fold=False that are folded
+    together by conv_tc_wgrad_fold."""
+    sizes = [_wgrad_scratch_floats(W) for W in weights]
+    if shared:
+        return torch.zeros(max(sizes + [4]), device=device, dtype=torch.float32)
+    sizes = [(n + 3) // 4 * 4 for n in sizes]
+    buf = torch.zeros(sum(sizes) + 4, device=device, dtype=torch.float32)
+    out, o = [], 0
+    for n in sizes:
+        out.append(buf[o:o + n])
+        o += n
+    return out
+
+
+def conv_tc_wgrad_fold(layers):
+    """layers: [(scratch, W, dW, db)] of conv_tc_bwd_weight(..., fold=False) calls; adds every scratch copy
+    into its dW / db in one launch and leaves the scratches zeroed."""
+    if not layers:
+        return
+    arr = (_lib.WgradFold * len(layers))()
+    for i, (sc, W, dW, db) in enumerate(layers):
+        taps = W.shape[2] if W.dim() == 3 else W.shape[2] * W.shape[3]
+        arr[i] = _lib.WgradFold(_p(sc), _p(dW), _p(db), W.shape[1], W.shape[0], taps)
+    check(_lib.lib().pvb_conv_tc_wgrad_fold(arr, len(layers), _stream()), "pvb_conv_tc_wgrad_fold")
+
+
+def conv_tc_bwd_weight(dpre, x, W, dW, db, scratch=None, fold=True):
     check(_lib.lib().pvb_conv_tc_wgrad(_p(dpre), _p(x), _p(dW), _p(db), *_conv_dims(x, W),
-                                       _p(scratch), _stream()), "pvb_conv_tc_wgrad")
+                                       _p(scratch), 1 if fold else 0, _stream()), "pvb_conv_tc_wgrad")

@@ -299,6 +299,17 @@ def test_tc_conv_kernels_vs_torch(shape):
     assert (db2 - 1 - br.grad).abs().max().item() <= 4e-3 * br.grad.abs().max().item() + 1e-3
     assert (dW2 - 1 - dW).abs().max().item() <= 1e-4 * wr.grad.abs().max().item() + 1e-6
     assert not sc.any().item()
+    # deferred: two layers keep their sums in their own scratch slices, ONE launch folds both
+    s1, s2 = ops.conv_tc_wgrad_scratch([wt, wt], "cuda", shared=False)
+    dW3, db3, dW4 = torch.zeros_like(wt), torch.zeros_like(b), torch.zeros_like(wt)
+    ops.conv_tc_bwd_weight(dpre, x, wt, dW3, db3, s1, fold=False)
+    ops.conv_tc_bwd_weight(dpre, x, wt, dW4, None, s2, fold=False)
+    assert not dW3.any().item() and s1.any().item()
+    ops.conv_tc_wgrad_fold([(s1, wt, dW3, db3), (s2, wt, dW4, None)])
+    for got in (dW3, dW4):
+        assert (got - dW).abs().max().item() <= 1e-4 * wr.grad.abs().max().item() + 1e-6
+    assert (db3 - db).abs().max().item() <= 1e-4 * br.grad.abs().max().item() + 1e-5
+    assert not s1.any().item() and not s2.any().item()
 
 
 @pytest.mark.parametrize("shape", [(3, 1, 32, 16, 16, 3, 2), (2, 3, 64, 1, 40, 3, 1), (4, 5, 16, 7, 5, 1, 2),
