@@ -431,6 +431,69 @@ __global__ void act_bwd_flat_kernel(const float* __restrict__ dy, const float* _
   for (int64_t k = 4 * n4 + i; k < n; k += stride) dpre[k] = dy[k] * pvb::act_grad(y[k], pre ? pre[k] : 0.f, act);
 }
 
+// Cout == 1, 1 x 1 kernel (the last decoder layer, nets/conv.py:141: hidden -> one output channel): a weighted
+// sum of Cin planes -- HBM-bound, one pass over x; four pixels per thread, 16-byte accesses (HW % 4 == 0).
+// The generic pixel-GEMM kernels spent 24 + 13 + 40 us on it at batch 512 x 32 x 128 (8 MB).
+__global__ void __launch_bounds__(256)
+conv_o1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                   float* __restrict__ y, float* __restrict__ pre, int64_t n4, int Cin, int HW4, int act) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const int64_t bi = i / HW4;
+  const int p4 = (int)(i - bi * HW4);
+  const float4* xp = reinterpret_cast<const float4*>(x) + bi * Cin * HW4 + p4;
+  const float b0 = b ? __ldg(b) : 0.f;
+  float4 acc = make_float4(b0, b0, b0, b0);
+#pragma unroll 8
+  for (int c = 0; c < Cin; ++c) {
+    const float4 v = __ldg(xp + (int64_t)c * HW4);
+    const float w = __ldg(W + c);
+    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+  }
+  if (pre) reinterpret_cast<float4*>(pre)[i] = acc;
+  reinterpret_cast<float4*>(y)[i] = make_float4(pvb::act_fwd(acc.x, act), pvb::act_fwd(acc.y, act),
+                                                pvb::act_fwd(acc.z, act), pvb::act_fwd(acc.w, act));
+}
+// dx[b][c][p] = W[c] dpre[b][p]
+__global__ void __launch_bounds__(256)
+conv_o1_bwd_data_kernel(const float* __restrict__ dpre, const float* __restrict__ W, float* __restrict__ dx,
+                        int64_t n4, int Cin, int HW4) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;     // over B x Cin x HW4
+  if (i >= n4) return;
+  const int64_t bc = i / HW4;
+  const int p4 = (int)(i - bc * HW4);
+  const int64_t bi = bc / Cin;
+  const int c = (int)(bc - bi * Cin);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(dpre) + bi * HW4 + p4);
+  const float w = __ldg(W + c);
+  reinterpret_cast<float4*>(dx)[i] = make_float4(w * g.x, w * g.y, w * g.z, w * g.w);
+}
+// dW[c] += sum_{b,p} dpre[b][p] x[b][c][p];  db += sum dpre.   grid (Cin, batch splits)
+__global__ void __launch_bounds__(256)
+conv_o1_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dW,
+                     float* __restrict__ db, int B, int Cin, int HW4, int rows_per_split) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const int b0 = (int)blockIdx.y * rows_per_split, b1 = min(B, b0 + rows_per_split);
+  const int64_t items = (int64_t)(b1 - b0) * HW4;
+  float acc = 0.f, accb = 0.f;
+  for (int64_t i = threadIdx.x; i < items; i += 256) {
+    const int64_t bi = b0 + i / HW4;
+    const int p4 = (int)(i % HW4);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dpre) + bi * HW4 + p4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + (bi * Cin + c) * HW4 + p4);
+    acc = fmaf(g.x, v.x, fmaf(g.y, v.y, fmaf(g.z, v.z, fmaf(g.w, v.w, acc))));
+    accb += (g.x + g.y) + (g.z + g.w);
+  }
+  acc = pvb::block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(dW + c, acc);
+  if (db && c == 0) {
+    accb = pvb::block_sum(accb, red);
+    if (threadIdx.x == 0) atomicAdd(db, accb);
+  }
+}
+
 // Cin == 1 (the first encoder layer): HBM-write bound, so no GEMM machinery -- one thread per
 // pixel keeps its <= 9 inputs in registers and streams the Cout outputs (coalesced per channel)
 __global__ void __launch_bounds__(256)
@@ -688,6 +751,13 @@ extern "C" int pvb_conv_fwd(const float* x, const float* W, const float* b, floa
   PVB_CHECK_ARG(act >= 0 && act <= PVB_ACT_SIGMOID, "pvb_conv_fwd: unknown activation %d", act);
   if (B == 0) return 0;
   int64_t M = (int64_t)B * H * Wd;
+  if (Cout == 1 && kh * kw == 1 && (H * Wd) % 4 == 0 &&
+      (((uintptr_t)x | (uintptr_t)y | (uintptr_t)pre) & 15) == 0) {
+    conv_o1_fwd_kernel<<<pvb::cdiv(M / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, W, b, y, pre, M / 4, Cin,
+                                                                                H * Wd / 4, act);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   if (Cin == 1 && Wd % 4 == 0 && Cout * 12 * sizeof(float) <= 40 * 1024 &&
       (((uintptr_t)x | (uintptr_t)y | (uintptr_t)pre) & 15) == 0) {
     const int64_t groups = M / 4;
@@ -716,6 +786,12 @@ extern "C" int pvb_conv_bwd_data(const float* dpre, const float* W, float* dx, i
   PVB_CHECK_ARG(dpre && W && dx, "pvb_conv_bwd_data: null pointer");
   if (B == 0) return 0;
   int64_t M = (int64_t)B * H * Wd;
+  if (Cout == 1 && kh * kw == 1 && (H * Wd) % 4 == 0 && (((uintptr_t)dpre | (uintptr_t)dx) & 15) == 0) {
+    const int64_t n4 = M / 4 * Cin;
+    conv_o1_bwd_data_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(dpre, W, dx, n4, Cin, H * Wd / 4);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   dim3 grid((unsigned)((M + BM - 1) / BM), (Cin + BN - 1) / BN);
   size_t smem = (size_t)Cout * kh * kw * sizeof(Tap);
   conv_pix_kernel<1><<<grid, NT, smem, (cudaStream_t)stream>>>(dpre, W, nullptr, dx, nullptr, d, 0);
@@ -730,6 +806,15 @@ extern "C" int pvb_conv_bwd_weight(const float* dpre, const float* x, float* dW,
   PVB_CHECK_ARG(dpre && x && dW, "pvb_conv_bwd_weight: null pointer");
   if (B == 0) return 0;
   int64_t M = (int64_t)B * H * Wd;
+  if (Cout == 1 && kh * kw == 1 && (H * Wd) % 4 == 0 && Cin <= 65535 && (((uintptr_t)x | (uintptr_t)dpre) & 15) == 0) {
+    int splits = (148 * 4 + Cin - 1) / Cin;
+    if (splits > B) splits = B;
+    const int rows = (B + splits - 1) / splits;
+    dim3 grid_o1((unsigned)Cin, (unsigned)((B + rows - 1) / rows));
+    conv_o1_wgrad_kernel<<<grid_o1, 256, 0, (cudaStream_t)stream>>>(dpre, x, dW, db, B, Cin, H * Wd / 4, rows);
+    pvb::count_launch();
+    return pvb::launch_status();
+  }
   if (Cin == 1 && M < (1ll << 31) - (1 << 20) && Wd % 4 == 0 &&
       (((uintptr_t)x | (uintptr_t)dpre) & 15) == 0) {
     const int cgroups4 = (Cout + C1_CO4 - 1) / C1_CO4;

@@ -164,6 +164,10 @@ def test_ved_inference_api():
     (3, 1, 12, 7, 9, 3, 2),      # W % 4 != 0: one pixel per thread
     (4, 1, 8, 1, 32, 3, 1),      # 1-D
     (2, 1, 16, 6, 8, 1, 2),      # 1x1
+    # one output channel, 1x1 (last decoder layer): direct kernels when H * W % 4 == 0
+    (6, 32, 1, 1, 128, 1, 1),
+    (3, 5, 1, 4, 6, 1, 2),
+    (2, 7, 1, 3, 5, 1, 2),       # H * W % 4 != 0: generic kernels
 ])
 @pytest.mark.parametrize("act", [None, "lrelu", "tanh"])
 def test_conv_kernels_vs_torch(shape, act):
