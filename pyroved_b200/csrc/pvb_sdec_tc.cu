@@ -112,10 +112,14 @@ __device__ long long g_wtrace[16][16];
   do {                                                                               \
     if (blockIdx.x == 0 && lane == 0 && trace_it == 3) g_wtrace[warp][ev] = clock64(); \
   } while (0)
+// whole-kernel milestones of CTA 0 (entry, set-up done, first tile, loop done, partials written, exit)
+__device__ long long g_ktrace[8];
+#define KTRACE(ev, cond) do { if (blockIdx.x == 0 && (cond)) g_ktrace[ev] = clock64(); } while (0)
 #else
 #define WTRACE(ev) do {} while (0)
 #define TRACE(role, ev) do {} while (0)
 #define TRACE_NEXT() do {} while (0)
+#define KTRACE(ev, cond) do {} while (0)
 #endif
 
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, cg = (warp >> 2) & 3;
   const int row = q * 32 + lane;        // tile row == TMEM lane owned by this thread
+  KTRACE(0, tid == 0);
 
   // ---- one-time setup ----------------------------------------------------------
   // weights: pre-packed fp16 operand tiles come in through the TMA engine (one thread, two bulk
@@ -361,6 +366,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
   umma::fence_after_sync();
   const uint32_t tm = *tmem_slot;
   const uint32_t tm_lane = tm + ((uint32_t)(q * 32) << 16);
+  KTRACE(1, tid == 0);
   float dl_sum = 0.f;  // sum of dl over this thread's rows (column group 0 only) -> dbo
   bool any_tile = false;
 #ifdef PVB_TC_TRACE
@@ -506,6 +512,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     stage_tile(P, f32, cur_c, tid, row, cg);
     cp_async_wait_all();
     epi_bar();
+    KTRACE(2, tid == 0);
     while (cur_c.tile < P.tiles) {
       const int64_t tile = cur_c.tile;
       any_tile = true;
@@ -748,6 +755,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
       cur_c = nxt_c;
       TRACE_NEXT();
     }
+    KTRACE(3, tid == 0);
     // last tile: wait for its MMAs, write its dUv partials
     if (P.backward && prev_tile >= 0) {
       umma::mbar_wait(bars + BAR_DUV, dph);
@@ -790,9 +798,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-        float4* dst = reinterpret_cast<float4*>(oW + row * HD + col0);
+        // A thread holds 32 columns of ONE row: stored directly, each warp instruction touched 32 different
+        // lines (8 192 store transactions per CTA, 13 k cycles = 6.6 us at the end of every launch, trace).  The
+        // warp's 32 x 32 block goes through a padded shared-memory block instead (the operand tiles are dead:
+        // every MMA has completed), and leaves as 32 full-line rows.
+        float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
+        __syncwarp();
+        float* og = oW + (q * 32) * HD + col0 + lane;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) og[r * HD] = tr[r * 33 + lane];
+        __syncwarp();
         if (cg == 3) {
           float b[16];
           if (any_tile) {
@@ -818,9 +835,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     float tot = pvb::block_sum(dl_sum, f32 + F_RED);
     if (tid == 0) o_dbo[0] = tot;
   }
+  KTRACE(4, tid == 0);
   umma::fence_before_sync();
   __syncthreads();
   if (warp == MMA_WARP) umma::tmem_dealloc<TM_COLS>(tm);
+  KTRACE(5, tid == 0);
 }
 
 // gUv[i][c][h] = sum over the tiles touching instance i of its slot partial
@@ -856,6 +875,9 @@ extern "C" int pvb_has_tcgen05(void) { return 1; }
 #ifdef PVB_TC_TRACE
 extern "C" int pvb_tc_trace_read(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 2 * 64 * 32);
+}
+extern "C" int pvb_tc_ktrace_read(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_ktrace, sizeof(long long) * 8);
 }
 extern "C" int pvb_tc_wtrace_read(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_wtrace, sizeof(long long) * 16 * 16);

@@ -20,7 +20,7 @@ for _ in range(3):
     tr.svi.step(x)
 torch.cuda.synchronize()
 buf = np.zeros((2, 64, 32), dtype=np.int64)
-lib = C.CDLL(os.path.join(ROOT, "pyroved_b200", "csrc", "libpvb.so"))
+lib = C.CDLL(_lib.LIB_PATH)
 rc = lib.pvb_tc_trace_read(buf.ctypes.data_as(C.POINTER(C.c_longlong)))
 assert rc == 0, rc
 E, M = buf[0], buf[1]
@@ -42,3 +42,8 @@ base = wb[:, 0].min()
 print("per-warp S4B of tile 3: [bar-arrive, bar, dl, c0-computed, c0..c3 published, stores done, smem signalled]")
 for w in range(16):
     print(w, (wb[w, :10] - base).tolist())
+
+kb = np.zeros(8, dtype=np.int64)
+if hasattr(lib, "pvb_tc_ktrace_read") and lib.pvb_tc_ktrace_read(kb.ctypes.data_as(C.POINTER(C.c_longlong))) == 0:
+    print("kernel milestones of CTA 0 (cycles from entry): set-up done, first tile, tile loop done, partials "
+          "written, exit:", (kb[1:6] - kb[0]).tolist())
