@@ -772,6 +772,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
     }
   }
 
+  KTRACE(6, tid == 0);
   // ---- weight-gradient partials of this CTA ---------------------------------------------------------------
   if (P.backward) {
     float* out = P.wgrad_part + (size_t)blockIdx.x * PVB_TC_WGRAD_STRIDE;
@@ -832,6 +833,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdec_tc_kernel(Params P) {
         o_dwo[row] = b[0];
       }
     }
+    KTRACE(7, tid == 0);
     float tot = pvb::block_sum(dl_sum, f32 + F_RED);
     if (tid == 0) o_dbo[0] = tot;
   }

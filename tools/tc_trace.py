@@ -46,4 +46,4 @@ for w in range(16):
 kb = np.zeros(8, dtype=np.int64)
 if hasattr(lib, "pvb_tc_ktrace_read") and lib.pvb_tc_ktrace_read(kb.ctypes.data_as(C.POINTER(C.c_longlong))) == 0:
     print("kernel milestones of CTA 0 (cycles from entry): set-up done, first tile, tile loop done, partials "
-          "written, exit:", (kb[1:6] - kb[0]).tolist())
+          "written, exit | last dUv written, dW tiles stored:", (kb[1:6] - kb[0]).tolist(), (kb[6:8] - kb[0]).tolist())
