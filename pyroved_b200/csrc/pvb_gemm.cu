@@ -707,6 +707,11 @@ extern "C" int pvb_linear_fwd(const float* x, const float* W, const float* b, fl
   // of the SMs get a tile
   if (M <= 8192 && (K % 4) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)W % 16) == 0) {
     int tiles = (int)(((M + SBM - 1) / SBM) * ((N + SBN - 1) / SBN));
+    // 16-wide tiles when the 32-wide ones cover half of the SMs or fewer (measured: 784 -> 128 at batch 512,
+    // 64 -> 128 CTAs: 9.4 -> 6.8 us; at batch 1024, 128 -> 256 CTAs, the repeated A fragments cost more than the
+    // extra SMs give: 10.5 -> 11.5 us, and 32.9 -> 39.9 us for the 4100 -> 128 layer)
+    const bool narrow = tiles <= 74 && N % 16 == 0;
+    if (narrow) tiles = (int)(((M + SBM - 1) / SBM) * ((N + 15) / 16));
     if (tiles >= 48 && tiles < 4 * 148) {
       if (M == 0) return 0;
       static bool attr = false;
@@ -715,7 +720,7 @@ extern "C" int pvb_linear_fwd(const float* x, const float* W, const float* b, fl
         cudaFuncSetAttribute(linear_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ls_smem_bytes<16>());
         attr = true;
       }
-      if (tiles <= 74 && N % 16 == 0) {     // half of the SMs or fewer: 16-wide tiles
+      if (narrow) {
         dim3 grid((N + 15) / 16, (unsigned)((M + SBM - 1) / SBM));
         linear_small_kernel<16><<<grid, LS_THREADS, ls_smem_bytes<16>(), (cudaStream_t)stream>>>(x, W, y, pre, b, (int)M,
                                                                                                  N, K, act);

@@ -264,7 +264,9 @@ __global__ void __launch_bounds__(MT) mlp_chain_bwd_kernel(pvb_mlp_chain_args a)
 // One 32 x 32 tile of one dW per CTA; the reduction over the M batch rows is split over WG_G = 4
 // thread groups of the CTA (own cp.async ring + named barrier each), partial tiles summed in a
 // fixed order.
-constexpr int WG_T = 32, WG_NT = 128, WG_MAXP = 8, WG_ST = 3, WG_G = 4;
+// (two cp.async stages: with the 40-float rows three would take 123 KB and leave one CTA per SM; the wide
+// first layer of the 64 x 64 models is 532 tiles)
+constexpr int WG_T = 32, WG_NT = 128, WG_MAXP = 8, WG_ST = 2, WG_G = 4;
 constexpr int WG_THREADS = WG_G * WG_NT;
 constexpr int WG_LD = WG_T + 8;     // row stride = 8 mod 32 banks: the MMA fragment loads (4 rows x 8 columns) are conflict-free
 constexpr int WG_SMEM = WG_G * WG_ST * 2 * WG_T * WG_LD * 4;
@@ -403,7 +405,10 @@ __global__ void __launch_bounds__(WG_THREADS) mlp_wgrad_kernel(WgradArgs a) {
 }
 
 // ---- per-instance latent-side backward ---------------------------------------------------------
-constexpr int LS_G = 512, LS_T = 128, LS_MAXR = 40;   // up to LS_G CTAs, one instance at a time
+// up to LS_G CTAs, one instance at a time.  An instance pass is a chain of dependent L2 round trips (~8 us), so
+// the kernel's time is passes per CTA x that: with 512 CTAs the 10 240 instances of the jiVAE benchmark took
+// 20 passes = 174 us; one full wave of co-resident CTAs and the batched tile loop below halve that.
+constexpr int LS_G = 148 * 8, LS_T = 128, LS_MAXR = 40;    // 64 registers x 128 threads: eight CTAs per SM, one wave
 
 __global__ void __launch_bounds__(LS_T)
 latent_side_bwd_kernel(pvb_fold_cfg cfg, const float* __restrict__ z, const float* __restrict__ cond,
@@ -441,13 +446,29 @@ latent_side_bwd_kernel(pvb_fold_cfg cfg, const float* __restrict__ z, const floa
       float g0, g1, gv;
       if (gUv_part) {
         // sum over the tiles touching instance i of its slot partial (fixed order)
+        // (loads of eight tiles issued together, added in tile order: 33 tiles per instance at 64 x 64)
         g0 = g1 = gv = 0.f;
-        for (int64_t tt = t0; tt <= t1; ++tt) {
-          int slot = (int)(i - (tt * TILE) / N);
-          const float* p = gUv_part + tt * (SLOTS * 3 * Hd) + slot * 3 * Hd;
-          g0 += p[h];
-          g1 += p[Hd + h];
-          gv += p[2 * Hd + h];
+        for (int64_t tb = t0; tb <= t1; tb += 8) {
+          float a0[8], a1[8], av[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int64_t tt = tb + u;
+            if (tt <= t1) {
+              const int slot = (int)(i - (tt * TILE) / N);
+              const float* p = gUv_part + tt * (SLOTS * 3 * Hd) + slot * 3 * Hd;
+              a0[u] = __ldg(p + h);
+              a1[u] = __ldg(p + Hd + h);
+              av[u] = __ldg(p + 2 * Hd + h);
+            } else {
+              a0[u] = a1[u] = av[u] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            g0 += a0[u];
+            g1 += a1[u];
+            gv += av[u];
+          }
         }
       } else {
         const float* g = gUv + i * 3 * Hd;
