@@ -1062,27 +1062,48 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(FoldArgs a) {
   if ((int)blockIdx.x >= cob * cib) return;
   const int co0 = ((int)blockIdx.x % cob) * 32, ci0 = ((int)blockIdx.x / cob) * 32;
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  // scratch -> tile (and clear): row (t, ci) of 32 consecutive co per warp
-  for (int r = wy; r < pr.taps * 32; r += 8) {
+  // scratch -> tile (and clear): row (t, ci) of 32 consecutive co per warp.  All of a warp's loads are issued
+  // before the first use (as a load / store / use loop each row paid a full memory latency: 28 us per launch)
+  constexpr int RPW = FOLD_MAX_TAPS * 32 / 8;      // rows per warp, upper bound
+  float vals[RPW];
+#pragma unroll
+  for (int k = 0; k < RPW; ++k) {
+    const int r = wy + 8 * k;
     const int t = r >> 5, ci = ci0 + (r & 31), co = co0 + lane;
-    float v = 0.f;
-    if (ci < pr.Cin && co < pr.Cout) {
-      float* sp = pr.scratch + ((int64_t)t * pr.Cin + ci) * pr.Cout + co;
-      v = *sp;
-      *sp = 0.f;
+    vals[k] = 0.f;
+    if (t < pr.taps && ci < pr.Cin && co < pr.Cout)
+      vals[k] = __ldcg(pr.scratch + ((int64_t)t * pr.Cin + ci) * pr.Cout + co);
+  }
+#pragma unroll
+  for (int k = 0; k < RPW; ++k) {
+    const int r = wy + 8 * k;
+    const int t = r >> 5, ci = ci0 + (r & 31), co = co0 + lane;
+    if (t < pr.taps) {
+      if (ci < pr.Cin && co < pr.Cout) pr.scratch[((int64_t)t * pr.Cin + ci) * pr.Cout + co] = 0.f;
+      tile[t][r & 31][lane] = vals[k];
     }
-    tile[t][r & 31][lane] = v;
   }
   __syncthreads();
-  // tile -> dW: for one co, the (ci, tap) block is nci * taps consecutive floats
+  // tile -> dW: for one co, the (ci, tap) block is nci * taps consecutive floats; again loads first
   const int nci = min(32, pr.Cin - ci0), run = nci * pr.taps;
-  for (int c = wy; c < 32; c += 8) {
-    const int co = co0 + c;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = wy + 8 * cc, co = co0 + c;
     if (co >= pr.Cout) break;
     float* wp = pr.dW + ((int64_t)co * pr.Cin + ci0) * pr.taps;
-    for (int e = lane; e < run; e += 32) {
-      const int ci = e / pr.taps, t = e - ci * pr.taps;
-      wp[e] += tile[t][ci][c] * (1.f / GRAD_SCALE);
+    float old[FOLD_MAX_TAPS];
+#pragma unroll
+    for (int u = 0; u < FOLD_MAX_TAPS; ++u) {
+      const int e = lane + 32 * u;
+      old[u] = e < run ? wp[e] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < FOLD_MAX_TAPS; ++u) {
+      const int e = lane + 32 * u;
+      if (e < run) {
+        const int ci = e / pr.taps, t = e - ci * pr.taps;
+        wp[e] = old[u] + tile[t][ci][c] * (1.f / GRAD_SCALE);
+      }
     }
   }
   if (blockIdx.x == 0) {
