@@ -541,6 +541,9 @@ skinny_fwd_rows_cluster_kernel(const float* __restrict__ x, const float* __restr
   __shared__ float red[8][SK_ROWS][4];
   __shared__ float cpart[SK_SPLIT][SK_ROWS][4];     // rank 0's copy collects every rank's partial sums
   const unsigned rank = cluster.block_rank();
+  // every CTA of the cluster must be running before another one writes into its shared memory: arrive now,
+  // wait just before the remote store (the wait is then hidden behind this CTA's own stream over x)
+  cluster.barrier_arrive();
   const int64_t row0 = (int64_t)blockIdx.x * SK_ROWS;
   const int K4 = K / 4, per = (K4 + SK_SPLIT - 1) / SK_SPLIT;
   const int k_lo = (int)rank * per, k_hi = min(K4, k_lo + per);
@@ -573,6 +576,7 @@ skinny_fwd_rows_cluster_kernel(const float* __restrict__ x, const float* __restr
       if (lane == 0) red[warp][r][n] = v;
     }
   __syncthreads();
+  cluster.barrier_wait();
   if (threadIdx.x < SK_ROWS * 4) {
     const int r = threadIdx.x >> 2, n = threadIdx.x & 3;
     float s2 = 0.f;
