@@ -408,9 +408,11 @@ __global__ void __launch_bounds__(WG_THREADS) mlp_wgrad_kernel(WgradArgs a) {
 // up to LS_G CTAs, one instance at a time.  An instance pass is a chain of dependent L2 round trips (~8 us), so
 // the kernel's time is passes per CTA x that: with 512 CTAs the 10 240 instances of the jiVAE benchmark took
 // 20 passes = 174 us; one full wave of co-resident CTAs and the batched tile loop below halve that.
-constexpr int LS_G = 148 * 8, LS_T = 128, LS_MAXR = 40;    // 64 registers x 128 threads: eight CTAs per SM, one wave
+// (bounding the registers for 12 or 16 CTAs per SM was measured: no change -- the pass is not occupancy-bound)
+constexpr int LS_OCC = 8;                    // CTAs per SM at 64 registers x 128 threads
+constexpr int LS_G = 148 * LS_OCC, LS_T = 128, LS_MAXR = 40;    // one wave
 
-__global__ void __launch_bounds__(LS_T)
+__global__ void __launch_bounds__(LS_T, LS_OCC)
 latent_side_bwd_kernel(pvb_fold_cfg cfg, const float* __restrict__ z, const float* __restrict__ cond,
                        const float* __restrict__ Wc, const float* __restrict__ Wz,
                        const float* __restrict__ gUv, const float* __restrict__ gUv_part, int N,
