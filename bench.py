@@ -603,6 +603,8 @@ def run_ours(args):
                 D.barrier()
             if rank == 0:
                 configs[name] = r
+            import gc
+            gc.collect()                 # the config's trainer (and its CUDA graphs) goes now, not mid-capture
             torch.cuda.empty_cache()
 
     if rank == 0:

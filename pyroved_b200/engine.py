@@ -16,6 +16,7 @@ Layout in HBM
     all-reduce(SUM) moves both.
   * activations/workspaces are allocated once per (batch shape) and reused.
 """
+import gc
 import math
 import os
 import warnings
@@ -1189,8 +1190,22 @@ class SVIEngine:
         if entry == "warm":
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.device)
-            with torch.cuda.graph(g):
-                fn()
+            # No CUDA graph may be DESTROYED while a capture is under way (cudaGraphExecDestroy is not
+            # permitted then and invalidates the capture).  Graphs of engines that went out of scope sit in
+            # reference cycles until the cyclic collector runs -- which torch.cuda.graph no longer forces --
+            # so collect them now and keep the collector off for the duration of the capture.
+            guard = os.environ.get("PVB_GC_GUARD", "1") != "0"      # "0": debugging only
+            if guard:
+                gc.collect()
+            gc_was_on = gc.isenabled()
+            if guard:
+                gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    fn()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             entry = g
         self.graphs[key] = entry          # most recently used last
         entry.replay()

@@ -133,3 +133,40 @@ def test_scale_factor_annealing_does_not_grow_the_graph_cache():
         tr.svi.step(x, scale_factor=1.0 + 0.01 * e)
         tr.svi.step(x, scale_factor=1.0 + 0.01 * e)
     assert len(tr.svi.graphs) <= tr.svi.MAX_GRAPHS
+
+
+def test_graph_capture_with_discarded_engines_pending_collection(monkeypatch):
+    """A trainer that went out of scope leaves its CUDA graphs in reference cycles until the cyclic collector
+    runs; destroying a graph while ANOTHER capture is under way invalidates that capture
+    (cudaErrorStreamCaptureInvalidated -- seen once in bench.py's configs block).  The engine collects before a
+    capture and keeps the collector off during it.  Here a captured graph sits in a garbage cycle and the
+    collector is made to run in the middle of the next engine's capture (a hook on the decoder launch)."""
+    import gc
+    x = (torch.rand(64, 12, 12, generator=torch.Generator().manual_seed(0)) < 0.3).float().cuda()
+    gc.disable()
+    try:
+        m = pv.models.iVAE((12, 12), 2, ['r', 't'], seed=1, device="cuda:0")
+        tr = pv.trainers.SVItrainer(m, seed=1, device="cuda:0")
+        for _ in range(3):
+            tr.svi.step(x)                       # eager, capture, replay
+        assert any(not isinstance(g, str) for g in tr.svi.graphs.values())
+        tr._cycle = tr                           # whatever the object graph looks like: certainly a cycle now
+        del m, tr                                # garbage, not collected yet (the collector is off)
+        m2 = pv.models.iVAE((12, 12), 2, ['r', 't'], seed=2, device="cuda:0")
+        tr2 = pv.trainers.SVItrainer(m2, seed=2, device="cuda:0")
+        tr2.svi.step(x)                          # eager
+        orig = ops.sdec_tc_step
+        calls = []
+
+        def hooked(*a, **k):
+            if gc.isenabled():                   # the engine's guard turns the collector off during a capture
+                calls.append(gc.collect())
+            return orig(*a, **k)
+        monkeypatch.setattr(ops, "sdec_tc_step", hooked)
+        gc.enable()
+        l1 = tr2.svi.step(x)                     # capture
+        l2 = tr2.svi.step(x)                     # replay
+        assert l1 == l1 and l2 == l2
+        assert not calls                         # the collector never ran inside the capture
+    finally:
+        gc.enable()
