@@ -594,13 +594,26 @@ def run_ours(args):
     if os.environ.get("PVB_BENCH_CONFIGS", "1") != "0":
         skip_cpu = os.environ.get("PVB_BENCH_SKIP_CPU") == "1"
         for name in ("cfg3", "cfg4", "cfg5"):
-            try:
-                # enough batches that the resident input pool exceeds the 126 MB L2
-                r = measure_config(D, name, {"cfg3": 44, "cfg4": 40, "cfg5": 20}[name], pk,
-                                   cpu=not skip_cpu)
-            except Exception as err:
-                r = {"error": repr(err)} if rank == 0 else None
-                D.barrier()
+            r = None
+            for attempt in ((0, 1) if D.world == 1 else (0,)):     # (a retry of one rank alone would desynchronise the ranks)
+                try:
+                    # enough batches that the resident input pool exceeds the 126 MB L2
+                    r = measure_config(D, name, {"cfg3": 44, "cfg4": 40, "cfg5": 20}[name], pk,
+                                       cpu=not skip_cpu)
+                    if attempt and r is not None:
+                        r["retried_after"] = first_error
+                    break
+                except Exception as err:          # one fresh attempt (new model, trainer, graphs); say so
+                    first_error = repr(err)[:300]
+                    r = {"error": repr(err)} if rank == 0 else None
+                    import gc
+                    gc.collect()
+                    try:
+                        torch.cuda.synchronize()
+                    except Exception:
+                        pass
+                    torch.cuda.empty_cache()
+                    D.barrier()
             if rank == 0:
                 configs[name] = r
             import gc
