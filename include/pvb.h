@@ -269,10 +269,12 @@ int pvb_latent_side_bwd(const pvb_fold_cfg* cfg, const float* z, const float* co
 int pvb_conv_fwd(const float* x, const float* W, const float* b, float* y,
                  float* pre, int B, int Cin, int Cout, int H, int Wd, int kh,
                  int kw, int act, void* stream);
-/* dx = conv_transpose(dpre, W)  (gradient wrt the layer input) */
+/* dx = conv_transpose(dpre, W)  (gradient wrt the layer input).  y_below (optional, shape of dx) =
+ * OUTPUT of the layer below, act = its activation (not gelu): dx *= act'(y_below), i.e. dx comes
+ * out as that layer's dpre. */
 int pvb_conv_bwd_data(const float* dpre, const float* W, float* dx, int B,
                       int Cin, int Cout, int H, int Wd, int kh, int kw,
-                      void* stream);
+                      const float* y_below, int act, void* stream);
 /* dW += dpre (*) x ; db[co] += sum dpre   (accumulate; db may be NULL) */
 int pvb_conv_bwd_weight(const float* dpre, const float* x, float* dW, float* db,
                         int B, int Cin, int Cout, int H, int Wd, int kh, int kw,
@@ -290,8 +292,10 @@ int pvb_maxpool2_bwd(const float* x, const float* dy, float* dx, int64_t BC,
 /* F.interpolate(scale_factor=2): nearest, or bilinear (2-D only, align_corners=False) */
 int pvb_upsample2_fwd(const float* x, float* y, int64_t BC, int H, int Wd,
                       int two_d, int bilinear, void* stream);
+/* y_below / act as in pvb_conv_bwd_data */
 int pvb_upsample2_bwd(const float* dy, float* dx, int64_t BC, int H, int Wd,
-                      int two_d, int bilinear, void* stream);
+                      int two_d, int bilinear, const float* y_below, int act,
+                      void* stream);
 
 /* ---- volumetric (3-D) variants of the conv-net layers (csrc/pvb_conv3d.cu; reference
  * nets/conv.py with ndim = 3) ----  NCDHW fp32, cubic kernel k = 1 | 3, stride 1, padding

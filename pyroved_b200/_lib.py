@@ -102,7 +102,7 @@ SIGNATURES = {
     "pvb_latent_side_bwd": [C.POINTER(FoldCfg), _f, _f, _f, _f, _f, _f, _i32, _f, _f, _f, _f, _f, _f,
                             _f, _fl, _f, _f, _i64, _st],
     "pvb_conv_fwd": [_f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
-    "pvb_conv_bwd_data": [_f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
+    "pvb_conv_bwd_data": [_f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f, _i32, _st],
     "pvb_conv_bwd_weight": [_f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_act_bwd": [_f, _f, _f, _f, _i64, _i32, _st],
     "pvb_conv3d_fwd": [_f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _st],
@@ -122,7 +122,7 @@ SIGNATURES = {
     "pvb_maxpool2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _st],
     "pvb_maxpool2_bwd": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _st],
     "pvb_upsample2_fwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
-    "pvb_upsample2_bwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _st],
+    "pvb_upsample2_bwd": [_f, _f, _i64, _i32, _i32, _i32, _i32, _f, _i32, _st],
     "pvb_normal_logprob": [_f, _f, _fl, _fl, _f, _f, _i64, _st],
     "pvb_linear_dx_cols": [_f, _f, _f, _i64, _i32, _i32, _i32, _i32, _i32, _st],
     "pvb_conv_tc_supported": [_i32, _i32, _i32, _i32],

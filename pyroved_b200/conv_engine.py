@@ -105,11 +105,11 @@ class ConvStack:
                 buf = self.gbuf[0] if d.data_ptr() != self.gbuf[0].data_ptr() else self.gbuf[1]
                 dx = buf[:xin.numel()].view_as(xin)
             # activation derivative of the layer BELOW folded into the kernel that produces dx
-            # (tensor-core backward-data epilogue, max-pool backward): saves a pass over dx
+            # (backward-data epilogue, max-pool / upsample backward): saves a pass over dx
             below = self.steps[k - 1] if k > 0 else None
             fuse = (below is not None and below["kind"] == "conv"
                     and below["act"] not in (None, "gelu") and not self.engine.force_generic
-                    and ((st["kind"] == "conv" and st["tc"]) or (st["kind"] == "pool" and xin.dim() < 5)))
+                    and (st["kind"] == "conv" or (st["kind"] in ("pool", "up") and xin.dim() < 5)))
             if st["kind"] == "conv":
                 if st["act"] is not None and not st.get("dpre_ready", False):
                     ops.act_bwd(d, st["y"], st["pre"], d, st["act"])     # in place: d = dpre
@@ -130,6 +130,9 @@ class ConvStack:
                             below["dpre_ready"] = True
                         else:
                             ops.conv_tc_bwd_data(d, m.weight.data, dx, st["ws_bwd"], prepped=pp)
+                    elif fuse:
+                        ops.conv_bwd_data(d, m.weight.data, dx, xin, below["act"])
+                        below["dpre_ready"] = True
                     else:
                         ops.conv_bwd_data(d, m.weight.data, dx)
             elif st["kind"] == "bn":
@@ -144,7 +147,11 @@ class ConvStack:
                         below["dpre_ready"] = True
             else:
                 if want_dx:
-                    ops.upsample2_bwd(d, dx, m.mode == "bilinear")
+                    if fuse:
+                        ops.upsample2_bwd(d, dx, m.mode == "bilinear", xin, below["act"])
+                        below["dpre_ready"] = True
+                    else:
+                        ops.upsample2_bwd(d, dx, m.mode == "bilinear")
             d = dx
         ops.conv_tc_wgrad_fold(folds)
         return d

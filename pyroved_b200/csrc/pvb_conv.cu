@@ -377,8 +377,11 @@ __global__ void upsample2_fwd_kernel(const float* __restrict__ x, float* __restr
          lh * ((1.f - lw) * p[h1 * W + w0] + lw * p[h1 * W + w1]);
 }
 // gather form of the adjoint: each input element collects from the <= 3 x 3 outputs that read it
+// y_below (optional) = output of the layer below with activation `act`: dx is multiplied by act'(y_below), i.e.
+// it comes out as that layer's dpre (saves a separate pass over dx)
 __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t BC,
-                                     int H, int W, int two_d, int bilinear) {
+                                     int H, int W, int two_d, int bilinear,
+                                     const float* __restrict__ y_below, int act) {
   const int Ho = two_d ? 2 * H : H, Wo = 2 * W;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= BC * H * W) return;
@@ -391,7 +394,7 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, float* __rest
     if (two_d) s = g[(2 * h) * Wo + 2 * w] + g[(2 * h) * Wo + 2 * w + 1] +
                    g[(2 * h + 1) * Wo + 2 * w] + g[(2 * h + 1) * Wo + 2 * w + 1];
     else s = g[h * Wo + 2 * w] + g[h * Wo + 2 * w + 1];
-    dx[i] = s;
+    dx[i] = y_below ? s * pvb::act_grad(y_below[i], 0.f, act) : s;
     return;
   }
   for (int ho = max(2 * h - 2, 0); ho <= min(2 * h + 2, Ho - 1); ++ho) {
@@ -408,7 +411,7 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, float* __rest
       if (cw != 0.f) s = fmaf(ch * cw, g[ho * Wo + wo], s);
     }
   }
-  dx[i] = s;
+  dx[i] = y_below ? s * pvb::act_grad(y_below[i], 0.f, act) : s;
 }
 
 __global__ void act_bwd_flat_kernel(const float* __restrict__ dy, const float* __restrict__ y,
@@ -455,10 +458,10 @@ conv_o1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, con
   reinterpret_cast<float4*>(y)[i] = make_float4(pvb::act_fwd(acc.x, act), pvb::act_fwd(acc.y, act),
                                                 pvb::act_fwd(acc.z, act), pvb::act_fwd(acc.w, act));
 }
-// dx[b][c][p] = W[c] dpre[b][p]
+// dx[b][c][p] = W[c] dpre[b][p]  (times act'(y_below[b][c][p]) when the layer below's output is given)
 __global__ void __launch_bounds__(256)
 conv_o1_bwd_data_kernel(const float* __restrict__ dpre, const float* __restrict__ W, float* __restrict__ dx,
-                        int64_t n4, int Cin, int HW4) {
+                        int64_t n4, int Cin, int HW4, const float* __restrict__ y_below, int act) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;     // over B x Cin x HW4
   if (i >= n4) return;
   const int64_t bc = i / HW4;
@@ -467,7 +470,13 @@ conv_o1_bwd_data_kernel(const float* __restrict__ dpre, const float* __restrict_
   const int c = (int)(bc - bi * Cin);
   const float4 g = __ldg(reinterpret_cast<const float4*>(dpre) + bi * HW4 + p4);
   const float w = __ldg(W + c);
-  reinterpret_cast<float4*>(dx)[i] = make_float4(w * g.x, w * g.y, w * g.z, w * g.w);
+  float4 o = make_float4(w * g.x, w * g.y, w * g.z, w * g.w);
+  if (y_below) {
+    const float4 yb = __ldg(reinterpret_cast<const float4*>(y_below) + i);
+    o.x *= pvb::act_grad(yb.x, 0.f, act); o.y *= pvb::act_grad(yb.y, 0.f, act);
+    o.z *= pvb::act_grad(yb.z, 0.f, act); o.w *= pvb::act_grad(yb.w, 0.f, act);
+  }
+  reinterpret_cast<float4*>(dx)[i] = o;
 }
 // dW[c] += sum_{b,p} dpre[b][p] x[b][c][p];  db += sum dpre.   grid (Cin, batch splits)
 __global__ void __launch_bounds__(256)
@@ -780,15 +789,20 @@ extern "C" int pvb_conv_fwd(const float* x, const float* W, const float* b, floa
 }
 
 extern "C" int pvb_conv_bwd_data(const float* dpre, const float* W, float* dx, int B, int Cin,
-                                 int Cout, int H, int Wd, int kh, int kw, void* stream) {
+                                 int Cout, int H, int Wd, int kh, int kw, const float* y_below, int act,
+                                 void* stream) {
   ConvDims d{B, Cin, Cout, H, Wd, kh, kw};
   if (check_dims(d, "pvb_conv_bwd_data")) return -1;
   PVB_CHECK_ARG(dpre && W && dx, "pvb_conv_bwd_data: null pointer");
+  PVB_CHECK_ARG(!y_below || (act >= 0 && act <= PVB_ACT_SIGMOID && act != PVB_ACT_GELU),
+                "pvb_conv_bwd_data: fused activation derivative needs an activation expressed from its output");
   if (B == 0) return 0;
   int64_t M = (int64_t)B * H * Wd;
-  if (Cout == 1 && kh * kw == 1 && (H * Wd) % 4 == 0 && (((uintptr_t)dpre | (uintptr_t)dx) & 15) == 0) {
+  if (Cout == 1 && kh * kw == 1 && (H * Wd) % 4 == 0 &&
+      (((uintptr_t)dpre | (uintptr_t)dx | (uintptr_t)y_below) & 15) == 0) {
     const int64_t n4 = M / 4 * Cin;
-    conv_o1_bwd_data_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(dpre, W, dx, n4, Cin, H * Wd / 4);
+    conv_o1_bwd_data_kernel<<<pvb::cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(dpre, W, dx, n4, Cin, H * Wd / 4,
+                                                                                  y_below, act);
     pvb::count_launch();
     return pvb::launch_status();
   }
@@ -796,6 +810,12 @@ extern "C" int pvb_conv_bwd_data(const float* dpre, const float* W, float* dx, i
   size_t smem = (size_t)Cout * kh * kw * sizeof(Tap);
   conv_pix_kernel<1><<<grid, NT, smem, (cudaStream_t)stream>>>(dpre, W, nullptr, dx, nullptr, d, 0);
   pvb::count_launch();
+  if (y_below) {      // no fused form on this path: a separate (16-byte) pass
+    const int64_t n = M * Cin;
+    int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    act_bwd_flat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dx, y_below, nullptr, dx, n, act);
+    pvb::count_launch();
+  }
   return pvb::launch_status();
 }
 
@@ -910,12 +930,15 @@ extern "C" int pvb_upsample2_fwd(const float* x, float* y, int64_t BC, int H, in
 }
 
 extern "C" int pvb_upsample2_bwd(const float* dy, float* dx, int64_t BC, int H, int Wd, int two_d,
-                                 int bilinear, void* stream) {
+                                 int bilinear, const float* y_below, int act, void* stream) {
   PVB_CHECK_ARG(dy && dx && BC >= 0 && H > 0 && Wd > 0, "pvb_upsample2_bwd: bad argument");
+  PVB_CHECK_ARG(!y_below || (act >= 0 && act <= PVB_ACT_SIGMOID && act != PVB_ACT_GELU),
+                "pvb_upsample2_bwd: fused activation derivative needs an activation expressed from its output");
   PVB_CHECK_ARG(!bilinear || two_d, "pvb_upsample2_bwd: bilinear is 2-D only");
   int64_t n = BC * H * Wd;
   if (n == 0) return 0;
-  upsample2_bwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, BC, H, Wd, two_d, bilinear);
+  upsample2_bwd_kernel<<<pvb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, BC, H, Wd, two_d, bilinear,
+                                                                          y_below, act);
   pvb::count_launch();
   return pvb::launch_status();
 }

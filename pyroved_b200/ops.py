@@ -390,12 +390,16 @@ def conv_fwd(x, W, b, act, out, pre=None):
     return out
 
 
-def conv_bwd_data(dpre, W, dx):
+def conv_bwd_data(dpre, W, dx, y_below=None, act_below=None):
+    """y_below / act_below: output and activation of the layer below -- dx *= act'(y_below)"""
     if dx.dim() == 5:
         check(_lib.lib().pvb_conv3d_bwd_data(_p(dpre), _p(W), _p(dx), *_conv3_dims(dx, W), _stream()),
               "pvb_conv3d_bwd_data")
+        if y_below is not None:
+            act_bwd(dx, y_below, None, dx, act_below)
         return
-    check(_lib.lib().pvb_conv_bwd_data(_p(dpre), _p(W), _p(dx), *_conv_dims(dx, W), _stream()),
+    check(_lib.lib().pvb_conv_bwd_data(_p(dpre), _p(W), _p(dx), *_conv_dims(dx, W), _p(y_below),
+                                       ACT[act_below if y_below is not None else None], _stream()),
           "pvb_conv_bwd_data")
 
 
@@ -495,11 +499,15 @@ def upsample2_fwd(x, y, bilinear):
           "pvb_upsample2_fwd")
 
 
-def upsample2_bwd(dy, dx, bilinear):
+def upsample2_bwd(dy, dx, bilinear, y_below=None, act_below=None):
+    """y_below / act_below: output and activation of the layer below -- dx *= act'(y_below)"""
     if dx.dim() == 5:
         check(_lib.lib().pvb_upsample3d_bwd(_p(dy), _p(dx), *_vol(dx), _stream()), "pvb_upsample3d_bwd")
+        if y_below is not None:
+            act_bwd(dx, y_below, None, dx, act_below)
         return
-    check(_lib.lib().pvb_upsample2_bwd(_p(dy), _p(dx), *_plane(dx), int(bool(bilinear)), _stream()),
+    check(_lib.lib().pvb_upsample2_bwd(_p(dy), _p(dx), *_plane(dx), int(bool(bilinear)), _p(y_below),
+                                       ACT[act_below if y_below is not None else None], _stream()),
           "pvb_upsample2_bwd")
 
 

@@ -197,6 +197,12 @@ def test_conv_kernels_vs_torch(shape, act):
     dx = torch.empty_like(x)
     ops.conv_bwd_data(dpre, wt, dx)
     assert torch.allclose(dx, xr.grad, atol=3e-4, rtol=1e-4), (dx - xr.grad).abs().max()
+    # with the output / activation of the layer below: dx * act'(y_below) (fused in the one-output kernel,
+    # a second pass on the generic path)
+    yb = torch.tanh(torch.randn(x.shape, generator=g)).to(dev)
+    dxa = torch.empty_like(x)
+    ops.conv_bwd_data(dpre, wt, dxa, yb, "tanh")
+    assert torch.allclose(dxa, dx * (1 - yb * yb), atol=1e-6, rtol=1e-5)
     dW, db = torch.zeros_like(wt), torch.zeros_like(b)
     ops.conv_bwd_weight(dpre, x, wt, dW, db)
     scale = wr.grad.abs().max().item()
@@ -237,6 +243,11 @@ def test_pool_and_upsample_kernels_vs_torch(shape):
         dx = torch.empty_like(x)
         ops.upsample2_bwd(dy, dx, mode == "bilinear")
         assert torch.allclose(dx, xr.grad, atol=1e-5)
+        # fused activation derivative of the layer below (x = its tanh output)
+        yb = torch.tanh(x)
+        dxa = torch.empty_like(x)
+        ops.upsample2_bwd(dy, dxa, mode == "bilinear", yb, "tanh")
+        assert torch.allclose(dxa, xr.grad * (1 - yb * yb), atol=1e-5)
 
 
 # ---- tensor-core convolutions (fp16 operands, fp32 accumulate) vs PyTorch fp32 ----------
