@@ -73,26 +73,33 @@ __device__ __forceinline__ bool grid_arrive_last(int32_t* ticket, int* s_last) {
   return *s_last != 0;
 }
 
-// Adam on one quad (n % 4 == 0, 16-byte aligned buffers: one 16-byte access per buffer)
-__device__ __forceinline__ void adam4(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                      const float* g4, int64_t j0, int64_t n, float lr, float b1,
-                                      float b2, float eps, int step,
-                                      const int32_t* __restrict__ first_step) {
-  const float4 m4 = *reinterpret_cast<const float4*>(m + j0);
-  const float4 v4 = *reinterpret_cast<const float4*>(v + j0);
-  const float4 p4 = *reinterpret_cast<const float4*>(p + j0);
-  float mq[4] = {m4.x, m4.y, m4.z, m4.w}, vq[4] = {v4.x, v4.y, v4.z, v4.w};
-  float pq[4] = {p4.x, p4.y, p4.z, p4.w};
-  int fq[4] = {0, 0, 0, 0};
-  if (first_step) {
-    const int4 f4 = *reinterpret_cast<const int4*>(first_step + j0);
-    fq[0] = f4.x; fq[1] = f4.y; fq[2] = f4.z; fq[3] = f4.w;
-  }
+// Adam on one quad (n % 4 == 0, 16-byte aligned buffers: one 16-byte access per buffer), in two halves: the
+// optimizer state is fetched BEFORE the (volatile) peer loads are issued, so its latency runs under theirs
+struct AdamQuad {
+  float4 m4, v4, p4;
+  int4 f4;
+};
+__device__ __forceinline__ AdamQuad adam_load(const float* __restrict__ p, const float* __restrict__ m,
+                                              const float* __restrict__ v,
+                                              const int32_t* __restrict__ first_step, int64_t j0) {
+  AdamQuad q;
+  q.m4 = *reinterpret_cast<const float4*>(m + j0);
+  q.v4 = *reinterpret_cast<const float4*>(v + j0);
+  q.p4 = *reinterpret_cast<const float4*>(p + j0);
+  q.f4 = first_step ? *reinterpret_cast<const int4*>(first_step + j0) : make_int4(0, 0, 0, 0);
+  return q;
+}
+__device__ __forceinline__ void adam_apply(const AdamQuad& q, float* __restrict__ p, float* __restrict__ m,
+                                           float* __restrict__ v, const float* g4, int64_t j0, float lr,
+                                           float b1, float b2, float eps, int step, bool per_param) {
+  float mq[4] = {q.m4.x, q.m4.y, q.m4.z, q.m4.w}, vq[4] = {q.v4.x, q.v4.y, q.v4.z, q.v4.w};
+  float pq[4] = {q.p4.x, q.p4.y, q.p4.z, q.p4.w};
+  const int fq[4] = {q.f4.x, q.f4.y, q.f4.z, q.f4.w};
   int last_t = -1;
   float step_size = 0.f, bc2s = 1.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int t = first_step ? (fq[k] < 0 ? 0 : step - fq[k]) : step;
+    const int t = per_param ? (fq[k] < 0 ? 0 : step - fq[k]) : step;
     if (t <= 0) continue;                      // parameter has never carried a gradient
     if (t != last_t) {
       step_size = lr / (1.f - powf(b1, (float)t));
@@ -107,6 +114,28 @@ __device__ __forceinline__ void adam4(float* __restrict__ p, float* __restrict__
   *reinterpret_cast<float4*>(m + j0) = make_float4(mq[0], mq[1], mq[2], mq[3]);
   *reinterpret_cast<float4*>(v + j0) = make_float4(vq[0], vq[1], vq[2], vq[3]);
   *reinterpret_cast<float4*>(p + j0) = make_float4(pq[0], pq[1], pq[2], pq[3]);
+}
+
+// quad i4 of every rank's buffer, summed in rank order 0 ... world-1 (the same order on every rank: the replicas
+// stay bit-identical).  ALL peer loads are issued before the first add: as a load-add loop the seven NVLink round
+// trips of an 8-rank step ran one after the other (each thread owns a single quad at these sizes).
+// (eight ranks per batch: 32 registers of loads in flight; the grid must stay co-resident, see the host side)
+__device__ __forceinline__ float4 sum_ranks(float* const* sp, const float4* g4p, int64_t i4, int rank, int world) {
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r0 = 0; r0 < world; r0 += 8) {
+    float4 a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + u;
+      if (r < world) a[u] = (r == rank) ? g4p[i4] : ld_peer4(sp[r] + 4 * i4);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r0 + u < world) {
+        s.x += a[u].x; s.y += a[u].y; s.z += a[u].z; s.w += a[u].w;
+      }
+  }
+  return s;
 }
 
 __global__ void __launch_bounds__(NT)
@@ -135,47 +164,43 @@ peer_exchange_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* _
   if (threadIdx.x < world) spin_until(mine + threadIdx.x, e);
   __syncthreads();
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) {     // global loss: slot n of every buffer
-    float L = 0.f;
-    for (int r = 0; r < world; ++r) L += (r == rank) ? g[n] : ld_peer1(sp[r] + n);
-    state[4] = __float_as_int(L);
+  if (blockIdx.x == 0) {                          // global loss: slot n of every buffer, one lane per rank
+    __shared__ float s_loss[MAX_WORLD];
+    if (threadIdx.x < world) s_loss[threadIdx.x] = (threadIdx.x == rank) ? g[n] : ld_peer1(sp[threadIdx.x] + n);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float L = 0.f;
+      for (int r = 0; r < world; ++r) L += s_loss[r];
+      state[4] = __float_as_int(L);
+    }
   }
 
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!two_shot) {
     // ---- 3. one-shot: every rank sums every buffer, fixed order ----
     for (int64_t i4 = tid0; i4 < n4; i4 += stride) {
-      float4 s = zero4;
-      for (int r = 0; r < world; ++r) {
-        const float4 a = (r == rank) ? g4p[i4] : ld_peer4(sp[r] + 4 * i4);
-        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-      }
+      const AdamQuad q = adam_load(p, m, v, first_step, 4 * i4);
+      const float4 s = sum_ranks(sp, g4p, i4, rank, world);
       const float gs[4] = {s.x, s.y, s.z, s.w};
-      adam4(p, m, v, gs, 4 * i4, n, lr, b1, b2, eps, step, first_step);
+      adam_apply(q, p, m, v, gs, 4 * i4, lr, b1, b2, eps, step, first_step != nullptr);
       g4p[i4] = zero4;                           // consumed: clean for the next step
     }
   } else {
     // ---- 3a. reduce-scatter: this rank sums slice `rank` of every buffer, in place ----
     const int64_t per = (n4 + world - 1) / world;
     const int64_t lo = (int64_t)rank * per, hi = (lo + per < n4) ? lo + per : n4;
-    for (int64_t i4 = lo + tid0; i4 < hi; i4 += stride) {
-      float4 s = zero4;
-      for (int r = 0; r < world; ++r) {
-        const float4 a = (r == rank) ? g4p[i4] : ld_peer4(sp[r] + 4 * i4);
-        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-      }
-      my_stage[i4] = s;
-    }
+    for (int64_t i4 = lo + tid0; i4 < hi; i4 += stride) my_stage[i4] = sum_ranks(sp, g4p, i4, rank, world);
     if (grid_arrive_last(state + 2, &s_last) && threadIdx.x < world)
       st_release_sys(peer_flags[threadIdx.x] + MAX_WORLD + rank, e);
     if (threadIdx.x < world) spin_until(mine + MAX_WORLD + threadIdx.x, e);
     __syncthreads();
     // ---- 3b. all-gather: every reduced slice from its owner ----
     for (int64_t i4 = tid0; i4 < n4; i4 += stride) {
-      const int q = (int)(i4 / per);
-      const float4 s = ld_peer4(sp[q] + 4 * i4);      // own slice too: written by other CTAs of this grid
+      const int owner = (int)(i4 / per);
+      const AdamQuad q = adam_load(p, m, v, first_step, 4 * i4);
+      const float4 s = ld_peer4(sp[owner] + 4 * i4);  // own slice too: written by other CTAs of this grid
       const float gs[4] = {s.x, s.y, s.z, s.w};
-      adam4(p, m, v, gs, 4 * i4, n, lr, b1, b2, eps, step, first_step);
+      adam_apply(q, p, m, v, gs, 4 * i4, lr, b1, b2, eps, step, first_step != nullptr);
       g4p[i4] = zero4;
     }
   }
@@ -216,7 +241,20 @@ extern "C" int pvb_peer_allreduce_adam(float* p, float* m, float* v, float* g, i
   PVB_CHECK_ARG((uintptr_t)first_step % 16 == 0, "pvb_peer_allreduce_adam: first_step must be 16-byte aligned");
   const int64_t n4 = n / 4;
   int64_t blocks = (n4 + NT - 1) / NT;
-  if (blocks > 148 * 4) blocks = 148 * 4;       // all CTAs co-resident (the kernel syncs grid-wide)
+  // the kernel waits grid-wide (tickets, peer flags), so every CTA must be resident at once: the cap comes from
+  // the occupancy the driver reports for this build of the kernel, not from an assumed register count
+  static int max_resident = 0;
+  if (max_resident == 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer_exchange_adam_kernel, NT, 0) != cudaSuccess ||
+        cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || per_sm < 1 || sms < 1) {
+      per_sm = 1;
+      sms = 148;
+    }
+    max_resident = per_sm * sms;
+  }
+  if (blocks > max_resident) blocks = max_resident;
   peer_exchange_adam_kernel<<<(unsigned)blocks, NT, 0, (cudaStream_t)stream>>>(
       p, m, v, g, n, reinterpret_cast<float* const*>(stage_ptrs),
       reinterpret_cast<uint32_t* const*>(peer_flags), state, rank, world, two_shot ? 1 : 0, lr, beta1,

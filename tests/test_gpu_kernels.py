@@ -179,12 +179,15 @@ def test_reductions_adam_and_regression_terms():
     assert torch.allclose(dxc, (dpre @ W)[:, 100:], atol=1e-4, rtol=1e-4)
 
 
-def test_peer_allreduce_adam_single_rank_equals_adam_flat_step():
+@pytest.mark.parametrize("n", [4 * 1000, 4 * 300_000])
+def test_peer_allreduce_adam_single_rank_equals_adam_flat_step(n):
     """world = 1 degenerate case of the fused NVLink exchange (csrc/pvb_peer.cu): with only its own
     buffer to read, the kernel must reproduce pvb_adam_flat_step bit for bit, publish the loss and
-    advance the step counter / epoch; run repeatedly (epoch flags re-arm)."""
+    advance the step counter / epoch; run repeatedly (epoch flags re-arm).  The large case (1.2 M
+    parameters, the ssiVAE benchmark's size) launches the grid at its co-residency cap: the kernel waits
+    grid-wide, so every CTA must be resident (a register increase once broke exactly that at 8 GPUs; the
+    host now sizes the grid from the occupancy the driver reports)."""
     torch.manual_seed(0)
-    n = 4 * 1000
     dev = "cuda"
     p0 = torch.randn(n, device=dev)
     g = torch.zeros(n + 4, device=dev)
