@@ -60,7 +60,12 @@ int pvb_has_tcgen05(void);
 
 /* ---- dense layers: nn.Linear + activation (nets/fc.py:55-61,307-324) ---- */
 /* y[M,N] = act(x[M,K] W[N,K]^T + b[N]);  pre (optional, may be NULL) receives
- * the pre-activation (only needed for PVB_ACT_GELU backward). */
+ * the pre-activation (only needed for PVB_ACT_GELU backward).
+ * Arithmetic: fp32 throughout.  The small-batch kernel (48..591 tiles of 32 x 32 / 32 x 16, K % 4 == 0,
+ * 16-byte aligned rows) and pvb_mlp_wgrad form their products on the warp-level tensor-core path
+ * with each fp32 operand split into two TF32 terms (three MMAs per product: error ~2^-22, i.e.
+ * fp32-grade); <= 8 outputs over K >= 2048 run on one-pass kernels (forward: a cluster of 8 CTAs
+ * along K, partial sums joined in rank order -- deterministic). */
 int pvb_linear_fwd(const float* x, const float* W, const float* b, float* y,
                    float* pre, int64_t M, int N, int K, int act, void* stream);
 /* Given dy (gradient wrt y), the saved output y (and pre for gelu):
