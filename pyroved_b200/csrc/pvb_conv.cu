@@ -414,9 +414,10 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, float* __rest
   dx[i] = y_below ? s * pvb::act_grad(y_below[i], 0.f, act) : s;
 }
 
-__global__ void act_bwd_flat_kernel(const float* __restrict__ dy, const float* __restrict__ y,
-                                    const float* __restrict__ pre, float* __restrict__ dpre, int64_t n,
-                                    int act) {
+// dy and dpre may be the SAME buffer (the engine applies the derivative in place): no __restrict__ on the
+// pair and plain loads of dy (a thread reads its element before it writes it)
+__global__ void act_bwd_flat_kernel(const float* dy, const float* __restrict__ y,
+                                    const float* __restrict__ pre, float* dpre, int64_t n, int act) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   // 16-byte accesses over the aligned body, scalar tail
@@ -424,7 +425,7 @@ __global__ void act_bwd_flat_kernel(const float* __restrict__ dy, const float* _
                      reinterpret_cast<uintptr_t>(dpre) | (pre ? reinterpret_cast<uintptr_t>(pre) : 0)) & 15) == 0;
   const int64_t n4 = vec ? n / 4 : 0;
   for (int64_t k = i; k < n4; k += stride) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + k);
+    const float4 g = reinterpret_cast<const float4*>(dy)[k];
     const float4 v = __ldg(reinterpret_cast<const float4*>(y) + k);
     const float4 p = pre ? __ldg(reinterpret_cast<const float4*>(pre) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
     reinterpret_cast<float4*>(dpre)[k] =

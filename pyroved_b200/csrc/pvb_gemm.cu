@@ -406,9 +406,9 @@ int launch_sgemm_small(const float* A, const float* B, float* C, float* Cpre, co
 }
 
 // dpre = dy * act'(y)   (elementwise; may run in place)
-__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
-                               const float* __restrict__ pre, float* __restrict__ dpre, int64_t n,
-                               int act) {
+// (dy and dpre may alias: no __restrict__ on the pair)
+__global__ void act_bwd_kernel(const float* dy, const float* __restrict__ y,
+                               const float* __restrict__ pre, float* dpre, int64_t n, int act) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
