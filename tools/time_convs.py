@@ -1,3 +1,5 @@
+"""Time the tensor-core convolution kernels (forward, backward data, weight gradient without / with the
+scratch read-out) on VED's layer shapes at batch 512, and the 1-D decoder weight gradients."""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 from pyroved_b200 import ops
