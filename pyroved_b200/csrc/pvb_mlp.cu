@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int RB = 4;        // batch rows per CTA
+constexpr int RB = 4;        // batch rows per CTA (2 and 8 measured at batch 512: tail 18.5 / 16.5 us against 12.6)
 constexpr int MT = 256;      // threads per CTA (thread n owns output column n of all RB rows)
 constexpr int MAXW = PVB_MLP_MAX_WIDTH;
 constexpr int MAXHD = PVB_MLP_MAX_HEAD_DIM;
